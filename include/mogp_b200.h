@@ -1,0 +1,135 @@
+/*
+ * mogp_b200 -- C ABI of the B200-native exact multi-output GP engine.
+ *
+ * This is the drop-in boundary for the exact-GP hot path of GAMES-UChile/mogptk
+ * (SURVEY.md section 8b).  The reference is pure Python on PyTorch and has no FFI
+ * of its own; the entry points below are what a ctypes binding placed behind the
+ * reference's `inference=` builder seam (mogptk/model.py:89-100,231) binds.  Each
+ * entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All matrices are fp64, row-major.
+ *   - pointers named *_dev are DEVICE pointers on the handle's device, pointers
+ *     named *_host are host pointers.  The library never frees or keeps caller
+ *     buffers past the call; scratch lives in the handle.
+ *   - rows of x / y are sorted by channel: channel c owns rows
+ *     [chan_off[c], chan_off[c+1]) ; chan_off has C+1 entries and lives on the HOST.
+ *     x holds the input coordinates only (N x D), not the channel-id column.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return value 0 = ok, <0 = error (text via mogp_last_error).  Cholesky
+ *     failure is NOT an error return: it is reported LAPACK-style as info = k > 0
+ *     ("leading minor k not positive definite") in the output block, and the
+ *     host raises mogptk.gpr.model.CholeskyException (gpr/model.py:71-78,255).
+ *
+ * Packed constrained hyper-parameters (`params`, length mogp_num_params()):
+ *   MOSM : weight[C][Q] | mean[C][Q][D] | variance[C][Q][D] | delay[C][Q][D] | phase[C][Q]
+ *          (mogptk/gpr/multioutput.py:156-171)
+ *   SM   : magnitude[C][Q] | mean[C][Q][D] | variance[C][Q][D]
+ *          (IndependentMultiOutputKernel of SpectralMixtureKernel,
+ *           gpr/multioutput.py:5-39, gpr/singleoutput.py:583-592)
+ *   CONV : weight[Q][C] | variance[Q][C][D] | base_variance[Q][D]
+ *          (MixtureKernel of GaussianConvolutionProcessKernel,
+ *           gpr/kernel.py:264-276, gpr/multioutput.py:520-529)
+ */
+#ifndef MOGP_B200_H
+#define MOGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mogp_handle_s* mogp_handle_t;
+
+enum { MOGP_KIND_MOSM = 0, MOGP_KIND_SM = 1, MOGP_KIND_CONV = 2 };
+enum { MOGP_MAX_D = 8 };
+
+/* library / ABI version (major*1000 + minor) */
+int mogp_version(void);
+
+/* Number of packed constrained kernel parameters for (kind, C, Q, D); <0 on bad args. */
+int mogp_num_params(int kind, int C, int Q, int D);
+
+/* Workspace for problems of up to max_n rows on CUDA device `device`.
+ * Replaces nothing in the reference (torch's caching allocator plays this role). */
+int mogp_create(int device, int64_t max_n, mogp_handle_t* out);
+int mogp_destroy(mogp_handle_t h);
+const char* mogp_last_error(mogp_handle_t h);
+
+/* K(X1, X2) -- replaces MultiOutputKernel.K (gpr/kernel.py:446-481) with the Ksub of
+ * MOSM (gpr/multioutput.py:178-204), SM (gpr/singleoutput.py:594-600 under
+ * gpr/multioutput.py:26-34) or CONV (gpr/multioutput.py:531-547 under gpr/kernel.py:242-243).
+ *   x2_dev == NULL  => Gram matrix of x1 (n2 = n1, chan_off2 ignored), full symmetric output.
+ *   noise_sigma_dev (C) / data_var_dev (n1) / jitter_rel are only used for the Gram
+ *   matrix: diag += sigma_c^2 + data_var_r, then diag += jitter_rel * mean(diag)
+ *   (gpr/model.py:440-442,244).  Pass NULL / 0.0 for the bare kernel matrix.
+ *   K_dev is n1 x n2 with leading dimension ldk (elements). */
+int mogp_kbuild(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                const double* x1_dev, const int32_t* chan_off1_host,
+                const double* x2_dev, const int32_t* chan_off2_host,
+                const double* noise_sigma_dev, const double* data_var_dev, double jitter_rel,
+                double* K_dev, int64_t ldk, void* stream);
+
+/* K_diag(X) -- replaces MultiOutputKernel.K_diag / Ksub_diag (gpr/kernel.py:483-495,
+ * gpr/multioutput.py:36-39,206-210,549-553).  out_dev has n entries. */
+int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+               const int32_t* chan_off_host, double* out_dev, void* stream);
+
+/* In-place lower Cholesky A = L L^T of an n x n row-major matrix (only the lower triangle
+ * is read; on return the lower triangle holds L, the strict upper triangle is unspecified).
+ * Replaces torch.linalg.cholesky at gpr/model.py:246.  *info_dev (device int32) = 0 or the
+ * 1-based index of the first non-positive pivot. */
+int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda, int32_t* info_dev, void* stream);
+
+/* One exact-GP evaluation -- replaces gpr.Exact.log_marginal_likelihood
+ * (gpr/model.py:438-453) and, with want_grad, the autograd backward of gpr.Model.loss
+ * (gpr/model.py:279-292) in constrained-parameter space.
+ *   y_dev: N targets with any mean function already subtracted (gpr/model.py:445-448).
+ *   noise_sigma_dev: C Gaussian-likelihood scales (gpr/likelihood.py:326-330).
+ *   out_dev: 2 + P + C doubles:
+ *     out[0]      log marginal likelihood
+ *     out[1]      info (0, or k>0: leading minor k not positive definite)
+ *     out[2..2+P) d(-LML)/d params   (packed layout above)          [want_grad only]
+ *     out[2+P..)  d(-LML)/d noise_sigma_c                            [want_grad only]
+ * The factor (L^-1, alpha) stays in the handle for mogp_predict. */
+int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                  const double* x_dev, const int32_t* chan_off_host, const double* y_dev,
+                  const double* noise_sigma_dev, const double* data_var_dev, double jitter_rel,
+                  int want_grad, double* out_dev, void* stream);
+
+/* Same evaluation with HOST buffers: copies inputs host->device, runs, copies the output
+ * block back and synchronises.  This is the call `bench.py`'s end-to-end leg times. */
+int mogp_lml_grad_host(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_host,
+                       const double* x_host, const int32_t* chan_off_host, const double* y_host,
+                       const double* noise_sigma_host, const double* data_var_host, double jitter_rel,
+                       int want_grad, double* out_host);
+
+/* Posterior of f at M test rows using the factor of the last mogp_lml_grad call --
+ * replaces gpr.Exact.predict_f (gpr/model.py:455-483), without re-factorising.
+ *   xs_dev: M x D test inputs sorted by channel, chan_off_s_host: C+1 offsets.
+ *   mu_dev: M means.  var_dev: M variances, or (full != 0) the M x M covariance, row-major. */
+int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t* chan_off_s_host,
+                 int full, double* mu_dev, double* var_dev, void* stream);
+
+/* ---- building blocks exposed for tests and micro-benchmarks --------------------------- */
+
+/* C = alpha * op(A) * op(B) + beta * C on the fp64 tensor pipe (DMMA).
+ * transa/transb: 0 = operand stored (rows x k) / (k x cols) "N", 1 = transposed storage.
+ * M, N multiples of 64, K multiple of 16; leading dimensions even. */
+int mogp_dgemm(mogp_handle_t h, int transa, int transb, int M, int N, int K, double alpha,
+               const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb,
+               double beta, double* C_dev, int64_t ldc, void* stream);
+
+/* Inverse of the lower Cholesky factor and (L L^T)^-1 (lower triangle), n multiple of 128,
+ * all matrices n x n with leading dimension n: used by tests of the inverse path. */
+int mogp_trtri_kinv(mogp_handle_t h, double* A_dev /* in: K, out: L */, double* Linv_dev,
+                    double* Kinv_dev, int64_t n, int32_t* info_dev, void* stream);
+
+/* Device micro-benchmarks: sustained DMMA (mma.sync m8n8k4 f64) and DFMA rates, TFLOP/s. */
+int mogp_peak_fp64(mogp_handle_t h, double* dmma_tflops_host, double* dfma_tflops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOGP_B200_H */

@@ -1,0 +1,145 @@
+// Internal declarations shared by the translation units of libmogp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mogp_b200.h"
+
+#define MOGP_TILE 64          // covariance tile edge (rows/cols of a channel-pair block)
+#define MOGP_NB 64            // Cholesky leaf / inner panel width
+#define MOGP_NB_OUT 256       // Cholesky outer panel width
+#define MOGP_PAD 128          // internal matrices are padded to a multiple of this
+
+// ------------------------------------------------------------------ block-component table
+// Every supported kernel is K_ij[a,b] = sum_r alpha_r exp(-1/2 sum_d v_rd u_d^2) cos(2 pi (sum_d m_rd u_d + phi_r)),
+// u_d = x_a,d - x_b,d + theta_rd, with per channel-pair (i,j) derived constants.
+// comp record layout (doubles): [alpha, phi, v[D], m[D], theta[D]]
+__host__ __device__ inline int comp_stride(int D) { return 2 + 3 * D; }
+
+struct KernSpec {
+    int kind, C, Q, D;
+    int R;            // components per channel pair (MOSM: Q, SM: Q*D, CONV: Q)
+    int P;            // packed constrained kernel parameters
+    bool has_cos;     // false for CONV (m = phi = 0)
+};
+
+inline int spec_init(KernSpec& s, int kind, int C, int Q, int D) {
+    if (C < 1 || Q < 1 || D < 1 || D > MOGP_MAX_D) return -1;
+    s.kind = kind; s.C = C; s.Q = Q; s.D = D;
+    switch (kind) {
+        case MOGP_KIND_MOSM: s.R = Q;     s.P = C * Q * (2 + 3 * D);       s.has_cos = true;  break;
+        case MOGP_KIND_SM:   s.R = Q * D; s.P = C * Q * (1 + 2 * D);       s.has_cos = true;  break;
+        case MOGP_KIND_CONV: s.R = Q;     s.P = Q * (C + C * D + D);       s.has_cos = false; break;
+        default: return -1;
+    }
+    return 0;
+}
+
+// One 64x64 (or ragged) tile of a channel-pair block.
+struct CovTile {
+    int pair;      // i*C + j
+    int r0, c0;    // global first row / col
+    int nr, nc;    // valid rows / cols (<= MOGP_TILE)
+    int flags;     // bit0: tile lies on the global diagonal (r0 == c0, Gram mode)
+};
+
+struct TileList {
+    std::vector<int32_t> off1, off2;   // key
+    int mode;                          // 0 = Gram lower, 1 = Gram full (mirrored), 2 = cross
+    std::vector<CovTile> host;
+    CovTile* dev = nullptr;
+    int n = 0;
+    std::vector<int32_t> pair_first;   // Gram-lower: first tile of each lower pair (for the finalize pass)
+    int32_t* pair_first_dev = nullptr;
+};
+
+// ------------------------------------------------------------------ GEMM descriptor
+struct GemmArgs {
+    const double* A; const double* B; double* C;
+    long long lda, ldb, ldc;
+    long long strideA, strideB, strideC;   // batch strides (elements)
+    int M, N, K;
+    int lower;      // 1: skip tiles strictly above the diagonal ((tm+1)*BM <= tn*BN)
+    int klo_mode;   // 0: 0        1: tn*BN     2: tm*BM
+    int khi_mode;   // 0: K        1: min(K,(tm+1)*BM)
+    int epi;        // 0: C = alpha*acc + beta*C      1: C = 0.5*(acc - avec[row]*avec[col])
+    double alpha, beta;
+    const double* avec;
+};
+
+// transa: 0 -> A stored [m][k] (k contiguous), 1 -> A stored [k][m]
+// transb: 0 -> B stored [k][n] (n contiguous), 1 -> B stored [n][k]
+cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s);
+
+// ------------------------------------------------------------------ handle
+struct mogp_handle_s {
+    int device = 0;
+    int64_t max_n = 0, np_max = 0;
+    double *A = nullptr, *Linv = nullptr, *W = nullptr;      // np_max^2 each
+    double *comps = nullptr; size_t comps_cap = 0;            // C*C*R*stride
+    double *chanbuf = nullptr;                                // per-channel scalars (see capi.cu)
+    double *vec = nullptr;                                    // 8 * np_max doubles of vector scratch
+    double *colpart = nullptr; size_t colpart_cap = 0;        // column-pass partials
+    double *tile_part = nullptr; size_t tile_part_cap = 0;    // gradient tile partials
+    double *xbuf = nullptr; size_t xbuf_cap = 0;              // copy of training x (N*D)
+    double *pbuf = nullptr; size_t pbuf_cap = 0;              // host-entry staging (params, sigma, y, dv)
+    double *out_dev = nullptr; size_t out_cap = 0;
+    double *pred_K = nullptr, *pred_V = nullptr, *pred_S = nullptr; size_t pred_cap = 0, pred_s_cap = 0;
+    double *logdet_part = nullptr;                            // np_max/64
+    int32_t *info = nullptr;
+    int32_t *chan_dev = nullptr;                              // device copy of chan_off (C+1)
+    std::vector<TileList*> tiles;
+    // state of the last factorisation (for predict)
+    bool have_factor = false;
+    KernSpec spec{};
+    std::vector<int32_t> chan_off;
+    int64_t N = 0, Np = 0;
+    std::string err;
+};
+
+#define MOGP_CHECK(h, expr)                                                          \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);           \
+            return -2;                                                               \
+        }                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------ covariance kernels (cov.cu)
+// chanbuf layout (doubles): [0..C) kdiag_gram | [C..2C) kdiag_api | [2C..3C) noise variance | [3C] jitter add | [3C+1] trW scratch
+cudaError_t launch_prep(const KernSpec& s, const double* params, const double* sigma, const double* data_var,
+                        const int32_t* chan_dev, int64_t N, double jitter_rel, double* comps, double* chanbuf,
+                        cudaStream_t st);
+// mode 0: Gram lower into padded A (ld = Np), also initialises the padding; mode 1: Gram full; mode 2: cross
+cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* comps, const double* chanbuf,
+                          const double* x1, const double* x2, const int32_t* chan1_dev, const double* data_var,
+                          int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st);
+cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t* chan_dev, int64_t N, double* out,
+                         cudaStream_t st);
+cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
+                               const double* W, long long ldw, double* tile_part, cudaStream_t st);
+// out: [0]=lml [1]=info [2..2+P) grad params [2+P..2+P+C) grad sigma
+cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad, const double* params,
+                            const double* sigma, const double* comps, const double* chanbuf,
+                            const double* tile_part, const double* z, const double* alpha, const double* kinv_diag,
+                            const double* logdet_part, const int32_t* info, const int32_t* chan_dev,
+                            int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st);
+
+// ------------------------------------------------------------------ dense linear algebra (linalg.cu)
+cudaError_t potrf_padded(mogp_handle_s* h, double* A, double* Linv, int64_t Np, long long ld, double* logdet_part,
+                         int32_t* info, cudaStream_t st);
+cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
+cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
+// z = Linv * y (lower-triangular mat-vec), rows [0,Np)
+cudaError_t launch_trmv_lower(const double* Linv, long long ld, const double* y, double* z, int64_t Np, cudaStream_t st);
+// column pass: out_dot[c] = sum_r M[r][c]*v[r], out_sq[c] = sum_r M[r][c]^2, rows [0,rows), cols [0,cols)
+cudaError_t launch_colpass(const double* M, long long ld, const double* v, int64_t rows, int64_t cols,
+                           double* part, size_t part_cap, double* out_dot, double* out_sq, cudaStream_t st);
+cudaError_t launch_pad_copy(const double* src, int64_t n, double* dst, int64_t np, cudaStream_t st);
+cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, long long ldw, int64_t n, int64_t np,
+                            cudaStream_t st);
+cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
+                            double* var, cudaStream_t st);
+cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);

@@ -1,0 +1,600 @@
+// Dense fp64 linear algebra for the exact-GP step on sm_100a:
+//   * a cp.async-pipelined GEMM on the fp64 tensor pipe (mma.sync m8n8k4 -> SASS DMMA.8x8x4;
+//     tcgen05.mma has no .kind::f64) with triangular k-clipping modes,
+//   * a 64x64 single-CTA Cholesky leaf that also inverts its block,
+//   * blocked right-looking Cholesky (two-level panels), level-batched triangular inverse,
+//     K^-1 = L^-T L^-1 with the W = (K^-1 - a a^T)/2 epilogue, triangular mat-vecs.
+// Replaces torch.linalg.cholesky / cholesky_solve / solve_triangular and their autograd
+// backward at mogptk/gpr/model.py:246,452,470 (reference) -- see include/mogp_b200.h.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+// ============================================================================ primitives
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ============================================================================ GEMM
+// C[M x N] (+)= alpha * op(A) * op(B), CTA tile BM x BN x 16, WM x WN warps, warp tile
+// (BM/WM) x (BN/WN) of m8n8k4 DMMA fragments, STAGES-deep cp.async pipeline.
+// TA: A stored [k][m] (m contiguous) instead of [m][k];  TB: B stored [n][k] instead of [k][n].
+// Shared-memory row pitches are == 4 (mod 16) doubles, which makes every fragment load
+// (lane (g,t) reads [g][t] or [t][g]) bank-conflict free.
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool TA, bool TB>
+__global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g) {
+    constexpr int BK = 16;
+    constexpr int NTH = WM * WN * 32;
+    constexpr int WTM = BM / WM, WTN = BN / WN, MT = WTM / 8, NT = WTN / 8;
+    constexpr int LDA_S = TA ? (BM + 4) : (BK + 4);
+    constexpr int LDB_S = TB ? (BK + 4) : (BN + 4);
+    constexpr int A_STAGE = TA ? BK * LDA_S : BM * LDA_S;
+    constexpr int B_STAGE = TB ? BN * LDB_S : BK * LDB_S;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+
+    const int tn = blockIdx.x, tm = blockIdx.y;
+    if (g.lower && (tm + 1) * BM <= tn * BN) return;
+    int klo = 0, khi = g.K;
+    if (g.klo_mode == 1) klo = tn * BN;
+    else if (g.klo_mode == 2) klo = tm * BM;
+    if (g.khi_mode == 1) khi = min(g.K, (tm + 1) * BM);
+    const long long bz = blockIdx.z;
+    const double* __restrict__ A = g.A + bz * g.strideA;
+    const double* __restrict__ B = g.B + bz * g.strideB;
+    double* C = g.C + bz * g.strideC;
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int tid = threadIdx.x;
+    const int mvalid = g.M - m0;
+    const long long lda = g.lda, ldb = g.ldb;
+
+    auto load_stage = [&](int stage, int k0) {
+        double* as = As + stage * A_STAGE;
+        double* bs = Bs + stage * B_STAGE;
+        if (!TA) {
+            constexpr int CH = BM * 8;
+#pragma unroll
+            for (int c = tid; c < CH; c += NTH) {
+                int row = c >> 3, cc = c & 7;
+                bool ok = row < mvalid;
+                const double* src = A + (long long)(m0 + (ok ? row : 0)) * lda + k0 + cc * 2;
+                cp_async16(as + row * LDA_S + cc * 2, src, ok);
+            }
+        } else {
+            constexpr int CPR = BM / 2;
+            constexpr int CH = BK * CPR;
+#pragma unroll
+            for (int c = tid; c < CH; c += NTH) {
+                int kr = c / CPR, cc = c % CPR;
+                bool ok = cc * 2 < mvalid;
+                const double* src = A + (long long)(k0 + kr) * lda + m0 + (ok ? cc * 2 : 0);
+                cp_async16(as + kr * LDA_S + cc * 2, src, ok);
+            }
+        }
+        if (TB) {
+            constexpr int CH = BN * 8;
+#pragma unroll
+            for (int c = tid; c < CH; c += NTH) {
+                int row = c >> 3, cc = c & 7;
+                const double* src = B + (long long)(n0 + row) * ldb + k0 + cc * 2;
+                cp_async16(bs + row * LDB_S + cc * 2, src, true);
+            }
+        } else {
+            constexpr int CPR = BN / 2;
+            constexpr int CH = BK * CPR;
+#pragma unroll
+            for (int c = tid; c < CH; c += NTH) {
+                int kr = c / CPR, cc = c % CPR;
+                const double* src = B + (long long)(k0 + kr) * ldb + n0 + cc * 2;
+                cp_async16(bs + kr * LDB_S + cc * 2, src, true);
+            }
+        }
+    };
+
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int am0 = (warp / WN) * WTM, bn0 = (warp % WN) * WTN;
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int kt0 = klo / BK, kt1 = khi / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (kt0 + s < kt1) load_stage(s, (kt0 + s) * BK);
+        cp_async_commit();
+    }
+    for (int kt = kt0; kt < kt1; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < kt1) load_stage((nk - kt0) % STAGES, nk * BK);
+            cp_async_commit();
+        }
+        const int stage = (kt - kt0) % STAGES;
+        const double* as = As + stage * A_STAGE;
+        const double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[MT], b[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+                a[i] = TA ? as[(kk + tq) * LDA_S + am0 + i * 8 + gq] : as[(am0 + i * 8 + gq) * LDA_S + kk + tq];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                b[j] = TB ? bs[(bn0 + j * 8 + gq) * LDB_S + kk + tq] : bs[(kk + tq) * LDB_S + bn0 + j * 8 + gq];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const long long ldc = g.ldc;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int row = am0 + i * 8 + gq;
+        if (row >= mvalid) continue;
+        const long long r = m0 + row;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int col = n0 + bn0 + j * 8 + 2 * tq;
+            double2* p = reinterpret_cast<double2*>(C + r * ldc + col);
+            double2 v;
+            if (g.epi == 0) {
+                v.x = g.alpha * acc[i][j][0];
+                v.y = g.alpha * acc[i][j][1];
+                if (g.beta != 0.0) {
+                    double2 o = *p;
+                    v.x += g.beta * o.x;
+                    v.y += g.beta * o.y;
+                }
+            } else {
+                const double ai = g.avec[r];
+                v.x = 0.5 * (acc[i][j][0] - ai * g.avec[col]);
+                v.y = 0.5 * (acc[i][j][1] - ai * g.avec[col + 1]);
+            }
+            *p = v;
+        }
+    }
+}
+
+static int g_gemm_cfg = -1;   // 0: 128x64 tiles, 128 threads, 2 CTAs/SM   1: 128x128 tiles, 256 threads
+
+extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
+
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool TA, bool TB>
+static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s) {
+    constexpr int BK = 16;
+    constexpr int LDA_S = TA ? (BM + 4) : (BK + 4);
+    constexpr int LDB_S = TB ? (BK + 4) : (BN + 4);
+    constexpr int A_STAGE = TA ? BK * LDA_S : BM * LDA_S;
+    constexpr int B_STAGE = TB ? BN * LDB_S : BK * LDB_S;
+    constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, TA, TB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
+    dim3 grid(g.N / BN, (g.M + BM - 1) / BM, batch);
+    kern<<<grid, WM * WN * 32, SMEM, s>>>(g);
+    return cudaGetLastError();
+}
+
+template <bool TA, bool TB>
+static cudaError_t launch_gemm_t(const GemmArgs& g, int batch, cudaStream_t s) {
+    if (g_gemm_cfg < 0) {
+        const char* e = getenv("MOGP_GEMM_CFG");
+        g_gemm_cfg = e ? atoi(e) : 0;
+    }
+    if (g_gemm_cfg == 1 && (g.N % 128) == 0)
+        return launch_gemm_cfg<128, 128, 2, 4, 3, 1, TA, TB>(g, batch, s);
+    return launch_gemm_cfg<128, 64, 2, 2, 3, 2, TA, TB>(g, batch, s);
+}
+
+cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s) {
+    if ((g.N % 64) || (g.K % 16) || (g.M % 64)) return cudaErrorInvalidValue;
+    if (transa == 0 && transb == 0) return launch_gemm_t<false, false>(g, batch, s);
+    if (transa == 0 && transb == 1) return launch_gemm_t<false, true>(g, batch, s);
+    if (transa == 1 && transb == 0) return launch_gemm_t<true, false>(g, batch, s);
+    return launch_gemm_t<true, true>(g, batch, s);
+}
+
+// ============================================================================ Cholesky leaf
+// Factor the 64x64 diagonal block `blk` in place (lower) and write its inverse (dense,
+// explicit zeros above the diagonal) into the same block position of Linv.
+// Right-looking column sweep in shared memory, then a recursive-doubling triangular
+// inverse: inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] for s = 1,2,...,32.
+#define LP 65
+__global__ void __launch_bounds__(256) potrf_leaf_kernel(double* __restrict__ A, long long lda,
+                                                         double* __restrict__ Linv, long long ldi, int blk,
+                                                         double* __restrict__ logdet_part, int32_t* info) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;
+    double* T = sm + 64 * LP;
+    double* U = T + 64 * LP;
+    double* dg = U + 64 * LP;
+    const int tid = threadIdx.x;
+    double* Ab = A + (long long)blk * 64 * lda + (long long)blk * 64;
+    for (int idx = tid; idx < 4096; idx += 256) {
+        int r = idx >> 6, c = idx & 63;
+        S[r * LP + c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
+        T[r * LP + c] = 0.0;
+    }
+    const int ti = tid >> 4, tk = tid & 15;
+    for (int j = 0; j < 64; ++j) {
+        __syncthreads();
+        double d = S[j * LP + j];
+        if (!(d > 0.0)) {
+            if (tid == 0) atomicCAS(info, 0, blk * 64 + j + 1);
+            d = 1.0;
+        }
+        const double r = sqrt(d);
+        if (tid > j && tid < 64) S[tid * LP + j] = S[tid * LP + j] / r;
+        if (tid == j) dg[j] = r;
+        __syncthreads();
+        for (int i = j + 1 + ti; i < 64; i += 16) {
+            const double lij = S[i * LP + j];
+            for (int k = j + 1 + tk; k <= i; k += 16) S[i * LP + k] -= lij * S[k * LP + j];
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        S[tid * LP + tid] = dg[tid];
+        T[tid * LP + tid] = 1.0 / dg[tid];
+    }
+    __syncthreads();
+    for (int s = 1; s < 64; s <<= 1) {
+        const int total = 32 * s, ss = s * s;
+        for (int e = tid; e < total; e += 256) {
+            int p = e / ss, rem = e - p * ss, rr = rem / s, cc = rem - rr * s;
+            int o = p * 2 * s;
+            double acc = 0.0;
+            for (int l = cc; l < s; ++l) acc += S[(o + s + rr) * LP + o + l] * T[(o + l) * LP + o + cc];
+            U[(o + s + rr) * LP + o + cc] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < total; e += 256) {
+            int p = e / ss, rem = e - p * ss, rr = rem / s, cc = rem - rr * s;
+            int o = p * 2 * s;
+            double acc = 0.0;
+            for (int l = 0; l <= rr; ++l) acc += T[(o + s + rr) * LP + o + s + l] * U[(o + s + l) * LP + o + cc];
+            T[(o + s + rr) * LP + o + cc] = -acc;
+        }
+        __syncthreads();
+    }
+    double* Lb = Linv + (long long)blk * 64 * ldi + (long long)blk * 64;
+    for (int idx = tid; idx < 4096; idx += 256) {
+        int r = idx >> 6, c = idx & 63;
+        if (c <= r) Ab[(long long)r * lda + c] = S[r * LP + c];
+        Lb[(long long)r * ldi + c] = T[r * LP + c];
+    }
+    if (tid < 32) {
+        double v = log(dg[tid]) + log(dg[tid + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tid == 0) logdet_part[blk] = v;
+    }
+}
+
+static cudaError_t launch_leaf(double* A, long long lda, double* Linv, long long ldi, int blk, double* logdet_part,
+                               int32_t* info, cudaStream_t st) {
+    const size_t smem = (3 * 64 * LP + 64) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    potrf_leaf_kernel<<<1, 256, smem, st>>>(A, lda, Linv, ldi, blk, logdet_part, info);
+    return cudaGetLastError();
+}
+
+// ============================================================================ blocked Cholesky
+// In-place lower Cholesky of the padded Np x Np matrix A (row-major, ld).  Two-level
+// right-looking: outer panels of MOGP_NB_OUT columns whose trailing update is one SYRK with
+// K = 256, inner 64-wide steps (leaf -> TRSM as GEMM with the leaf's explicit inverse ->
+// update of the remaining panel columns).  Diagonal blocks of Linv receive inv(L_kk).
+cudaError_t potrf_padded(mogp_handle_s* h, double* A, double* Linv, int64_t Np, long long ld, double* logdet_part,
+                         int32_t* info, cudaStream_t st) {
+    (void)h;
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT) {
+        const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
+        for (int64_t k = K0; k < Kend; k += MOGP_NB) {
+            e = launch_leaf(A, ld, Linv, ld, (int)(k / MOGP_NB), logdet_part, info, st);
+            if (e != cudaSuccess) return e;
+            const int64_t r0 = k + MOGP_NB, M = Np - r0;
+            if (M <= 0) continue;
+            GemmArgs g{};
+            g.A = A + r0 * ld + k; g.lda = ld;
+            g.B = Linv + k * ld + k; g.ldb = ld;
+            g.C = A + r0 * ld + k; g.ldc = ld;
+            g.M = (int)M; g.N = MOGP_NB; g.K = MOGP_NB;
+            g.alpha = 1.0; g.beta = 0.0;
+            e = launch_gemm(0, 1, g, 1, st);           // L21 = A21 * inv(L11)^T
+            if (e != cudaSuccess) return e;
+            const int64_t Nc = Kend - r0;
+            if (Nc > 0) {                                // remaining columns of this outer panel
+                GemmArgs u{};
+                u.A = A + r0 * ld + k; u.lda = ld;
+                u.B = A + r0 * ld + k; u.ldb = ld;
+                u.C = A + r0 * ld + r0; u.ldc = ld;
+                u.M = (int)M; u.N = (int)Nc; u.K = MOGP_NB;
+                u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
+                e = launch_gemm(0, 1, u, 1, st);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        const int64_t M = Np - Kend;
+        if (M > 0) {                                     // trailing SYRK, K = panel width
+            GemmArgs u{};
+            u.A = A + Kend * ld + K0; u.lda = ld;
+            u.B = A + Kend * ld + K0; u.ldb = ld;
+            u.C = A + Kend * ld + Kend; u.ldc = ld;
+            u.M = (int)M; u.N = (int)M; u.K = (int)Wd;
+            u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
+            e = launch_gemm(0, 1, u, 1, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+// ============================================================================ triangular inverse
+// Linv = L^-1 by level-batched block doubling: at level s (in 64-blocks) every pair of
+// adjacent diagonal super-blocks (A, B) gets Linv_BA = -Linv_BB * (L_BA * Linv_AA).
+// Two batched GEMMs per level (+2 for a ragged last pair); `scratch` holds L_BA*Linv_AA.
+cudaError_t trtri_padded(double* L, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st) {
+    const int64_t nblk = Np / 64;
+    for (int64_t s = 1; s < nblk; s *= 2) {
+        const int64_t S = s * 64;
+        const int64_t nfull = nblk / (2 * s);
+        const int64_t o_rem = nfull * 2 * S;
+        const int64_t remB = (nblk - nfull * 2 * s > s) ? (nblk - nfull * 2 * s - s) * 64 : 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int64_t o = pass == 0 ? 0 : o_rem;
+            const int64_t MB = pass == 0 ? S : remB;
+            const int batch = pass == 0 ? (int)nfull : 1;
+            if (MB <= 0 || batch <= 0) continue;
+            GemmArgs a{};
+            a.A = L + (o + S) * ld + o; a.lda = ld; a.strideA = 2 * S * (ld + 1);
+            a.B = Linv + o * ld + o; a.ldb = ld; a.strideB = 2 * S * (ld + 1);
+            a.C = scratch + (o + S) * ld + o; a.ldc = ld; a.strideC = 2 * S * (ld + 1);
+            a.M = (int)MB; a.N = (int)S; a.K = (int)S;
+            a.klo_mode = 1; a.alpha = 1.0; a.beta = 0.0;
+            cudaError_t e = launch_gemm(0, 0, a, batch, st);
+            if (e != cudaSuccess) return e;
+            GemmArgs b{};
+            b.A = Linv + (o + S) * ld + (o + S); b.lda = ld; b.strideA = 2 * S * (ld + 1);
+            b.B = scratch + (o + S) * ld + o; b.ldb = ld; b.strideB = 2 * S * (ld + 1);
+            b.C = Linv + (o + S) * ld + o; b.ldc = ld; b.strideC = 2 * S * (ld + 1);
+            b.M = (int)MB; b.N = (int)S; b.K = (int)MB;
+            b.khi_mode = 1; b.alpha = -1.0; b.beta = 0.0;
+            e = launch_gemm(0, 0, b, batch, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+// W(lower) = 0.5 * (Linv^T Linv - avec avec^T)   (avec == NULL -> plain K^-1 lower)
+__global__ void zero_vec_kernel(double* v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = 0.0;
+}
+
+cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = Linv; g.lda = ld;
+    g.B = Linv; g.ldb = ld;
+    g.C = W; g.ldc = ld;
+    g.M = (int)Np; g.N = (int)Np; g.K = (int)Np;
+    g.lower = 1; g.klo_mode = 2;
+    if (avec) { g.epi = 1; g.avec = avec; }
+    else { g.epi = 0; g.alpha = 1.0; g.beta = 0.0; }
+    return launch_gemm(1, 0, g, 1, st);
+}
+
+// ============================================================================ mat-vecs
+// z[r] = sum_{c<=r} Linv[r][c] * y[c]; one warp per row.
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ Linv, long long ld,
+                                                         const double* __restrict__ y, double* __restrict__ z,
+                                                         int64_t Np) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= Np) return;
+    const double* row = Linv + r * ld;
+    double acc = 0.0;
+    for (int64_t c = lane; c <= r; c += 32) acc += row[c] * y[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) z[r] = acc;
+}
+
+cudaError_t launch_trmv_lower(const double* Linv, long long ld, const double* y, double* z, int64_t Np, cudaStream_t st) {
+    trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Linv, ld, y, z, Np);
+    return cudaGetLastError();
+}
+
+// column pass, two deterministic phases.
+__global__ void __launch_bounds__(256) colpass_kernel(const double* __restrict__ M, long long ld,
+                                                      const double* __restrict__ v, int64_t rows, int64_t cols,
+                                                      int64_t rows_per, double* __restrict__ part) {
+    __shared__ double sd[4][64], sq[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int64_t c = blockIdx.x * 64 + tx;
+    const int64_t rb = blockIdx.y * rows_per, re = min(rows, rb + rows_per);
+    double ad = 0.0, aq = 0.0;
+    if (c < cols)
+        for (int64_t r = rb + ty; r < re; r += 4) {
+            const double m = M[r * ld + c];
+            ad += m * v[r];
+            aq += m * m;
+        }
+    sd[ty][tx] = ad;
+    sq[ty][tx] = aq;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        ad = (sd[0][tx] + sd[1][tx]) + (sd[2][tx] + sd[3][tx]);
+        aq = (sq[0][tx] + sq[1][tx]) + (sq[2][tx] + sq[3][tx]);
+        part[(blockIdx.y * 2 + 0) * cols + c] = ad;
+        part[(blockIdx.y * 2 + 1) * cols + c] = aq;
+    }
+}
+__global__ void colpass_reduce_kernel(const double* __restrict__ part, int nsplit, int64_t cols,
+                                      double* __restrict__ out_dot, double* __restrict__ out_sq) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double ad = 0.0, aq = 0.0;
+    for (int s = 0; s < nsplit; ++s) {
+        ad += part[(s * 2 + 0) * cols + c];
+        aq += part[(s * 2 + 1) * cols + c];
+    }
+    if (out_dot) out_dot[c] = ad;
+    if (out_sq) out_sq[c] = aq;
+}
+
+cudaError_t launch_colpass(const double* M, long long ld, const double* v, int64_t rows, int64_t cols, double* part,
+                           size_t part_cap, double* out_dot, double* out_sq, cudaStream_t st) {
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(64, rows / 128));
+    while ((size_t)(nsplit * 2 * cols) > part_cap && nsplit > 1) nsplit /= 2;
+    if ((size_t)(nsplit * 2 * cols) > part_cap) return cudaErrorInvalidValue;
+    const int64_t rows_per = (rows + nsplit - 1) / nsplit;
+    dim3 grid((unsigned)((cols + 63) / 64), (unsigned)nsplit);
+    colpass_kernel<<<grid, 256, 0, st>>>(M, ld, v, rows, cols, rows_per, part);
+    colpass_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(part, (int)nsplit, cols, out_dot, out_sq);
+    return cudaGetLastError();
+}
+
+__global__ void pad_copy_kernel(const double* __restrict__ src, int64_t n, double* __restrict__ dst, int64_t np) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < np) dst[i] = i < n ? src[i] : 0.0;
+}
+cudaError_t launch_pad_copy(const double* src, int64_t n, double* dst, int64_t np, cudaStream_t st) {
+    pad_copy_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(src, n, dst, np);
+    return cudaGetLastError();
+}
+
+// dir 0: lower triangle of user (n x n) -> padded work (np x np, identity padding)
+// dir 1: lower triangle of work -> user
+__global__ void copy_tri_kernel(int dir, double* user, long long ldu, double* work, long long ldw, int64_t n, int64_t np) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c > r || r >= np) return;
+    if (dir == 0) {
+        double v = (r < n) ? user[r * ldu + c] : (r == c ? 1.0 : 0.0);
+        work[r * ldw + c] = v;
+    } else if (r < n) {
+        user[r * ldu + c] = work[r * ldw + c];
+    }
+}
+cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, long long ldw, int64_t n, int64_t np,
+                            cudaStream_t st) {
+    dim3 grid((unsigned)((np + 255) / 256), (unsigned)np);
+    copy_tri_kernel<<<grid, 256, 0, st>>>(dir, user, ldu, work, ldw, n, np);
+    return cudaGetLastError();
+}
+
+__global__ void pred_var_kernel(const double* __restrict__ chanbuf, int C, const int32_t* __restrict__ chan_s,
+                                const double* __restrict__ colsq, int64_t M, double* __restrict__ var) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= M) return;
+    int c = 0;
+    while (c + 1 < C && s >= chan_s[c + 1]) ++c;
+    var[s] = chanbuf[C + c] - colsq[s];
+}
+cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
+                            double* var, cudaStream_t st) {
+    pred_var_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(chanbuf, C, chan_s_dev, colsq, M, var);
+    return cudaGetLastError();
+}
+
+// ============================================================================ fp64 peak probes
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) {
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+
+cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops) {
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 8);
+    if (e != cudaSuccess) return e;
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    const int blocks = prop.multiProcessorCount * 4, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float ms = 0.f;
+    const int iters = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        peak_dmma_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    // one m8n8k4 = 8*8*4 FMA = 512 flop per warp
+    *dmma_tflops = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0 / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        peak_dfma_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    *dfma_tflops = (double)blocks * threads * (double)iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    e = cudaGetLastError();
+    cudaFree(d);
+    return e;
+}
