@@ -1,0 +1,82 @@
+"""ctypes binding of libmogp_b200.so (the C ABI declared in include/mogp_b200.h).
+
+The library is the product: if it is missing this module raises -- there is no CPU or
+PyTorch fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mogp_b200.h")
+
+KIND = {"MOSM": 0, "SM": 1, "CONV": 2}
+
+_lib = None
+
+c_dp = C.c_void_p      # device / host double*
+c_ip = C.POINTER(C.c_int32)
+
+_SIGNATURES = {
+    "mogp_version": (C.c_int, []),
+    "mogp_num_params": (C.c_int, [C.c_int] * 4),
+    "mogp_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "mogp_destroy": (C.c_int, [C.c_void_p]),
+    "mogp_last_error": (C.c_char_p, [C.c_void_p]),
+    "mogp_kbuild": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_ip,
+                              c_dp, c_dp, C.c_double, c_dp, C.c_int64, C.c_void_p]),
+    "mogp_kdiag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_void_p]),
+    "mogp_potrf": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mogp_lml_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp,
+                                C.c_double, C.c_int, c_dp, C.c_void_p]),
+    "mogp_lml_grad_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp,
+                                     C.c_double, C.c_int, c_dp]),
+    "mogp_predict": (C.c_int, [C.c_void_p, c_dp, c_ip, C.c_int, c_dp, c_dp, C.c_void_p]),
+    "mogp_dgemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, C.c_int64,
+                             c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.c_void_p]),
+    "mogp_trtri_kinv": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mogp_peak_fp64": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+# not part of the public header: tuning / host self-check hooks
+_EXTRA = {
+    "mogp_set_gemm_config": (None, [C.c_int]),
+    "mogp_launch_count": (C.c_longlong, []),
+    "mogp_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "mogp_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mogp_host_pair_comps": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp]),
+    "mogp_host_chain": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp, c_dp, c_dp]),
+}
+
+
+def header_symbols():
+    """Function names declared in include/mogp_b200.h."""
+    with open(HEADER_PATH) as f:
+        txt = f.read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mogp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load(check_symbols=False):
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "mogptk_b200: %s is missing -- build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_EXTRA}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if check_symbols:
+        missing = [s for s in header_symbols() if not hasattr(_lib, s)]
+        if missing:
+            raise RuntimeError("libmogp_b200.so does not export: %s" % ", ".join(missing))
+        undeclared = [s for s in _SIGNATURES if s not in header_symbols()]
+        if undeclared:
+            raise RuntimeError("bound but not declared in the header: %s" % ", ".join(undeclared))
+    return _lib

@@ -1,0 +1,461 @@
+// C ABI of libmogp_b200.so: workspace handle, tile lists, the fused exact-GP step.
+// See include/mogp_b200.h for the contract and the reference interfaces each entry replaces.
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+
+#define MOGP_VERSION 1000
+
+static int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+#define H_ARG(h, cond, msg)             \
+    do {                                \
+        if (!(cond)) {                  \
+            (h)->err = (msg);           \
+            return -1;                  \
+        }                               \
+    } while (0)
+
+template <typename T>
+static int ensure(mogp_handle_s* h, T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap && ptr) return 0;
+    if (ptr) MOGP_CHECK(h, cudaFree(ptr));
+    ptr = nullptr; cap = 0;
+    size_t want = need + need / 4 + 64;
+    MOGP_CHECK(h, cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+
+extern "C" int mogp_version(void) { return MOGP_VERSION; }
+
+extern "C" int mogp_num_params(int kind, int C, int Q, int D) {
+    KernSpec s;
+    if (spec_init(s, kind, C, Q, D)) return -1;
+    return s.P;
+}
+
+extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
+    if (!out || max_n < 1) return -1;
+    *out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return -2;
+    mogp_handle_s* h = new mogp_handle_s();
+    h->device = device;
+    h->max_n = max_n;
+    h->np_max = round_up(max_n, MOGP_PAD);
+    const size_t nn = (size_t)h->np_max * h->np_max;
+    auto fail = [&](cudaError_t err) { (void)err; mogp_destroy(h); return -2; };
+    if ((e = cudaMalloc(&h->A, nn * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->Linv, nn * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->W, nn * 8)) != cudaSuccess) return fail(e);
+    // invariant: everything above the diagonal blocks of Linv is zero (GEMM k-clipping relies on it)
+    if ((e = cudaMemset(h->Linv, 0, nn * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->vec, 8 * (size_t)h->np_max * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->chanbuf, 1024 * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->chanbuf2, 1024 * 8)) != cudaSuccess) return fail(e);
+    h->linv_np = h->np_max;
+    if ((e = cudaMalloc(&h->logdet_part, (size_t)(h->np_max / 64 + 1) * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->info, 64)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&h->chan_dev, 4 * 260 * 2)) != cudaSuccess) return fail(e);
+    h->colpart_cap = (size_t)64 * 2 * h->np_max;
+    if ((e = cudaMalloc(&h->colpart, h->colpart_cap * 8)) != cudaSuccess) return fail(e);
+    *out = h;
+    return 0;
+}
+
+extern "C" int mogp_destroy(mogp_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (TileList* t : h->tiles) {
+        if (t->dev) cudaFree(t->dev);
+        if (t->pair_first_dev) cudaFree(t->pair_first_dev);
+        delete t;
+    }
+    void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
+                    h->comps, h->comps2, h->chanbuf2, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* mogp_last_error(mogp_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+// ------------------------------------------------------------------ tile lists
+static TileList* get_tiles(mogp_handle_s* h, int C, const int32_t* off1, const int32_t* off2, int mode, cudaStream_t st) {
+    std::vector<int32_t> o1(off1, off1 + C + 1), o2;
+    if (off2) o2.assign(off2, off2 + C + 1);
+    for (TileList* t : h->tiles)
+        if (t->mode == mode && t->off1 == o1 && t->off2 == o2) return t;
+    TileList* t = new TileList();
+    t->mode = mode; t->off1 = o1; t->off2 = o2;
+    const int T = MOGP_TILE;
+    if (mode == 2) {
+        for (int i = 0; i < C; ++i)
+            for (int j = 0; j < C; ++j)
+                for (int r = o1[i]; r < o1[i + 1]; r += T)
+                    for (int c = o2[j]; c < o2[j + 1]; c += T)
+                        t->host.push_back({i * C + j, r, c, std::min(T, o1[i + 1] - r), std::min(T, o2[j + 1] - c), 0});
+    } else {
+        for (int i = 0; i < C; ++i)
+            for (int j = 0; j <= i; ++j) {
+                t->pair_first.push_back((int32_t)t->host.size());
+                for (int r = o1[i]; r < o1[i + 1]; r += T)
+                    for (int c = o1[j]; c < o1[j + 1]; c += T) {
+                        if (i == j && c > r) continue;
+                        t->host.push_back({i * C + j, r, c, std::min(T, o1[i + 1] - r), std::min(T, o1[j + 1] - c),
+                                           (i == j && r == c) ? 1 : 0});
+                    }
+            }
+        t->pair_first.push_back((int32_t)t->host.size());
+    }
+    t->n = (int)t->host.size();
+    if (t->n > 0) {
+        if (cudaMalloc(&t->dev, t->host.size() * sizeof(CovTile)) != cudaSuccess) { delete t; return nullptr; }
+        cudaMemcpyAsync(t->dev, t->host.data(), t->host.size() * sizeof(CovTile), cudaMemcpyHostToDevice, st);
+    }
+    if (!t->pair_first.empty()) {
+        if (cudaMalloc(&t->pair_first_dev, t->pair_first.size() * 4) != cudaSuccess) { delete t; return nullptr; }
+        cudaMemcpyAsync(t->pair_first_dev, t->pair_first.data(), t->pair_first.size() * 4, cudaMemcpyHostToDevice, st);
+    }
+    if (h->tiles.size() > 64) {   // bounded cache
+        TileList* old = h->tiles.front();
+        cudaStreamSynchronize(st);
+        if (old->dev) cudaFree(old->dev);
+        if (old->pair_first_dev) cudaFree(old->pair_first_dev);
+        delete old;
+        h->tiles.erase(h->tiles.begin());
+    }
+    h->tiles.push_back(t);
+    return t;
+}
+
+static int check_offsets(mogp_handle_s* h, int C, const int32_t* off) {
+    H_ARG(h, off != nullptr, "chan_off is NULL");
+    H_ARG(h, off[0] == 0, "chan_off[0] must be 0");
+    for (int c = 0; c < C; ++c) H_ARG(h, off[c + 1] >= off[c], "chan_off must be non-decreasing");
+    return 0;
+}
+
+static int upload_chan(mogp_handle_s* h, int C, const int32_t* off, int slot, cudaStream_t st) {
+    MOGP_CHECK(h, cudaMemcpyAsync(h->chan_dev + slot * 260, off, (C + 1) * 4, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static int prep_common(mogp_handle_s* h, KernSpec& s, int kind, int C, int Q, int D, const double* params_dev,
+                       const double* sigma_dev, const double* data_var_dev, const int32_t* off, int64_t N,
+                       double jitter_rel, bool scratch, cudaStream_t st) {
+    H_ARG(h, spec_init(s, kind, C, Q, D) == 0, "bad kernel spec (kind, C, Q, D)");
+    H_ARG(h, C <= 64, "at most 64 channels");
+    H_ARG(h, (size_t)(3 * C + 2) <= 1024, "too many channels");
+    if (check_offsets(h, C, off)) return -1;
+    if (upload_chan(h, C, off, 0, st)) return -2;
+    double*& comps = scratch ? h->comps2 : h->comps;
+    size_t& cap = scratch ? h->comps2_cap : h->comps_cap;
+    if (ensure(h, comps, cap, (size_t)C * C * s.R * comp_stride(D))) return -2;
+    MOGP_CHECK(h, launch_prep(s, params_dev, sigma_dev, data_var_dev, h->chan_dev, N, jitter_rel, comps,
+                              scratch ? h->chanbuf2 : h->chanbuf, st));
+    return 0;
+}
+
+// Linv relies on "zero above the diagonal blocks" for its current leading dimension.
+static int zero_linv_for(mogp_handle_s* h, int64_t Np, cudaStream_t st) {
+    if (h->linv_np == Np) return 0;
+    MOGP_CHECK(h, cudaMemsetAsync(h->Linv, 0, (size_t)Np * Np * 8, st));
+    h->linv_np = Np;
+    h->have_factor = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------ K(X1, X2), K_diag
+extern "C" int mogp_kbuild(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                           const double* x1_dev, const int32_t* chan_off1_host, const double* x2_dev,
+                           const int32_t* chan_off2_host, const double* noise_sigma_dev, const double* data_var_dev,
+                           double jitter_rel, double* K_dev, int64_t ldk, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    KernSpec s;
+    if (check_offsets(h, C, chan_off1_host)) return -1;
+    const int64_t N1 = chan_off1_host[C];
+    const bool gram = (x2_dev == nullptr);
+    if (!gram && check_offsets(h, C, chan_off2_host)) return -1;
+    const int add_diag = gram && (noise_sigma_dev || data_var_dev || jitter_rel != 0.0);
+    int rc = prep_common(h, s, kind, C, Q, D, params_dev, noise_sigma_dev, gram ? data_var_dev : nullptr, chan_off1_host,
+                         N1, gram ? jitter_rel : 0.0, true, st);
+    if (rc) return rc;
+    TileList* tl = get_tiles(h, C, chan_off1_host, gram ? nullptr : chan_off2_host, gram ? 1 : 2, st);
+    H_ARG(h, tl != nullptr, "tile list allocation failed");
+    MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps2, h->chanbuf2, x1_dev, gram ? nullptr : x2_dev, h->chan_dev,
+                                gram ? data_var_dev : nullptr, add_diag, K_dev, ldk, N1, N1, st));
+    return 0;
+}
+
+extern "C" int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                          const int32_t* chan_off_host, double* out_dev, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    KernSpec s;
+    if (check_offsets(h, C, chan_off_host)) return -1;
+    const int64_t N = chan_off_host[C];
+    int rc = prep_common(h, s, kind, C, Q, D, params_dev, nullptr, nullptr, chan_off_host, std::max<int64_t>(N, 1), 0.0, true, st);
+    if (rc) return rc;
+    if (N > 0) MOGP_CHECK(h, launch_kdiag(s, h->chanbuf2, h->chan_dev, N, out_dev, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ Cholesky
+extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda, int32_t* info_dev, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, n >= 1 && n <= h->max_n, "n exceeds the handle's max_n");
+    H_ARG(h, lda >= n, "lda < n");
+    const int64_t Np = round_up(n, MOGP_PAD);
+    if (zero_linv_for(h, Np, st)) return -2;
+    h->have_factor = false;
+    if (n == Np && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(A_dev) % 16) == 0) {
+        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, Np, h->logdet_part, h->info, st));
+    } else {
+        MOGP_CHECK(h, launch_copy_tri(0, A_dev, lda, h->A, Np, n, Np, st));
+        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, Np, h->logdet_part, h->info, st));
+        MOGP_CHECK(h, launch_copy_tri(1, A_dev, lda, h->A, Np, n, Np, st));
+    }
+    if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev, double* Kinv_dev, int64_t n,
+                               int32_t* info_dev, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
+    MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, n, h->logdet_part, h->info, st));
+    MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
+    MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
+    if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
+    h->have_factor = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------ the exact-GP step
+// vec layout (np_max each): 0 y_pad | 1 z | 2 alpha | 3 kinv_diag
+extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                             const double* x_dev, const int32_t* chan_off_host, const double* y_dev,
+                             const double* noise_sigma_dev, const double* data_var_dev, double jitter_rel, int want_grad,
+                             double* out_dev, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, params_dev && x_dev && y_dev && noise_sigma_dev && out_dev, "NULL argument");
+    if (check_offsets(h, C, chan_off_host)) return -1;
+    const int64_t N = chan_off_host[C];
+    H_ARG(h, N >= 1 && N <= h->max_n, "N out of range for this handle");
+    KernSpec s;
+    int rc = prep_common(h, s, kind, C, Q, D, params_dev, noise_sigma_dev, data_var_dev, chan_off_host, N, jitter_rel, false, st);
+    if (rc) return rc;
+    const int64_t Np = round_up(N, MOGP_PAD);
+    if (zero_linv_for(h, Np, st)) return -2;
+    const long long ld = Np;
+    double* ypad = h->vec;
+    double* z = h->vec + h->np_max;
+    double* alpha = h->vec + 2 * h->np_max;
+    double* kdiag = h->vec + 3 * h->np_max;
+
+    TileList* tl = get_tiles(h, C, chan_off_host, nullptr, 0, st);
+    H_ARG(h, tl != nullptr, "tile list allocation failed");
+    if (ensure(h, h->xbuf, h->xbuf_cap, (size_t)N * D)) return -2;
+    if (x_dev != h->xbuf)
+        MOGP_CHECK(h, cudaMemcpyAsync(h->xbuf, x_dev, (size_t)N * D * 8, cudaMemcpyDeviceToDevice, st));
+
+#define STAGE_MARK()                                                            \
+    do {                                                                        \
+        if (h->profile && h->n_ev < 8) cudaEventRecord(h->ev[h->n_ev++], st);   \
+    } while (0)
+    h->n_ev = 0;
+    STAGE_MARK();
+    // K~ (lower) -> L, diag blocks of Linv
+    MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, data_var_dev, 1, h->A, ld, N,
+                                Np, st));
+    STAGE_MARK();
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, Np, h->logdet_part, h->info, st));
+    STAGE_MARK();
+    // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
+    MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
+    STAGE_MARK();
+    MOGP_CHECK(h, launch_pad_copy(y_dev, N, ypad, Np, st));
+    MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
+    MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
+    STAGE_MARK();
+    if (want_grad) {
+        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, alpha, st));
+        STAGE_MARK();
+        const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * comp_stride(D);
+        if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
+        MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, h->tile_part, st));
+    }
+    MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params_dev, noise_sigma_dev, h->comps, h->chanbuf, h->tile_part, z,
+                                  alpha, kdiag, h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out_dev, st));
+    STAGE_MARK();
+    h->have_factor = true;
+    h->spec = s;
+    h->chan_off.assign(chan_off_host, chan_off_host + C + 1);
+    h->N = N;
+    h->Np = Np;
+    return 0;
+}
+
+extern "C" int mogp_lml_grad_host(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_host,
+                                  const double* x_host, const int32_t* chan_off_host, const double* y_host,
+                                  const double* noise_sigma_host, const double* data_var_host, double jitter_rel,
+                                  int want_grad, double* out_host) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    KernSpec s;
+    H_ARG(h, spec_init(s, kind, C, Q, D) == 0, "bad kernel spec (kind, C, Q, D)");
+    if (check_offsets(h, C, chan_off_host)) return -1;
+    const int64_t N = chan_off_host[C];
+    H_ARG(h, N >= 1 && N <= h->max_n, "N out of range for this handle");
+    const size_t nP = s.P, nout = 2 + s.P + C;
+    const size_t need = nP + C + (size_t)N * (1 + D) + (data_var_host ? N : 0) + 8;
+    if (ensure(h, h->pbuf, h->pbuf_cap, need)) return -2;
+    if (ensure(h, h->out_dev, h->out_cap, nout)) return -2;
+    if (ensure(h, h->xbuf, h->xbuf_cap, (size_t)N * D)) return -2;
+    cudaStream_t st = 0;
+    double* p_dev = h->pbuf;
+    double* sig_dev = p_dev + nP;
+    double* y_dev = sig_dev + C;
+    double* dv_dev = data_var_host ? y_dev + N : nullptr;
+    MOGP_CHECK(h, cudaMemcpyAsync(p_dev, params_host, nP * 8, cudaMemcpyHostToDevice, st));
+    MOGP_CHECK(h, cudaMemcpyAsync(sig_dev, noise_sigma_host, C * 8, cudaMemcpyHostToDevice, st));
+    MOGP_CHECK(h, cudaMemcpyAsync(y_dev, y_host, N * 8, cudaMemcpyHostToDevice, st));
+    MOGP_CHECK(h, cudaMemcpyAsync(h->xbuf, x_host, (size_t)N * D * 8, cudaMemcpyHostToDevice, st));
+    if (dv_dev) MOGP_CHECK(h, cudaMemcpyAsync(dv_dev, data_var_host, N * 8, cudaMemcpyHostToDevice, st));
+    int rc = mogp_lml_grad(h, kind, C, Q, D, p_dev, h->xbuf, chan_off_host, y_dev, sig_dev, dv_dev, jitter_rel, want_grad,
+                           h->out_dev, (void*)st);
+    if (rc) return rc;
+    MOGP_CHECK(h, cudaMemcpyAsync(out_host, h->out_dev, (want_grad ? nout : 2) * 8, cudaMemcpyDeviceToHost, st));
+    MOGP_CHECK(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ prediction
+extern "C" int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t* chan_off_s_host, int full,
+                            double* mu_dev, double* var_dev, void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, h->have_factor, "mogp_predict needs a preceding mogp_lml_grad on this handle");
+    const KernSpec s = h->spec;
+    if (check_offsets(h, s.C, chan_off_s_host)) return -1;
+    const int64_t M = chan_off_s_host[s.C];
+    H_ARG(h, M >= 1, "no test points");
+    const int64_t Mp = round_up(M, 128), Np = h->Np, N = h->N;
+    const size_t need = (size_t)Np * Mp;
+    if (need > h->pred_cap) {
+        if (h->pred_K) cudaFree(h->pred_K);
+        if (h->pred_V) cudaFree(h->pred_V);
+        h->pred_K = h->pred_V = nullptr; h->pred_cap = 0;
+        MOGP_CHECK(h, cudaMalloc(&h->pred_K, need * 8));
+        MOGP_CHECK(h, cudaMalloc(&h->pred_V, need * 8));
+        h->pred_cap = need;
+    }
+    if (upload_chan(h, s.C, chan_off_s_host, 1, st)) return -2;
+    const int32_t* chan_s_dev = h->chan_dev + 260;
+    TileList* tl = get_tiles(h, s.C, h->chan_off.data(), chan_off_s_host, 2, st);
+    H_ARG(h, tl != nullptr, "tile list allocation failed");
+    double* alpha = h->vec + 2 * h->np_max;
+    double* colsq = h->vec + 4 * h->np_max;      // needs Mp <= np_max ... guarded below
+    double* mu_tmp = h->vec + 5 * h->np_max;
+    H_ARG(h, Mp <= h->np_max, "too many test points for one call (chunk on the host side)");
+    if ((size_t)(64 * 2 * Mp) > h->colpart_cap) { h->err = "column-pass scratch too small"; return -1; }
+
+    MOGP_CHECK(h, cudaMemsetAsync(h->pred_K, 0, need * 8, st));
+    MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, xs_dev, h->chan_dev, nullptr, 0, h->pred_K, Mp, N,
+                                N, st));
+    // mu = Kfs^T alpha
+    MOGP_CHECK(h, launch_colpass(h->pred_K, Mp, alpha, Np, Mp, h->colpart, h->colpart_cap, mu_tmp, nullptr, st));
+    MOGP_CHECK(h, cudaMemcpyAsync(mu_dev, mu_tmp, M * 8, cudaMemcpyDeviceToDevice, st));
+    // V = Linv * Kfs
+    GemmArgs g{};
+    g.A = h->Linv; g.lda = Np;
+    g.B = h->pred_K; g.ldb = Mp;
+    g.C = h->pred_V; g.ldc = Mp;
+    g.M = (int)Np; g.N = (int)Mp; g.K = (int)Np;
+    g.khi_mode = 1; g.alpha = 1.0; g.beta = 0.0;
+    MOGP_CHECK(h, launch_gemm(0, 0, g, 1, st));
+    if (!full) {
+        MOGP_CHECK(h, launch_colpass(h->pred_V, Mp, alpha, Np, Mp, h->colpart, h->colpart_cap, nullptr, colsq, st));
+        MOGP_CHECK(h, launch_pred_var(h->chanbuf, s.C, chan_s_dev, colsq, M, var_dev, st));
+    } else {
+        const size_t sneed = (size_t)Mp * Mp;
+        if (sneed > h->pred_s_cap) {
+            if (h->pred_S) cudaFree(h->pred_S);
+            h->pred_S = nullptr; h->pred_s_cap = 0;
+            MOGP_CHECK(h, cudaMalloc(&h->pred_S, sneed * 8));
+            h->pred_s_cap = sneed;
+        }
+        MOGP_CHECK(h, cudaMemsetAsync(h->pred_S, 0, sneed * 8, st));
+        TileList* tg = get_tiles(h, s.C, chan_off_s_host, nullptr, 1, st);
+        H_ARG(h, tg != nullptr, "tile list allocation failed");
+        MOGP_CHECK(h, launch_kbuild(s, *tg, h->comps, h->chanbuf, xs_dev, nullptr, chan_s_dev, nullptr, 0, h->pred_S, Mp, M,
+                                    M, st));
+        GemmArgs c{};
+        c.A = h->pred_V; c.lda = Mp;
+        c.B = h->pred_V; c.ldb = Mp;
+        c.C = h->pred_S; c.ldc = Mp;
+        c.M = (int)Mp; c.N = (int)Mp; c.K = (int)Np;
+        c.alpha = -1.0; c.beta = 1.0;
+        MOGP_CHECK(h, launch_gemm(1, 0, c, 1, st));
+        MOGP_CHECK(h, cudaMemcpy2DAsync(var_dev, M * 8, h->pred_S, Mp * 8, M * 8, M, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ building blocks
+extern "C" int mogp_dgemm(mogp_handle_t h, int transa, int transb, int M, int N, int K, double alpha,
+                          const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev,
+                          int64_t ldc, void* stream) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, M % 64 == 0 && N % 64 == 0 && K % 16 == 0, "M, N multiples of 64 and K multiple of 16 required");
+    H_ARG(h, lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0, "leading dimensions must be even");
+    GemmArgs g{};
+    g.A = A_dev; g.lda = lda; g.B = B_dev; g.ldb = ldb; g.C = C_dev; g.ldc = ldc;
+    g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+    // header convention: transa=0 -> A is (M x K) row-major; transb=0 -> B is (K x N) row-major
+    MOGP_CHECK(h, launch_gemm(transa ? 1 : 0, transb ? 1 : 0, g, 1, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" long long mogp_launch_count(void) { return g_mogp_launches; }
+
+// Stage timing of mogp_lml_grad (diagnostics for bench.py): with want_grad the stages are
+// [kbuild, potrf, trtri, solves, kinv, grad+finalize]; returns the number of stages written.
+extern "C" int mogp_set_profile(mogp_handle_t h, int on) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i < 8; ++i) MOGP_CHECK(h, cudaEventCreate(&h->ev[i]));
+    h->profile = on != 0;
+    h->n_ev = 0;
+    return 0;
+}
+extern "C" int mogp_stage_times(mogp_handle_t h, float* ms_out) {
+    if (!h || !h->profile || h->n_ev < 2) return 0;
+    cudaEventSynchronize(h->ev[h->n_ev - 1]);
+    for (int i = 0; i + 1 < h->n_ev; ++i) cudaEventElapsedTime(&ms_out[i], h->ev[i], h->ev[i + 1]);
+    return h->n_ev - 1;
+}
+
+extern "C" int mogp_peak_fp64(mogp_handle_t h, double* dmma_tflops_host, double* dfma_tflops_host) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    MOGP_CHECK(h, run_peak_fp64(dmma_tflops_host, dfma_tflops_host));
+    return 0;
+}

@@ -77,8 +77,11 @@ struct mogp_handle_s {
     int device = 0;
     int64_t max_n = 0, np_max = 0;
     double *A = nullptr, *Linv = nullptr, *W = nullptr;      // np_max^2 each
-    double *comps = nullptr; size_t comps_cap = 0;            // C*C*R*stride
-    double *chanbuf = nullptr;                                // per-channel scalars (see capi.cu)
+    double *comps = nullptr; size_t comps_cap = 0;            // C*C*R*stride (state of the last lml_grad)
+    double *chanbuf = nullptr;                                // per-channel scalars of the last lml_grad
+    double *comps2 = nullptr; size_t comps2_cap = 0;          // same, scratch of mogp_kbuild / mogp_kdiag
+    double *chanbuf2 = nullptr;
+    int64_t linv_np = 0;                                      // layout (ld) Linv was last zero-initialised for
     double *vec = nullptr;                                    // 8 * np_max doubles of vector scratch
     double *colpart = nullptr; size_t colpart_cap = 0;        // column-pass partials
     double *tile_part = nullptr; size_t tile_part_cap = 0;    // gradient tile partials
@@ -96,6 +99,10 @@ struct mogp_handle_s {
     std::vector<int32_t> chan_off;
     int64_t N = 0, Np = 0;
     std::string err;
+    // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
+    bool profile = false;
+    cudaEvent_t ev[8] = {};
+    int n_ev = 0;
 };
 
 #define MOGP_CHECK(h, expr)                                                          \
@@ -106,6 +113,10 @@ struct mogp_handle_s {
             return -2;                                                               \
         }                                                                            \
     } while (0)
+
+// number of kernels launched by this library since load (bench.py reports it as gpu_launches)
+extern long long g_mogp_launches;
+#define MOGP_COUNT(n) (g_mogp_launches += (n))
 
 // ------------------------------------------------------------------ covariance kernels (cov.cu)
 // chanbuf layout (doubles): [0..C) kdiag_gram | [C..2C) kdiag_api | [2C..3C) noise variance | [3C] jitter add | [3C+1] trW scratch
@@ -128,7 +139,7 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
                             int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st);
 
 // ------------------------------------------------------------------ dense linear algebra (linalg.cu)
-cudaError_t potrf_padded(mogp_handle_s* h, double* A, double* Linv, int64_t Np, long long ld, double* logdet_part,
+cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, int64_t Np, double* logdet_part,
                          int32_t* info, cudaStream_t st);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);

@@ -1,0 +1,619 @@
+// Covariance kernels of the exact-GP step (sm_100a):
+//   prep        : constrained parameters -> per channel-pair component table, diagonal constants
+//   kbuild      : tiled Gram / cross-covariance build (replaces MultiOutputKernel.K + Ksub,
+//                 mogptk/gpr/kernel.py:446-481, gpr/multioutput.py:178-204,531-547, gpr/singleoutput.py:594-600)
+//   grad_reduce : sum_{r,s} W_rs dK_rs/d(derived constants) without materialising dK/dtheta
+//   finalize    : log-marginal likelihood, noise gradient, chain rule to the packed parameters
+// The x tile of every CTA is staged into shared memory with a 1-D TMA bulk copy
+// (cp.async.bulk + mbarrier); outputs are written with 16-byte vector stores.
+#include "covmath.cuh"
+#include <cstdio>
+
+#define RC 8   // components processed per shared-memory trig table
+
+// ------------------------------------------------------------------ TMA bulk helpers
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+
+// Stage `n` rows x D doubles starting at src into dst (shared).  Uses one TMA bulk copy when
+// the source is 16-byte aligned and the byte count is a multiple of 16, else plain loads.
+__device__ __forceinline__ void stage_x(double* dst, const double* src, int n, int D, uint64_t* bar, unsigned& phase,
+                                        int tid, int nthreads) {
+    const unsigned bytes = (unsigned)(n * D * sizeof(double));
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes > 0;
+    if (tma_ok) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_bulk_g2s(dst, src, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+    } else {
+        for (int i = tid; i < n * D; i += nthreads) dst[i] = src[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ prep
+// chanbuf: [0..C) kdiag_gram | [C..2C) kdiag_api | [2C..3C) sigma^2 | [3C] jitter_add
+__global__ void __launch_bounds__(256) prep_kernel(KernSpec s, const double* __restrict__ params,
+                                                   const double* __restrict__ sigma, const double* __restrict__ data_var,
+                                                   const int32_t* __restrict__ chan, long long N, double jitter_rel,
+                                                   double* __restrict__ comps, double* __restrict__ chanbuf) {
+    __shared__ double red[256];
+    const int tid = threadIdx.x;
+    const int st = comp_stride(s.D);
+    const int total = s.C * s.C * s.R;
+    for (int e = tid; e < total; e += 256) {
+        const int r = e % s.R, pj = e / s.R, j = pj % s.C, i = pj / s.C;
+        pair_comp(s.kind, s.C, s.Q, s.D, params, i, j, r, comps + (size_t)e * st);
+    }
+    double dv = 0.0;
+    if (data_var)
+        for (long long r = tid; r < N; r += 256) dv += data_var[r];
+    red[tid] = dv;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid < s.C) {
+        const int c = tid;
+        double kd = 0.0;
+        for (int r = 0; r < s.R; ++r) kd += comps[(size_t)((c * s.C + c) * s.R + r) * st];
+        chanbuf[c] = kd;
+        chanbuf[s.C + c] = kdiag_api_value(s.kind, s.C, s.Q, s.D, params, comps, s.R, c);
+        chanbuf[2 * s.C + c] = sigma ? sigma[c] * sigma[c] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = red[0];
+        for (int c = 0; c < s.C; ++c) tot += (double)(chan[c + 1] - chan[c]) * (chanbuf[c] + chanbuf[2 * s.C + c]);
+        chanbuf[3 * s.C] = jitter_rel * tot / (double)N;
+    }
+}
+
+cudaError_t launch_prep(const KernSpec& s, const double* params, const double* sigma, const double* data_var,
+                        const int32_t* chan_dev, int64_t N, double jitter_rel, double* comps, double* chanbuf,
+                        cudaStream_t st) {
+    prep_kernel<<<1, 256, 0, st>>>(s, params, sigma, data_var, chan_dev, (long long)N, jitter_rel, comps, chanbuf);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ shared tile machinery
+// Thread (ty, tx) of 256 owns rows ty + 16*i (i<4) and columns tx*4 + j (j<4) of the 64x64 tile.
+struct TileSmem {
+    double xa[MOGP_TILE * MOGP_MAX_D];
+    double xb[MOGP_TILE * MOGP_MAX_D];
+    double rc[RC][MOGP_TILE], rs[RC][MOGP_TILE];     // cos/sin of the row angles
+    double cc[RC][MOGP_TILE], cs[RC][MOGP_TILE];     // cos/sin of the column angles
+    double comp[RC][2 + 3 * MOGP_MAX_D];
+    uint64_t bar;
+};
+
+template <int DT>
+__device__ __forceinline__ int dims(int D) { return DT > 0 ? DT : D; }
+
+// Loads x rows/cols of the tile (shifted by the tile's first column coordinate) into smem.
+template <int DT>
+__device__ __forceinline__ void load_tile_x(TileSmem& sm, const CovTile& t, const double* __restrict__ x1,
+                                            const double* __restrict__ x2, int Drt, unsigned& phase, int tid) {
+    const int D = dims<DT>(Drt);
+    stage_x(sm.xa, x1 + (size_t)t.r0 * D, t.nr, D, &sm.bar, phase, tid, 256);
+    stage_x(sm.xb, x2 + (size_t)t.c0 * D, t.nc, D, &sm.bar, phase, tid, 256);
+    __syncthreads();
+    // shift by x0 = first column point so that the trig arguments stay small
+    double x0[MOGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+        if (d < D) x0[d] = sm.xb[d];
+    __syncthreads();
+    for (int e = tid; e < MOGP_TILE * D; e += 256) {
+        const int d = e % D, r = e / D;
+        sm.xa[e] = (r < t.nr) ? sm.xa[e] - x0[d] : 0.0;
+        sm.xb[e] = (r < t.nc) ? sm.xb[e] - x0[d] : 0.0;
+    }
+}
+
+// Fills the comp records and trig tables for components [rbase, rbase+nr) of `pair`.
+template <int DT, bool COS>
+__device__ __forceinline__ void fill_tables(TileSmem& sm, const double* __restrict__ comps, int pair, int R, int rbase,
+                                            int nrc, int Drt, int tid) {
+    const int D = dims<DT>(Drt);
+    const int st = comp_stride(D);
+    for (int e = tid; e < nrc * st; e += 256) sm.comp[e / st][e % st] = comps[(size_t)(pair * R + rbase) * st + e];
+    __syncthreads();
+    if (COS) {
+        for (int e = tid; e < nrc * 2 * MOGP_TILE; e += 256) {
+            const int r = e / (2 * MOGP_TILE), w = e % (2 * MOGP_TILE);
+            const double* cp = sm.comp[r];
+            const double* m = cp + 2 + D;
+            const double* th = cp + 2 + 2 * D;
+            double sn, cs;
+            if (w < MOGP_TILE) {
+                double a = cp[1];
+                for (int d = 0; d < D; ++d) a += m[d] * (sm.xa[w * D + d] + th[d]);
+                sincospi(2.0 * a, &sn, &cs);
+                sm.rc[r][w] = cs; sm.rs[r][w] = sn;
+            } else {
+                const int c = w - MOGP_TILE;
+                double a = 0.0;
+                for (int d = 0; d < D; ++d) a += m[d] * sm.xb[c * D + d];
+                sincospi(2.0 * a, &sn, &cs);
+                sm.cc[r][c] = cs; sm.cs[r][c] = sn;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ kbuild
+// mode 0: Gram lower tiles into the padded factor buffer (+ padding rows);  mode 1: Gram, every
+// lower tile is also written transposed (full symmetric output);  mode 2: cross-covariance.
+template <int DT, bool COS>
+__global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* __restrict__ tiles, int ntiles, int mode,
+                                                     const double* __restrict__ comps, const double* __restrict__ chanbuf,
+                                                     const double* __restrict__ x1, const double* __restrict__ x2,
+                                                     const double* __restrict__ data_var, int add_diag,
+                                                     double* __restrict__ K, long long ldk, long long N, long long Np) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smraw);
+    double* tbuf = reinterpret_cast<double*>(smraw + sizeof(TileSmem));   // 64 x 65 transpose staging (mode 1)
+    const int tid = threadIdx.x;
+
+    if ((int)blockIdx.x >= ntiles) {                  // padding row of the factor buffer: unit diagonal
+        const long long r = N + (blockIdx.x - ntiles);
+        if (r < Np) {
+            for (long long c = tid; c <= r; c += 256) K[r * ldk + c] = (c == r) ? 1.0 : 0.0;
+        }
+        return;
+    }
+    const CovTile t = tiles[blockIdx.x];
+    const int D = dims<DT>(s.D);
+    const int ty = tid >> 4, tx = tid & 15;
+    const int pi = t.pair / s.C, pj = t.pair % s.C;
+    const bool zero_block = (s.kind == MOGP_KIND_SM) && (pi != pj);
+
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    if (!zero_block) {
+        if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init_fence(); }
+        __syncthreads();
+        unsigned phase = 0;
+        load_tile_x<DT>(sm, t, x1, x2 ? x2 : x1, s.D, phase, tid);
+        for (int rbase = 0; rbase < s.R; rbase += RC) {
+            const int nrc = min(RC, s.R - rbase);
+            __syncthreads();
+            fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, tid);
+            double xb[4][DT > 0 ? DT : MOGP_MAX_D];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                    if (d < D) xb[j][d] = sm.xb[(tx * 4 + j) * D + d];
+            for (int r = 0; r < nrc; ++r) {
+                const double* cp = sm.comp[r];
+                const double alpha = cp[0];
+                double cB[4], sB[4];
+                if (COS) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx * 4 + j]; sB[j] = sm.cs[r][tx * 4 + j]; }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = ty + 16 * i;
+                    double ua[DT > 0 ? DT : MOGP_MAX_D];
+#pragma unroll
+                    for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                        if (d < D) ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                    double cA = 1.0, sA = 0.0;
+                    if (COS) { cA = sm.rc[r][row]; sA = sm.rs[r][row]; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double e = 0.0;
+#pragma unroll
+                        for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                            if (d < D) { const double u = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u, u, e); }
+                        double val = alpha * exp(-0.5 * e);
+                        if (COS) val *= fma(cA, cB[j], sA * sB[j]);
+                        acc[i][j] += val;
+                    }
+                }
+            }
+        }
+    }
+
+    // diagonal of the Gram matrix: exact K_diag value (+ noise, data variance, relative jitter)
+    if (mode != 2 && (t.flags & 1)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = ty + 16 * i, col = tx * 4 + j;
+                if (row == col && row < t.nr) {
+                    double v = chanbuf[pi];
+                    if (add_diag) {
+                        v += chanbuf[2 * s.C + pi];
+                        if (data_var) v += data_var[t.r0 + row];
+                        v += chanbuf[3 * s.C];
+                    }
+                    acc[i][j] = v;
+                }
+            }
+    }
+
+    const bool vec_ok = ((ldk & 1) == 0) && ((t.c0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = ty + 16 * i;
+        if (row >= t.nr) continue;
+        double* dst = K + (long long)(t.r0 + row) * ldk + t.c0 + tx * 4;
+        const int colb = tx * 4;
+        if (vec_ok && colb + 3 < t.nc) {
+            reinterpret_cast<double2*>(dst)[0] = make_double2(acc[i][0], acc[i][1]);
+            reinterpret_cast<double2*>(dst)[1] = make_double2(acc[i][2], acc[i][3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (colb + j < t.nc) dst[j] = acc[i][j];
+        }
+    }
+    if (mode == 1 && !(t.flags & 1)) {                // mirrored copy, transposed through shared memory
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tbuf[(ty + 16 * i) * 65 + tx * 4 + j] = acc[i][j];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int orow = ty + 16 * i;            // output row = original column
+            if (orow >= t.nc) continue;
+            double* dst = K + (long long)(t.c0 + orow) * ldk + t.r0 + tx * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (tx * 4 + j < t.nr) dst[j] = tbuf[(tx * 4 + j) * 65 + orow];
+        }
+    }
+}
+
+template <int DT, bool COS>
+static cudaError_t launch_kbuild_t(const KernSpec& s, const TileList& tl, int nblocks, const double* comps,
+                                   const double* chanbuf, const double* x1, const double* x2, const double* data_var,
+                                   int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
+    const size_t smem = sizeof(TileSmem) + 64 * 65 * sizeof(double);
+    auto kern = kbuild_kernel<DT, COS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (nblocks <= 0) return cudaSuccess;
+    kern<<<nblocks, 256, smem, st>>>(s, tl.dev, tl.n, tl.mode, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk,
+                                     (long long)N, (long long)Np);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* comps, const double* chanbuf,
+                          const double* x1, const double* x2, const int32_t* chan1_dev, const double* data_var,
+                          int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
+    (void)chan1_dev;
+    const int nblocks = tl.n + (tl.mode == 0 ? (int)(Np - N) : 0);
+    if (s.D == 1) {
+        if (s.has_cos) return launch_kbuild_t<1, true>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+        return launch_kbuild_t<1, false>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+    }
+    if (s.has_cos) return launch_kbuild_t<0, true>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+    return launch_kbuild_t<0, false>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+}
+
+__global__ void kdiag_kernel(int C, const double* __restrict__ chanbuf, const int32_t* __restrict__ chan, long long N,
+                             double* __restrict__ out) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int c = 0;
+    while (c + 1 < C && r >= chan[c + 1]) ++c;
+    out[r] = chanbuf[C + c];
+}
+cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t* chan_dev, int64_t N, double* out,
+                         cudaStream_t st) {
+    kdiag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s.C, chanbuf, chan_dev, (long long)N, out);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ grad_reduce
+// Per tile and component: [S0, S4, S1[D], S2[D], S3[D]] with the symmetric weight folded into W.
+template <int DT, bool COS>
+__global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovTile* __restrict__ tiles,
+                                                          const double* __restrict__ comps, const double* __restrict__ x,
+                                                          const double* __restrict__ W, long long ldw,
+                                                          double* __restrict__ tile_part) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smraw);
+    double* wpart = reinterpret_cast<double*>(smraw + sizeof(TileSmem));   // [8 warps][RC][stride]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const CovTile t = tiles[blockIdx.x];
+    const int D = dims<DT>(s.D);
+    const int st = comp_stride(D);
+    const int ty = tid >> 4, tx = tid & 15;
+    const int pi = t.pair / s.C, pj = t.pair % s.C;
+    double* outp = tile_part + (size_t)blockIdx.x * s.R * st;
+    if (s.kind == MOGP_KIND_SM && pi != pj) {
+        for (int e = tid; e < s.R * st; e += 256) outp[e] = 0.0;
+        return;
+    }
+    if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init_fence(); }
+    __syncthreads();
+    unsigned phase = 0;
+    load_tile_x<DT>(sm, t, x, x, s.D, phase, tid);
+
+    // weighted W values of this thread's 4x4 patch (lower triangle of the global matrix only)
+    double wv[4][4];
+    const bool diag_tile = (t.flags & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = ty + 16 * i, col = tx * 4 + j;
+            double v = 0.0;
+            if (row < t.nr && col < t.nc) {
+                double wgt = 2.0;
+                if (diag_tile) wgt = row > col ? 2.0 : (row == col ? 1.0 : 0.0);
+                if (wgt != 0.0) v = wgt * W[(long long)(t.r0 + row) * ldw + t.c0 + col];
+            }
+            wv[i][j] = v;
+        }
+
+    for (int rbase = 0; rbase < s.R; rbase += RC) {
+        const int nrc = min(RC, s.R - rbase);
+        __syncthreads();
+        fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, tid);
+        double xb[4][DT > 0 ? DT : MOGP_MAX_D];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                if (d < D) xb[j][d] = sm.xb[(tx * 4 + j) * D + d];
+        for (int r = 0; r < nrc; ++r) {
+            const double* cp = sm.comp[r];
+            double s0 = 0.0, s4 = 0.0;
+            double s1[DT > 0 ? DT : MOGP_MAX_D], s2[DT > 0 ? DT : MOGP_MAX_D], s3[DT > 0 ? DT : MOGP_MAX_D];
+#pragma unroll
+            for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d) s1[d] = s2[d] = s3[d] = 0.0;
+            double cB[4], sB[4];
+            if (COS) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx * 4 + j]; sB[j] = sm.cs[r][tx * 4 + j]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = ty + 16 * i;
+                double ua[DT > 0 ? DT : MOGP_MAX_D];
+#pragma unroll
+                for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                    if (d < D) ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                double cA = 1.0, sA = 0.0;
+                if (COS) { cA = sm.rc[r][row]; sA = sm.rs[r][row]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double u[DT > 0 ? DT : MOGP_MAX_D];
+                    double e = 0.0;
+#pragma unroll
+                    for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                        if (d < D) { u[d] = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u[d], u[d], e); }
+                    const double we = wv[i][j] * exp(-0.5 * e);
+                    double wec = we, wes = 0.0;
+                    if (COS) {
+                        wec = we * fma(cA, cB[j], sA * sB[j]);      // cos(A - B)
+                        wes = we * fma(sA, cB[j], -cA * sB[j]);     // sin(A - B)
+                    }
+                    s0 += wec;
+                    s4 += wes;
+#pragma unroll
+                    for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                        if (d < D) {
+                            const double wu = wec * u[d];
+                            s3[d] += wu;
+                            s1[d] = fma(wu, u[d], s1[d]);
+                            s2[d] = fma(wes, u[d], s2[d]);
+                        }
+                }
+            }
+            // warp reduction, lane 0 parks the warp's partial in shared memory
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+#pragma unroll
+                for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                    if (d < D) {
+                        s1[d] += __shfl_xor_sync(0xffffffffu, s1[d], o);
+                        s2[d] += __shfl_xor_sync(0xffffffffu, s2[d], o);
+                        s3[d] += __shfl_xor_sync(0xffffffffu, s3[d], o);
+                    }
+            }
+            if (lane == 0) {
+                double* wp = wpart + (size_t)(warp * RC + r) * st;
+                wp[0] = s0; wp[1] = s4;
+#pragma unroll
+                for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
+                    if (d < D) { wp[2 + d] = s1[d]; wp[2 + D + d] = s2[d]; wp[2 + 2 * D + d] = s3[d]; }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nrc * st; e += 256) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += wpart[(size_t)(w * RC) * st + e];
+            outp[(size_t)rbase * st + e] = a;
+        }
+    }
+}
+
+cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
+                               const double* W, long long ldw, double* tile_part, cudaStream_t st) {
+    const size_t smem = sizeof(TileSmem) + (size_t)8 * RC * (2 + 3 * MOGP_MAX_D) * sizeof(double);
+    if (tl.n <= 0) return cudaSuccess;
+#define LAUNCH_GR(DT, COS)                                                                                         \
+    do {                                                                                                           \
+        auto kern = grad_reduce_kernel<DT, COS>;                                                                   \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (e != cudaSuccess) return e;                                                                        \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        kern<<<tl.n, 256, smem, st>>>(s, tl.dev, comps, x, W, ldw, tile_part);                                     \
+        MOGP_COUNT(1);                                                                                             \
+    } while (0)
+    if (s.D == 1) { if (s.has_cos) LAUNCH_GR(1, true); else LAUNCH_GR(1, false); }
+    else { if (s.has_cos) LAUNCH_GR(0, true); else LAUNCH_GR(0, false); }
+#undef LAUNCH_GR
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ finalize
+// pairsum: gsum[pl][r][k] = sum over the tiles of lower pair pl, in tile order (deterministic).
+__global__ void pairsum_kernel(int R, int st, const int32_t* __restrict__ pair_first, const double* __restrict__ tile_part,
+                               double* __restrict__ gsum) {
+    const int pl = blockIdx.x;
+    const int t0 = pair_first[pl], t1 = pair_first[pl + 1];
+    for (int e = threadIdx.x; e < R * st; e += blockDim.x) {
+        double a = 0.0;
+        for (int t = t0; t < t1; ++t) a += tile_part[(size_t)t * R * st + e];
+        gsum[(size_t)pl * R * st + e] = a;
+    }
+}
+
+__device__ double block_sum_256(double v, double* red) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    red[tid] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(KernSpec s, int want_grad, const double* __restrict__ params,
+                                                       const double* __restrict__ sigma, const double* __restrict__ comps,
+                                                       const double* __restrict__ gsum, const double* __restrict__ z,
+                                                       const double* __restrict__ alpha, const double* __restrict__ kinv_diag,
+                                                       const double* __restrict__ logdet_part, const int32_t* __restrict__ info,
+                                                       const int32_t* __restrict__ chan, long long N, long long Np,
+                                                       double jitter_rel, double* __restrict__ out) {
+    __shared__ double red[256];
+    __shared__ double adj[64], csum[64];
+    __shared__ double trW_s;
+    const int tid = threadIdx.x;
+    double zz = 0.0;
+    for (long long r = tid; r < Np; r += 256) zz += z[r] * z[r];
+    zz = block_sum_256(zz, red);
+    double ld = 0.0;
+    for (long long b = tid; b < Np / 64; b += 256) ld += logdet_part[b];
+    ld = block_sum_256(ld, red);
+    if (tid == 0) {
+        out[0] = -0.5 * (double)N * log(2.0 * MOGP_PI) - ld - 0.5 * zz;
+        out[1] = (double)info[0];
+    }
+    if (!want_grad) return;
+    double tr = 0.0;
+    for (int c = 0; c < s.C; ++c) {
+        double a = 0.0;
+        for (long long r = chan[c] + tid; r < chan[c + 1]; r += 256) a += 0.5 * (kinv_diag[r] - alpha[r] * alpha[r]);
+        a = block_sum_256(a, red);
+        if (tid == 0) csum[c] = a;
+        tr += a;
+    }
+    if (tid == 0) trW_s = tr;
+    __syncthreads();
+    const double trW = trW_s;
+    if (tid < s.C) adj[tid] = jitter_rel / (double)N * trW * (double)(chan[tid + 1] - chan[tid]);
+    __syncthreads();
+    const int owners = n_chain_owners(s.kind, s.C, s.Q);
+    for (int o = tid; o < owners; o += 256) chain_owner(s.kind, s.C, s.Q, s.D, params, comps, gsum, adj, o, out + 2);
+    if (tid < s.C)
+        out[2 + s.P + tid] = 2.0 * sigma[tid] * (csum[tid] + adj[tid]);
+}
+
+cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad, const double* params,
+                            const double* sigma, const double* comps, const double* chanbuf, const double* tile_part,
+                            const double* z, const double* alpha, const double* kinv_diag, const double* logdet_part,
+                            const int32_t* info, const int32_t* chan_dev, int64_t N, int64_t Np, double jitter_rel,
+                            double* out, cudaStream_t st) {
+    (void)chanbuf;
+    if (s.C > 64) return cudaErrorInvalidValue;
+    const int stc = comp_stride(s.D);
+    double* gsum = nullptr;
+    if (want_grad) {
+        const int npl = s.C * (s.C + 1) / 2;
+        gsum = const_cast<double*>(tile_part) + (size_t)tl->n * s.R * stc;
+        pairsum_kernel<<<npl, 128, 0, st>>>(s.R, stc, tl->pair_first_dev, tile_part, gsum);
+        MOGP_COUNT(1);
+    }
+    finalize_kernel<<<1, 256, 0, st>>>(s, want_grad, params, sigma, comps, gsum, z, alpha, kinv_diag, logdet_part, info,
+                                       chan_dev, (long long)N, (long long)Np, jitter_rel, out);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ host-side self-check hooks
+// Run the same closed forms on the CPU (used by the CPU test-suite; no device involved).
+extern "C" int mogp_host_pair_comps(int kind, int C, int Q, int D, const double* params, double* comps_out) {
+    KernSpec s;
+    if (spec_init(s, kind, C, Q, D)) return -1;
+    const int st = comp_stride(D);
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j)
+            for (int r = 0; r < s.R; ++r) pair_comp(kind, C, Q, D, params, i, j, r, comps_out + (size_t)((i * C + j) * s.R + r) * st);
+    return s.R;
+}
+extern "C" int mogp_host_chain(int kind, int C, int Q, int D, const double* params, const double* gsum,
+                               const double* adj, double* grad_out) {
+    KernSpec s;
+    if (spec_init(s, kind, C, Q, D)) return -1;
+    const int st = comp_stride(D);
+    std::vector<double> comps((size_t)C * C * s.R * st);
+    mogp_host_pair_comps(kind, C, Q, D, params, comps.data());
+    const int owners = n_chain_owners(kind, C, Q);
+    for (int o = 0; o < owners; ++o) chain_owner(kind, C, Q, D, params, comps.data(), gsum, adj, o, grad_out);
+    return s.P;
+}

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     }
 }
 
+long long g_mogp_launches = 0;
 static int g_gemm_cfg = -1;   // 0: 128x64 tiles, 128 threads, 2 CTAs/SM   1: 128x128 tiles, 256 threads
 
 extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
@@ -198,6 +199,7 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
     dim3 grid(g.N / BN, (g.M + BM - 1) / BM, batch);
     kern<<<grid, WM * WN * 32, SMEM, s>>>(g);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
@@ -307,6 +309,7 @@ static cudaError_t launch_leaf(double* A, long long lda, double* Linv, long long
         attr_done = true;
     }
     potrf_leaf_kernel<<<1, 256, smem, st>>>(A, lda, Linv, ldi, blk, logdet_part, info);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
@@ -315,21 +318,20 @@ static cudaError_t launch_leaf(double* A, long long lda, double* Linv, long long
 // right-looking: outer panels of MOGP_NB_OUT columns whose trailing update is one SYRK with
 // K = 256, inner 64-wide steps (leaf -> TRSM as GEMM with the leaf's explicit inverse ->
 // update of the remaining panel columns).  Diagonal blocks of Linv receive inv(L_kk).
-cudaError_t potrf_padded(mogp_handle_s* h, double* A, double* Linv, int64_t Np, long long ld, double* logdet_part,
+cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, int64_t Np, double* logdet_part,
                          int32_t* info, cudaStream_t st) {
-    (void)h;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT) {
         const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
         for (int64_t k = K0; k < Kend; k += MOGP_NB) {
-            e = launch_leaf(A, ld, Linv, ld, (int)(k / MOGP_NB), logdet_part, info, st);
+            e = launch_leaf(A, ld, Linv, ldi, (int)(k / MOGP_NB), logdet_part, info, st);
             if (e != cudaSuccess) return e;
             const int64_t r0 = k + MOGP_NB, M = Np - r0;
             if (M <= 0) continue;
             GemmArgs g{};
             g.A = A + r0 * ld + k; g.lda = ld;
-            g.B = Linv + k * ld + k; g.ldb = ld;
+            g.B = Linv + k * ldi + k; g.ldb = ldi;
             g.C = A + r0 * ld + k; g.ldc = ld;
             g.M = (int)M; g.N = MOGP_NB; g.K = MOGP_NB;
             g.alpha = 1.0; g.beta = 0.0;
@@ -435,6 +437,7 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
 
 cudaError_t launch_trmv_lower(const double* Linv, long long ld, const double* y, double* z, int64_t Np, cudaStream_t st) {
     trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Linv, ld, y, z, Np);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
@@ -485,6 +488,7 @@ cudaError_t launch_colpass(const double* M, long long ld, const double* v, int64
     dim3 grid((unsigned)((cols + 63) / 64), (unsigned)nsplit);
     colpass_kernel<<<grid, 256, 0, st>>>(M, ld, v, rows, cols, rows_per, part);
     colpass_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(part, (int)nsplit, cols, out_dot, out_sq);
+    MOGP_COUNT(2);
     return cudaGetLastError();
 }
 
@@ -494,6 +498,7 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, int64_t n, doubl
 }
 cudaError_t launch_pad_copy(const double* src, int64_t n, double* dst, int64_t np, cudaStream_t st) {
     pad_copy_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(src, n, dst, np);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
@@ -514,6 +519,7 @@ cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, 
                             cudaStream_t st) {
     dim3 grid((unsigned)((np + 255) / 256), (unsigned)np);
     copy_tri_kernel<<<grid, 256, 0, st>>>(dir, user, ldu, work, ldw, n, np);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
@@ -528,6 +534,7 @@ __global__ void pred_var_kernel(const double* __restrict__ chanbuf, int C, const
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
                             double* var, cudaStream_t st) {
     pred_var_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(chanbuf, C, chan_s_dev, colsq, M, var);
+    MOGP_COUNT(1);
     return cudaGetLastError();
 }
 

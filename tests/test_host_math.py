@@ -1,0 +1,113 @@
+"""CPU: the closed forms shared by the CUDA kernels (csrc/covmath.cuh), run on the host
+through the library's self-check hooks, against the oracle:
+  * derived per channel-pair constants  -> K rebuilt in numpy equals the oracle K,
+  * analytic chain rule                 -> gradient equals the oracle's autograd gradient."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from mogptk_b200 import _cabi
+from mogptk_b200.engine import pack_params, unpack_grads, kernel_dims
+from oracle import mogp_oracle as orc
+
+CASES = [n for n in golden_names() if not n.startswith("cfg")]
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def comps_of(lib, g):
+    kind = g["kind"]
+    Cn, Q, D = kernel_dims(kind, g["params"])
+    p = pack_params(kind, g["params"]).numpy().copy()
+    st = 2 + 3 * D
+    R = Q * D if kind == "SM" else Q
+    comps = np.zeros(Cn * Cn * R * st)
+    r = lib.mogp_host_pair_comps(_cabi.KIND[kind], Cn, Q, D, _ptr(p), _ptr(comps))
+    assert r == R
+    return p, comps.reshape(Cn, Cn, R, st), (Cn, Q, D, R, st)
+
+
+def block_terms(comp, xa, xb, D):
+    """E*C, E*S and u for one component of one pair; xa (n,D), xb (m,D)."""
+    alpha, phi = comp[0], comp[1]
+    v, m, th = comp[2:2 + D], comp[2 + D:2 + 2 * D], comp[2 + 2 * D:2 + 3 * D]
+    u = xa[:, None, :] - xb[None, :, :] + th[None, None, :]
+    E = np.exp(-0.5 * (u ** 2 * v).sum(-1))
+    ang = 2 * np.pi * ((u * m).sum(-1) + phi)
+    return alpha, E * np.cos(ang), E * np.sin(ang), u
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pair_constants_rebuild_K(lib, name):
+    g = load_golden(name)
+    p, comps, (Cn, Q, D, R, st) = comps_of(lib, g)
+    X = g["X"]
+    order = np.argsort(X[:, 0], kind="stable")
+    Xs = X[order]
+    off = np.concatenate([[0], np.cumsum(np.bincount(Xs[:, 0].astype(int), minlength=Cn))])
+    N = X.shape[0]
+    K = np.zeros((N, N))
+    for i in range(Cn):
+        for j in range(Cn):
+            xa, xb = Xs[off[i]:off[i + 1], 1:], Xs[off[j]:off[j + 1], 1:]
+            blk = np.zeros((xa.shape[0], xb.shape[0]))
+            for r in range(R):
+                a, EC, _, _ = block_terms(comps[i, j, r], xa, xb, D)
+                blk += a * EC
+            K[off[i]:off[i + 1], off[j]:off[j + 1]] = blk
+    Kref = orc.K(g["kind"], g["params"], torch.tensor(Xs)).numpy()
+    assert np.abs(K - Kref).max() <= 1e-13 * np.abs(Kref).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_chain_rule_matches_autograd(lib, name):
+    g = load_golden(name)
+    kind = g["kind"]
+    p, comps, (Cn, Q, D, R, st) = comps_of(lib, g)
+    X, y = g["X"], g["y"]
+    order = np.argsort(X[:, 0], kind="stable")
+    Xs, ys = X[order], y[order]
+    dv = g["data_var"][order] if "data_var" in g else None
+    off = np.concatenate([[0], np.cumsum(np.bincount(Xs[:, 0].astype(int), minlength=Cn))])
+    N = X.shape[0]
+    Xt = torch.tensor(Xs)
+    Kt = orc._noisy_gram(kind, g["params"], g["sigma_t"], Xt, g["jitter"], dv).numpy()
+    Kinv = np.linalg.inv(Kt)
+    al = Kinv @ ys
+    W = 0.5 * (Kinv - np.outer(al, al))
+    # weighted sums per lower pair: [S0, S4, S1[D], S2[D], S3[D]]
+    npl = Cn * (Cn + 1) // 2
+    gsum = np.zeros((npl, R, st))
+    for i in range(Cn):
+        for j in range(i + 1):
+            xa, xb = Xs[off[i]:off[i + 1], 1:], Xs[off[j]:off[j + 1], 1:]
+            Wb = W[off[i]:off[i + 1], off[j]:off[j + 1]] * (1.0 if i == j else 2.0)
+            for r in range(R):
+                _, EC, ES, u = block_terms(comps[i, j, r], xa, xb, D)
+                rec = gsum[i * (i + 1) // 2 + j, r]
+                rec[0] = (Wb * EC).sum()
+                rec[1] = (Wb * ES).sum()
+                for d in range(D):
+                    rec[2 + d] = (Wb * EC * u[..., d] ** 2).sum()
+                    rec[2 + D + d] = (Wb * ES * u[..., d]).sum()
+                    rec[2 + 2 * D + d] = (Wb * EC * u[..., d]).sum()
+    trW = np.trace(W)
+    nc = np.diff(off)
+    adj = g["jitter"] / N * trW * nc.astype(float)
+    grad = np.zeros(p.size)
+    P = lib.mogp_host_chain(_cabi.KIND[kind], Cn, Q, D, _ptr(p), _ptr(gsum), _ptr(adj), _ptr(grad))
+    assert P == p.size
+    got = unpack_grads(kind, Cn, Q, D, torch.tensor(grad))
+    _, ref = orc.loss_and_grad(kind, g["params"], g["sigma_t"], Xt, ys, g["jitter"], dv)
+    for k, v in got.items():
+        scale = max(float(ref[k].abs().max()), 1e-12)
+        assert float((v - ref[k]).abs().max()) <= 1e-7 * scale, (k, v, ref[k])
+    # noise gradient formula used by the finalize kernel
+    sig = g["sigma"]
+    gs = np.array([2 * sig[c] * (np.trace(W[off[c]:off[c + 1], off[c]:off[c + 1]]) + adj[c]) for c in range(Cn)])
+    assert np.abs(gs - ref["sigma"].numpy()).max() <= 1e-7 * max(np.abs(ref["sigma"].numpy()).max(), 1e-12)

@@ -1,0 +1,209 @@
+#!/usr/bin/env python
+"""Bring-up diagnostics for a gpurun call: each section runs in its own process (see
+tools/gpu_diag.sh) so that a CUDA fault in one does not hide the others.
+Usage: python tools/gpu_diag.py <section>"""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, float)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def ev_time(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def sec_peak(eng):
+    print("device:", torch.cuda.get_device_name(0), torch.cuda.get_device_properties(0).multi_processor_count, "SMs")
+    for _ in range(2):
+        d, f = eng.peak_fp64()
+        print("peak fp64: DMMA %.2f TFLOP/s   DFMA %.2f TFLOP/s" % (d, f))
+
+
+def sec_gemm(eng):
+    for cfg in (0, 1):
+        eng.lib.mogp_set_gemm_config(cfg)
+        for ta in (0, 1):
+            for tb in (0, 1):
+                for (M, N, K) in [(64, 64, 16), (128, 128, 64), (192, 128, 256), (448, 384, 96)]:
+                    g = torch.Generator().manual_seed(1)
+                    A = torch.randn((K, M) if ta else (M, K), generator=g, dtype=torch.float64).cuda()
+                    B = torch.randn((N, K) if tb else (K, N), generator=g, dtype=torch.float64).cuda()
+                    C0 = torch.randn((M, N), generator=g, dtype=torch.float64).cuda()
+                    ref = 0.7 * (A.T if ta else A) @ (B.T if tb else B) - 1.3 * C0
+                    out = eng.dgemm(ta, tb, 0.7, A, B, -1.3, C0.clone())
+                    torch.cuda.synchronize()
+                    print("gemm cfg%d ta=%d tb=%d %4dx%4dx%4d relerr %.2e" % (cfg, ta, tb, M, N, K, rel(out, ref)))
+        for n in (2048, 4096, 8192):
+            A = torch.randn((n, n), dtype=torch.float64, device="cuda")
+            B = torch.randn((n, n), dtype=torch.float64, device="cuda")
+            Cm = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+            for ta, tb in ((0, 1), (0, 0), (1, 0)):
+                med, mn = ev_time(lambda: eng.dgemm(ta, tb, 1.0, A, B, 0.0, Cm), reps=3, warm=1)
+                print("gemm cfg%d ta=%d tb=%d n=%d: %.3f ms  %.2f TFLOP/s" % (cfg, ta, tb, n, mn, 2.0 * n ** 3 / mn / 1e9))
+            med, mn = ev_time(lambda: torch.matmul(A, B, out=Cm), reps=3, warm=1)
+            print("   cuBLAS dgemm n=%d: %.3f ms  %.2f TFLOP/s" % (n, mn, 2.0 * n ** 3 / mn / 1e9))
+    eng.lib.mogp_set_gemm_config(0)
+
+
+def spd(n, seed=0, shift=0.5):
+    g = torch.Generator().manual_seed(seed)
+    B = torch.randn((n, n + 8), generator=g, dtype=torch.float64)
+    return B @ B.T / n + shift * torch.eye(n, dtype=torch.float64)
+
+
+def sec_potrf(eng):
+    for n in (64, 128, 200, 256, 640, 1024, 2048):
+        A = spd(n, n)
+        Lref = torch.linalg.cholesky(A)
+        Ad = A.cuda().clone()
+        info = eng.potrf_(Ad)
+        L = torch.tril(Ad).cpu()
+        print("potrf n=%4d info=%d  relerr(L) %.2e  relerr(LL^T) %.2e" % (n, info, rel(L, Lref), rel(L @ L.T, A)))
+    A = spd(300, 5)
+    A[150, 150] = -1.0
+    print("potrf bad pivot -> info", eng.potrf_(A.cuda().clone()), "(expect 151)")
+    for cfg in (0, 1):
+        eng.lib.mogp_set_gemm_config(cfg)
+        for n in (2048, 4096, 8192):
+            A = spd(n, 1).cuda()
+            W = A.clone()
+
+            def run():
+                W.copy_(A)
+                eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+            def cp():
+                W.copy_(A)
+            t_all, _ = ev_time(run, reps=3, warm=1)
+            t_cp, _ = ev_time(cp, reps=3, warm=1)
+            t = t_all - t_cp
+            print("potrf cfg%d n=%d: %.3f ms  %.2f TFLOP/s" % (cfg, n, t, n ** 3 / 3.0 / t / 1e9))
+            if cfg == 0:
+                def cus():
+                    torch.linalg.cholesky(A, out=W)
+                t2, _ = ev_time(cus, reps=3, warm=1)
+                print("   cuSOLVER potrf n=%d: %.3f ms  %.2f TFLOP/s" % (n, t2, n ** 3 / 3.0 / t2 / 1e9))
+    eng.lib.mogp_set_gemm_config(0)
+
+
+def sec_trtri(eng):
+    for n in (128, 384, 1024, 2048):
+        A = spd(n, n + 1, 0.3)
+        Ad = A.cuda().clone()
+        Linv, Kinv, info = eng.trtri_kinv_(Ad)
+        Lref = torch.linalg.cholesky(A)
+        print("trtri n=%4d info=%d relerr(L) %.2e relerr(Linv) %.2e relerr(Kinv) %.2e" % (
+            n, info, rel(torch.tril(Ad).cpu(), Lref), rel(torch.tril(Linv).cpu(), torch.linalg.inv(Lref)),
+            rel(torch.tril(Kinv).cpu(), torch.tril(torch.linalg.inv(A)))))
+
+
+def sec_cov(eng):
+    from conftest import golden_names, load_golden
+    for name in golden_names():
+        if name == "cfg3":
+            continue
+        try:
+            g = load_golden(name)
+            K = eng.K(g["kind"], g["params"], g["X"]).cpu().numpy()
+            if "K_full" in g:
+                e = rel(K, g["K_full"])
+            else:
+                idx = g["K_idx"]
+                e = np.abs(K[idx[:, 0], idx[:, 1]] - g["K_val"]).max() / np.abs(g["K_val"]).max()
+            kd = eng.K_diag(g["kind"], g["params"], g["X"]).cpu().numpy()
+            Kfs = eng.K(g["kind"], g["params"], g["X"], g["Xs"]).cpu().numpy()
+            e2 = np.abs(Kfs[::int(g["Kfs_row_stride"])] - g["Kfs_rows"]).max() / max(np.abs(g["K_diag"]).max(), 1e-300)
+            print("K %-14s relerr %.2e  sym %s  kdiag==diag %s  cross relerr %.2e" % (
+                name, e, np.array_equal(K, K.T), np.array_equal(kd, np.diagonal(K)), e2))
+        except Exception:
+            print("K %-14s FAILED" % name)
+            traceback.print_exc()
+
+
+def sec_lml(eng):
+    from conftest import golden_names, load_golden
+    for name in golden_names():
+        try:
+            g = load_golden(name)
+            res = eng.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], True,
+                               data_var=g.get("data_var"))
+            errs = []
+            for k, got in res["grad"].items():
+                ref = g["gc_" + k]
+                errs.append("%s %.1e" % (k[:4], np.abs(got.numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-12)))
+            print("lml %-14s info=%d lml %.10f ref %.10f rel %.2e | grad %s" % (
+                name, res["info"], res["lml"], float(g["lml"]), abs(res["lml"] - float(g["lml"])) / abs(float(g["lml"])),
+                " ".join(errs)))
+            if "pred_mu" in g:
+                mu, var = eng.predict(g["Xs"])
+                line = "    predict mu %.2e var %.2e" % (rel(mu, g["pred_mu"]), np.abs(var.cpu().numpy() - g["pred_var"]).max() / np.abs(g["pred_var"]).max())
+                if "pred_cov" in g:
+                    _, cov = eng.predict(g["Xs"], full=True)
+                    line += " cov %.2e" % rel(cov, g["pred_cov"])
+                print(line)
+        except Exception:
+            print("lml %-14s FAILED" % name)
+            traceback.print_exc()
+
+
+def sec_time(eng):
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params
+    for cfg in (0, 1):
+        eng.lib.mogp_set_gemm_config(cfg)
+        for name in ("cfg1", "cfg2", "cfg4", "cfg3"):
+            g = load_golden(name)
+            rows = eng.prepare(g["kind"], g["params"], g["X"], g["y"])
+            p = pack_params(g["kind"], g["params"], eng.device)
+            sig = torch.tensor(g["sigma"], device=eng.device)
+            N = g["X"].shape[0]
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=5, warm=2)
+            t0, m0 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], False, check=False), reps=5, warm=2)
+            Kout = torch.empty((N, N), dtype=torch.float64, device=eng.device)
+            def kb():
+                eng.lib.mogp_kbuild(eng.h, {"MOSM": 0, "SM": 1, "CONV": 2}[g["kind"]], *rows.dims, eng._p(p), eng._p(rows.x),
+                                    rows.off_p, None, None, None, None, 0.0, eng._p(Kout), N, eng._stream())
+            tk, mk = ev_time(kb, reps=5, warm=2)
+            print("time cfg%d %-5s N=%d: loss+grad %.3f ms (min %.3f) -> %.1f it/s | lml only %.3f ms | K full %.3f ms = %.0f GB/s" % (
+                cfg, name, N, t1, m1, 1e3 / t1, t0, tk, 8.0 * N * N / mk / 1e6))
+    eng.lib.mogp_set_gemm_config(0)
+
+
+SECTIONS = {"peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+            "lml": sec_lml, "time": sec_time}
+
+if __name__ == "__main__":
+    from mogptk_b200.engine import Engine
+    name = sys.argv[1]
+    t0 = time.time()
+    eng = Engine(device=0, max_n=8192)
+    print("=== section %s (engine up in %.1fs)" % (name, time.time() - t0), flush=True)
+    try:
+        SECTIONS[name](eng)
+    except Exception:
+        traceback.print_exc()
+    torch.cuda.synchronize()
+    print("=== section %s done in %.1fs" % (name, time.time() - t0), flush=True)
