@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- log-marginal-likelihood iterations/sec (fp64) of the exact-GP hot path.
+
+A "step" is one loss()-equivalent evaluation of one exact multi-output GP model:
+K~ build + Cholesky + LML + full analytic gradient (mogptk/gpr/model.py:279-292, 438-453).
+Workload at N GPUs = BASELINE.json configs[1] ("MOSM 4 channels, Q=5, N=2048, 1D, fp64")
+per GPU; with N > 1 every rank evaluates an independent replica (another random restart,
+seed = rank) and the ranks exchange only their final losses (one NCCL all-gather):
+"replicas only", scaling = weak.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl reference]
+
+`--impl reference` times the reference's own CPU path restated in oracle/ (torch-CPU,
+autograd, all host threads) on the same config and metric (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mogptk_b200 import synth  # noqa: E402
+
+METRIC = "lml_iters_per_sec"
+UNIT = "it/s"
+DMMA_PEAK_FALLBACK_TFLOPS = 37.15     # own probe (mogp_peak_fp64) on this pool, see DESIGN.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="cfg2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg):
+    kind, C, n, Q = synth.CONFIGS[cfg]
+    return "%s %d channels, Q=%d, N=%d total (%d per channel), 1D input, Exact, fp64" % (kind, C, Q, C * n, n)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=3)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(cfg, seed, steps, warmup, budget_s=25.0):
+    """The reference's CPU path (oracle port: torch-CPU fp64, autograd) on all host threads."""
+    from oracle import mogp_oracle as orc
+    kind, p, sigma, X, y = synth.make_config(cfg, seed)
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = orc.RawModel(kind, p, sigma, X, y, 1e-8)
+    times, last = [], None
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        last = float(m.loss().detach())
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    med = float(np.median(times))
+    return {"value": 1.0 / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d timed loss() calls (forward + autograd backward) of the torch-CPU oracle on %s, median"
+                      % (len(times), cfg), "ms_per_step": med * 1e3, "loss": last}, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, n = cpu_baseline(args.config, 0, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": n, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "config": args.config},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from mogptk_b200.engine import Engine, pack_params, kernel_dims
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    kind, p, sigma, X, y = synth.make_config(args.config, seed=rank)     # replica = another restart
+    N = X.shape[0]
+    eng = Engine(device=local, max_n=N)
+    rows = eng.prepare(kind, p, X, y)
+    dims = rows.dims
+    P = int(sum(v.numel() for v in p.values()))
+    packed = pack_params(kind, p, eng.device)
+    sig = sigma.to(eng.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)   # > 126 MB L2
+
+    def step(pk):
+        return eng.lml_grad_prepared(rows, pk, sig, 1e-8, True, check=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(max(3, args.warmup)):
+        out = step(packed)
+    torch.cuda.synchronize()
+    info0 = int(out[1].item())
+    launches0 = eng.lib.mogp_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pk = packed.clone()
+    barrier()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for e0, e1 in evs:
+            flush.zero_()                                   # L2 flush, outside the per-step events
+            e0.record()
+            out = step(pk)
+            e1.record()
+            pk = pk - 1e-7 * out[2:2 + P]                   # move the parameters: nothing can be cached
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = eng.lib.mogp_launch_count() - launches0
+    dev_ms = float(np.sum([a.elapsed_time(b) for a, b in evs]))
+    final_loss = -float(out[0].item())
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        losses = [torch.zeros(1, dtype=torch.float64, device=eng.device) for _ in range(world)]
+        dist.all_gather(losses, torch.tensor([final_loss], dtype=torch.float64, device=eng.device))
+        losses = [float(l.item()) for l in losses]
+    else:
+        losses = [final_loss]
+    dev_ms = float(tmax.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---------------- stage breakdown (one profiled step, events inside the library)
+    eng.lib.mogp_set_profile(eng.h, 1)
+    for _ in range(3):
+        step(packed)
+    st = (C.c_float * 8)()
+    ns = eng.lib.mogp_stage_times(eng.h, st)
+    eng.lib.mogp_set_profile(eng.h, 0)
+    names = ["kbuild", "potrf", "trtri", "solves", "kinv", "grad_finalize"]
+    stages = {names[i]: round(float(st[i]), 4) for i in range(min(ns, len(names)))}
+
+    # ---------------- end to end through the C ABI with HOST buffers (`e2e`)
+    Pk = packed.cpu().numpy().copy()
+    xh = torch.from_numpy(rows.x_host).pin_memory().numpy()
+    yh = rows.y.cpu().pin_memory().numpy()
+    ph = torch.from_numpy(Pk).pin_memory().numpy()
+    sh = sigma.clone().pin_memory().numpy()
+    oh = torch.empty(2 + P + dims[0], dtype=torch.float64).pin_memory().numpy()
+    for _ in range(3):
+        eng.lml_grad_host(kind, dims, ph, xh, rows.chan_off, yh, sh, 1e-8, True, oh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.lml_grad_host(kind, dims, ph, xh, rows.chan_off, yh, sh, 1e-8, True, oh)   # synchronises itself
+        ph[:] = ph - 1e-7 * oh[2:2 + P]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps / float(te.item())
+    h2d = 8 * (P + dims[0] + N * dims[2] + N)
+    d2h = 8 * (2 + P + dims[0])
+
+    if rank == 0:
+        try:
+            dmma, dfma = eng.peak_fp64()
+        except Exception:
+            dmma, dfma = DMMA_PEAK_FALLBACK_TFLOPS, None
+        flops = synth.flops_per_iteration(N)
+        ach = flops / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "config": args.config, "parallelism": "replicas x%d" % world,
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
+                       "n_params": P + dims[0], "info": info0, "final_losses": losses,
+                       "wall_s_incl_flush": round(t_wall, 4)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": dmma, "unit": "TFLOP/s", "frac": ach / dmma,
+                         "traffic": None,
+                         "what": "whole step: N^3 algorithmic flop (potrf N^3/3 + inverse 2N^3/3) / CUDA-event step time; "
+                                 "peak = fp64 tensor-pipe (DMMA m8n8k4) probe measured in this run "
+                                 "(MEASURED_PEAKS.json holds no fp64 figure); DFMA probe %.2f" % (dfma or 0.0),
+                         "stage_ms": stages},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_baseline(args.config, 0, 20, 2)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -218,10 +218,10 @@ extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda
     if (zero_linv_for(h, Np, st)) return -2;
     h->have_factor = false;
     if (n == Np && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(A_dev) % 16) == 0) {
-        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, Np, h->logdet_part, h->info, st));
+        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st));
     } else {
         MOGP_CHECK(h, launch_copy_tri(0, A_dev, lda, h->A, Np, n, Np, st));
-        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, Np, h->logdet_part, h->info, st));
+        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st));
         MOGP_CHECK(h, launch_copy_tri(1, A_dev, lda, h->A, Np, n, Np, st));
     }
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -235,7 +235,7 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     MOGP_CHECK(h, cudaSetDevice(h->device));
     H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
-    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, n, h->logdet_part, h->info, st));
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st));
     MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
     MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -283,7 +283,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, data_var_dev, 1, h->A, ld, N,
                                 Np, st));
     STAGE_MARK();
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, Np, h->logdet_part, h->info, st));
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st));
     STAGE_MARK();
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
     MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));

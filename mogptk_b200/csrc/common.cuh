@@ -139,8 +139,8 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
                             int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st);
 
 // ------------------------------------------------------------------ dense linear algebra (linalg.cu)
-cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, int64_t Np, double* logdet_part,
-                         int32_t* info, cudaStream_t st);
+cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
 // z = Linv * y (lower-triangular mat-vec), rows [0,Np)

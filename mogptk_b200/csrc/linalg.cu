@@ -17,6 +17,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
     int sz = pred ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -177,7 +181,8 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
 }
 
 long long g_mogp_launches = 0;
-static int g_gemm_cfg = -1;   // 0: 128x64 tiles, 128 threads, 2 CTAs/SM   1: 128x128 tiles, 256 threads
+// 0 (default): pick by tile count   1: force 128x128 tiles (256 threads)   2: force 64x64 tiles   3: force 128x64 tiles
+static int g_gemm_cfg = -1;
 
 extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
@@ -211,6 +216,12 @@ static cudaError_t launch_gemm_t(const GemmArgs& g, int batch, cudaStream_t s) {
     }
     if (g_gemm_cfg == 1 && (g.N % 128) == 0)
         return launch_gemm_cfg<128, 128, 2, 4, 3, 1, TA, TB>(g, batch, s);
+    // Small problems do not fill 148 SMs x 2 CTAs with 128x64 tiles: use 64x64 tiles (3 CTAs/SM)
+    // so that the longest CTA is shorter and every SM has work.
+    long long tiles = (long long)((g.M + 127) / 128) * (g.N / 64) * batch;
+    if (g.lower) tiles = tiles / 2 + 1;
+    if (g_gemm_cfg == 2 || (g_gemm_cfg != 3 && tiles < 1200))
+        return launch_gemm_cfg<64, 64, 2, 2, 3, 3, TA, TB>(g, batch, s);
     return launch_gemm_cfg<128, 64, 2, 2, 3, 2, TA, TB>(g, batch, s);
 }
 
@@ -222,49 +233,158 @@ cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cu
     return launch_gemm_t<true, true>(g, batch, s);
 }
 
-// ============================================================================ Cholesky leaf
-// Factor the 64x64 diagonal block `blk` in place (lower) and write its inverse (dense,
-// explicit zeros above the diagonal) into the same block position of Linv.
-// Right-looking column sweep in shared memory, then a recursive-doubling triangular
-// inverse: inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] for s = 1,2,...,32.
+// ============================================================================ Cholesky panel step
+// One launch per 64-column step.  Every CTA redundantly factors the 64x64 diagonal block in
+// shared memory (8-column sub-panels; the 8x8 pivot block is factored in registers by every
+// row-owning thread, so the only block-wide barriers are two per sub-panel) and carries its
+// own 64 rows of the panel below through the same sweep (fused triangular solve by
+// substitution: no explicit inverse on the critical path).  CTA 0 parks L_kk in `Ltmp`
+// (the diagonal block of a scratch matrix) because other CTAs may still be reading A_kk.
+#define PS 65    // pitch of the row-major staging tile (conflict-free row-per-thread access)
+#define PL 128   // pitch of the column-major copy of finished columns (rows contiguous)
+__global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict__ A, long long lda,
+                                                             double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
+                                                             int32_t* info, long long* dbg) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                  // [128][PS] staging: rows 0..63 diagonal block, 64..127 this CTA's rows below
+    double* Lc = sm + 128 * PS;      // [64][PL]  finished columns, column-major: Lc[col][row]
+    double* Dsm = Lc + 64 * PL;      // [8][8]    the updated pivot block of the current sub-panel
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const bool has_rows = b < nrb;
+    if (dbg && tid == 64 && b == 0) dbg[0] = clock64();
+    const double* Ad = A + (long long)k0 * lda + k0;
+    double* Ar = A + (long long)(k0 + 64 + 64 * b) * lda + k0;
+    // all loads in flight at once (8-byte cp.async: the padded pitch is not 16-byte aligned)
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+        const int idx = tid + it * 128;
+        const int r = idx >> 6, c = idx & 63;
+        cp_async8(S + r * PS + c, Ad + (long long)r * lda + c);
+        if (has_rows) cp_async8(S + (64 + r) * PS + c, Ar + (long long)r * lda + c);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int nrows = has_rows ? 128 : 64;
+    const bool active_row = tid < nrows;
+    // Left-looking sweep, one thread per row.  Finished columns live in Lc (column-major, so a
+    // thread re-reads its own row conflict-free and the 8 pivot values of a column are one
+    // aligned 64-byte broadcast); the code stays small enough for the instruction cache.
+    if (dbg && tid == 64 && b == 0) dbg[1] = clock64();
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = p * 8;
+        const bool act = active_row && tid >= c0;
+        double acc[8];
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = S[tid * PS + c0 + c];
+#pragma unroll 4
+            for (int cp = 0; cp < c0; ++cp) {          // subtract the finished columns (8 independent chains)
+                const double2* pv = reinterpret_cast<const double2*>(Lc + cp * PL + c0);
+                const double2 v0 = pv[0], v1 = pv[1], v2 = pv[2], v3 = pv[3];
+                const double m = -Lc[cp * PL + tid];
+                acc[0] = fma(m, v0.x, acc[0]); acc[1] = fma(m, v0.y, acc[1]);
+                acc[2] = fma(m, v1.x, acc[2]); acc[3] = fma(m, v1.y, acc[3]);
+                acc[4] = fma(m, v2.x, acc[4]); acc[5] = fma(m, v2.y, acc[5]);
+                acc[6] = fma(m, v3.x, acc[6]); acc[7] = fma(m, v3.y, acc[7]);
+            }
+            if (tid < c0 + 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Dsm[(tid - c0) * 8 + c] = acc[c];
+            }
+        }
+        __syncthreads();
+        if (dbg && tid == 64 && b == 0) dbg[2 + 2 * p] = clock64();
+        if (act) {
+            double D[8][8], rinv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double d = D[c][c];
+                if (!(d > 0.0)) {
+                    if (tid == c0 && b == 0) atomicCAS(info, 0, k0 + c0 + c + 1);
+                    d = 1.0;
+                }
+                const double ri = rsqrt(d);
+                rinv[c] = ri;
+                D[c][c] = d * ri;
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i)
+#pragma unroll
+                    for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
+            }
+            if (tid < c0 + 8) {                       // a row of the pivot block itself
+                const int jrow = tid - c0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    if (jrow == jj) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[c] = (c <= jj) ? D[jj][c] : 0.0;
+                    }
+            } else {                                  // forward substitution for a row below
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double xc = acc[c] * rinv[c];
+                    acc[c] = xc;
+#pragma unroll
+                    for (int cc = c + 1; cc < 8; ++cc) acc[cc] = fma(-xc, D[cc][c], acc[cc]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                Lc[(c0 + c) * PL + tid] = acc[c];
+                S[tid * PS + c0 + c] = acc[c];
+            }
+        }
+        __syncthreads();
+        if (dbg && tid == 64 && b == 0) dbg[3 + 2 * p] = clock64();
+    }
+    if (has_rows)
+        for (int idx = tid; idx < 4096; idx += 128) {
+            const int r = idx >> 6, c = idx & 63;
+            Ar[(long long)r * lda + c] = S[(64 + r) * PS + c];
+        }
+    if (b == 0) {
+        double* Lt = Ltmp + (long long)k0 * ldt + k0;
+        for (int idx = tid; idx < 4096; idx += 128) {
+            const int r = idx >> 6, c = idx & 63;
+            if (c <= r) Lt[(long long)r * ldt + c] = S[r * PS + c];
+        }
+    }
+    if (dbg && tid == 64 && b == 0) dbg[18] = clock64();
+}
+
+// After the sweep, for every diagonal block at once: move L_kk from Ltmp into A, invert it by
+// recursive doubling  inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]]  (s = 1,2,..,32) into
+// the diagonal block of Linv (explicit zeros above the diagonal), and emit sum(log diag).
 #define LP 65
-__global__ void __launch_bounds__(256) potrf_leaf_kernel(double* __restrict__ A, long long lda,
-                                                         double* __restrict__ Linv, long long ldi, int blk,
-                                                         double* __restrict__ logdet_part, int32_t* info) {
+__global__ void __launch_bounds__(256) diag_finish_kernel(double* __restrict__ A, long long lda,
+                                                          const double* __restrict__ Ltmp, long long ldt,
+                                                          double* __restrict__ Linv, long long ldi,
+                                                          double* __restrict__ logdet_part) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* T = sm + 64 * LP;
     double* U = T + 64 * LP;
-    double* dg = U + 64 * LP;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, blk = blockIdx.x;
+    const double* Lt = Ltmp + (long long)blk * 64 * ldt + (long long)blk * 64;
     double* Ab = A + (long long)blk * 64 * lda + (long long)blk * 64;
     for (int idx = tid; idx < 4096; idx += 256) {
-        int r = idx >> 6, c = idx & 63;
-        S[r * LP + c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
+        const int r = idx >> 6, c = idx & 63;
+        const double v = (c <= r) ? Lt[(long long)r * ldt + c] : 0.0;
+        S[r * LP + c] = v;
         T[r * LP + c] = 0.0;
-    }
-    const int ti = tid >> 4, tk = tid & 15;
-    for (int j = 0; j < 64; ++j) {
-        __syncthreads();
-        double d = S[j * LP + j];
-        if (!(d > 0.0)) {
-            if (tid == 0) atomicCAS(info, 0, blk * 64 + j + 1);
-            d = 1.0;
-        }
-        const double r = sqrt(d);
-        if (tid > j && tid < 64) S[tid * LP + j] = S[tid * LP + j] / r;
-        if (tid == j) dg[j] = r;
-        __syncthreads();
-        for (int i = j + 1 + ti; i < 64; i += 16) {
-            const double lij = S[i * LP + j];
-            for (int k = j + 1 + tk; k <= i; k += 16) S[i * LP + k] -= lij * S[k * LP + j];
-        }
+        if (c <= r) Ab[(long long)r * lda + c] = v;
     }
     __syncthreads();
-    if (tid < 64) {
-        S[tid * LP + tid] = dg[tid];
-        T[tid * LP + tid] = 1.0 / dg[tid];
-    }
+    if (tid < 64) T[tid * LP + tid] = 1.0 / S[tid * LP + tid];
     __syncthreads();
     for (int s = 1; s < 64; s <<= 1) {
         const int total = 32 * s, ss = s * s;
@@ -287,58 +407,59 @@ __global__ void __launch_bounds__(256) potrf_leaf_kernel(double* __restrict__ A,
     }
     double* Lb = Linv + (long long)blk * 64 * ldi + (long long)blk * 64;
     for (int idx = tid; idx < 4096; idx += 256) {
-        int r = idx >> 6, c = idx & 63;
-        if (c <= r) Ab[(long long)r * lda + c] = S[r * LP + c];
+        const int r = idx >> 6, c = idx & 63;
         Lb[(long long)r * ldi + c] = T[r * LP + c];
     }
     if (tid < 32) {
-        double v = log(dg[tid]) + log(dg[tid + 32]);
+        double v = log(S[tid * LP + tid]) + log(S[(tid + 32) * LP + tid + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (tid == 0) logdet_part[blk] = v;
     }
 }
 
-static cudaError_t launch_leaf(double* A, long long lda, double* Linv, long long ldi, int blk, double* logdet_part,
-                               int32_t* info, cudaStream_t st) {
-    const size_t smem = (3 * 64 * LP + 64) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
+static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
+extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
+    if (!g_panel_dbg) {
+        if (cudaMalloc(&g_panel_dbg, 32 * 8) != cudaSuccess) return -2;
+        cudaMemset(g_panel_dbg, 0, 32 * 8);
+        return 1;
     }
-    potrf_leaf_kernel<<<1, 256, smem, st>>>(A, lda, Linv, ldi, blk, logdet_part, info);
-    MOGP_COUNT(1);
-    return cudaGetLastError();
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out_host, g_panel_dbg, 19 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 // ============================================================================ blocked Cholesky
-// In-place lower Cholesky of the padded Np x Np matrix A (row-major, ld).  Two-level
-// right-looking: outer panels of MOGP_NB_OUT columns whose trailing update is one SYRK with
-// K = 256, inner 64-wide steps (leaf -> TRSM as GEMM with the leaf's explicit inverse ->
-// update of the remaining panel columns).  Diagonal blocks of Linv receive inv(L_kk).
-cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, int64_t Np, double* logdet_part,
-                         int32_t* info, cudaStream_t st) {
+// In-place lower Cholesky of the padded Np x Np matrix A (row-major, lda): per 64-column step
+// one panel kernel (above) and one trailing GEMM update; for large matrices the updates are
+// two-level (inner: remaining columns of a 256-wide outer panel, K = 64; outer: one SYRK
+// with K = 256) to cut the passes over the trailing matrix.  Ltmp is an Np x Np scratch
+// whose diagonal blocks are used; diagonal blocks of Linv receive inv(L_kk).
+cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
-    for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT) {
-        const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
+    const size_t smem_p = (size_t)(128 * PS + 64 * PL + 64) * sizeof(double);
+    const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(diag_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t nb_out = (Np > 4096) ? MOGP_NB_OUT : MOGP_NB;
+    for (int64_t K0 = 0; K0 < Np; K0 += nb_out) {
+        const int64_t Wd = std::min<int64_t>(nb_out, Np - K0), Kend = K0 + Wd;
         for (int64_t k = K0; k < Kend; k += MOGP_NB) {
-            e = launch_leaf(A, ld, Linv, ldi, (int)(k / MOGP_NB), logdet_part, info, st);
-            if (e != cudaSuccess) return e;
             const int64_t r0 = k + MOGP_NB, M = Np - r0;
-            if (M <= 0) continue;
-            GemmArgs g{};
-            g.A = A + r0 * ld + k; g.lda = ld;
-            g.B = Linv + k * ldi + k; g.ldb = ldi;
-            g.C = A + r0 * ld + k; g.ldc = ld;
-            g.M = (int)M; g.N = MOGP_NB; g.K = MOGP_NB;
-            g.alpha = 1.0; g.beta = 0.0;
-            e = launch_gemm(0, 1, g, 1, st);           // L21 = A21 * inv(L11)^T
-            if (e != cudaSuccess) return e;
+            const int nrb = (int)(M / 64);
+            potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, info,
+                                                                      (k == 0) ? g_panel_dbg : nullptr);
+            MOGP_COUNT(1);
             const int64_t Nc = Kend - r0;
-            if (Nc > 0) {                                // remaining columns of this outer panel
+            if (M > 0 && Nc > 0) {                       // remaining columns of this outer panel
                 GemmArgs u{};
                 u.A = A + r0 * ld + k; u.lda = ld;
                 u.B = A + r0 * ld + k; u.ldb = ld;
@@ -361,8 +482,11 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, i
             if (e != cudaSuccess) return e;
         }
     }
-    return cudaSuccess;
+    diag_finish_kernel<<<(unsigned)(Np / 64), 256, smem_d, st>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
 }
+
 
 // ============================================================================ triangular inverse
 // Linv = L^-1 by level-batched block doubling: at level s (in 64-blocks) every pair of
@@ -604,4 +728,76 @@ cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops) {
     e = cudaGetLastError();
     cudaFree(d);
     return e;
+}
+
+// ============================================================================ latency probes
+// Single-warp dependent-chain latencies (cycles per op), used to budget the Cholesky panel chain.
+__global__ void latency_probe_kernel(double* out, double seed) {
+    __shared__ double sbuf[64];
+    const int n = 256;
+    double x = seed + threadIdx.x * 1e-9, y = 1.0000001, z = 1e-9;
+    long long t0, t1;
+    sbuf[threadIdx.x] = x; sbuf[threadIdx.x + 32] = y;
+    __syncthreads();
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = fma(x, y, z);
+    t1 = clock64();
+    double r0 = (double)(t1 - t0) / n;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = x * y;
+    t1 = clock64();
+    double r1 = (double)(t1 - t0) / n;
+    x = fabs(x) + 2.0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = rsqrt(x) + 2.0;
+    t1 = clock64();
+    double r2 = (double)(t1 - t0) / n;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = sqrt(x) + 2.0;
+    t1 = clock64();
+    double r3 = (double)(t1 - t0) / n;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = 1.0 / x + 2.0;
+    t1 = clock64();
+    double r4 = (double)(t1 - t0) / n;
+    int idx = threadIdx.x;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) idx = (int)sbuf[idx & 63] & 31;
+    t1 = clock64();
+    double r5 = (double)(t1 - t0) / n;
+    double c0 = x, c1 = y;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) dmma884(c0, c1, y, z);
+    t1 = clock64();
+    double r6 = (double)(t1 - t0) / n;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) x = __shfl_xor_sync(0xffffffffu, x, 1) + 1.0;
+    t1 = clock64();
+    double r7 = (double)(t1 - t0) / n;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) __syncthreads();
+    t1 = clock64();
+    double r8 = (double)(t1 - t0) / n;
+    if (threadIdx.x == 0) {
+        out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6; out[7] = r7; out[8] = r8;
+        out[9] = x + idx + c0 + c1;
+    }
+}
+extern "C" int mogp_probe_latency(double* out_host /*10*/) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, 10 * 8) != cudaSuccess) return -2;
+    latency_probe_kernel<<<1, 32>>>(d, 1.5);
+    latency_probe_kernel<<<1, 32>>>(d, 1.5);
+    cudaError_t e = cudaMemcpy(out_host, d, 10 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : -2;
 }

@@ -41,10 +41,15 @@ def sec_peak(eng):
     for _ in range(2):
         d, f = eng.peak_fp64()
         print("peak fp64: DMMA %.2f TFLOP/s   DFMA %.2f TFLOP/s" % (d, f))
+    import ctypes as C
+    lat = (C.c_double * 10)()
+    eng.lib.mogp_probe_latency(lat)
+    names = ["DFMA", "DMUL", "rsqrt+add", "sqrt+add", "div+add", "LDS->addr", "DMMA", "SHFL64+add", "BAR(1 warp)"]
+    print("dependent-chain latency (cycles/op): " + "  ".join("%s %.1f" % (n, lat[i]) for i, n in enumerate(names)))
 
 
 def sec_gemm(eng):
-    for cfg in (0, 1):
+    for cfg in (3, 2):
         eng.lib.mogp_set_gemm_config(cfg)
         for ta in (0, 1):
             for tb in (0, 1):
@@ -86,7 +91,7 @@ def sec_potrf(eng):
     A = spd(300, 5)
     A[150, 150] = -1.0
     print("potrf bad pivot -> info", eng.potrf_(A.cuda().clone()), "(expect 151)")
-    for cfg in (0, 1):
+    for cfg in (0,):
         eng.lib.mogp_set_gemm_config(cfg)
         for n in (2048, 4096, 8192):
             A = spd(n, 1).cuda()
@@ -172,7 +177,7 @@ def sec_lml(eng):
 def sec_time(eng):
     from conftest import load_golden
     from mogptk_b200.engine import pack_params
-    for cfg in (0, 1):
+    for cfg in (0,):
         eng.lib.mogp_set_gemm_config(cfg)
         for name in ("cfg1", "cfg2", "cfg4", "cfg3"):
             g = load_golden(name)
@@ -192,7 +197,22 @@ def sec_time(eng):
     eng.lib.mogp_set_gemm_config(0)
 
 
-SECTIONS = {"peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+def sec_panel(eng):
+    import ctypes as C
+    buf = (C.c_longlong * 19)()
+    eng.lib.mogp_panel_debug(buf)          # arms the timestamps
+    for n in (2048, 8192):
+        A = spd(n, 1).cuda()
+        for _ in range(3):
+            W = A.clone()
+            eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+        torch.cuda.synchronize()
+        eng.lib.mogp_panel_debug(buf)
+        t = [int(v) for v in buf]
+        print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
+
+
+SECTIONS = {"panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
