@@ -1,0 +1,813 @@
+"""Host-side mirror of the reference's operator interface for the exact-GP hot path.
+
+Same class names, argument meaning and error behaviour as ``mogptk.gpr`` (GAMES-UChile/mogptk
+v0.5.1) for exactly the pieces the path needs -- constrained ``Parameter``s, the MOSM / SM /
+CONV kernels as *parameter containers*, the Gaussian likelihood scale, and the ``Exact``
+model -- but every O(N^2) / O(N^3) operation goes through libmogp_b200.so (hand-written
+sm_100a CUDA behind the C ABI in include/mogp_b200.h).  Nothing here evaluates a kernel
+matrix or factorises anything in PyTorch, and there is no CPU fallback: without a GPU the
+model raises.
+
+``Exact`` also accepts the reference's *own* kernel objects (duck-typed by class name), which
+is how ``mogptk.MOSM(dataset, Q, inference=B200Exact())`` plugs this engine in behind the
+reference's builder seam (mogptk/model.py:89-100,231) -- see mogptk_b200/inference.py and
+INTEGRATION.md.
+
+Reference lines restated here are cited inline (file:line under /root/reference/mogptk/).
+"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+
+# --------------------------------------------------------------------------------------
+# config  (gpr/config.py:3-10)
+# --------------------------------------------------------------------------------------
+class Config:
+    dtype = torch.float64
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    positive_minimum = 1e-8
+
+
+config = Config()
+
+
+def use_gpu(n=None):
+    """Select CUDA device n (gpr/config.py:51-62)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA is not available")
+    if n is None:
+        n = torch.cuda.current_device()
+    if n < 0 or n >= torch.cuda.device_count():
+        raise ValueError("CUDA device %d does not exist" % n)
+    torch.cuda.set_device(n)
+    config.device = torch.device("cuda", n)
+
+
+# --------------------------------------------------------------------------------------
+# transforms + Parameter  (gpr/parameter.py:30-346)
+# --------------------------------------------------------------------------------------
+class Softplus:
+    """y = lower + log(1 + exp(beta x)) / beta  (gpr/parameter.py:30-59)."""
+
+    def __init__(self, lower=0.0, beta=0.1, threshold=20.0):
+        self.lower, self.beta, self.threshold = lower, beta, threshold
+
+    def forward(self, x):
+        return self.lower + torch.nn.functional.softplus(x, beta=self.beta, threshold=self.threshold)
+
+    def inverse(self, y):
+        if self.beta < 0.0:
+            if torch.any(self.lower < y):
+                raise ValueError("values must be smaller than %s" % self.lower)
+        elif torch.any(y < self.lower):
+            raise ValueError("values must be greater than %s" % self.lower)
+        # the reference's expression (parameter.py:59): note -beta*y - lower, kept for parity
+        return (y - self.lower) + torch.log(-torch.expm1(-self.beta * y - self.lower)) / self.beta
+
+
+class Sigmoid:
+    """y = lower + (upper - lower) sigmoid(x)  (gpr/parameter.py:61-96)."""
+
+    def __init__(self, lower=0.0, upper=1.0):
+        self.lower, self.upper = lower, upper
+
+    def forward(self, x):
+        return self.lower + (self.upper - self.lower) * torch.sigmoid(x)
+
+    def inverse(self, y):
+        if torch.any(y < self.lower) or torch.any(self.upper < y):
+            raise ValueError("values must be between %s and %s" % (self.lower, self.upper))
+        s = (y - self.lower) / (self.upper - self.lower)
+        lo = torch.as_tensor(self.lower, dtype=s.dtype, device=s.device).expand_as(s)
+        up = torch.as_tensor(self.upper, dtype=s.dtype, device=s.device).expand_as(s)
+        s = torch.where(torch.isclose(lo, up), torch.full_like(s, sys.float_info.epsilon), s)
+        return torch.log(s) - torch.log(1 - s)
+
+
+def _bound(b, like):
+    if b is None:
+        return None
+    if not isinstance(b, torch.Tensor):
+        b = torch.tensor(b, device=config.device, dtype=config.dtype)
+    else:
+        b = b.detach().to(config.device, config.dtype)
+    if b.ndim != 0:
+        while b.ndim < like.ndim and like.shape[b.ndim] == 1:
+            b = b.unsqueeze(-1)
+        while like.ndim < b.ndim and b.shape[-1] == 1:
+            b = b.squeeze(-1)
+        if b.shape != like.shape:
+            raise ValueError("bound and value must match shapes: %s != %s" % (b.shape, like.shape))
+    return b
+
+
+class Parameter(torch.nn.Parameter):
+    """Trainable parameter stored unconstrained; ``p()`` is the constrained value
+    (gpr/parameter.py:99-346).  The optimiser updates the raw leaf tensor, gradients
+    arrive in ``p.grad`` through torch autograd of the transform."""
+
+    def __new__(cls, value, name=None, lower=None, upper=None, prior=None, train=True):
+        value = Parameter.to_tensor(value)
+        self = super().__new__(cls, value)
+        self._name = name
+        self.lower = self.upper = None
+        self.prior = prior
+        self.train = train
+        self.pegged_parameter = self.pegged_transform = None
+        self.transform = None
+        self.num_parameters = int(np.prod(self.shape))
+        self.assign(value, lower=lower, upper=upper)
+        return self
+
+    def __repr__(self):
+        vals = self.constrained.tolist()
+        return "{}".format(vals) if self._name is None else "{}={}".format(self._name, vals)
+
+    def __call__(self):
+        return self.constrained
+
+    def _copy_meta(self, other):
+        for k in ("_name", "lower", "upper", "prior", "train", "pegged_parameter", "pegged_transform", "num_parameters"):
+            setattr(other, k, getattr(self, k))
+        other.transform = Parameter.to_transform(self.lower, self.upper)
+
+    def __deepcopy__(self, memo):
+        out = torch.nn.Parameter(self.data.clone(memory_format=torch.preserve_format), self.requires_grad)
+        out.__class__ = self.__class__
+        self._copy_meta(out)
+        memo[id(self)] = out
+        return out
+
+    def __reduce_ex__(self, proto):
+        parent = super().__reduce_ex__(proto)
+        return (Parameter._rebuild, (parent[0], parent[1], self._name, self.lower, self.upper, self.prior, self.train,
+                                     self.pegged_parameter, self.pegged_transform, self.num_parameters))
+
+    @staticmethod
+    def _rebuild(call, args, name, lower, upper, prior, train, pegged_parameter, pegged_transform, num_parameters):
+        out = call(*args)
+        out.__class__ = Parameter
+        out._name, out.lower, out.upper, out.prior, out.train = name, lower, upper, prior, train
+        out.pegged_parameter, out.pegged_transform, out.num_parameters = pegged_parameter, pegged_transform, num_parameters
+        out.transform = Parameter.to_transform(lower, upper)
+        return out
+
+    @property
+    def pegged(self):
+        return self.pegged_parameter is not None
+
+    @property
+    def constrained(self):
+        if self.pegged:
+            other = self.pegged_parameter.constrained
+            return self.pegged_transform(other) if self.pegged_transform is not None else other
+        return self.transform.forward(self) if self.transform is not None else self
+
+    def numpy(self):
+        return self.constrained.detach().cpu().numpy()
+
+    @staticmethod
+    def to_tensor(value):
+        if isinstance(value, Parameter):
+            return value.constrained.detach()
+        if isinstance(value, torch.Tensor):
+            return value.detach().to(config.device, config.dtype)
+        return torch.tensor(np.array(value), device=config.device, dtype=config.dtype)
+
+    @staticmethod
+    def to_transform(lower, upper):
+        if lower is not None and upper is not None:
+            if torch.any(upper < lower):
+                raise ValueError("lower limit %s must be lower than upper limit %s" % (lower, upper))
+            return Sigmoid(lower=lower, upper=upper)
+        if lower is not None:
+            return Softplus(lower=lower)
+        if upper is not None:
+            return Softplus(lower=upper, beta=-0.1)
+        return None
+
+    def assign(self, value=None, name=None, lower=None, upper=None, prior=None, train=None):
+        """Assign a constrained value and/or new bounds (gpr/parameter.py:232-319).  As in the
+        reference, passing bounds without a value re-interprets the stored raw tensor as the
+        constrained value."""
+        if value is not None:
+            value = Parameter.to_tensor(value)
+            orig = value.shape
+            while value.ndim < self.ndim and self.shape[value.ndim] == 1:
+                value = value.unsqueeze(-1)
+            while self.ndim < value.ndim and value.shape[-1] == 1:
+                value = value.squeeze(-1)
+            if value.shape != self.shape:
+                raise ValueError("parameter shape must match: %s != %s" % (orig, self.shape))
+        else:
+            value = self.data
+        lower = _bound(lower, value) if lower is not None else self.lower
+        upper = _bound(upper, value) if upper is not None else self.upper
+        if name is not None and self._name is not None and "." in self._name:
+            name = self._name[:self._name.rfind(".") + 1] + name
+        transform = Parameter.to_transform(lower, upper)
+        if transform is not None:
+            if lower is not None:
+                value = torch.where(value < lower, lower * torch.ones_like(value), value)
+            if upper is not None:
+                value = torch.where(upper < value, upper * torch.ones_like(value), value)
+            value = transform.inverse(value)
+        value.requires_grad = True
+        self._name = name if name is not None else self._name
+        self.data = value
+        self.lower, self.upper, self.transform = lower, upper, transform
+        self.prior = prior if prior is not None else self.prior
+        if train is None:
+            train = True if self.pegged else self.train
+        self.train = train
+        self.pegged_parameter = self.pegged_transform = None
+
+    def peg(self, other, transform=None):
+        if not isinstance(other, Parameter):
+            raise ValueError("parameter must be pegged to other parameter object")
+        if other.pegged:
+            raise ValueError("cannot peg parameter to another pegged parameter")
+        self.pegged_parameter, self.pegged_transform, self.train = other, transform, False
+
+    def log_prior(self):
+        return 0.0 if self.prior is None else self.prior.log_prob(self()).sum()
+
+
+class _Named(torch.nn.Module):
+    """Naming / read-only rules shared by kernels, likelihoods and models
+    (gpr/kernel.py:37-51, gpr/model.py:138-147)."""
+
+    def __setattr__(self, name, val):
+        if name == "train" and not isinstance(self, Exact):
+            for p in self.parameters():
+                p.train = val
+            return
+        if hasattr(self, name) and isinstance(getattr(self, name), Parameter):
+            raise AttributeError("parameter is read-only, use Parameter.assign()")
+        if isinstance(val, Parameter) and val._name is None:
+            val._name = "%s.%s" % (self.__class__.__name__, name)
+        elif isinstance(val, torch.nn.ModuleList):
+            for i, item in enumerate(val):
+                for p in item.parameters():
+                    p._name = "%s[%d].%s" % (self.__class__.__name__, i, p._name)
+        super().__setattr__(name, val)
+
+    def name(self):
+        return self.__class__.__name__
+
+
+# --------------------------------------------------------------------------------------
+# kernels as parameter containers; K / K_diag run on the engine
+# --------------------------------------------------------------------------------------
+_ENGINES = {}
+
+
+def default_engine(n_rows, device=None):
+    """One workspace handle per device, grown on demand."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("mogptk_b200: no CUDA device -- the B200 engine has no CPU fallback")
+    dev = config.device if device is None else device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    eng = _ENGINES.get(idx)
+    if eng is None or eng.max_n < n_rows:
+        if eng is not None:
+            eng.close()
+        eng = _engine.Engine(device=idx, max_n=max(int(n_rows), 256))
+        _ENGINES[idx] = eng
+    return eng
+
+
+def kernel_spec(kernel):
+    """Recognise the kernels this engine implements and return (kind, params, (C,Q,D)), where
+    params holds the *constrained* tensors (autograd-connected) in the packed order of
+    include/mogp_b200.h.  Works for the mirror classes below and for the reference's classes
+    of the same name.  Anything else raises NotImplementedError: there is no fallback."""
+    cname = kernel.__class__.__name__
+    if cname == "MultiOutputSpectralMixtureKernel":
+        p = {"weight": kernel.weight(), "mean": kernel.mean(), "variance": kernel.variance(),
+             "delay": kernel.delay(), "phase": kernel.phase()}
+        C_, Q, D = p["mean"].shape
+        return "MOSM", p, (int(C_), int(Q), int(D))
+    if cname == "IndependentMultiOutputKernel":
+        subs = list(kernel.kernels)
+        if all(k.__class__.__name__ == "SpectralMixtureKernel" for k in subs):
+            if len({tuple(k.mean.shape) for k in subs}) != 1:
+                raise NotImplementedError("SM kernels of all channels must share Q and input_dims")
+            if any(getattr(k, "active_dims", None) is not None and
+                   list(np.asarray(k.active_dims.cpu() if torch.is_tensor(k.active_dims) else k.active_dims)) !=
+                   list(range(1, k.mean.shape[1] + 1)) for k in subs):
+                raise NotImplementedError("active_dims other than all inputs are not supported")
+            p = {"magnitude": torch.stack([k.magnitude() for k in subs]),
+                 "mean": torch.stack([k.mean() for k in subs]),
+                 "variance": torch.stack([k.variance() for k in subs])}
+            C_, Q, D = p["mean"].shape
+            return "SM", p, (int(C_), int(Q), int(D))
+    if cname in ("MixtureKernel", "AddKernel"):
+        subs = list(kernel.kernels)
+        if all(k.__class__.__name__ == "GaussianConvolutionProcessKernel" for k in subs):
+            p = {"weight": torch.stack([k.weight() for k in subs]),
+                 "variance": torch.stack([k.variance() for k in subs]),
+                 "base_variance": torch.stack([k.base_variance() for k in subs])}
+            Q, C_, D = p["variance"].shape
+            return "CONV", p, (int(C_), int(Q), int(D))
+    if cname == "GaussianConvolutionProcessKernel":
+        p = {"weight": kernel.weight()[None], "variance": kernel.variance()[None],
+             "base_variance": kernel.base_variance()[None]}
+        Q, C_, D = p["variance"].shape
+        return "CONV", p, (int(C_), int(Q), int(D))
+    raise NotImplementedError(
+        "mogptk_b200 implements the exact-GP path for MOSM, SM (IndependentMultiOutputKernel of "
+        "SpectralMixtureKernel) and CONV (MixtureKernel of GaussianConvolutionProcessKernel) only; got %s" % cname)
+
+
+def _param_tensors(kind, kernel):
+    """The Parameter objects behind kernel_spec's tensors, in the same order (for gradient routing)."""
+    if kind == "MOSM":
+        return [[kernel.weight], [kernel.mean], [kernel.variance], [kernel.delay], [kernel.phase]]
+    if kind == "SM":
+        subs = list(kernel.kernels)
+        return [[k.magnitude for k in subs], [k.mean for k in subs], [k.variance for k in subs]]
+    subs = list(kernel.kernels) if hasattr(kernel, "kernels") else [kernel]
+    return [[k.weight for k in subs], [k.variance for k in subs], [k.base_variance for k in subs]]
+
+
+class Kernel(_Named):
+    """Base kernel (gpr/kernel.py:5-191): same call / validation behaviour; K and K_diag are
+    computed by the CUDA engine."""
+
+    def __init__(self, input_dims=None, active_dims=None):
+        super().__init__()
+        self.input_dims = input_dims
+        self.active_dims = active_dims
+        self.output_dims = None
+
+    def __call__(self, X1, X2=None):
+        X1, X2 = self._check_input(X1, X2)
+        return self.K(X1, X2)
+
+    def _check_input(self, X1, X2=None):                       # gpr/kernel.py:60-80
+        def chk(X):
+            if not torch.is_tensor(X):
+                X = torch.tensor(np.asarray(X), device=config.device, dtype=config.dtype)
+            elif X.device != config.device or X.dtype != config.dtype:
+                X = X.to(config.device, config.dtype)
+            if X.ndim != 2:
+                raise ValueError("X should have two dimensions (data_points,input_dims)")
+            return X
+        X1 = chk(X1)
+        if X1.shape[0] == 0 or X1.shape[1] == 0:
+            raise ValueError("X must not be empty")
+        if X2 is not None:
+            X2 = chk(X2)
+            if X2.shape[0] == 0:
+                raise ValueError("X must not be empty")
+            if X1.shape[1] != X2.shape[1]:
+                raise ValueError("input dimensions for X1 and X2 must match")
+        return X1, X2
+
+    def iterkernels(self):
+        yield self
+
+    def K(self, X1, X2=None):
+        kind, p, _ = kernel_spec(self)
+        n = X1.shape[0] if X2 is None else max(X1.shape[0], X2.shape[0])
+        with torch.no_grad():
+            return default_engine(n).K(kind, p, X1, X2)
+
+    def K_diag(self, X1):
+        kind, p, _ = kernel_spec(self)
+        with torch.no_grad():
+            return default_engine(X1.shape[0]).K_diag(kind, p, X1)
+
+
+class MultiOutputKernel(Kernel):
+    """Channel ids live in column 0 of X (gpr/kernel.py:381-404)."""
+
+    def __init__(self, output_dims, input_dims=None, active_dims=None):
+        super().__init__(input_dims, active_dims)
+        self.output_dims = output_dims
+
+    def _check_input(self, X1, X2=None):
+        X1, X2 = super()._check_input(X1, X2)
+        for X in (X1, X2):
+            if X is None:
+                continue
+            if not torch.all(X[:, 0] == X[:, 0].long()) or not torch.all(X[:, 0] < self.output_dims):
+                raise ValueError("X must have integers for the channel IDs in the first input dimension")
+        return X1, X2
+
+
+class MultiOutputSpectralMixtureKernel(MultiOutputKernel):
+    """MOSM parameters (gpr/multioutput.py:156-176): weight (C,Q), mean/variance/delay (C,Q,D), phase (C,Q)."""
+
+    def __init__(self, Q, output_dims, input_dims=1, active_dims=None):
+        super().__init__(output_dims, input_dims, active_dims)
+        self.input_dims = input_dims
+        self.weight = Parameter(torch.ones(output_dims, Q), lower=config.positive_minimum)
+        self.mean = Parameter(torch.zeros(output_dims, Q, input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(output_dims, Q, input_dims), lower=config.positive_minimum)
+        self.delay = Parameter(torch.zeros(output_dims, Q, input_dims))
+        self.phase = Parameter(torch.zeros(output_dims, Q))
+        if output_dims == 1:
+            self.delay.train = False
+            self.phase.train = False
+
+
+class SpectralMixtureKernel(Kernel):
+    """SM parameters (gpr/singleoutput.py:583-592): magnitude (Q,), mean/variance (Q,D)."""
+
+    def __init__(self, Q=1, input_dims=1, active_dims=None):
+        super().__init__(input_dims, active_dims)
+        self.magnitude = Parameter(torch.ones(Q), lower=config.positive_minimum)
+        self.mean = Parameter(torch.zeros(Q, input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(Q, input_dims), lower=config.positive_minimum)
+
+    def K(self, X1, X2=None):
+        raise NotImplementedError("use IndependentMultiOutputKernel([SpectralMixtureKernel...]) (what mogptk.SM builds)")
+
+
+def _kernel_list(kernels, length=None):
+    """gpr/kernel.py:82-110 (argument normalisation and checks)."""
+    if isinstance(kernels, tuple):
+        kernels = kernels[0] if len(kernels) == 1 and isinstance(kernels[0], list) else list(kernels)
+    elif not isinstance(kernels, list):
+        kernels = [kernels]
+    if len(kernels) == 0:
+        raise ValueError("must pass at least one kernel")
+    if length is not None and len(kernels) != length:
+        if len(kernels) != 1:
+            raise ValueError("must pass %d kernels" % length)
+        import copy
+        kernels = kernels + [copy.deepcopy(kernels[0]) for _ in range(length - 1)]
+    for k in kernels:
+        if not isinstance(k, Kernel):
+            raise ValueError("must pass kernels")
+    if any(k.input_dims != kernels[0].input_dims for k in kernels[1:]):
+        raise ValueError("kernels must have same input dimensions")
+    return kernels
+
+
+class IndependentMultiOutputKernel(MultiOutputKernel):
+    """One sub-kernel per channel, zero cross-covariance (gpr/multioutput.py:5-39)."""
+
+    def __init__(self, *kernels, output_dims=None):
+        if output_dims is None:
+            output_dims = len(kernels[0]) if len(kernels) == 1 and isinstance(kernels[0], list) else len(kernels)
+        super().__init__(output_dims)
+        self.kernels = torch.nn.ModuleList(_kernel_list(kernels, output_dims))
+        self.input_dims = self.kernels[0].input_dims
+
+    def __getitem__(self, key):
+        return self.kernels[key]
+
+    def name(self):
+        return "%s[%s]" % (self.__class__.__name__, ",".join(k.name() for k in self.kernels))
+
+    def iterkernels(self):
+        yield self
+        for k in self.kernels:
+            yield k
+
+
+class GaussianConvolutionProcessKernel(MultiOutputKernel):
+    """CONV parameters (gpr/multioutput.py:520-529): weight (C,), variance (C,D) >= 0, base_variance (D,)."""
+
+    def __init__(self, output_dims, input_dims=1, active_dims=None):
+        super().__init__(output_dims, input_dims, active_dims)
+        self.weight = Parameter(torch.ones(output_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(output_dims, input_dims), lower=0.0)
+        self.base_variance = Parameter(torch.ones(input_dims), lower=config.positive_minimum)
+
+
+class AddKernel(Kernel):
+    """Sum of kernels (gpr/kernel.py:232-246); only sums of CONV kernels reach the engine."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        ks = _kernel_list(kernels)
+        self.kernels = torch.nn.ModuleList(ks)
+        self.input_dims = ks[0].input_dims
+        outs = [k.output_dims for k in ks if k.output_dims is not None]
+        self.output_dims = outs[0] if outs else None
+
+    def __getitem__(self, key):
+        return self.kernels[key]
+
+    def name(self):
+        return "[%s]" % ",".join(k.name() for k in self.kernels)
+
+    def iterkernels(self):
+        yield self
+        for k in self.kernels:
+            yield k
+
+    def _check_input(self, X1, X2=None):
+        return self.kernels[0]._check_input(X1, X2)
+
+
+class MixtureKernel(AddKernel):
+    """Q copies of one kernel, summed (gpr/kernel.py:264-276)."""
+
+    def __init__(self, kernel, Q):
+        if not isinstance(kernel, Kernel):
+            raise ValueError("must pass kernel")
+        super().__init__(*_kernel_list(kernel, Q))
+
+
+# --------------------------------------------------------------------------------------
+# likelihood  (gpr/likelihood.py:312-378)
+# --------------------------------------------------------------------------------------
+class GaussianLikelihood(_Named):
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.output_dims = None
+        self.scale = Parameter(scale, lower=config.positive_minimum)
+        if self.scale.ndim == 1:
+            self.output_dims = self.scale.shape[0]
+
+    def validate_y(self, X, y):
+        pass
+
+    def conditional_sample(self, X, f):
+        scale = self.scale()
+        if self.output_dims is not None:
+            scale = scale[X[:, 0].long()].reshape(-1, *([1] * (f.ndim - 1)))
+        return torch.distributions.normal.Normal(f, scale=scale).sample()
+
+    def predict(self, X, mu, var, ci=None, sigma=None, n=10000):
+        """Confidence band (gpr/likelihood.py:351-378).  For a per-channel scale the reference
+        replaces the predictive variance by scale^2 (:355-356): mirrored."""
+        if ci is None and sigma is None:
+            return mu
+        if self.output_dims is not None:
+            scale = self.scale()[X[:, 0].long()].reshape(-1, 1)
+            if sigma is None:
+                c = torch.tensor(ci, device=config.device, dtype=config.dtype)
+                lower = mu + math.sqrt(2.0) * scale * torch.erfinv(2.0 * c[0] - 1.0)
+                upper = mu + math.sqrt(2.0) * scale * torch.erfinv(2.0 * c[1] - 1.0)
+            else:
+                lower, upper = mu - sigma * scale, mu + sigma * scale
+            return mu, lower, upper
+        var = var + self.scale() ** 2
+        if sigma is None:
+            c = torch.tensor(ci, device=config.device, dtype=config.dtype)
+            lower = mu + torch.sqrt(2.0 * var) * torch.erfinv(2.0 * c[0] - 1.0)
+            upper = mu + torch.sqrt(2.0 * var) * torch.erfinv(2.0 * c[1] - 1.0)
+        else:
+            lower, upper = mu - sigma * var.sqrt(), mu + sigma * var.sqrt()
+        return mu, lower, upper
+
+
+# --------------------------------------------------------------------------------------
+# the model  (gpr/model.py:71-483)
+# --------------------------------------------------------------------------------------
+class CholeskyException(Exception):
+    """gpr/model.py:71-78.  (When the reference is importable, ``Exact`` raises the reference's
+    own class instead so that ``except mogptk.CholeskyException`` keeps working.)"""
+
+    def __init__(self, message, K, model):
+        self.message, self.K, self.model = message, K, model
+
+    def __str__(self):
+        return self.message
+
+
+class _ExactLML(torch.autograd.Function):
+    """log p(y) with the analytic gradient from the CUDA engine: forward = one fused
+    mogp_lml_grad call (K build, Cholesky, inverse, LML, gradient), backward = a scale."""
+
+    @staticmethod
+    def forward(ctx, packed, sigma, model):
+        out = model._evaluate(packed.detach(), sigma.detach(), want_grad=True)
+        P = packed.numel()
+        ctx.save_for_backward(out[2:2 + P].to(packed.device), out[2 + P:2 + P + sigma.numel()].to(sigma.device))
+        return out[0].clone().to(packed.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        gp, gs = ctx.saved_tensors          # d(-LML)/d constrained
+        return -g * gp, -g * gs, None
+
+
+class Exact(_Named):
+    """Exact GP regression with a Gaussian likelihood (gpr/model.py:403-483) on the B200 engine.
+
+    Same constructor arguments, attributes (kernel, likelihood, mean, X, y, jitter, input_dims)
+    and methods as the reference model, so ``mogptk.Model`` can drive it through
+    ``loss()/parameters()/predict_y()/K()/sample_y()``."""
+
+    def __init__(self, kernel, X, y, variance=1.0, data_variance=None, jitter=1e-8, mean=None, engine=None,
+                 likelihood_cls=None, cholesky_exception=None):
+        super().__init__()
+        self._kind, _, self._dims = kernel_spec(kernel)       # raises NotImplementedError for other kernels
+        X, y = self._check_input(X, y)
+        if mean is not None:
+            mu = mean(X).reshape(-1, 1)
+            if mu.shape != y.shape:
+                raise ValueError("mean and y data must match shapes: %s != %s" % (mu.shape, y.shape))
+        variance = Parameter.to_tensor(variance)
+        channels = kernel.output_dims if kernel.output_dims is not None else 1
+        if 1 < variance.ndim or variance.ndim == 1 and variance.shape[0] != channels:
+            raise ValueError("variance must be float or have shape (channels,)")
+        if data_variance is not None:
+            data_variance = Parameter.to_tensor(data_variance)
+            if data_variance.ndim != 1 or data_variance.shape[0] != X.shape[0]:
+                raise ValueError("data variance must have shape (data_points,)")
+        if config.dtype != torch.float64:
+            raise NotImplementedError("the B200 engine computes in float64 only")
+        self.data_variance = data_variance
+        self.kernel = kernel
+        self.X, self.y, self.mean = X, y, mean
+        self.likelihood = (likelihood_cls or GaussianLikelihood)(torch.sqrt(variance))
+        self.jitter = max(jitter, 1e-15)                       # gpr/model.py:107-110
+        self.input_dims = X.shape[1]
+        self._compiled_forward = None
+        self._engine = engine
+        self._rows = None
+        self._factor_key = None
+        self._chol_exc = cholesky_exception or CholeskyException
+        self.log_marginal_likelihood_constant = 0.5 * X.shape[0] * math.log(2.0 * math.pi)
+
+    # ---- reference surface ----------------------------------------------------------
+    def name(self):
+        return "Exact"
+
+    def _get_name(self):
+        return "Exact"
+
+    def compile(self):
+        """The reference traces forward() with torch.jit (gpr/model.py:127-129); the fused CUDA
+        step has nothing to trace, so this is a no-op kept for API compatibility."""
+        self._compiled_forward = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None          # device handles are not pickled (recreated lazily)
+        state["_rows"] = None
+        state["_factor_key"] = None
+        return state
+
+    def _check_input(self, X, y=None):                          # gpr/model.py:149-181
+        X = torch.as_tensor(np.asarray(X) if not torch.is_tensor(X) else X).to(config.device, config.dtype)
+        if X.ndim == 0:
+            X = X.reshape(1, 1)
+        elif X.ndim == 1:
+            X = X.reshape(-1, 1)
+        elif X.ndim != 2:
+            raise ValueError("X must have dimensions (data_points,input_dims) with input_dims optional")
+        if X.shape[0] == 0 or X.shape[1] == 0:
+            raise ValueError("X must not be empty")
+        if y is None:
+            if X.shape[1] != self.input_dims:
+                raise ValueError("X must have %s input dimensions" % self.input_dims)
+            return X
+        y = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(config.device, config.dtype)
+        if y.ndim == 0:
+            y = y.reshape(1, 1)
+        elif y.ndim == 1:
+            y = y.reshape(-1, 1)
+        elif y.ndim != 2 or y.shape[1] != 1:
+            raise ValueError("y must have one dimension (data_points,)")
+        if X.shape[0] != y.shape[0]:
+            raise ValueError("number of data points for X and y must match")
+        return X, y
+
+    def print_parameters(self, file=None):
+        rows = [(p._name, p.numpy().tolist()) for p in self.parameters()]
+        width = max([len(r[0]) for r in rows] + [4])
+        print("%-*s  %s" % (width, "Name", "Value"), file=file)
+        for n, v in rows:
+            print("%-*s  %s" % (width, n, v), file=file)
+
+    def log_prior(self):
+        return sum(p.log_prior() for p in self.parameters())
+
+    def forward(self, x=None):
+        return -self.log_marginal_likelihood() - self.log_prior()
+
+    def loss(self):
+        """zero_grad, forward, backward -- one training iteration's evaluation (gpr/model.py:279-292)."""
+        self.zero_grad(set_to_none=True)
+        loss = self.forward()
+        loss.backward()
+        return loss
+
+    # ---- engine plumbing -------------------------------------------------------------
+    def _eng(self):
+        if self._engine is None:
+            self._engine = default_engine(self.X.shape[0], self.X.device)
+        return self._engine
+
+    def _sigma(self):
+        s = self.likelihood.scale().reshape(-1)
+        C_ = self._dims[0]
+        return s.expand(C_) if s.numel() == 1 and C_ > 1 else s
+
+    def _targets(self):
+        y = self.y
+        if self.mean is not None:
+            y = y - self.mean(self.X).reshape(-1, 1)
+        return y.reshape(-1)
+
+    def _evaluate(self, packed, sigma, want_grad):
+        eng = self._eng()
+        kind, p, dims = kernel_spec(self.kernel)
+        if self._rows is None or self._rows.owner is not eng:
+            rows = eng.prepare(kind, {k: v.detach() for k, v in p.items()}, self.X, self._targets().detach(),
+                               self.data_variance)
+            rows.owner = eng
+            self._rows = rows
+        elif self.mean is not None:
+            self._rows.y = self._rows.sort_vec(self._targets().detach(), eng.device)
+        out = eng.lml_grad_prepared(self._rows, packed.to(eng.device, torch.float64).contiguous(),
+                                    sigma.to(eng.device, torch.float64).contiguous(), self.jitter, want_grad, check=False)
+        info = int(out[1].item())            # the reference also synchronises here (float(loss))
+        if info != 0:
+            msg = "linalg.cholesky: the leading minor of order %d is not positive-definite" % info
+            with torch.no_grad():
+                K = eng.K(kind, {k: v.detach() for k, v in p.items()}, self.X, sigma=sigma,
+                          data_var=self.data_variance, jitter=self.jitter)
+            print("ERROR:", msg, file=sys.__stdout__)
+            if K.isnan().any():
+                print("ERROR: kernel matrix has NaNs!", file=sys.__stdout__)
+            if K.isinf().any():
+                print("ERROR: kernel matrix has infinities!", file=sys.__stdout__)
+            raise self._chol_exc(msg, K, self)
+        self._factor_key = self._state_key(packed, sigma)
+        return out
+
+    def _state_key(self, packed, sigma):
+        return (packed.detach().clone(), sigma.detach().clone())
+
+    def _packed(self):
+        kind, p, _ = kernel_spec(self.kernel)
+        return torch.cat([p[n].reshape(-1) for n in _engine.PARAM_ORDER[kind]])
+
+    def log_marginal_likelihood(self):
+        """log p(y) (gpr/model.py:438-453); differentiable w.r.t. the raw parameters."""
+        packed, sigma = self._packed(), self._sigma()
+        if torch.is_grad_enabled() and (packed.requires_grad or sigma.requires_grad):
+            return _ExactLML.apply(packed, sigma, self)
+        return self._evaluate(packed.detach(), sigma.detach(), want_grad=False)[0].clone()
+
+    def _ensure_factor(self):
+        """The reference re-factorises on every predict (gpr/model.py:463-469); here the factor of
+        the last evaluation is reused when the parameters have not changed."""
+        packed, sigma = self._packed().detach(), self._sigma().detach()
+        key = self._factor_key
+        eng = self._eng()
+        if (key is None or eng._train is not self._rows or not torch.equal(key[0], packed)
+                or not torch.equal(key[1], sigma)):
+            self._evaluate(packed, sigma, want_grad=False)
+
+    def K(self, X1, X2=None):
+        with torch.inference_mode():
+            return self.kernel(X1, X2)
+
+    def predict_f(self, X, full=False):
+        """Posterior mean / variance of f (gpr/model.py:455-483)."""
+        with torch.no_grad():
+            X = self._check_input(X)
+            self._ensure_factor()
+            mu, var = self._eng().predict(X, full=full)
+            mu = mu.reshape(-1, 1)
+            if self.mean is not None:
+                mu = mu + self.mean(X).reshape(-1, 1)
+            if not full:
+                var = var.reshape(-1, 1)
+            return mu, var
+
+    def predict_y(self, X, ci=None, sigma=None, n=10000):       # gpr/model.py:322-344
+        with torch.no_grad():
+            X = self._check_input(X)
+            mu, var = self.predict_f(X)
+            if ci is None and sigma is not None:
+                p = 0.5 * (1.0 + math.erf(sigma / math.sqrt(2.0)))
+                ci = [1.0 - p, p]
+            return self.likelihood.predict(X, mu, var, ci, sigma=sigma, n=n)
+
+    def sample_f(self, Z, n=None, prior=False):                 # gpr/model.py:346-376
+        with torch.no_grad():
+            Z = self._check_input(Z)
+            S = 1 if n is None else n
+            if prior:
+                mu = self.mean(Z).reshape(-1) if self.mean is not None else torch.zeros(Z.shape[0], device=Z.device, dtype=Z.dtype)
+                var = self.kernel(Z)
+            else:
+                mu, var = self.predict_f(Z, full=True)
+            var = var + self.jitter * var.diagonal().mean() * torch.eye(var.shape[0], device=var.device, dtype=var.dtype)
+            samples = torch.distributions.multivariate_normal.MultivariateNormal(mu.reshape(-1), var).sample([S])
+            return samples.squeeze() if n is None else samples
+
+    def sample_y(self, Z, n=None):                              # gpr/model.py:378-401
+        with torch.no_grad():
+            Z = self._check_input(Z)
+            S = 1 if n is None else n
+            f = self.sample_f(Z, n=S)
+            ys = self.likelihood.conditional_sample(Z, f.T).T
+            return ys.squeeze() if n is None else ys

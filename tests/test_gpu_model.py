@@ -1,0 +1,105 @@
+"""GPU: the reference-facing model layer (mogptk_b200.gpr.Exact on the real CUDA engine) against
+the golden vectors of the live reference: loss() fills raw-space p.grad, predict_f / predict_y,
+K / K_diag, CholeskyException, pickling, a short Adam run against the oracle trajectory."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpr():
+    from mogptk_b200 import gpr as g
+    g.use_gpu(0)
+    return g
+
+
+def build(gpr, g):
+    from test_host_layer import build_mirror
+    return build_mirror(g, None)
+
+
+@pytest.mark.parametrize("name", ["mosm_small", "mosm_shuffled", "mosm_datavar", "mosm_c1", "mosm_mid", "sm_small",
+                                  "sm_small_d2", "conv_small", "conv_small_d2", "mosm_small_d2", "cfg1", "cfg2_rdp"])
+def test_loss_and_raw_gradients(gpr, name):
+    g = load_golden(name)
+    m, plist = build(gpr, g)
+    loss = m.loss()
+    assert loss.is_cuda
+    assert abs(float(loss) - float(g["loss"])) <= 1e-8 * abs(float(g["loss"]))       # LML rtol 1e-8
+    for n, lst in plist.items():
+        ref = torch.tensor(g["gr_" + n])
+        got = (lst[0].grad if len(lst) == 1 else torch.stack([p.grad for p in lst])).cpu()
+        assert float((got.reshape(ref.shape) - ref).abs().max()) <= 1e-6 * max(float(ref.abs().max()), 1e-12), n
+    lml = m.log_marginal_likelihood()
+    assert abs(float(lml) - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+    mu, var = m.predict_f(g["Xs"])
+    assert mu.shape == (g["Xs"].shape[0], 1) and var.shape == (g["Xs"].shape[0], 1)
+    assert np.abs(mu.cpu().numpy().ravel() - g["pred_mu"]).max() <= 1e-6 * np.abs(g["pred_mu"]).max()
+    assert np.abs(var.cpu().numpy().ravel() - g["pred_var"]).max() <= 1e-6 * np.abs(g["pred_var"]).max()
+
+
+def test_predict_y_and_kernel_calls(gpr):
+    g = load_golden("mosm_small")
+    m, _ = build(gpr, g)
+    mu, lo, up = m.predict_y(g["Xs"], sigma=2.0)
+    scale = torch.tensor(g["sigma"])[torch.tensor(g["Xs"][:, 0]).long()].reshape(-1, 1)
+    assert np.abs(mu.cpu().numpy().ravel() - g["pred_mu"]).max() <= 1e-6 * np.abs(g["pred_mu"]).max()
+    # reference quirk (gpr/likelihood.py:355-367): multi-output band = mu -/+ sigma * scale_c
+    assert torch.allclose((up - lo).cpu(), 4.0 * scale.to(torch.float64), rtol=1e-12)
+    K = m.K(g["X"])
+    assert np.abs(K.cpu().numpy() - g["K_full"]).max() <= 1e-12 * np.abs(g["K_full"]).max()
+    assert torch.equal(m.kernel.K_diag(torch.tensor(g["X"], device=K.device)), K.diagonal())
+    with pytest.raises(ValueError):
+        m.kernel(torch.tensor([[7.0, 1.0]]))                    # channel id out of range
+    s = m.sample_y(g["Xs"], n=3)
+    assert s.shape == (3, g["Xs"].shape[0]) and torch.isfinite(s).all()
+
+
+def test_cholesky_exception_and_pickle(gpr):
+    g = load_golden("mosm_small")
+    m, _ = build(gpr, g)
+    m.loss()
+    m2 = pickle.loads(pickle.dumps(m))
+    assert abs(float(m2.log_marginal_likelihood()) - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+    m.kernel.weight.data.fill_(float("nan"))
+    with pytest.raises(gpr.CholeskyException) as ei:
+        m.loss()
+    assert "not positive-definite" in str(ei.value) and ei.value.K is not None and ei.value.model is m
+
+
+def test_adam_training_matches_the_oracle_trajectory(gpr):
+    from oracle import mogp_oracle as orc
+    g = load_golden("mosm_mid")
+    m, _ = build(gpr, g)
+    ref = orc.RawModel(g["kind"], g["params"], g["sigma_t"], g["X"], g["y"], g["jitter"])
+    for k in list(ref.raw):
+        ref.raw[k] = torch.tensor(g["r_" + k], dtype=torch.float64).requires_grad_(True)
+    oa = torch.optim.Adam(m.parameters(), lr=0.05)
+    ob = torch.optim.Adam(list(ref.raw.values()), lr=0.05)
+    first = None
+    for _ in range(8):
+        la = m.loss(); oa.step()
+        lb = ref.loss(); ob.step()
+        first = first if first is not None else float(lb)
+        assert abs(float(la) - float(lb)) <= 1e-7 * abs(float(lb))
+    assert float(lb) < first
+
+
+def test_plugin_builder_returns_the_engine_model(gpr):
+    import mogptk_b200 as mb
+    g = load_golden("conv_small")
+    k = gpr.MixtureKernel(gpr.GaussianConvolutionProcessKernel(output_dims=g["C"], input_dims=g["D"]), g["Q"])
+    for q in range(g["Q"]):
+        k[q].weight.assign(g["params"]["weight"][q])
+        k[q].variance.assign(g["params"]["variance"][q])
+        k[q].base_variance.assign(g["params"]["base_variance"][q])
+    model = mb.B200Exact(variance=(g["sigma"] ** 2).tolist(), jitter=g["jitter"])._build(k, g["X"], g["y"].reshape(-1, 1))
+    assert isinstance(model, gpr.Exact) and model.likelihood.scale.shape == (g["C"],)
+    lml = float(model.log_marginal_likelihood())
+    assert abs(lml - float(g["lml"])) <= 1e-6 * abs(float(g["lml"]))    # assign() round trip moves params by ~1e-7
