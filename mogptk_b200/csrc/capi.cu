@@ -58,6 +58,20 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
     if ((e = cudaMalloc(&h->logdet_part, (size_t)(h->np_max / 64 + 1) * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&h->info, 64)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&h->chan_dev, 4 * 260 * 2)) != cudaSuccess) return fail(e);
+    {   // look-ahead stream + events for the blocked Cholesky
+        const int nev = (int)(h->np_max / 64) + 2;
+        int plo = 0, phi = 0;
+        cudaDeviceGetStreamPriorityRange(&plo, &phi);      // bulk updates yield to the panel chain
+        if ((e = cudaStreamCreateWithPriority(&h->ps.s2, cudaStreamNonBlocking, plo)) != cudaSuccess) return fail(e);
+        if ((e = cudaStreamCreateWithPriority(&h->ps.s1, cudaStreamNonBlocking, phi)) != cudaSuccess) return fail(e);
+        h->ps.ev1 = new cudaEvent_t[nev + 2]();
+        h->ps.ev2 = new cudaEvent_t[nev + 2]();
+        for (int i = 0; i < nev + 2; ++i) {
+            if ((e = cudaEventCreateWithFlags(&h->ps.ev1[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+            if ((e = cudaEventCreateWithFlags(&h->ps.ev2[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+        }
+        h->ps.nev = nev;
+    }
     h->colpart_cap = (size_t)64 * 2 * h->np_max;
     if ((e = cudaMalloc(&h->colpart, h->colpart_cap * 8)) != cudaSuccess) return fail(e);
     *out = h;
@@ -73,6 +87,15 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         if (t->pair_first_dev) cudaFree(t->pair_first_dev);
         delete t;
     }
+    if (h->ps.ev1)
+        for (int i = 0; i < h->ps.nev + 2; ++i) {
+            if (h->ps.ev1[i]) cudaEventDestroy(h->ps.ev1[i]);
+            if (h->ps.ev2[i]) cudaEventDestroy(h->ps.ev2[i]);
+        }
+    delete[] h->ps.ev1;
+    delete[] h->ps.ev2;
+    if (h->ps.s2) cudaStreamDestroy(h->ps.s2);
+    if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
     void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
                     h->comps, h->comps2, h->chanbuf2, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)
@@ -218,10 +241,10 @@ extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda
     if (zero_linv_for(h, Np, st)) return -2;
     h->have_factor = false;
     if (n == Np && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(A_dev) % 16) == 0) {
-        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st));
+        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps));
     } else {
         MOGP_CHECK(h, launch_copy_tri(0, A_dev, lda, h->A, Np, n, Np, st));
-        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st));
+        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps));
         MOGP_CHECK(h, launch_copy_tri(1, A_dev, lda, h->A, Np, n, Np, st));
     }
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -235,7 +258,7 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     MOGP_CHECK(h, cudaSetDevice(h->device));
     H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
-    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st));
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps));
     MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
     MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -283,7 +306,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, data_var_dev, 1, h->A, ld, N,
                                 Np, st));
     STAGE_MARK();
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st));
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps));
     STAGE_MARK();
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
     MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));

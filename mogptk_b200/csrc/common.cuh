@@ -73,6 +73,13 @@ struct GemmArgs {
 cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s);
 
 // ------------------------------------------------------------------ handle
+struct PotrfStreams {          // look-ahead resources owned by the handle
+    cudaStream_t s1 = nullptr;    // high priority: the panel chain
+    cudaStream_t s2 = nullptr;    // low priority: bulk trailing updates
+    cudaEvent_t* ev1 = nullptr;   // [nev + 2] recorded on the caller's stream after panel steps
+    cudaEvent_t* ev2 = nullptr;   // [nev + 2] recorded on s2 after bulk updates
+    int nev = 0;
+};
 struct mogp_handle_s {
     int device = 0;
     int64_t max_n = 0, np_max = 0;
@@ -99,6 +106,7 @@ struct mogp_handle_s {
     std::vector<int32_t> chan_off;
     int64_t N = 0, Np = 0;
     std::string err;
+    PotrfStreams ps;
     // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
     bool profile = false;
     cudaEvent_t ev[8] = {};
@@ -140,7 +148,7 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 
 // ------------------------------------------------------------------ dense linear algebra (linalg.cu)
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
-                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st);
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
 // z = Linv * y (lower-triangular mat-vec), rows [0,Np)

@@ -199,6 +199,10 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
+        // same (maximal) shared-memory carve-out as the Cholesky panel kernel, so that both can be
+        // resident on one SM while the look-ahead overlaps them
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         attr_done = true;
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
@@ -216,11 +220,10 @@ static cudaError_t launch_gemm_t(const GemmArgs& g, int batch, cudaStream_t s) {
     }
     if (g_gemm_cfg == 1 && (g.N % 128) == 0)
         return launch_gemm_cfg<128, 128, 2, 4, 3, 1, TA, TB>(g, batch, s);
-    // Small problems do not fill 148 SMs x 2 CTAs with 128x64 tiles: use 64x64 tiles (3 CTAs/SM)
-    // so that the longest CTA is shorter and every SM has work.
-    long long tiles = (long long)((g.M + 127) / 128) * (g.N / 64) * batch;
-    if (g.lower) tiles = tiles / 2 + 1;
-    if (g_gemm_cfg == 2 || (g_gemm_cfg != 3 && tiles < 1200))
+    // Measured on B200 (profiles/r01_gemm_sweep.txt): 64x64 tiles at 3 CTAs/SM beat 128x64 (2 CTAs/SM) and
+    // 128x128 (1 CTA/SM) at every size we use (e.g. 8192x8192x256: 31.9 vs 27.9 vs 25.9 TFLOP/s), so they
+    // are the default; the other shapes stay selectable for experiments (mogp_set_gemm_config).
+    if (g_gemm_cfg != 3)
         return launch_gemm_cfg<64, 64, 2, 2, 3, 3, TA, TB>(g, batch, s);
     return launch_gemm_cfg<128, 64, 2, 2, 3, 2, TA, TB>(g, batch, s);
 }
@@ -238,17 +241,22 @@ cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cu
 // shared memory (8-column sub-panels; the 8x8 pivot block is factored in registers by every
 // row-owning thread, so the only block-wide barriers are two per sub-panel) and carries its
 // own 64 rows of the panel below through the same sweep (fused triangular solve by
-// substitution: no explicit inverse on the critical path).  CTA 0 parks L_kk in `Ltmp`
-// (the diagonal block of a scratch matrix) because other CTAs may still be reading A_kk.
+// substitution: no explicit inverse on the critical path).  With has_prev the CTA first applies
+// the previous panel's rank-64 update to its 128 x 64 tile on the tensor pipe (look-ahead: the
+// rest of that update runs concurrently on a second stream, see potrf_padded).  CTA 0 parks
+// L_kk in `Ltmp` (the diagonal block of a scratch matrix) because other CTAs may still be
+// reading A_kk.
 #define PS 65    // pitch of the row-major staging tile (conflict-free row-per-thread access)
 #define PL 128   // pitch of the column-major copy of finished columns (rows contiguous)
+#define PZ 68    // pitch of the previous-panel operand tiles (conflict-free DMMA fragment loads)
 __global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict__ A, long long lda,
                                                              double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                             int32_t* info, long long* dbg) {
+                                                             int has_prev, int32_t* info, long long* dbg) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;                  // [128][PS] staging: rows 0..63 diagonal block, 64..127 this CTA's rows below
-    double* Lc = sm + 128 * PS;      // [64][PL]  finished columns, column-major: Lc[col][row]
-    double* Dsm = Lc + 64 * PL;      // [8][8]    the updated pivot block of the current sub-panel
+    double* Lc = sm + 128 * PS;      // [64][PL]  finished columns, column-major: Lc[col][row]  (16-byte aligned)
+    double* ZZ = Lc;                 // [128][PZ] previous-panel values of the same 128 rows (aliases Lc, used first)
+    double* Dsm = Lc + 128 * PZ;     // [8][8]    the updated pivot block of the current sub-panel
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
     const bool has_rows = b < nrb;
@@ -263,9 +271,53 @@ __global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict_
         cp_async8(S + r * PS + c, Ad + (long long)r * lda + c);
         if (has_rows) cp_async8(S + (64 + r) * PS + c, Ar + (long long)r * lda + c);
     }
+    if (has_prev) {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int idx = tid + it * 128;              // 2048 16-byte chunks per 64 x 64 tile
+            const int r = idx >> 5, cc = idx & 31;
+            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
+            if (has_rows) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
+        }
+    }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    if (has_prev) {
+        // S[r][c] -= sum_k ZZ[r][k] * ZZ[c][k]   (rows of this CTA x the 64 rows of the diagonal block)
+        const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+        if (warp < 2 || has_rows) {
+            const int r0 = warp * 32;
+            double acc[4][8][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[i][j][0] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq];
+                    acc[i][j][1] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1];
+                }
+#pragma unroll 4
+            for (int kk = 0; kk < 64; kk += 4) {
+                double a[4], bb[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = -ZZ[(r0 + i * 8 + gq) * PZ + kk + tq];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bb[j] = ZZ[(j * 8 + gq) * PZ + kk + tq];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq] = acc[i][j][0];
+                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1] = acc[i][j][1];
+                }
+        }
+        __syncthreads();
+    }
     const int nrows = has_rows ? 128 : 64;
     const bool active_row = tid < nrows;
     // Left-looking sweep, one thread per row.  Finished columns live in Lc (column-major, so a
@@ -430,63 +482,142 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
 }
 
 // ============================================================================ blocked Cholesky
-// In-place lower Cholesky of the padded Np x Np matrix A (row-major, lda): per 64-column step
-// one panel kernel (above) and one trailing GEMM update; for large matrices the updates are
-// two-level (inner: remaining columns of a 256-wide outer panel, K = 64; outer: one SYRK
-// with K = 256) to cut the passes over the trailing matrix.  Ltmp is an Np x Np scratch
-// whose diagonal blocks are used; diagonal blocks of Linv receive inv(L_kk).
+// In-place lower Cholesky of the padded Np x Np matrix A (row-major, lda), right-looking with
+// one step of look-ahead over two streams:
+//   S1 (caller's stream): panel step s = previous panel's update of column block s (fused, on
+//                         the tensor pipe) + factor + solve of the rows below;
+//   S2 (handle's stream): bulk(s) = rank-64 update of the column blocks >= s+2 with panel s,
+//                         as one lower-triangular GEMM.
+// panel(s+1) runs concurrently with bulk(s); panel(s+2) waits for bulk(s).  For small matrices
+// the step time is the panel chain, for large ones the chain hides behind the GEMMs.
+// Ltmp is an Np x Np scratch whose diagonal blocks are used; diagonal blocks of Linv get inv(L_kk).
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
-                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st) {
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps) {
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
-    const size_t smem_p = (size_t)(128 * PS + 64 * PL + 64) * sizeof(double);
+    const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64) * sizeof(double);
     const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(diag_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int64_t nb_out = (Np > 4096) ? MOGP_NB_OUT : MOGP_NB;
-    for (int64_t K0 = 0; K0 < Np; K0 += nb_out) {
-        const int64_t Wd = std::min<int64_t>(nb_out, Np - K0), Kend = K0 + Wd;
-        for (int64_t k = K0; k < Kend; k += MOGP_NB) {
-            const int64_t r0 = k + MOGP_NB, M = Np - r0;
-            const int nrb = (int)(M / 64);
-            potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, info,
-                                                                      (k == 0) ? g_panel_dbg : nullptr);
-            MOGP_COUNT(1);
-            const int64_t Nc = Kend - r0;
-            if (M > 0 && Nc > 0) {                       // remaining columns of this outer panel
+    const int nb = (int)(Np / MOGP_NB);
+    const bool two = ps != nullptr && ps->s2 != nullptr && ps->s1 != nullptr && nb > 2 && nb <= ps->nev;
+    // The panel chain runs on a high-priority stream so that its CTAs are scheduled ahead of the bulk
+    // GEMM's (same-priority kernels would serialise behind a saturating GEMM grid).
+    cudaStream_t user = st;
+    cudaStream_t s2 = two ? ps->s2 : st;
+    if (two) {
+        if ((e = cudaEventRecord(ps->ev1[0], user)) != cudaSuccess) return e;      // order both streams after the caller's prior work
+        if ((e = cudaStreamWaitEvent(ps->s1, ps->ev1[0], 0)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s2, ps->ev1[0], 0)) != cudaSuccess) return e;
+        st = ps->s1;
+    }
+    auto finish = [&](cudaEvent_t last_bulk_ev) -> cudaError_t {
+        cudaError_t ee;
+        if (two) {
+            if (last_bulk_ev && (ee = cudaStreamWaitEvent(user, last_bulk_ev, 0)) != cudaSuccess) return ee;
+            if ((ee = cudaEventRecord(ps->ev1[ps->nev + 1], st)) != cudaSuccess) return ee;
+            if ((ee = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return ee;
+        }
+        diag_finish_kernel<<<(unsigned)(Np / 64), 256, smem_d, user>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part);
+        MOGP_COUNT(1);
+        return cudaGetLastError();
+    };
+    if (Np > 4096) {
+        // Large matrices: two-level updates (K = 64 inside a 256-column outer panel, one K = 256 SYRK per
+        // outer panel) keep the trailing-matrix traffic down.  The SYRK is split into the next outer
+        // panel's columns (priority) and the rest; both run on S2 while S1 factors the next outer panel.
+        cudaEvent_t last = nullptr;
+        int J = 0;
+        for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT, ++J) {
+            const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
+            if (two && J >= 1 && (e = cudaStreamWaitEvent(st, ps->ev2[2 * (J - 1)], 0)) != cudaSuccess) return e;
+            for (int64_t k = K0; k < Kend; k += MOGP_NB) {
+                const int nrb = (int)((Np - k - MOGP_NB) / MOGP_NB);
+                potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, k > K0 ? 1 : 0,
+                                                                          info, nullptr);
+                MOGP_COUNT(1);
+                const int64_t c0 = k + 2 * MOGP_NB, Nc = Kend - c0, M = Np - c0;
+                if (Nc > 0 && M > 0) {                      // remaining columns of this outer panel
+                    GemmArgs u{};
+                    u.A = A + c0 * ld + k; u.lda = ld;
+                    u.B = A + c0 * ld + k; u.ldb = ld;
+                    u.C = A + c0 * ld + c0; u.ldc = ld;
+                    u.M = (int)M; u.N = (int)Nc; u.K = MOGP_NB;
+                    u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
+                    if ((e = launch_gemm(0, 1, u, 1, st)) != cudaSuccess) return e;
+                }
+            }
+            if (Kend >= Np) break;
+            if (two) {
+                if ((e = cudaEventRecord(ps->ev1[J + 1], st)) != cudaSuccess) return e;
+                if ((e = cudaStreamWaitEvent(s2, ps->ev1[J + 1], 0)) != cudaSuccess) return e;
+            }
+            const int64_t W2 = std::min<int64_t>(MOGP_NB_OUT, Np - Kend);
+            {                                               // priority: columns of the next outer panel
                 GemmArgs u{};
-                u.A = A + r0 * ld + k; u.lda = ld;
-                u.B = A + r0 * ld + k; u.ldb = ld;
-                u.C = A + r0 * ld + r0; u.ldc = ld;
-                u.M = (int)M; u.N = (int)Nc; u.K = MOGP_NB;
+                u.A = A + Kend * ld + K0; u.lda = ld;
+                u.B = A + Kend * ld + K0; u.ldb = ld;
+                u.C = A + Kend * ld + Kend; u.ldc = ld;
+                u.M = (int)(Np - Kend); u.N = (int)W2; u.K = (int)Wd;
                 u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
-                e = launch_gemm(0, 1, u, 1, st);
-                if (e != cudaSuccess) return e;
+                if ((e = launch_gemm(0, 1, u, 1, s2)) != cudaSuccess) return e;
+                if (two && (e = cudaEventRecord(ps->ev2[2 * J], s2)) != cudaSuccess) return e;
+                last = two ? ps->ev2[2 * J] : nullptr;
+            }
+            const int64_t R0 = Kend + W2, MR = Np - R0;
+            if (MR > 0) {                                   // the rest of the trailing matrix
+                GemmArgs u{};
+                u.A = A + R0 * ld + K0; u.lda = ld;
+                u.B = A + R0 * ld + K0; u.ldb = ld;
+                u.C = A + R0 * ld + R0; u.ldc = ld;
+                u.M = (int)MR; u.N = (int)MR; u.K = (int)Wd;
+                u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
+                if ((e = launch_gemm(0, 1, u, 1, s2)) != cudaSuccess) return e;
+                if (two && (e = cudaEventRecord(ps->ev2[2 * J + 1], s2)) != cudaSuccess) return e;
+                last = two ? ps->ev2[2 * J + 1] : nullptr;
             }
         }
-        const int64_t M = Np - Kend;
-        if (M > 0) {                                     // trailing SYRK, K = panel width
+        return finish(last);
+    }
+    int last_bulk = -1;
+    for (int s = 0; s < nb; ++s) {
+        const int64_t k = (int64_t)s * MOGP_NB;
+        const int nrb = nb - s - 1;
+        if (two && s >= 2 && (e = cudaStreamWaitEvent(st, ps->ev2[s - 2], 0)) != cudaSuccess) return e;
+        potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, s > 0 ? 1 : 0, info,
+                                                                  (s == 1) ? g_panel_dbg : nullptr);
+        MOGP_COUNT(1);
+        const int64_t c0 = k + 2 * MOGP_NB, M = Np - c0;                          // column blocks >= s+2
+        if (M > 0) {
+            if (two) {
+                if ((e = cudaEventRecord(ps->ev1[s + 1], st)) != cudaSuccess) return e;
+                if ((e = cudaStreamWaitEvent(s2, ps->ev1[s + 1], 0)) != cudaSuccess) return e;
+            }
             GemmArgs u{};
-            u.A = A + Kend * ld + K0; u.lda = ld;
-            u.B = A + Kend * ld + K0; u.ldb = ld;
-            u.C = A + Kend * ld + Kend; u.ldc = ld;
-            u.M = (int)M; u.N = (int)M; u.K = (int)Wd;
+            u.A = A + c0 * ld + k; u.lda = ld;
+            u.B = A + c0 * ld + k; u.ldb = ld;
+            u.C = A + c0 * ld + c0; u.ldc = ld;
+            u.M = (int)M; u.N = (int)M; u.K = MOGP_NB;
             u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
-            e = launch_gemm(0, 1, u, 1, st);
+            e = launch_gemm(0, 1, u, 1, s2);
             if (e != cudaSuccess) return e;
+            if (two) {
+                if ((e = cudaEventRecord(ps->ev2[s], s2)) != cudaSuccess) return e;
+                last_bulk = s;
+            }
         }
     }
-    diag_finish_kernel<<<(unsigned)(Np / 64), 256, smem_d, st>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part);
-    MOGP_COUNT(1);
-    return cudaGetLastError();
+    return finish(two && last_bulk >= 0 ? ps->ev2[last_bulk] : nullptr);
 }
-
 
 // ============================================================================ triangular inverse
 // Linv = L^-1 by level-batched block doubling: at level s (in 64-blocks) every pair of

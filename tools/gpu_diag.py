@@ -212,7 +212,25 @@ def sec_panel(eng):
         print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
 
 
-SECTIONS = {"panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+def sec_gemmk(eng):
+    """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
+    for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
+                      (2048, 2048, 64), (2048, 2048, 2048), (1024, 1024, 1024)]:
+        A = torch.randn((M, K), dtype=torch.float64, device="cuda")
+        B = torch.randn((N, K), dtype=torch.float64, device="cuda")
+        Cm = torch.zeros((M, N), dtype=torch.float64, device="cuda")
+        line = "gemm NT %5dx%5dx%5d beta=1:" % (M, N, K)
+        for cfg in (3, 2, 1):
+            eng.lib.mogp_set_gemm_config(cfg)
+            med, mn = ev_time(lambda: eng.dgemm(0, 1, -1.0, A, B, 1.0, Cm), reps=5, warm=2)
+            line += "  cfg%d %.3f ms %.1f TF" % (cfg, mn, 2.0 * M * N * K / mn / 1e9)
+        med, mn = ev_time(lambda: torch.addmm(Cm, A, B.T, beta=1.0, alpha=-1.0, out=Cm), reps=5, warm=2)
+        line += "  | cuBLAS %.3f ms %.1f TF" % (mn, 2.0 * M * N * K / mn / 1e9)
+        print(line)
+    eng.lib.mogp_set_gemm_config(0)
+
+
+SECTIONS = {"gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
