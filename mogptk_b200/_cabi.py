@@ -42,6 +42,7 @@ _SIGNATURES = {
 # not part of the public header: tuning / host self-check hooks
 _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
+    "mogp_set_small_tile_threshold": (None, [C.c_longlong]),
     "mogp_launch_count": (C.c_longlong, []),
     "mogp_panel_debug": (C.c_int, [C.POINTER(C.c_longlong)]),
     "mogp_probe_latency": (C.c_int, [C.POINTER(C.c_double)]),
@@ -68,7 +69,7 @@ def load(check_symbols=False):
             raise RuntimeError(
                 "mogptk_b200: %s is missing -- build it with `python __graft_entry__.py` "
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(LIB_PATH, mode=os.RTLD_NOW)
         for name, (res, args) in {**_SIGNATURES, **_EXTRA}.items():
             fn = getattr(lib, name)
             fn.restype = res

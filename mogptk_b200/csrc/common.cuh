@@ -63,7 +63,9 @@ struct GemmArgs {
     int lower;      // 1: skip tiles strictly above the diagonal ((tm+1)*BM <= tn*BN)
     int klo_mode;   // 0: 0        1: tn*BN     2: tm*BM
     int khi_mode;   // 0: K        1: min(K,(tm+1)*BM)
-    int epi;        // 0: C = alpha*acc + beta*C      1: C = 0.5*(acc - avec[row]*avec[col])
+    int epi;        // 0: C = alpha*acc + beta*C      1: C = 0.5*((alpha*acc + beta*C) - avec[row]*avec[col])
+    int pair;       // 0: one tile per CTA   1: also tile (ntn-1-tn) (with klo_mode 1)   2: also tile (ntm-1-tm) (khi_mode 1)
+    int first_touch_row1; // 0: off; else tiles whose first row is >= (value - 1) use beta = 0 (first touch)
     double alpha, beta;
     const double* avec;
 };

@@ -50,7 +50,25 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
 
-    const int tn = blockIdx.x, tm = blockIdx.y;
+    // pair mode: the CTA computes two tiles whose clipped k-ranges are complementary (tile t and
+    // tile n_tiles-1-t), so every CTA of a triangular-operand GEMM does the same amount of work.
+    const int ntn = g.N / BN, ntm = (g.M + BM - 1) / BM;
+    for (int rep = 0; rep < 2; ++rep) {
+    int tn = blockIdx.x, tm = blockIdx.y;
+    if (g.pair == 1) { if (rep == 1) { tn = ntn - 1 - tn; if (tn <= (int)blockIdx.x) break; } }
+    else if (g.pair == 2) { if (rep == 1) { tm = ntm - 1 - tm; if (tm <= (int)blockIdx.y) break; } }
+    else if (g.pair == 3) {
+        // lower-triangular output whose k-range starts at the row tile (K^-1 = Linv^T Linv): row tm has
+        // tm+1 tiles of depth K - tm*BM.  Row tm is paired with row ntm-1-tm (same column), which makes the
+        // heaviest CTAs K + BM deep instead of leaving single K-deep tiles as the critical path.
+        const int mirror = ntm - 1 - tm;
+        if (tm > mirror) return;
+        if (tm == mirror) { if (rep == 1) break; if (tn > tm) return; }
+        else if (tn <= tm) { if (rep == 1) tm = mirror; }
+        else { if (rep == 1) break; if (tn > mirror) return; tm = mirror; }
+    }
+    else if (rep == 1) break;
+    if (rep == 1) __syncthreads();
     if (g.lower && (tm + 1) * BM <= tn * BN) return;
     int klo = 0, khi = g.K;
     if (g.klo_mode == 1) klo = tn * BN;
@@ -152,6 +170,7 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     cp_async_wait<0>();
 
     const long long ldc = g.ldc;
+    const double beta = (g.first_touch_row1 > 0 && m0 >= g.first_touch_row1 - 1) ? 0.0 : g.beta;   // first touch of this tile
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int row = am0 + i * 8 + gq;
@@ -162,27 +181,29 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
             const int col = n0 + bn0 + j * 8 + 2 * tq;
             double2* p = reinterpret_cast<double2*>(C + r * ldc + col);
             double2 v;
-            if (g.epi == 0) {
-                v.x = g.alpha * acc[i][j][0];
-                v.y = g.alpha * acc[i][j][1];
-                if (g.beta != 0.0) {
-                    double2 o = *p;
-                    v.x += g.beta * o.x;
-                    v.y += g.beta * o.y;
-                }
-            } else {
+            v.x = g.alpha * acc[i][j][0];
+            v.y = g.alpha * acc[i][j][1];
+            if (beta != 0.0) {
+                double2 o = *p;
+                v.x += beta * o.x;
+                v.y += beta * o.y;
+            }
+            if (g.epi == 1) {
                 const double ai = g.avec[r];
-                v.x = 0.5 * (acc[i][j][0] - ai * g.avec[col]);
-                v.y = 0.5 * (acc[i][j][1] - ai * g.avec[col + 1]);
+                v.x = 0.5 * (v.x - ai * g.avec[col]);
+                v.y = 0.5 * (v.y - ai * g.avec[col + 1]);
             }
             *p = v;
         }
     }
+    }   // pair loop
 }
 
 long long g_mogp_launches = 0;
-// 0 (default): pick by tile count   1: force 128x128 tiles (256 threads)   2: force 64x64 tiles   3: force 128x64 tiles
+// 0 (default): 64x64 tiles   1: force 128x128 tiles (256 threads)   3: force 128x64 tiles
 static int g_gemm_cfg = -1;
+static long long g_small_tile_threshold = 1400;
+extern "C" void mogp_set_small_tile_threshold(long long t) { g_small_tile_threshold = t; }
 
 extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
@@ -207,6 +228,8 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
     dim3 grid(g.N / BN, (g.M + BM - 1) / BM, batch);
+    if (g.pair == 1) grid.x = (grid.x + 1) / 2;
+    if (g.pair == 2) grid.y = (grid.y + 1) / 2;
     kern<<<grid, WM * WN * 32, SMEM, s>>>(g);
     MOGP_COUNT(1);
     return cudaGetLastError();
@@ -223,8 +246,15 @@ static cudaError_t launch_gemm_t(const GemmArgs& g, int batch, cudaStream_t s) {
     // Measured on B200 (profiles/r01_gemm_sweep.txt): 64x64 tiles at 3 CTAs/SM beat 128x64 (2 CTAs/SM) and
     // 128x128 (1 CTA/SM) at every size we use (e.g. 8192x8192x256: 31.9 vs 27.9 vs 25.9 TFLOP/s), so they
     // are the default; the other shapes stay selectable for experiments (mogp_set_gemm_config).
-    if (g_gemm_cfg != 3)
+    if (g_gemm_cfg != 3) {
+        // mid-size problems (about one wave of 64x64 tiles or less): 32x64 tiles give twice the CTAs with half
+        // the depth each, which shortens the tail that dominates there
+        long long tiles = (long long)(g.M / 64) * (g.N / 64) * batch;
+        if (g.lower) tiles = tiles / 2 + 1;
+        if (g_gemm_cfg == 4 || (g_gemm_cfg != 2 && tiles < g_small_tile_threshold))
+            return launch_gemm_cfg<32, 64, 2, 2, 3, 4, TA, TB>(g, batch, s);
         return launch_gemm_cfg<64, 64, 2, 2, 3, 3, TA, TB>(g, batch, s);
+    }
     return launch_gemm_cfg<128, 64, 2, 2, 3, 2, TA, TB>(g, batch, s);
 }
 
@@ -247,9 +277,9 @@ cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cu
 // L_kk in `Ltmp` (the diagonal block of a scratch matrix) because other CTAs may still be
 // reading A_kk.
 #define PS 65    // pitch of the row-major staging tile (conflict-free row-per-thread access)
-#define PL 128   // pitch of the column-major copy of finished columns (rows contiguous)
+#define PL 132   // pitch of the column-major copy of finished columns (rows contiguous; == 4 mod 16)
 #define PZ 68    // pitch of the previous-panel operand tiles (conflict-free DMMA fragment loads)
-__global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict__ A, long long lda,
+__global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict__ A, long long lda,
                                                              double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
                                                              int has_prev, int32_t* info, long long* dbg) {
     extern __shared__ __align__(16) double sm[];
@@ -257,24 +287,29 @@ __global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict_
     double* Lc = sm + 128 * PS;      // [64][PL]  finished columns, column-major: Lc[col][row]  (16-byte aligned)
     double* ZZ = Lc;                 // [128][PZ] previous-panel values of the same 128 rows (aliases Lc, used first)
     double* Dsm = Lc + 128 * PZ;     // [8][8]    the updated pivot block of the current sub-panel
+    double* Xr = Dsm + 64;           // [128][8]  fragment <-> row-per-thread exchange
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
     const bool has_rows = b < nrb;
+    // 8 warps feed the tensor pipe (a lone warp per SM sub-partition only reaches about half the DMMA issue
+    // rate); threads 0..127 additionally own one row each for the scalar pivot / substitution phases.
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16;        // rows of this warp in the tensor-pipe phases
     if (dbg && tid == 64 && b == 0) dbg[0] = clock64();
     const double* Ad = A + (long long)k0 * lda + k0;
     double* Ar = A + (long long)(k0 + 64 + 64 * b) * lda + k0;
     // all loads in flight at once (8-byte cp.async: the padded pitch is not 16-byte aligned)
 #pragma unroll
-    for (int it = 0; it < 32; ++it) {
-        const int idx = tid + it * 128;
+    for (int it = 0; it < 16; ++it) {
+        const int idx = tid + it * 256;
         const int r = idx >> 6, c = idx & 63;
         cp_async8(S + r * PS + c, Ad + (long long)r * lda + c);
         if (has_rows) cp_async8(S + (64 + r) * PS + c, Ar + (long long)r * lda + c);
     }
     if (has_prev) {
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int idx = tid + it * 128;              // 2048 16-byte chunks per 64 x 64 tile
+        for (int it = 0; it < 8; ++it) {
+            const int idx = tid + it * 256;              // 2048 16-byte chunks per 64 x 64 tile
             const int r = idx >> 5, cc = idx & 31;
             cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
             if (has_rows) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
@@ -283,65 +318,76 @@ __global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict_
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    const int nrows = has_rows ? 128 : 64;
     if (has_prev) {
         // S[r][c] -= sum_k ZZ[r][k] * ZZ[c][k]   (rows of this CTA x the 64 rows of the diagonal block)
-        const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-        if (warp < 2 || has_rows) {
-            const int r0 = warp * 32;
-            double acc[4][8][2];
+        if (r0 < nrows) {
+            double acc2[2][8][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    acc[i][j][0] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq];
-                    acc[i][j][1] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1];
+                    acc2[i][j][0] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq];
+                    acc2[i][j][1] = S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1];
                 }
 #pragma unroll 4
             for (int kk = 0; kk < 64; kk += 4) {
-                double a[4], bb[8];
+                double a[2], bb[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = -ZZ[(r0 + i * 8 + gq) * PZ + kk + tq];
+                for (int i = 0; i < 2; ++i) a[i] = -ZZ[(r0 + i * 8 + gq) * PZ + kk + tq];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) bb[j] = ZZ[(j * 8 + gq) * PZ + kk + tq];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+                    for (int j = 0; j < 8; ++j) dmma884(acc2[i][j][0], acc2[i][j][1], a[i], bb[j]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq] = acc[i][j][0];
-                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1] = acc[i][j][1];
+                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq] = acc2[i][j][0];
+                    S[(r0 + i * 8 + gq) * PS + j * 8 + 2 * tq + 1] = acc2[i][j][1];
                 }
         }
         __syncthreads();
     }
-    const int nrows = has_rows ? 128 : 64;
-    const bool active_row = tid < nrows;
-    // Left-looking sweep, one thread per row.  Finished columns live in Lc (column-major, so a
-    // thread re-reads its own row conflict-free and the 8 pivot values of a column are one
-    // aligned 64-byte broadcast); the code stays small enough for the instruction cache.
+    const bool active_row = tid < nrows;          // nrows <= 128: threads 128..255 own no row
     if (dbg && tid == 64 && b == 0) dbg[1] = clock64();
+    // Left-looking sweep over 8-column sub-panels.  Finished columns live in Lc (column-major).
 #pragma unroll 1
     for (int p = 0; p < 8; ++p) {
         const int c0 = p * 8;
         const bool act = active_row && tid >= c0;
+        // acc[row][0..8) = A[row][c0..c0+8) - sum_{cp<c0} L[row][cp] * L[c0+.][cp] for the warp's 16 rows, on the
+        // tensor pipe (scalar FMAs with broadcast shared-memory operands were LSU-bound: ~70 cycles per column):
+        // 2 row tiles x (c0/4) k-steps of DMMA.8x8x4 with A = -L rows and B = pivot rows, both from the
+        // column-major copy Lc (pitch == 4 mod 16: conflict-free fragment loads).
+        if (r0 < nrows && r0 + 16 > c0) {
+            double cf[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cf[i][0] = S[(r0 + 8 * i + gq) * PS + c0 + 2 * tq];
+                cf[i][1] = S[(r0 + 8 * i + gq) * PS + c0 + 2 * tq + 1];
+            }
+#pragma unroll 4
+            for (int k = 0; k < c0; k += 4) {
+                const double bfrag = Lc[(k + tq) * PL + c0 + gq];
+                const double a0 = -Lc[(k + tq) * PL + r0 + gq], a1 = -Lc[(k + tq) * PL + r0 + 8 + gq];
+                dmma884(cf[0][0], cf[0][1], a0, bfrag);
+                dmma884(cf[1][0], cf[1][1], a1, bfrag);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                *reinterpret_cast<double2*>(Xr + (r0 + 8 * i + gq) * 8 + 2 * tq) = make_double2(cf[i][0], cf[i][1]);
+        }
+        __syncthreads();
         double acc[8];
         if (act) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = S[tid * PS + c0 + c];
-#pragma unroll 4
-            for (int cp = 0; cp < c0; ++cp) {          // subtract the finished columns (8 independent chains)
-                const double2* pv = reinterpret_cast<const double2*>(Lc + cp * PL + c0);
-                const double2 v0 = pv[0], v1 = pv[1], v2 = pv[2], v3 = pv[3];
-                const double m = -Lc[cp * PL + tid];
-                acc[0] = fma(m, v0.x, acc[0]); acc[1] = fma(m, v0.y, acc[1]);
-                acc[2] = fma(m, v1.x, acc[2]); acc[3] = fma(m, v1.y, acc[3]);
-                acc[4] = fma(m, v2.x, acc[4]); acc[5] = fma(m, v2.y, acc[5]);
-                acc[6] = fma(m, v3.x, acc[6]); acc[7] = fma(m, v3.y, acc[7]);
-            }
+            const double2* q = reinterpret_cast<const double2*>(Xr + tid * 8);
+            const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+            acc[0] = v0.x; acc[1] = v0.y; acc[2] = v1.x; acc[3] = v1.y;
+            acc[4] = v2.x; acc[5] = v2.y; acc[6] = v3.x; acc[7] = v3.y;
             if (tid < c0 + 8) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) Dsm[(tid - c0) * 8 + c] = acc[c];
@@ -399,13 +445,13 @@ __global__ void __launch_bounds__(128, 1) potrf_panel_kernel(double* __restrict_
         if (dbg && tid == 64 && b == 0) dbg[3 + 2 * p] = clock64();
     }
     if (has_rows)
-        for (int idx = tid; idx < 4096; idx += 128) {
+        for (int idx = tid; idx < 4096; idx += 256) {
             const int r = idx >> 6, c = idx & 63;
             Ar[(long long)r * lda + c] = S[(64 + r) * PS + c];
         }
     if (b == 0) {
         double* Lt = Ltmp + (long long)k0 * ldt + k0;
-        for (int idx = tid; idx < 4096; idx += 128) {
+        for (int idx = tid; idx < 4096; idx += 256) {
             const int r = idx >> 6, c = idx & 63;
             if (c <= r) Lt[(long long)r * ldt + c] = S[r * PS + c];
         }
@@ -495,7 +541,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps) {
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
-    const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64) * sizeof(double);
+    const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
     const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
@@ -542,7 +588,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
             if (two && J >= 1 && (e = cudaStreamWaitEvent(st, ps->ev2[2 * (J - 1)], 0)) != cudaSuccess) return e;
             for (int64_t k = K0; k < Kend; k += MOGP_NB) {
                 const int nrb = (int)((Np - k - MOGP_NB) / MOGP_NB);
-                potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, k > K0 ? 1 : 0,
+                potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, k > K0 ? 1 : 0,
                                                                           info, nullptr);
                 MOGP_COUNT(1);
                 const int64_t c0 = k + 2 * MOGP_NB, Nc = Kend - c0, M = Np - c0;
@@ -593,7 +639,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         const int64_t k = (int64_t)s * MOGP_NB;
         const int nrb = nb - s - 1;
         if (two && s >= 2 && (e = cudaStreamWaitEvent(st, ps->ev2[s - 2], 0)) != cudaSuccess) return e;
-        potrf_panel_kernel<<<std::max(1, nrb), 128, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, s > 0 ? 1 : 0, info,
+        potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, s > 0 ? 1 : 0, info,
                                                                   (s == 1) ? g_panel_dbg : nullptr);
         MOGP_COUNT(1);
         const int64_t c0 = k + 2 * MOGP_NB, M = Np - c0;                          // column blocks >= s+2
@@ -640,7 +686,7 @@ cudaError_t trtri_padded(double* L, double* Linv, double* scratch, int64_t Np, l
             a.B = Linv + o * ld + o; a.ldb = ld; a.strideB = 2 * S * (ld + 1);
             a.C = scratch + (o + S) * ld + o; a.ldc = ld; a.strideC = 2 * S * (ld + 1);
             a.M = (int)MB; a.N = (int)S; a.K = (int)S;
-            a.klo_mode = 1; a.alpha = 1.0; a.beta = 0.0;
+            a.klo_mode = 1; a.pair = 1; a.alpha = 1.0; a.beta = 0.0;
             cudaError_t e = launch_gemm(0, 0, a, batch, st);
             if (e != cudaSuccess) return e;
             GemmArgs b{};
@@ -648,7 +694,7 @@ cudaError_t trtri_padded(double* L, double* Linv, double* scratch, int64_t Np, l
             b.B = scratch + (o + S) * ld + o; b.ldb = ld; b.strideB = 2 * S * (ld + 1);
             b.C = Linv + (o + S) * ld + o; b.ldc = ld; b.strideC = 2 * S * (ld + 1);
             b.M = (int)MB; b.N = (int)S; b.K = (int)MB;
-            b.khi_mode = 1; b.alpha = -1.0; b.beta = 0.0;
+            b.khi_mode = 1; b.pair = 2; b.alpha = -1.0; b.beta = 0.0;
             e = launch_gemm(0, 0, b, batch, st);
             if (e != cudaSuccess) return e;
         }
@@ -663,14 +709,19 @@ __global__ void zero_vec_kernel(double* v, int64_t n) {
 }
 
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st) {
+    // K^-1[i][j] = sum_{k >= max(i,j)} Linv[k][i] Linv[k][j]: one TN GEMM over the lower tiles with the k-range
+    // clipped at the row tile.  Measured alternatives that were slower and are not used: accumulating over
+    // uniform-K row panels (0.25 vs 0.17 ms at N=2048, 6.8 vs 5.7 ms at N=8192) and pairing heavy with light
+    // rows in one CTA (pair mode 3: 0.25 ms at N=2048) -- a lone 4-warp CTA reaches only ~60% of an SM's DMMA
+    // rate, so longer CTAs lengthen the critical path more than the balance gains.
     GemmArgs g{};
     g.A = Linv; g.lda = ld;
     g.B = Linv; g.ldb = ld;
     g.C = W; g.ldc = ld;
     g.M = (int)Np; g.N = (int)Np; g.K = (int)Np;
     g.lower = 1; g.klo_mode = 2;
+    g.alpha = 1.0; g.beta = 0.0;
     if (avec) { g.epi = 1; g.avec = avec; }
-    else { g.epi = 0; g.alpha = 1.0; g.beta = 0.0; }
     return launch_gemm(1, 0, g, 1, st);
 }
 

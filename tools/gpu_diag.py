@@ -220,7 +220,7 @@ def sec_gemmk(eng):
         B = torch.randn((N, K), dtype=torch.float64, device="cuda")
         Cm = torch.zeros((M, N), dtype=torch.float64, device="cuda")
         line = "gemm NT %5dx%5dx%5d beta=1:" % (M, N, K)
-        for cfg in (3, 2, 1):
+        for cfg in (3, 2, 4):
             eng.lib.mogp_set_gemm_config(cfg)
             med, mn = ev_time(lambda: eng.dgemm(0, 1, -1.0, A, B, 1.0, Cm), reps=5, warm=2)
             line += "  cfg%d %.3f ms %.1f TF" % (cfg, mn, 2.0 * M * N * K / mn / 1e9)
@@ -230,7 +230,29 @@ def sec_gemmk(eng):
     eng.lib.mogp_set_gemm_config(0)
 
 
-SECTIONS = {"gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+def sec_thresh(eng):
+    """Stage times of the exact-GP step versus the 32x64-tile threshold."""
+    import ctypes as C
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params
+    for name in ("cfg2", "cfg4", "cfg3"):
+        g = load_golden(name)
+        rows = eng.prepare(g["kind"], g["params"], g["X"], g["y"])
+        p = pack_params(g["kind"], g["params"], eng.device)
+        sig = torch.tensor(g["sigma"], device=eng.device)
+        for thr in (0, 300, 700, 1400, 3000, 100000):
+            eng.lib.mogp_set_small_tile_threshold(thr)
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=7, warm=2)
+            eng.lib.mogp_set_profile(eng.h, 1)
+            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            st = (C.c_float * 8)()
+            ns = eng.lib.mogp_stage_times(eng.h, st)
+            eng.lib.mogp_set_profile(eng.h, 0)
+            print("thresh %-6s thr=%6d: step %.3f ms | potrf %.3f trtri %.3f kinv %.3f" % (name, thr, m1, st[1], st[2], st[4]))
+    eng.lib.mogp_set_small_tile_threshold(1400)
+
+
+SECTIONS = {"thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
