@@ -42,6 +42,7 @@ _SIGNATURES = {
 # not part of the public header: tuning / host self-check hooks
 _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
+    "mogp_set_graphs": (None, [C.c_int]),
     "mogp_set_small_tile_threshold": (None, [C.c_longlong]),
     "mogp_launch_count": (C.c_longlong, []),
     "mogp_panel_debug": (C.c_int, [C.POINTER(C.c_longlong)]),

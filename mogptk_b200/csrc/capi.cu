@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #define MOGP_VERSION 1000
 
@@ -24,6 +25,7 @@ static int ensure(mogp_handle_s* h, T*& ptr, size_t& cap, size_t need) {
     size_t want = need + need / 4 + 64;
     MOGP_CHECK(h, cudaMalloc(&ptr, want * sizeof(T)));
     cap = want;
+    h->realloc_epoch++;          // captured graphs hold the old pointer: they are re-captured on next use
     return 0;
 }
 
@@ -58,6 +60,9 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
     if ((e = cudaMalloc(&h->logdet_part, (size_t)(h->np_max / 64 + 1) * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&h->info, 64)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&h->chan_dev, 4 * 260 * 2)) != cudaSuccess) return fail(e);
+    if ((e = cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
     {   // look-ahead stream + events for the blocked Cholesky
         const int nev = (int)(h->np_max / 64) + 2;
         int plo = 0, phi = 0;
@@ -87,6 +92,10 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         if (t->pair_first_dev) cudaFree(t->pair_first_dev);
         delete t;
     }
+    for (StepGraph* g : h->graphs) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        delete g;
+    }
     if (h->ps.ev1)
         for (int i = 0; i < h->ps.nev + 2; ++i) {
             if (h->ps.ev1[i]) cudaEventDestroy(h->ps.ev1[i]);
@@ -94,10 +103,13 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         }
     delete[] h->ps.ev1;
     delete[] h->ps.ev2;
+    if (h->hs) cudaStreamDestroy(h->hs);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->ps.s2) cudaStreamDestroy(h->ps.s2);
     if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
     void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
-                    h->comps, h->comps2, h->chanbuf2, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
+                    h->comps, h->comps2, h->chanbuf2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -175,6 +187,7 @@ static int prep_common(mogp_handle_s* h, KernSpec& s, int kind, int C, int Q, in
     H_ARG(h, (size_t)(3 * C + 2) <= 1024, "too many channels");
     if (check_offsets(h, C, off)) return -1;
     if (upload_chan(h, C, off, 0, st)) return -2;
+    h->chan_uploaded.assign(off, off + C + 1);
     double*& comps = scratch ? h->comps2 : h->comps;
     size_t& cap = scratch ? h->comps2_cap : h->comps_cap;
     if (ensure(h, comps, cap, (size_t)C * C * s.R * comp_stride(D))) return -2;
@@ -267,7 +280,71 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
 }
 
 // ------------------------------------------------------------------ the exact-GP step
-// vec layout (np_max each): 0 y_pad | 1 z | 2 alpha | 3 kinv_diag
+// vec layout (np_max each): 0 y_pad | 1 z | 2 alpha | 3 kinv_diag | 4 colsq | 5 mu_tmp | 6.. staging (see below)
+//
+// The launch sequence of one evaluation (~100 kernels over three streams) is fixed for a given problem shape,
+// so it is captured into a CUDA graph once and replayed (launch latency dominates the small
+// configurations).  Graph kernels only touch handle-owned buffers; the caller's params / sigma / y / x / data_var
+// are copied into them by one small staging kernel before the graph, and the output block is copied out after it.
+__global__ void stage_inputs_kernel(const double* __restrict__ params, int P, const double* __restrict__ sigma, int C,
+                                    const double* __restrict__ y, const double* __restrict__ dv,
+                                    const double* __restrict__ x, long long N, int D, double* __restrict__ gp,
+                                    double* __restrict__ gs, double* __restrict__ gy, double* __restrict__ gdv,
+                                    double* __restrict__ gx) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < P) gp[i] = params[i];
+    if (i < C) gs[i] = sigma[i];
+    if (i < N) { gy[i] = y[i]; if (dv) gdv[i] = dv[i]; }
+    if (i < N * D && x != gx) gx[i] = x[i];
+}
+__global__ void copy_out_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// Pure enqueue of the step (kernel launches + event fork/join only: capturable).
+static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64_t N, int64_t Np, const double* params,
+                        const double* sigma, const double* y, const double* dv, double jitter_rel, int want_grad,
+                        double* out, cudaStream_t st) {
+    const long long ld = Np;
+    double* ypad = h->vec;
+    double* z = h->vec + h->np_max;
+    double* alpha = h->vec + 2 * h->np_max;
+    double* kdiag = h->vec + 3 * h->np_max;
+#define STAGE_MARK()                                                            \
+    do {                                                                        \
+        if (h->profile && h->n_ev < 8) cudaEventRecord(h->ev[h->n_ev++], st);   \
+    } while (0)
+    h->n_ev = 0;
+    STAGE_MARK();
+    MOGP_CHECK(h, launch_prep(s, params, sigma, dv, h->chan_dev, N, jitter_rel, h->comps, h->chanbuf, st));
+    // K~ (lower) -> L, diag blocks of Linv
+    MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, dv, 1, h->A, ld, N, Np, st));
+    STAGE_MARK();
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps));
+    STAGE_MARK();
+    // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
+    MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
+    STAGE_MARK();
+    MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
+    MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
+    MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
+    STAGE_MARK();
+    if (want_grad) {
+        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, alpha, st));
+        STAGE_MARK();
+        MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, h->tile_part, st));
+    }
+    MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params, sigma, h->comps, h->chanbuf, h->tile_part, z, alpha, kdiag,
+                                  h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out, st));
+    STAGE_MARK();
+#undef STAGE_MARK
+    return 0;
+}
+
+static int g_use_graphs = -1;
+extern "C" void mogp_set_graphs(int on) { g_use_graphs = on ? 1 : 0; }
+
 extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
                              const double* x_dev, const int32_t* chan_off_host, const double* y_dev,
                              const double* noise_sigma_dev, const double* data_var_dev, double jitter_rel, int want_grad,
@@ -280,51 +357,112 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     const int64_t N = chan_off_host[C];
     H_ARG(h, N >= 1 && N <= h->max_n, "N out of range for this handle");
     KernSpec s;
-    int rc = prep_common(h, s, kind, C, Q, D, params_dev, noise_sigma_dev, data_var_dev, chan_off_host, N, jitter_rel, false, st);
-    if (rc) return rc;
+    H_ARG(h, spec_init(s, kind, C, Q, D) == 0, "bad kernel spec (kind, C, Q, D)");
+    H_ARG(h, C <= 64, "at most 64 channels");
     const int64_t Np = round_up(N, MOGP_PAD);
+    if (g_use_graphs < 0) {
+        const char* e = getenv("MOGP_GRAPH");
+        g_use_graphs = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    // ---- host-side preparation (allocations, uploads): never captured
+    std::vector<int32_t> off(chan_off_host, chan_off_host + C + 1);
+    if (off != h->chan_uploaded) {
+        if (upload_chan(h, C, chan_off_host, 0, st)) return -2;
+        h->chan_uploaded = off;
+    }
+    if (ensure(h, h->comps, h->comps_cap, (size_t)C * C * s.R * comp_stride(D))) return -2;
     if (zero_linv_for(h, Np, st)) return -2;
-    const long long ld = Np;
-    double* ypad = h->vec;
-    double* z = h->vec + h->np_max;
-    double* alpha = h->vec + 2 * h->np_max;
-    double* kdiag = h->vec + 3 * h->np_max;
-
     TileList* tl = get_tiles(h, C, chan_off_host, nullptr, 0, st);
     H_ARG(h, tl != nullptr, "tile list allocation failed");
     if (ensure(h, h->xbuf, h->xbuf_cap, (size_t)N * D)) return -2;
-    if (x_dev != h->xbuf)
-        MOGP_CHECK(h, cudaMemcpyAsync(h->xbuf, x_dev, (size_t)N * D * 8, cudaMemcpyDeviceToDevice, st));
-
-#define STAGE_MARK()                                                            \
-    do {                                                                        \
-        if (h->profile && h->n_ev < 8) cudaEventRecord(h->ev[h->n_ev++], st);   \
-    } while (0)
-    h->n_ev = 0;
-    STAGE_MARK();
-    // K~ (lower) -> L, diag blocks of Linv
-    MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, data_var_dev, 1, h->A, ld, N,
-                                Np, st));
-    STAGE_MARK();
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps));
-    STAGE_MARK();
-    // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
-    MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
-    STAGE_MARK();
-    MOGP_CHECK(h, launch_pad_copy(y_dev, N, ypad, Np, st));
-    MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
-    MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
-    STAGE_MARK();
     if (want_grad) {
-        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, alpha, st));
-        STAGE_MARK();
         const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * comp_stride(D);
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
-        MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, h->tile_part, st));
     }
-    MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params_dev, noise_sigma_dev, h->comps, h->chanbuf, h->tile_part, z,
-                                  alpha, kdiag, h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out_dev, st));
-    STAGE_MARK();
+    const size_t nout = 2 + (size_t)s.P + C;
+    const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;
+    if (ensure(h, h->gbuf, h->gbuf_cap, stage_need)) return -2;
+    double* gp = h->gbuf;
+    double* gs = gp + s.P;
+    double* gy = gs + C;
+    double* gdv = gy + N;
+    double* gout = gdv + N;
+
+    // Replayed graphs lose the stream priorities the Cholesky look-ahead relies on (measured: 7% slower at
+    // N=4096, 2% at N=8192) while the launch-latency savings only matter for small problems.
+    const bool graphs = g_use_graphs == 1 && !h->profile && Np <= 3072;
+    if (!graphs) {
+        if (x_dev != h->xbuf)
+            MOGP_CHECK(h, cudaMemcpyAsync(h->xbuf, x_dev, (size_t)N * D * 8, cudaMemcpyDeviceToDevice, st));
+        int rc = enqueue_step(h, s, tl, N, Np, params_dev, noise_sigma_dev, y_dev, data_var_dev, jitter_rel, want_grad,
+                              out_dev, st);
+        if (rc) return rc;
+    } else {
+        // stage the caller's buffers, then replay (or first run / capture) the step on handle-owned buffers.
+        // Everything runs on the handle's own stream (capture is not allowed on the legacy default stream that
+        // PyTorch uses by default), forked from / joined to the caller's stream with events.
+        cudaStream_t user = st;
+        MOGP_CHECK(h, cudaEventRecord(h->ev_in, user));
+        st = h->hs;
+        MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
+        const long long nmax = std::max<long long>(std::max<long long>(s.P, C), N * D);
+        stage_inputs_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(params_dev, s.P, noise_sigma_dev, C, y_dev,
+                                                                            data_var_dev, x_dev, N, D, gp, gs, gy, gdv,
+                                                                            h->xbuf);
+        MOGP_COUNT(1);
+        StepGraph* sg = nullptr;
+        for (StepGraph* c : h->graphs)
+            if (c->kind == kind && c->C == C && c->Q == Q && c->D == D && c->N == N && c->want_grad == want_grad &&
+                c->jitter == jitter_rel && c->has_dv == (data_var_dev != nullptr) && c->off == off) { sg = c; break; }
+        if (!sg) {
+            sg = new StepGraph();
+            sg->kind = kind; sg->C = C; sg->Q = Q; sg->D = D; sg->N = N; sg->want_grad = want_grad;
+            sg->jitter = jitter_rel; sg->has_dv = data_var_dev != nullptr; sg->off = off;
+            if (h->graphs.size() >= 16) {
+                StepGraph* old = h->graphs.front();
+                if (old->exec) cudaGraphExecDestroy(old->exec);
+                delete old;
+                h->graphs.erase(h->graphs.begin());
+            }
+            h->graphs.push_back(sg);
+        }
+        const double* dvp = data_var_dev ? gdv : nullptr;
+        if (sg->exec && sg->epoch != h->realloc_epoch) {      // a workspace buffer moved since the capture
+            cudaGraphExecDestroy(sg->exec);
+            sg->exec = nullptr;
+        }
+        if (sg->exec) {
+            MOGP_CHECK(h, cudaGraphLaunch(sg->exec, st));
+            MOGP_COUNT(sg->launches);
+        } else if (sg->uses == 0) {                  // first use: plain run (also sets kernel attributes, warms caches)
+            int rc = enqueue_step(h, s, tl, N, Np, gp, gs, gy, dvp, jitter_rel, want_grad, gout, st);
+            if (rc) return rc;
+        } else {                                     // second use: capture, instantiate, launch
+            const long long l0 = g_mogp_launches;
+            MOGP_CHECK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_step(h, s, tl, N, Np, gp, gs, gy, dvp, jitter_rel, want_grad, gout, st);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                h->err = "CUDA graph capture of the step failed";
+                g_use_graphs = 0;                    // fall back to plain launches from now on
+                return rc ? rc : -2;
+            }
+            sg->launches = g_mogp_launches - l0;
+            sg->epoch = h->realloc_epoch;
+            ce = cudaGraphInstantiate(&sg->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { sg->exec = nullptr; h->err = "cudaGraphInstantiate failed"; g_use_graphs = 0; return -2; }
+            MOGP_CHECK(h, cudaGraphLaunch(sg->exec, st));
+        }
+        sg->uses++;
+        copy_out_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(gout, out_dev, (int)(want_grad ? nout : 2));
+        MOGP_COUNT(1);
+        MOGP_CHECK(h, cudaEventRecord(h->ev_out, st));
+        MOGP_CHECK(h, cudaStreamWaitEvent(user, h->ev_out, 0));
+    }
     h->have_factor = true;
     h->spec = s;
     h->chan_off.assign(chan_off_host, chan_off_host + C + 1);

@@ -75,6 +75,14 @@ struct GemmArgs {
 cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s);
 
 // ------------------------------------------------------------------ handle
+struct StepGraph {             // one captured exact-GP step (see capi.cu)
+    int kind = 0, C = 0, Q = 0, D = 0, want_grad = 0, has_dv = 0, uses = 0;
+    int64_t N = 0;
+    double jitter = 0.0;
+    long long launches = 0, epoch = 0;
+    std::vector<int32_t> off;
+    cudaGraphExec_t exec = nullptr;
+};
 struct PotrfStreams {          // look-ahead resources owned by the handle
     cudaStream_t s1 = nullptr;    // high priority: the panel chain
     cudaStream_t s2 = nullptr;    // low priority: bulk trailing updates
@@ -109,6 +117,12 @@ struct mogp_handle_s {
     int64_t N = 0, Np = 0;
     std::string err;
     PotrfStreams ps;
+    std::vector<StepGraph*> graphs;
+    long long realloc_epoch = 0;
+    cudaStream_t hs = nullptr;                                // the step runs here in graph mode
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    std::vector<int32_t> chan_uploaded;                       // content of chan_dev slot 0
+    double *gbuf = nullptr; size_t gbuf_cap = 0;              // graph staging: params | sigma | y | data_var | out
     // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
     bool profile = false;
     cudaEvent_t ev[8] = {};

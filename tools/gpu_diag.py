@@ -185,8 +185,12 @@ def sec_time(eng):
             p = pack_params(g["kind"], g["params"], eng.device)
             sig = torch.tensor(g["sigma"], device=eng.device)
             N = g["X"].shape[0]
-            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=5, warm=2)
-            t0, m0 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], False, check=False), reps=5, warm=2)
+            eng.lib.mogp_set_graphs(0)
+            tn, mn_ = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=9, warm=3)
+            eng.lib.mogp_set_graphs(1)
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=9, warm=3)
+            t0, m0 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], False, check=False), reps=9, warm=3)
+            print("   graphs off: loss+grad %.3f ms (min %.3f)" % (tn, mn_))
             Kout = torch.empty((N, N), dtype=torch.float64, device=eng.device)
             def kb():
                 eng.lib.mogp_kbuild(eng.h, {"MOSM": 0, "SM": 1, "CONV": 2}[g["kind"]], *rows.dims, eng._p(p), eng._p(rows.x),
