@@ -69,11 +69,14 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
         cudaDeviceGetStreamPriorityRange(&plo, &phi);      // bulk updates yield to the panel chain
         if ((e = cudaStreamCreateWithPriority(&h->ps.s2, cudaStreamNonBlocking, plo)) != cudaSuccess) return fail(e);
         if ((e = cudaStreamCreateWithPriority(&h->ps.s1, cudaStreamNonBlocking, phi)) != cudaSuccess) return fail(e);
+        if ((e = cudaStreamCreateWithPriority(&h->ps.s3, cudaStreamNonBlocking, phi)) != cudaSuccess) return fail(e);
         h->ps.ev1 = new cudaEvent_t[nev + 2]();
         h->ps.ev2 = new cudaEvent_t[nev + 2]();
+        h->ps.ev3 = new cudaEvent_t[nev + 2]();
         for (int i = 0; i < nev + 2; ++i) {
             if ((e = cudaEventCreateWithFlags(&h->ps.ev1[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
             if ((e = cudaEventCreateWithFlags(&h->ps.ev2[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+            if ((e = cudaEventCreateWithFlags(&h->ps.ev3[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
         }
         h->ps.nev = nev;
     }
@@ -100,14 +103,17 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         for (int i = 0; i < h->ps.nev + 2; ++i) {
             if (h->ps.ev1[i]) cudaEventDestroy(h->ps.ev1[i]);
             if (h->ps.ev2[i]) cudaEventDestroy(h->ps.ev2[i]);
+            if (h->ps.ev3 && h->ps.ev3[i]) cudaEventDestroy(h->ps.ev3[i]);
         }
     delete[] h->ps.ev1;
     delete[] h->ps.ev2;
+    delete[] h->ps.ev3;
     if (h->hs) cudaStreamDestroy(h->hs);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->ps.s2) cudaStreamDestroy(h->ps.s2);
     if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
+    if (h->ps.s3) cudaStreamDestroy(h->ps.s3);
     void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
                     h->comps, h->comps2, h->chanbuf2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)

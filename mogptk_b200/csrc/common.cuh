@@ -86,6 +86,8 @@ struct StepGraph {             // one captured exact-GP step (see capi.cu)
 struct PotrfStreams {          // look-ahead resources owned by the handle
     cudaStream_t s1 = nullptr;    // high priority: the panel chain
     cudaStream_t s2 = nullptr;    // low priority: bulk trailing updates
+    cudaStream_t s3 = nullptr;    // high priority: inner updates of the two-level variant
+    cudaEvent_t* ev3 = nullptr;   // [nev + 2] recorded on s3
     cudaEvent_t* ev1 = nullptr;   // [nev + 2] recorded on the caller's stream after panel steps
     cudaEvent_t* ev2 = nullptr;   // [nev + 2] recorded on s2 after bulk updates
     int nev = 0;

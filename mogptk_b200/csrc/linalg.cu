@@ -582,26 +582,42 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         // outer panel) keep the trailing-matrix traffic down.  The SYRK is split into the next outer
         // panel's columns (priority) and the rest; both run on S2 while S1 factors the next outer panel.
         cudaEvent_t last = nullptr;
+        const bool two3 = two && ps->s3 != nullptr;
         int J = 0;
         for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT, ++J) {
             const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
             if (two && J >= 1 && (e = cudaStreamWaitEvent(st, ps->ev2[2 * (J - 1)], 0)) != cudaSuccess) return e;
+            cudaEvent_t last_inner = nullptr;
             for (int64_t k = K0; k < Kend; k += MOGP_NB) {
                 const int nrb = (int)((Np - k - MOGP_NB) / MOGP_NB);
+                const int ks = (int)(k / MOGP_NB);
+                // panel(k) reads its column updated by the inner update issued two steps earlier (third stream)
+                if (two3 && k >= K0 + 2 * MOGP_NB && (e = cudaStreamWaitEvent(st, ps->ev3[ks - 2], 0)) != cudaSuccess) return e;
                 potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, k > K0 ? 1 : 0,
                                                                           info, nullptr);
                 MOGP_COUNT(1);
                 const int64_t c0 = k + 2 * MOGP_NB, Nc = Kend - c0, M = Np - c0;
                 if (Nc > 0 && M > 0) {                      // remaining columns of this outer panel
+                    cudaStream_t si = st;
+                    if (two3) {                             // off the panel chain: overlaps the next panel step
+                        if ((e = cudaEventRecord(ps->ev3[ps->nev + 1], st)) != cudaSuccess) return e;
+                        if ((e = cudaStreamWaitEvent(ps->s3, ps->ev3[ps->nev + 1], 0)) != cudaSuccess) return e;
+                        si = ps->s3;
+                    }
                     GemmArgs u{};
                     u.A = A + c0 * ld + k; u.lda = ld;
                     u.B = A + c0 * ld + k; u.ldb = ld;
                     u.C = A + c0 * ld + c0; u.ldc = ld;
                     u.M = (int)M; u.N = (int)Nc; u.K = MOGP_NB;
                     u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
-                    if ((e = launch_gemm(0, 1, u, 1, st)) != cudaSuccess) return e;
+                    if ((e = launch_gemm(0, 1, u, 1, si)) != cudaSuccess) return e;
+                    if (two3) {
+                        if ((e = cudaEventRecord(ps->ev3[ks], si)) != cudaSuccess) return e;
+                        last_inner = ps->ev3[ks];
+                    }
                 }
             }
+            if (two3 && last_inner && (e = cudaStreamWaitEvent(st, last_inner, 0)) != cudaSuccess) return e;   // join s3
             if (Kend >= Np) break;
             if (two) {
                 if ((e = cudaEventRecord(ps->ev1[J + 1], st)) != cudaSuccess) return e;
