@@ -266,6 +266,19 @@ cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cu
     return launch_gemm_t<true, true>(g, batch, s);
 }
 
+// 1/sqrt(d) for a positive, normal d without the library routine's special-case branches: hardware
+// approximation (MUFU.RSQ64H) refined by two Newton steps (relative error ~1 ulp).  Valid for every
+// normal positive double (0.5*d*y*y stays ~0.5); subnormal pivots flush to zero and give inf, which
+// only happens for matrices no factorisation would survive.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 // ============================================================================ Cholesky panel step
 // One launch per 64-column step.  Every CTA redundantly factors the 64x64 diagonal block in
 // shared memory (8-column sub-panels; the 8x8 pivot block is factored in registers by every
@@ -401,14 +414,16 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
+            int badcol = 8;                       // first non-positive pivot of this block (8 = none)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+                // branch-free pivot step (keeps the 8 columns in one basic block so that the compiler can
+                // interleave the substitution of finished columns with the pivot chain)
                 double d = D[c][c];
-                if (!(d > 0.0)) {
-                    if (tid == c0 && b == 0) atomicCAS(info, 0, k0 + c0 + c + 1);
-                    d = 1.0;
-                }
-                const double ri = rsqrt(d);
+                const bool ok = d > 0.0;
+                badcol = (!ok && badcol == 8) ? c : badcol;
+                d = ok ? d : 1.0;
+                const double ri = rsqrt_pos(d);
                 rinv[c] = ri;
                 D[c][c] = d * ri;
 #pragma unroll
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
 #pragma unroll
                     for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
             }
+            if (badcol < 8 && tid == c0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
             if (tid < c0 + 8) {                       // a row of the pivot block itself
                 const int jrow = tid - c0;
 #pragma unroll
