@@ -11,6 +11,51 @@
 
 #define RC 8   // components processed per shared-memory trig table
 
+// ------------------------------------------------------------------ exp for non-positive arguments
+// The covariance kernels are bound by the fp64 pipe (one exp per element and component), so the library exp
+// (~28 fp64-pipe instructions with its special-case handling) is replaced by: x = (64 m + j) ln2/64 + r,
+// exp(x) = 2^m * 2^(j/64) * p(r) with a 64-entry table (staged in shared memory) and a degree-5 polynomial on
+// |r| <= ln2/128 (~11 fp64 instructions, max relative error 4e-16).  Arguments are always <= 0 here; results
+// below ~1e-307 flush to 0, NaN propagates.
+__device__ const double EXP2_TABLE[64] = {
+    1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00,
+    1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00,
+    1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00,
+    1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00,
+    1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00,
+    1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00,
+    1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00,
+    1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00,
+    1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00,
+    1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00,
+    1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00,
+    1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00,
+    1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00,
+    1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00,
+    1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00,
+    1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
+
+__device__ __forceinline__ double exp_nonpos(double x, const double* __restrict__ tab /* shared */) {
+    const double INV = 9.23324826168936567683e+01;        // 64 / ln 2
+    const double C_HI = 1.08304246932675596327e-02;       // ln 2 / 64, 32 significant bits
+    const double C_LO = 2.98158582698529328128e-12;
+    const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, INV, MAGIC);
+    const int k = __double2loint(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -C_HI, x);
+    r = fma(kf, -C_LO, r);
+    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = tab[k & 63] * p;
+    const int hi = __double2hiint(res) + ((k >> 6) << 20);          // scale by 2^(k>>6)
+    const double scaled = __hiloint2double(hi, __double2loint(res));
+    return (x >= -708.0) ? scaled : ((x < -708.0) ? 0.0 : x);
+}
+
 // ------------------------------------------------------------------ TMA bulk helpers
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -43,23 +88,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
 }
 
-// Stage `n` rows x D doubles starting at src into dst (shared).  Uses one TMA bulk copy when
-// the source is 16-byte aligned and the byte count is a multiple of 16, else plain loads.
-__device__ __forceinline__ void stage_x(double* dst, const double* src, int n, int D, uint64_t* bar, unsigned& phase,
-                                        int tid, int nthreads) {
-    const unsigned bytes = (unsigned)(n * D * sizeof(double));
-    const bool tma_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes > 0;
+// Stage the row and column coordinates of a tile (na / nb rows x D doubles) into shared memory.  When both
+// sources are 16-byte aligned with sizes that are multiples of 16 bytes, thread 0 issues two TMA bulk copies
+// that complete ONE mbarrier phase (a single expect_tx covering both), and everybody waits on that phase; a
+// second, separate phase could complete before a slow thread has observed the first (parity aliasing) and
+// dead-lock it.  Otherwise plain loads.  Ends with the data visible to all threads.
+__device__ __forceinline__ void stage_xy(double* dsta, const double* srca, int na, double* dstb, const double* srcb,
+                                         int nb, int D, uint64_t* bar, unsigned& phase, int tid, int nthreads) {
+    const unsigned ba = (unsigned)(na * D * sizeof(double)), bb = (unsigned)(nb * D * sizeof(double));
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(srca) & 15) == 0) && ((ba & 15) == 0) && ba > 0 &&
+                        ((reinterpret_cast<uintptr_t>(srcb) & 15) == 0) && ((bb & 15) == 0) && bb > 0;
     if (tma_ok) {
         if (tid == 0) {
-            mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(dst, src, bytes, bar);
+            mbar_expect_tx(bar, ba + bb);
+            tma_bulk_g2s(dsta, srca, ba, bar);
+            tma_bulk_g2s(dstb, srcb, bb, bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
     } else {
-        for (int i = tid; i < n * D; i += nthreads) dst[i] = src[i];
-        __syncthreads();
+        for (int i = tid; i < na * D; i += nthreads) dsta[i] = srca[i];
+        for (int i = tid; i < nb * D; i += nthreads) dstb[i] = srcb[i];
     }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------ prep
@@ -117,6 +168,7 @@ struct TileSmem {
     double rc[RC][MOGP_TILE], rs[RC][MOGP_TILE];     // cos/sin of the row angles
     double cc[RC][MOGP_TILE], cs[RC][MOGP_TILE];     // cos/sin of the column angles
     double comp[RC][2 + 3 * MOGP_MAX_D];
+    double expt[64];                                 // 2^(j/64), see exp_nonpos
     uint64_t bar;
 };
 
@@ -128,9 +180,8 @@ template <int DT>
 __device__ __forceinline__ void load_tile_x(TileSmem& sm, const CovTile& t, const double* __restrict__ x1,
                                             const double* __restrict__ x2, int Drt, unsigned& phase, int tid) {
     const int D = dims<DT>(Drt);
-    stage_x(sm.xa, x1 + (size_t)t.r0 * D, t.nr, D, &sm.bar, phase, tid, 256);
-    stage_x(sm.xb, x2 + (size_t)t.c0 * D, t.nc, D, &sm.bar, phase, tid, 256);
-    __syncthreads();
+    if (tid < 64) sm.expt[tid] = EXP2_TABLE[tid];
+    stage_xy(sm.xa, x1 + (size_t)t.r0 * D, t.nr, sm.xb, x2 + (size_t)t.c0 * D, t.nc, D, &sm.bar, phase, tid, 256);
     // shift by x0 = first column point so that the trig arguments stay small
     double x0[MOGP_MAX_D];
 #pragma unroll
@@ -247,7 +298,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* 
 #pragma unroll
                         for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
                             if (d < D) { const double u = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u, u, e); }
-                        double val = alpha * exp(-0.5 * e);
+                        double val = alpha * exp_nonpos(-0.5 * e, sm.expt);
                         if (COS) val *= fma(cA, cB[j], sA * sB[j]);
                         acc[i][j] += val;
                     }
@@ -437,7 +488,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
 #pragma unroll
                     for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
                         if (d < D) { u[d] = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u[d], u[d], e); }
-                    const double we = wv[i][j] * exp(-0.5 * e);
+                    const double we = wv[i][j] * exp_nonpos(-0.5 * e, sm.expt);
                     double wec = we, wes = 0.0;
                     if (COS) {
                         wec = we * fma(cA, cB[j], sA * sB[j]);      // cos(A - B)

@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
         // tensor pipe (scalar FMAs with broadcast shared-memory operands were LSU-bound: ~70 cycles per column):
         // 2 row tiles x (c0/4) k-steps of DMMA.8x8x4 with A = -L rows and B = pivot rows, both from the
         // column-major copy Lc (pitch == 4 mod 16: conflict-free fragment loads).
+        if (dbg && p == 4 && tid == 64 && b == 0) dbg[19] = clock64();
         if (r0 < nrows && r0 + 16 > c0) {
             double cf[2][2];
 #pragma unroll
@@ -390,11 +391,14 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 dmma884(cf[0][0], cf[0][1], a0, bfrag);
                 dmma884(cf[1][0], cf[1][1], a1, bfrag);
             }
+            if (dbg && p == 4 && tid == 64 && b == 0) dbg[20] = clock64();
 #pragma unroll
             for (int i = 0; i < 2; ++i)
                 *reinterpret_cast<double2*>(Xr + (r0 + 8 * i + gq) * 8 + 2 * tq) = make_double2(cf[i][0], cf[i][1]);
         }
+        if (dbg && p == 4 && tid == 64 && b == 0) dbg[21] = clock64();
         __syncthreads();
+        if (dbg && p == 4 && tid == 64 && b == 0) dbg[22] = clock64();
         double acc[8];
         if (act) {
             const double2* q = reinterpret_cast<const double2*>(Xr + tid * 8);
@@ -540,7 +544,7 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
         return 1;
     }
     cudaDeviceSynchronize();
-    return cudaMemcpy(out_host, g_panel_dbg, 19 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    return cudaMemcpy(out_host, g_panel_dbg, 24 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 // ============================================================================ blocked Cholesky

@@ -203,7 +203,7 @@ def sec_time(eng):
 
 def sec_panel(eng):
     import ctypes as C
-    buf = (C.c_longlong * 19)()
+    buf = (C.c_longlong * 24)()
     eng.lib.mogp_panel_debug(buf)          # arms the timestamps
     for n in (2048, 8192):
         A = spd(n, 1).cuda()
@@ -214,6 +214,8 @@ def sec_panel(eng):
         eng.lib.mogp_panel_debug(buf)
         t = [int(v) for v in buf]
         print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
+        print("   p4 f-phase detail: start->loop end %d (from u-end %d), xr store %d, sync1 %d, rest(acc load, Dsm, sync2) %d" % (
+            t[20] - t[19], t[19] - t[9], t[21] - t[20], t[22] - t[21], t[10] - t[22]))
 
 
 def sec_gemmk(eng):
