@@ -223,3 +223,40 @@ def test_properties_at_cfg2_size(engine):
     fd = -(up - dn) / (2 * eps)                                          # d(-LML)/d direction
     an = float((a["grad"]["weight"] * d).sum())
     assert abs(fd - an) <= 1e-5 * abs(an)
+
+
+# ------------------------------------------------------------------ CUDA-graph replay of the step
+def test_repeated_evaluations_replay_the_graph_and_survive_reallocation(engine):
+    """The first evaluation of a configuration runs plain, the second is captured into a CUDA graph, later ones
+    replay it; a larger problem in between reallocates workspace buffers and must invalidate the capture."""
+    small = load_golden("mosm_datavar")          # exercises the data-variance pointer inside the graph
+    mid = load_golden("mosm_mid")
+    big = load_golden("cfg2")
+
+    def ev(g, grad=True):
+        return engine.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], grad,
+                               data_var=g.get("data_var"))
+
+    first = {n: ev(g) for n, g in (("small", small), ("mid", mid))}
+    for rep in range(3):                          # capture on rep 0, replay afterwards
+        for n, g in (("small", small), ("mid", mid)):
+            r = ev(g)
+            assert r["lml"] == first[n]["lml"] and r["info"] == 0
+            for k in r["grad"]:
+                assert torch.equal(r["grad"][k], first[n]["grad"][k])
+    ref_big = ev(big)                             # bigger problem: workspace buffers move
+    assert abs(ref_big["lml"] - float(big["lml"])) <= 1e-8 * abs(float(big["lml"]))
+    for n, g in (("small", small), ("mid", mid)):
+        for rep in range(2):
+            r = ev(g)
+            assert r["lml"] == first[n]["lml"]
+            for k in r["grad"]:
+                assert torch.equal(r["grad"][k], first[n]["grad"][k])
+    mu, var = engine.predict(mid["Xs"])           # the factor of a replayed step serves predictions
+    assert rel(mu, mid["pred_mu"]) < 1e-6
+    p2 = {k: v.clone() for k, v in mid["params"].items()}
+    p2["weight"] = p2["weight"] * 1.01            # new parameter values through the same captured graph
+    a = engine.lml_grad(mid["kind"], p2, mid["sigma"], mid["X"], mid["y"], mid["jitter"], True)
+    from oracle import mogp_oracle as orc
+    ref = float(orc.lml(mid["kind"], p2, mid["sigma_t"], torch.tensor(mid["X"]), mid["y"], mid["jitter"]))
+    assert abs(a["lml"] - ref) <= 1e-8 * abs(ref)
