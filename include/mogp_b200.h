@@ -112,6 +112,32 @@ int mogp_lml_grad_host(mogp_handle_t h, int kind, int C, int Q, int D, const dou
 int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t* chan_off_s_host,
                  int full, double* mu_dev, double* var_dev, void* stream);
 
+/* ---- constrained parameters on the device ------------------------------------------------
+ * Replaces Parameter.constrained / Softplus.forward / Sigmoid.forward (gpr/parameter.py:30-96,186-201) and
+ * their autograd backward for the training loop (mogptk/model.py:563-565): forward maps the raw leaves to the
+ * packed constrained vector that mogp_lml_grad consumes (kernel parameters, then the C noise scales) and
+ * records d constrained / d raw; backward multiplies the gradient block of mogp_lml_grad by it and writes the
+ * raw-space gradients into the p.grad buffers.  Entries live in HOST memory; pointers inside are DEVICE. */
+typedef struct {
+    const double* raw;     /* n raw (unconstrained) values */
+    double* grad;          /* n raw-space gradients to fill, or NULL */
+    const double* lower;   /* lower bound(s): lower_n == 1 (broadcast) or n values; NULL for type 0 */
+    const double* upper;   /* upper bound(s), type 2 only */
+    int64_t n;             /* elements */
+    int64_t off;           /* offset of this parameter in the packed vector */
+    int32_t type;          /* 0: identity, 1: Softplus(lower, beta), 2: Sigmoid(lower, upper) */
+    int32_t lower_n, upper_n, pad;
+    double beta;           /* Softplus slope (reference default 0.1; -0.1 for an upper-only bound) */
+} mogp_param_entry;
+
+int mogp_params_forward(mogp_handle_t h, const mogp_param_entry* entries_host, int n_entries,
+                        double* packed_dev, double* dcons_dev, void* stream);
+/* gcons_dev: d(-LML)/d constrained in packed order (= out + 2 of mogp_lml_grad); lml_dev: out of mogp_lml_grad;
+ * loss_out_dev (optional): receives -lml. */
+int mogp_params_backward(mogp_handle_t h, const mogp_param_entry* entries_host, int n_entries,
+                         const double* gcons_dev, const double* dcons_dev, const double* lml_dev,
+                         double* loss_out_dev, void* stream);
+
 /* ---- building blocks exposed for tests and micro-benchmarks --------------------------- */
 
 /* C = alpha * op(A) * op(B) + beta * C on the fp64 tensor pipe (DMMA).

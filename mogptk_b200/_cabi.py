@@ -18,6 +18,13 @@ _lib = None
 c_dp = C.c_void_p      # device / host double*
 c_ip = C.POINTER(C.c_int32)
 
+class ParamEntry(C.Structure):
+    """mogp_param_entry of include/mogp_b200.h."""
+    _fields_ = [("raw", C.c_void_p), ("grad", C.c_void_p), ("lower", C.c_void_p), ("upper", C.c_void_p),
+                ("n", C.c_int64), ("off", C.c_int64), ("type", C.c_int32), ("lower_n", C.c_int32),
+                ("upper_n", C.c_int32), ("pad", C.c_int32), ("beta", C.c_double)]
+
+
 _SIGNATURES = {
     "mogp_version": (C.c_int, []),
     "mogp_num_params": (C.c_int, [C.c_int] * 4),
@@ -33,6 +40,8 @@ _SIGNATURES = {
     "mogp_lml_grad_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp,
                                      C.c_double, C.c_int, c_dp]),
     "mogp_predict": (C.c_int, [C.c_void_p, c_dp, c_ip, C.c_int, c_dp, c_dp, C.c_void_p]),
+    "mogp_params_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, C.c_void_p]),
+    "mogp_params_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "mogp_dgemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, C.c_int64,
                              c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.c_void_p]),
     "mogp_trtri_kinv": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, C.c_int64, C.c_void_p, C.c_void_p]),

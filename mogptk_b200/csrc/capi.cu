@@ -95,6 +95,8 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         if (t->pair_first_dev) cudaFree(t->pair_first_dev);
         delete t;
     }
+    if (h->pent_dev) cudaFree(h->pent_dev);
+    if (h->pent_host) cudaFreeHost(h->pent_host);
     for (StepGraph* g : h->graphs) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
         delete g;

@@ -121,6 +121,7 @@ struct mogp_handle_s {
     PotrfStreams ps;
     std::vector<StepGraph*> graphs;
     long long realloc_epoch = 0;
+    void *pent_dev = nullptr, *pent_host = nullptr; size_t pent_cap = 0; int pent_n = 0;   // parameter-entry table
     cudaStream_t hs = nullptr;                                // the step runs here in graph mode
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     std::vector<int32_t> chan_uploaded;                       // content of chan_dev slot 0

@@ -650,6 +650,7 @@ class Exact(_Named):
         state["_engine"] = None          # device handles are not pickled (recreated lazily)
         state["_rows"] = None
         state["_factor_key"] = None
+        state.pop("_fast_cache", None)
         return state
 
     def _check_input(self, X, y=None):                          # gpr/model.py:149-181
@@ -691,11 +692,133 @@ class Exact(_Named):
         return -self.log_marginal_likelihood() - self.log_prior()
 
     def loss(self):
-        """zero_grad, forward, backward -- one training iteration's evaluation (gpr/model.py:279-292)."""
-        self.zero_grad(set_to_none=True)
-        loss = self.forward()
-        loss.backward()
-        return loss
+        """zero_grad, forward, backward -- one training iteration's evaluation (gpr/model.py:279-292).
+
+        When nothing needs torch's autograd (no mean function, priors or pegged parameters) the whole
+        iteration stays on the device: raw leaves -> constrained values (mogp_params_forward), the fused
+        exact-GP step (mogp_lml_grad, a replayed CUDA graph for small problems), chain rule into the
+        ``p.grad`` buffers (mogp_params_backward) -- three C calls and one synchronisation (the reference
+        also synchronises once per iteration on float(loss), mogptk/model.py:384)."""
+        fast = self._fast_table()
+        if fast is None:
+            self.zero_grad(set_to_none=True)
+            loss = self.forward()
+            loss.backward()
+            return loss
+        return self._fast_loss(*fast)
+
+    # ---- device-resident iteration (SURVEY 8f rank 1) --------------------------------
+    def _fast_table(self):
+        """Entry table for mogp_params_forward/backward, or None if the general autograd path is needed."""
+        import ctypes as C
+        from ._cabi import ParamEntry
+        if self.mean is not None or not torch.cuda.is_available():
+            return None
+        eng = self._eng()
+        if not hasattr(eng, "lib"):
+            return None                                        # test double
+        kind = self._kind
+        groups = _param_tensors(kind, self.kernel) + [[self.likelihood.scale]]
+        plist = [q for grp in groups for q in grp]
+        C_ = self._dims[0]
+        cache = self.__dict__.setdefault("_fast_cache", {})
+        for q in plist:
+            if getattr(q, "prior", None) is not None or getattr(q, "pegged", False):
+                return None
+            if not (q.is_cuda and q.dtype == torch.float64 and q.is_contiguous() and q.device == eng.device):
+                return None
+        if self.likelihood.scale.numel() != C_:
+            return None
+        sig = tuple((id(q), q.data_ptr(), id(q.transform)) for q in plist)
+        if cache.get("sig") == sig:
+            for q, gb in zip(plist, cache["grads"]):
+                if q.grad is not gb:
+                    q.grad = gb
+            return cache["entries"], len(plist), cache["P"], plist
+        entries = (ParamEntry * len(plist))()
+        keep, grads, off = [], [], 0
+
+        def dev(v, like):
+            t = v if torch.is_tensor(v) else torch.tensor(float(v))
+            t = t.detach().to(device=eng.device, dtype=torch.float64)
+            if t.numel() != 1:
+                t = t.expand_as(like)
+            return t.reshape(-1).contiguous()
+
+        for i, q in enumerate(plist):
+            t = q.transform
+            e = entries[i]
+            e.raw, e.n, e.off = q.data_ptr(), q.numel(), off
+            gb = torch.zeros_like(q.data)
+            q.grad = gb
+            grads.append(gb)
+            e.grad = gb.data_ptr()
+            e.lower = e.upper = None
+            e.lower_n = e.upper_n = 0
+            e.type, e.beta = 0, 0.0
+            if t is not None:
+                name = t.__class__.__name__
+                if name == "Softplus" and getattr(t, "threshold", 20.0) == 20.0:
+                    lo = dev(t.lower, q.data)
+                    keep.append(lo)
+                    e.type, e.beta, e.lower, e.lower_n = 1, float(t.beta), lo.data_ptr(), lo.numel()
+                elif name == "Sigmoid":
+                    lo, up = dev(t.lower, q.data), dev(t.upper, q.data)
+                    keep += [lo, up]
+                    e.type, e.lower, e.lower_n, e.upper, e.upper_n = 2, lo.data_ptr(), lo.numel(), up.data_ptr(), up.numel()
+                else:
+                    return None
+            off += q.numel()
+        P = off - C_
+        n = 2 + P + C_
+        bufs = torch.zeros(3 * n + 8, dtype=torch.float64, device=eng.device)
+        cache.update(sig=sig, entries=entries, keep=keep, grads=grads, P=P, bufs=bufs)
+        return entries, len(plist), P, plist
+
+    def _fast_loss(self, entries, n_entries, P, plist):
+        import ctypes as C
+        from . import _cabi
+        eng = self._eng()
+        lib = eng.lib
+        C_, Q, D = self._dims
+        cache = self._fast_cache
+        bufs = cache["bufs"]
+        n = 2 + P + C_
+        packed, dcons, out, lossb = bufs[:n], bufs[n:2 * n], bufs[2 * n:3 * n], bufs[3 * n:3 * n + 1]
+        if self._rows is None or self._rows.owner is not eng:
+            kind, p, _ = kernel_spec(self.kernel)
+            rows = eng.prepare(kind, {k: v.detach() for k, v in p.items()}, self.X, self._targets().detach(),
+                               self.data_variance)
+            rows.owner = eng
+            self._rows = rows
+        rows = self._rows
+        st = eng._stream()
+        base = bufs.data_ptr()
+        pp, pd, po, pl = base, base + 8 * n, base + 16 * n, base + 24 * n
+        eng._check(lib.mogp_params_forward(eng.h, C.addressof(entries), n_entries, pp, pd, st))
+        eng._check(lib.mogp_lml_grad(eng.h, _cabi.KIND[self._kind], C_, Q, D, pp, eng._p(rows.x), rows.off_p,
+                                     eng._p(rows.y), pp + 8 * P, eng._p(rows.dv), float(self.jitter), 1, po, st))
+        eng._check(lib.mogp_params_backward(eng.h, C.addressof(entries), n_entries, po + 16, pd, po, pl, st))
+        eng._train, eng._kind = rows, self._kind
+        lml, info = out[:2].tolist()                           # the iteration's one synchronisation
+        if info != 0:
+            self._raise_cholesky(int(info), packed[:P], packed[P:P + C_])
+        self._factor_key = ("v", tuple((q.data_ptr(), q._version) for q in plist))
+        return lossb.clone()[0]
+
+    def _raise_cholesky(self, info, packed, sigma):
+        eng = self._eng()
+        kind, p, _ = kernel_spec(self.kernel)
+        msg = "linalg.cholesky: the leading minor of order %d is not positive-definite" % info
+        with torch.no_grad():
+            K = eng.K(kind, {k: v.detach() for k, v in p.items()}, self.X, sigma=sigma, data_var=self.data_variance,
+                      jitter=self.jitter)
+        print("ERROR:", msg, file=sys.__stdout__)
+        if K.isnan().any():
+            print("ERROR: kernel matrix has NaNs!", file=sys.__stdout__)
+        if K.isinf().any():
+            print("ERROR: kernel matrix has infinities!", file=sys.__stdout__)
+        raise self._chol_exc(msg, K, self)
 
     # ---- engine plumbing -------------------------------------------------------------
     def _eng(self):
@@ -728,16 +851,7 @@ class Exact(_Named):
                                     sigma.to(eng.device, torch.float64).contiguous(), self.jitter, want_grad, check=False)
         info = int(out[1].item())            # the reference also synchronises here (float(loss))
         if info != 0:
-            msg = "linalg.cholesky: the leading minor of order %d is not positive-definite" % info
-            with torch.no_grad():
-                K = eng.K(kind, {k: v.detach() for k, v in p.items()}, self.X, sigma=sigma,
-                          data_var=self.data_variance, jitter=self.jitter)
-            print("ERROR:", msg, file=sys.__stdout__)
-            if K.isnan().any():
-                print("ERROR: kernel matrix has NaNs!", file=sys.__stdout__)
-            if K.isinf().any():
-                print("ERROR: kernel matrix has infinities!", file=sys.__stdout__)
-            raise self._chol_exc(msg, K, self)
+            self._raise_cholesky(info, packed, sigma)
         self._factor_key = self._state_key(packed, sigma)
         return out
 
@@ -758,9 +872,14 @@ class Exact(_Named):
     def _ensure_factor(self):
         """The reference re-factorises on every predict (gpr/model.py:463-469); here the factor of
         the last evaluation is reused when the parameters have not changed."""
-        packed, sigma = self._packed().detach(), self._sigma().detach()
         key = self._factor_key
         eng = self._eng()
+        if key is not None and key[0] == "v" and eng._train is self._rows:
+            groups = _param_tensors(self._kind, self.kernel) + [[self.likelihood.scale]]
+            if key[1] == tuple((q.data_ptr(), q._version) for grp in groups for q in grp):
+                return
+            key = None
+        packed, sigma = self._packed().detach(), self._sigma().detach()
         if (key is None or eng._train is not self._rows or not torch.equal(key[0], packed)
                 or not torch.equal(key[1], sigma)):
             self._evaluate(packed, sigma, want_grad=False)

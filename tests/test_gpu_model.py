@@ -103,3 +103,35 @@ def test_plugin_builder_returns_the_engine_model(gpr):
     assert isinstance(model, gpr.Exact) and model.likelihood.scale.shape == (g["C"],)
     lml = float(model.log_marginal_likelihood())
     assert abs(lml - float(g["lml"])) <= 1e-6 * abs(float(g["lml"]))    # assign() round trip moves params by ~1e-7
+
+
+@pytest.mark.parametrize("name", ["mosm_mid", "sm_small", "conv_small"])
+def test_device_resident_iteration_equals_the_autograd_path(gpr, name):
+    """loss() normally runs transforms + chain rule on the device (mogp_params_forward/backward); forcing the
+    general torch-autograd path must give the same loss and raw gradients."""
+    g = load_golden(name)
+    m, plist = build(gpr, g)
+    assert m._fast_table() is not None
+    la = m.loss()
+    fast = {n: [p.grad.clone() for p in lst] for n, lst in plist.items()}
+    m._fast_table = lambda: None                      # general path: torch autograd through Softplus / Sigmoid
+    lb = m.loss()
+    assert abs(float(la) - float(lb)) <= 1e-13 * abs(float(lb))
+    for n, lst in plist.items():
+        for p, ga in zip(lst, fast[n]):
+            scale = max(float(p.grad.abs().max()), 1e-12)
+            assert float((p.grad - ga).abs().max()) <= 1e-12 * scale, n
+
+
+def test_sigmoid_bounded_parameter_on_the_device_path(gpr):
+    """An upper bound turns the transform into a Sigmoid (what mogptk.MOSM does with the Nyquist frequency)."""
+    g = load_golden("mosm_small")
+    m, plist = build(gpr, g)
+    m.kernel.mean.assign(m.kernel.mean().detach(), upper=torch.full_like(m.kernel.mean().detach(), 5.0))
+    assert m.kernel.mean.transform.__class__.__name__ == "Sigmoid"
+    la = m.loss()
+    ga = m.kernel.mean.grad.clone()
+    m._fast_table = lambda: None
+    lb = m.loss()
+    assert abs(float(la) - float(lb)) <= 1e-13 * abs(float(lb))
+    assert float((m.kernel.mean.grad - ga).abs().max()) <= 1e-12 * max(float(ga.abs().max()), 1e-12)

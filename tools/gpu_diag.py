@@ -258,7 +258,37 @@ def sec_thresh(eng):
     eng.lib.mogp_set_small_tile_threshold(1400)
 
 
-SECTIONS = {"thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+def sec_train(eng):
+    """Throughput of the reference-facing training loop: gpr.Exact.loss() + torch Adam step (what mogptk.Model.train runs)."""
+    import time as _t
+    from conftest import load_golden
+    from test_host_layer import build_mirror
+    from mogptk_b200 import gpr
+    gpr.use_gpu(0)
+    for name in ("cfg1", "cfg2", "cfg4"):
+        g = load_golden(name)
+        m, _ = build_mirror(g, eng, raw_from_golden=False)
+        opt = torch.optim.Adam(m.parameters(), lr=0.01)
+        for _ in range(5):
+            float(m.loss()); opt.step()
+        torch.cuda.synchronize()
+        n = 60
+        t0 = _t.perf_counter()
+        for _ in range(n):
+            l = float(m.loss())          # the reference's loop also synchronises on float(loss) (mogptk/model.py:384)
+            opt.step()
+        torch.cuda.synchronize()
+        dt = (_t.perf_counter() - t0) / n
+        t0 = _t.perf_counter()
+        for _ in range(n):
+            l = m.loss()
+        torch.cuda.synchronize()
+        dt2 = (_t.perf_counter() - t0) / n
+        print("train %-5s: loss()+Adam %.3f ms/it (%.0f it/s) | loss() only, no per-it sync %.3f ms | final loss %.6f" % (
+            name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
+
+
+SECTIONS = {"train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
