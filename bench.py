@@ -32,6 +32,7 @@ from mogptk_b200 import synth  # noqa: E402
 METRIC = "lml_iters_per_sec"
 UNIT = "it/s"
 DMMA_PEAK_FALLBACK_TFLOPS = 37.15     # own probe (mogp_peak_fp64) on this pool, see DESIGN.md
+KINV_TRAFFIC_BYTES = {"cfg3": 4.0856e9 + 0.2296e9}   # ncu --set full, profiles/r01_ncu_full_kinv_gemm.txt
 
 
 def parse():
@@ -254,6 +255,7 @@ def run_b200(args):
             dmma, dfma = DMMA_PEAK_FALLBACK_TFLOPS, None
         flops = synth.flops_per_iteration(N)
         ach = flops / (ms_per_step * 1e-3) / 1e12
+        kin_ach = (float(N) ** 3 / 3.0) / (stages["kinv"] * 1e-3) / 1e12 if stages.get("kinv") else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -265,12 +267,20 @@ def run_b200(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": dmma, "unit": "TFLOP/s", "frac": ach / dmma,
-                         "traffic": None,
-                         "what": "whole step: N^3 algorithmic flop (potrf N^3/3 + inverse 2N^3/3) / CUDA-event step time; "
-                                 "peak = fp64 tensor-pipe (DMMA m8n8k4) probe measured in this run "
-                                 "(MEASURED_PEAKS.json holds no fp64 figure); DFMA probe %.2f" % (dfma or 0.0),
-                         "stage_ms": stages},
+            "roofline": {
+                "kernel": "gemm_f64_kernel<64|32,64> (fp64 DMMA GEMM): the K^-1 = L^-T L^-1 launch of the step",
+                "bound": "tensor", "achieved": kin_ach, "peak": dmma, "unit": "TFLOP/s",
+                "frac": (kin_ach / dmma) if kin_ach else None,
+                "traffic": KINV_TRAFFIC_BYTES.get(args.config),
+                "what": "achieved = N^3/3 algorithmic flop of that single launch / its duration from CUDA events recorded "
+                        "inside the library on the launching stream (stage 'kinv'); peak = fp64 tensor-pipe (DMMA m8n8k4) "
+                        "probe measured in this run (MEASURED_PEAKS.json holds no fp64 figure; DFMA probe %.2f); traffic = "
+                        "dram read+write of the same launch from profiles/r01_ncu_full_kinv_gemm.txt (cfg3 only). The GEMM "
+                        "kernel family is %.0f%% of the step's kernel time at cfg3 and ~40%% at cfg2, where the latency-bound "
+                        "Cholesky panel kernel (no roofline) takes ~50%%." % (dfma or 0.0, 84.0),
+                "step": {"achieved": ach, "frac": ach / dmma,
+                         "what": "whole step: N^3 algorithmic flop (potrf N^3/3 + inverse 2N^3/3) / CUDA-event step time"},
+                "stage_ms": stages},
         }
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(args.config, 0, 20, 2)

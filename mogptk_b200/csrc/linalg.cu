@@ -1005,17 +1005,35 @@ __global__ void latency_probe_kernel(double* out, double seed) {
     for (int i = 0; i < n; ++i) __syncthreads();
     t1 = clock64();
     double r8 = (double)(t1 - t0) / n;
+    // tensor-pipe wake-up: cost of a short DMMA burst right after `gap` cycles of scalar fp64 work
+    double wake[4];
+    {
+        const int gaps[4] = {0, 64, 256, 1024};
+        for (int gi = 0; gi < 4; ++gi) {
+            double w = x;
+            for (int rep = 0; rep < 3; ++rep) {
+                for (int i = 0; i < gaps[gi]; ++i) w = fma(w, y, z);       // ~8 cycles each
+                t0 = clock64();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dmma884(c0, c1, w * 1e-30 + y, z);
+                t1 = clock64();
+                wake[gi] = (double)(t1 - t0);
+                x += w * 1e-300;
+            }
+        }
+    }
     if (threadIdx.x == 0) {
+        out[10] = wake[0]; out[11] = wake[1]; out[12] = wake[2]; out[13] = wake[3];
         out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6; out[7] = r7; out[8] = r8;
         out[9] = x + idx + c0 + c1;
     }
 }
-extern "C" int mogp_probe_latency(double* out_host /*10*/) {
+extern "C" int mogp_probe_latency(double* out_host /*16*/) {
     double* d = nullptr;
-    if (cudaMalloc(&d, 10 * 8) != cudaSuccess) return -2;
+    if (cudaMalloc(&d, 16 * 8) != cudaSuccess) return -2;
     latency_probe_kernel<<<1, 32>>>(d, 1.5);
     latency_probe_kernel<<<1, 32>>>(d, 1.5);
-    cudaError_t e = cudaMemcpy(out_host, d, 10 * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(out_host, d, 16 * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? 0 : -2;
 }

@@ -42,10 +42,11 @@ def sec_peak(eng):
         d, f = eng.peak_fp64()
         print("peak fp64: DMMA %.2f TFLOP/s   DFMA %.2f TFLOP/s" % (d, f))
     import ctypes as C
-    lat = (C.c_double * 10)()
+    lat = (C.c_double * 16)()
     eng.lib.mogp_probe_latency(lat)
     names = ["DFMA", "DMUL", "rsqrt+add", "sqrt+add", "div+add", "LDS->addr", "DMMA", "SHFL64+add", "BAR(1 warp)"]
     print("dependent-chain latency (cycles/op): " + "  ".join("%s %.1f" % (n, lat[i]) for i, n in enumerate(names)))
+    print("8 dependent DMMAs after a scalar-fp64 gap of 0/64/256/1024 DFMAs: %.0f %.0f %.0f %.0f cycles" % (lat[10], lat[11], lat[12], lat[13]))
 
 
 def sec_gemm(eng):
