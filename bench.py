@@ -168,6 +168,8 @@ def run_b200(args):
     import ctypes as C
 
     rank, world, local = replicas.env()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (the banner goes to stdout)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
