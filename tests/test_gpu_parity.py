@@ -178,6 +178,7 @@ def test_predict_f_matches_reference(engine, name):
     ("MOSM", 2, [130, 65], 4, 1, 21), ("MOSM", 5, [31, 64, 1, 129, 77], 9, 1, 22), ("MOSM", 3, [40, 50, 60], 2, 3, 23),
     ("SM", 3, [100, 3, 64], 4, 1, 24), ("CONV", 4, [64, 64, 64, 64], 3, 1, 25), ("CONV", 2, [90, 45], 1, 2, 26),
     ("MOSM", 3, [0, 80, 50], 2, 1, 27),
+    ("MOSM", 1, [1], 1, 1, 28), ("SM", 2, [1, 2], 2, 1, 29), ("CONV", 2, [3, 2], 1, 5, 30), ("MOSM", 2, [70, 60], 2, 8, 31),
 ])
 def test_random_cases_against_oracle(engine, kind, C, ns, Q, D, seed):
     from mogptk_b200 import synth
@@ -190,8 +191,11 @@ def test_random_cases_against_oracle(engine, kind, C, ns, Q, D, seed):
     res = engine.lml_grad(kind, p, sigma, X, y, 1e-8, True)
     loss, gref = orc.loss_and_grad(kind, p, sigma, Xt, y, 1e-8)
     assert abs(res["lml"] + float(loss)) <= 1e-8 * abs(float(loss))
+    gmax = max(float(v.abs().max()) for v in gref.values())
     for k, got in res["grad"].items():
-        scale = max(float(gref[k].abs().max()), 1e-12)
+        # tensors whose gradient is pure round-off next to the others (e.g. delays between channels that are
+        # uncorrelated in 8 input dimensions) are compared on the scale of the largest gradient
+        scale = max(float(gref[k].abs().max()), 1e-7 * gmax, 1e-12)
         assert float((got.reshape(gref[k].shape) - gref[k]).abs().max()) <= 1e-6 * scale, k
     rng = np.random.default_rng(seed)
     Xs = np.concatenate([rng.integers(0, C, 37).astype(float)[:, None], rng.uniform(0, 10, (37, D))], axis=1)
