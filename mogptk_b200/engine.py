@@ -282,6 +282,14 @@ class Engine:
         if self._train is None:
             raise RuntimeError("predict() needs a preceding lml_grad() on this engine")
         C_, Q, D = self._train.dims
+        if not hasattr(Xs, "shape"):
+            Xs = np.asarray(Xs, dtype=np.float64)
+        n_s = Xs.shape[0]
+        if n_s > self.max_n:                     # the workspace is sized for max_n columns: predict in slices
+            if full:
+                raise ValueError("full covariance of %d test points exceeds this engine's max_n=%d" % (n_s, self.max_n))
+            parts = [self.predict(Xs[i:i + self.max_n]) for i in range(0, n_s, self.max_n)]
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
         rs = Rows(Xs, C_, self.device)
         if rs.D != D:
             raise ValueError("X must have %d input dimensions" % D)

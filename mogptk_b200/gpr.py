@@ -275,8 +275,8 @@ def default_engine(n_rows, device=None):
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     eng = _ENGINES.get(idx)
     if eng is None or eng.max_n < n_rows:
-        if eng is not None:
-            eng.close()
+        # a smaller engine may still be referenced by existing models: it is left alone (and released with
+        # them); new models get the larger one
         eng = _engine.Engine(device=idx, max_n=max(int(n_rows), 256))
         _ENGINES[idx] = eng
     return eng

@@ -264,3 +264,22 @@ def test_repeated_evaluations_replay_the_graph_and_survive_reallocation(engine):
     from oracle import mogp_oracle as orc
     ref = float(orc.lml(mid["kind"], p2, mid["sigma_t"], torch.tensor(mid["X"]), mid["y"], mid["jitter"]))
     assert abs(a["lml"] - ref) <= 1e-8 * abs(ref)
+
+
+def test_prediction_beyond_the_workspace_size_is_chunked():
+    """More test points than the engine's max_n: predict() works through slices (diagonal variances only)."""
+    from mogptk_b200.engine import Engine
+    from oracle import mogp_oracle as orc
+    g = load_golden("mosm_small")
+    eng = Engine(device=0, max_n=64)
+    try:
+        eng.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], False)
+        rng = np.random.default_rng(3)
+        Xs = np.concatenate([rng.integers(0, g["C"], 150).astype(float)[:, None], rng.uniform(0, 10, (150, 1))], axis=1)
+        mu, var = eng.predict(Xs)
+        mu_r, var_r = orc.predict_f(g["kind"], g["params"], g["sigma_t"], torch.tensor(g["X"]), g["y"], Xs, g["jitter"])
+        assert rel(mu, mu_r.ravel()) < 1e-6 and rel(var, var_r.ravel()) < 1e-6
+        with pytest.raises(ValueError):
+            eng.predict(Xs, full=True)
+    finally:
+        eng.close()
