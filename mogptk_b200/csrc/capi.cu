@@ -63,6 +63,8 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
     if ((e = cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
     if ((e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
     if ((e = cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_f1, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_f2, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
     {   // look-ahead stream + events for the blocked Cholesky
         const int nev = (int)(h->np_max / 64) + 2;
         int plo = 0, phi = 0;
@@ -113,6 +115,8 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
     if (h->hs) cudaStreamDestroy(h->hs);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->ev_f1) cudaEventDestroy(h->ev_f1);
+    if (h->ev_f2) cudaEventDestroy(h->ev_f2);
     if (h->ps.s2) cudaStreamDestroy(h->ps.s2);
     if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
     if (h->ps.s3) cudaStreamDestroy(h->ps.s3);
@@ -334,14 +338,25 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
     MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
     STAGE_MARK();
+    // K^-1 = Linv^T Linv does not need alpha: it runs on a second stream concurrently with the solves
+    // (z = Linv y, alpha = Linv^T z, diag K^-1); the gradient kernel subtracts alpha alpha^T while loading.
+    // (Profiling keeps the stages sequential so that the stage timers stay meaningful.)
+    const bool fork = want_grad && !h->profile && h->ps.s3 != nullptr;
+    if (fork) {
+        MOGP_CHECK(h, cudaEventRecord(h->ev_f1, st));
+        MOGP_CHECK(h, cudaStreamWaitEvent(h->ps.s3, h->ev_f1, 0));
+        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, nullptr, h->ps.s3));
+        MOGP_CHECK(h, cudaEventRecord(h->ev_f2, h->ps.s3));
+    }
     MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
     MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
     MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
     STAGE_MARK();
     if (want_grad) {
-        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, alpha, st));
+        if (fork) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ev_f2, 0));
+        else MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, nullptr, st));
         STAGE_MARK();
-        MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, h->tile_part, st));
+        MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, alpha, h->tile_part, st));
     }
     MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params, sigma, h->comps, h->chanbuf, h->tile_part, z, alpha, kdiag,
                                   h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out, st));

@@ -123,7 +123,7 @@ struct mogp_handle_s {
     long long realloc_epoch = 0;
     void *pent_dev = nullptr, *pent_host = nullptr; size_t pent_cap = 0; int pent_n = 0;   // parameter-entry table
     cudaStream_t hs = nullptr;                                // the step runs here in graph mode
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_f1 = nullptr, ev_f2 = nullptr;
     std::vector<int32_t> chan_uploaded;                       // content of chan_dev slot 0
     double *gbuf = nullptr; size_t gbuf_cap = 0;              // graph staging: params | sigma | y | data_var | out
     // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
@@ -156,8 +156,9 @@ cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* c
                           int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st);
 cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t* chan_dev, int64_t N, double* out,
                          cudaStream_t st);
+// avec != NULL: W holds K^-1 and the kernel forms (K^-1 - avec avec^T)/2 while loading
 cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
-                               const double* W, long long ldw, double* tile_part, cudaStream_t st);
+                               const double* W, long long ldw, const double* avec, double* tile_part, cudaStream_t st);
 // out: [0]=lml [1]=info [2..2+P) grad params [2+P..2+P+C) grad sigma
 cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad, const double* params,
                             const double* sigma, const double* comps, const double* chanbuf,

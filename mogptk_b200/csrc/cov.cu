@@ -414,6 +414,7 @@ template <int DT, bool COS>
 __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovTile* __restrict__ tiles,
                                                           const double* __restrict__ comps, const double* __restrict__ x,
                                                           const double* __restrict__ W, long long ldw,
+                                                          const double* __restrict__ avec,
                                                           double* __restrict__ tile_part) {
     extern __shared__ __align__(16) unsigned char smraw[];
     TileSmem& sm = *reinterpret_cast<TileSmem*>(smraw);
@@ -446,7 +447,13 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
             if (row < t.nr && col < t.nc) {
                 double wgt = 2.0;
                 if (diag_tile) wgt = row > col ? 2.0 : (row == col ? 1.0 : 0.0);
-                if (wgt != 0.0) v = wgt * W[(long long)(t.r0 + row) * ldw + t.c0 + col];
+                if (wgt != 0.0) {
+                    v = W[(long long)(t.r0 + row) * ldw + t.c0 + col];
+                    // W holds K^-1 when avec is given: form (K^-1 - a a^T)/2 on the fly (lets the K^-1 GEMM run
+                    // concurrently with the solves that produce a)
+                    if (avec) v = 0.5 * (v - avec[t.r0 + row] * avec[t.c0 + col]);
+                    v *= wgt;
+                }
             }
             wv[i][j] = v;
         }
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
 }
 
 cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
-                               const double* W, long long ldw, double* tile_part, cudaStream_t st) {
+                               const double* W, long long ldw, const double* avec, double* tile_part, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem) + (size_t)8 * RC * (2 + 3 * MOGP_MAX_D) * sizeof(double);
     if (tl.n <= 0) return cudaSuccess;
 #define LAUNCH_GR(DT, COS)                                                                                         \
@@ -550,7 +557,7 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
             if (e != cudaSuccess) return e;                                                                        \
             attr_done = true;                                                                                      \
         }                                                                                                          \
-        kern<<<tl.n, 256, smem, st>>>(s, tl.dev, comps, x, W, ldw, tile_part);                                     \
+        kern<<<tl.n, 256, smem, st>>>(s, tl.dev, comps, x, W, ldw, avec, tile_part);                                     \
         MOGP_COUNT(1);                                                                                             \
     } while (0)
     if (s.D == 1) { if (s.has_cos) LAUNCH_GR(1, true); else LAUNCH_GR(1, false); }
