@@ -156,3 +156,68 @@ def test_drop_in_under_the_reference_model_classes():
     assert abs(a.log_marginal_likelihood() - b.log_marginal_likelihood()) <= 1e-8 * abs(a.log_marginal_likelihood())
     assert a.num_parameters() == b.num_parameters()
     b.print_parameters()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout only exists in the build container")
+@pytest.mark.parametrize("family", ["SM", "CONV"])
+def test_drop_in_for_the_other_two_model_families(family):
+    """mogptk.SM (independent SM kernels) and mogptk.CONV (mixture of CONV kernels) through the plug-in."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from make_golden import import_reference
+    mogptk = import_reference()
+    from mogptk_b200 import synth
+    Xd, yd = synth.make_data(2, [30, 24], seed=6)
+
+    def dataset():
+        ds = mogptk.DataSet()
+        for c in range(2):
+            msk = Xd[:, 0] == c
+            ds.append(mogptk.Data(Xd[msk, 1], yd[msk], name=str(c)))
+        return ds
+
+    cls = getattr(mogptk, family)
+    torch.manual_seed(1)
+    a = cls(dataset(), Q=2)
+    torch.manual_seed(1)
+    b = cls(dataset(), Q=2, inference=mb.B200Exact(engine=FakeEngine()))
+    if family == "SM":                                   # the constructor pins `mean` (SURVEY 3.5): assign explicitly
+        for mdl in (a, b):
+            for c in range(2):
+                mdl.gpr.kernel[c].mean.assign(torch.tensor([[0.3], [0.8]]))
+    la, _ = a.train(method="Adam", iters=3, lr=0.05, verbose=False, jit=False)
+    lb, _ = b.train(method="Adam", iters=3, lr=0.05, verbose=False, jit=False)
+    assert np.abs(la - lb).max() <= 1e-8 * np.abs(la).max()
+    _, Ma, _, _ = a.predict()
+    _, Mb, _, _ = b.predict()
+    for u, v in zip(Ma, Mb):
+        assert np.abs(u - v).max() <= 1e-7 * max(np.abs(u).max(), 1e-12)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout only exists in the build container")
+def test_lbfgs_closure_and_resume_through_the_plugin():
+    """mogptk.Model.train(method='LBFGS') wraps loss() in a closure (mogptk/model.py:546-553); a second train()
+    call resumes and appends to the loss history (:501-509)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from make_golden import import_reference
+    mogptk = import_reference()
+    from mogptk_b200 import synth
+    Xd, yd = synth.make_data(2, [26, 20], seed=9)
+
+    def model(**kw):
+        ds = mogptk.DataSet()
+        for c in range(2):
+            msk = Xd[:, 0] == c
+            ds.append(mogptk.Data(Xd[msk, 1], yd[msk], name=str(c)))
+        torch.manual_seed(2)
+        m = mogptk.MOSM(ds, Q=2, **kw)
+        m.gpr.kernel.mean.assign(torch.full((2, 2, 1), 0.5))
+        return m
+
+    a, b = model(), model(inference=mb.B200Exact(engine=FakeEngine()))
+    la, _ = a.train(method="LBFGS", iters=4, verbose=False, jit=False)
+    lb, _ = b.train(method="LBFGS", iters=4, verbose=False, jit=False)
+    assert len(la) == len(lb) and np.abs(la - lb).max() <= 1e-7 * np.abs(la).max()
+    b.train(method="Adam", iters=2, lr=0.01, verbose=False, jit=True)       # jit=True -> compile() is a no-op here
+    assert len(b.losses) == len(lb) + 2
+    import pickle
+    pickle.loads(pickle.dumps(b.gpr))                                       # what model.save() relies on
