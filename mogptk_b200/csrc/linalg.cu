@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 *reinterpret_cast<double2*>(Xr + (r0 + 8 * i + gq) * 8 + 2 * tq) = make_double2(cf[i][0], cf[i][1]);
         }
         if (dbg && p == 4 && tid == 64 && b == 0) dbg[21] = clock64();
+        if (dbg && p == 4 && lane == 0 && b == 0) dbg[32 + warp] = clock64();          // arrival at the exchange barrier
         __syncthreads();
         if (dbg && p == 4 && tid == 64 && b == 0) dbg[22] = clock64();
         double acc[8];
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 for (int c = 0; c < 8; ++c) Dsm[(tid - c0) * 8 + c] = acc[c];
             }
         }
+        if (dbg && p == 4 && lane == 0 && b == 0) dbg[40 + warp] = clock64();          // arrival at the pivot-block barrier
         __syncthreads();
         if (dbg && tid == 64 && b == 0) dbg[2 + 2 * p] = clock64();
         if (act) {
@@ -438,22 +440,17 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                     for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
             }
             if (badcol < 8 && tid == c0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
-            if (tid < c0 + 8) {                       // a row of the pivot block itself
-                const int jrow = tid - c0;
+            // Forward substitution of this row against the factored pivot block.  A row of the pivot block
+            // itself goes through the same arithmetic (it reproduces its row of the factor bit for bit up to
+            // the diagonal) and only masks the entries right of the diagonal: no divergent special case -- an
+            // 8-way branch over the pivot rows used to cost their warp ~1000 cycles per sub-panel.
+            const int jrow = tid - c0;                // >= 8 for the rows below the pivot block
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    if (jrow == jj) {
+            for (int c = 0; c < 8; ++c) {
+                const double xc = acc[c] * rinv[c];
+                acc[c] = (c <= jrow) ? xc : 0.0;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[c] = (c <= jj) ? D[jj][c] : 0.0;
-                    }
-            } else {                                  // forward substitution for a row below
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double xc = acc[c] * rinv[c];
-                    acc[c] = xc;
-#pragma unroll
-                    for (int cc = c + 1; cc < 8; ++cc) acc[cc] = fma(-xc, D[cc][c], acc[cc]);
-                }
+                for (int cc = c + 1; cc < 8; ++cc) acc[cc] = fma(-xc, D[cc][c], acc[cc]);
             }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -461,6 +458,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 S[tid * PS + c0 + c] = acc[c];
             }
         }
+        if (dbg && p == 3 && lane == 0 && b == 0) dbg[48 + warp] = clock64();          // arrival at the end-of-sub-panel barrier
         __syncthreads();
         if (dbg && tid == 64 && b == 0) dbg[3 + 2 * p] = clock64();
     }
@@ -477,6 +475,203 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
         }
     }
     if (dbg && tid == 64 && b == 0) dbg[18] = clock64();
+}
+
+// ---------------------------------------------------------------------------- warp-specialised panel step
+// Same contract as potrf_panel_kernel, different schedule.  Measured on B200: a dependent DFMA chain slows from
+// 8.5 to 40 cycles per op when a DMMA stream runs on the same SM sub-partition (they share the fp64 pipe), so
+// tensor work cannot simply be overlapped with the pivot chain.  Here warp 0 alone (sub-partition 0) carries the
+// scalar chain for all 128 rows of the CTA (4 rows per lane: one redundant 8x8 pivot factorisation per lane
+// instead of one per row), warps 1,2,3,5,6,7 (sub-partitions 1..3, two warps each) do every DMMA, and warp 4 --
+// which would share sub-partition 0 with the chain -- retires after the prologue.  For sub-panel p the tensor warps
+// accumulate, while the chain is still busy with sub-panel p-1,
+//     E = -[previous panel rows] [previous panel rows of the pivots]^T - L[:, <c0-8] L[piv, <c0-8]^T
+// (the previous panel's rank-64 update is applied lazily, 8 columns at a time, instead of up front), then wait
+// for the chain, add the last 8 finished columns (two k-steps), add the matrix entries (read straight from
+// global memory, issued before the accumulation) and hand the 128 x 8 block to the chain through Xr.  Finished
+// values go from the chain's registers to global memory directly.  Named barriers: 1 = "Xr full" (tensor warps
+// arrive, chain waits), 2 = "columns done" (chain arrives, tensor warps wait).
+#define XP 10    // pitch of the exchange tile (16-byte aligned rows, conflict-free 128-bit row reads)
+#define WS_BAR_THREADS 224      // chain warp + six tensor warps
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restrict__ A, long long lda,
+                                                                double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
+                                                                int has_prev, int32_t* info, long long* dbg) {
+    extern __shared__ __align__(16) double sm[];
+    double* ZZ = sm;                 // [128][PZ] previous-panel values of the diagonal-block rows and of this CTA's rows
+    double* Lc = sm + 128 * PZ;      // [64][PL]  finished columns, column-major: Lc[col][row]
+    double* Xr = Lc + 64 * PL;       // [128][XP] tensor warps -> chain exchange
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const bool has_rows = b < nrb;
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const double* Ad = A + (long long)k0 * lda + k0;
+    double* Ar = A + (long long)(k0 + 64 + 64 * b) * lda + k0;
+    if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
+    if (has_prev) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = tid + it * 256;              // 2048 16-byte chunks per 64 x 64 tile
+            const int r = idx >> 5, cc = idx & 31;
+            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
+            if (has_rows) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
+    if (warp == 4) return;
+
+    if (warp != 0) {
+        // ------------------------------------------------------------------ tensor warps
+        // m-tiles (8 rows each): 0..7 = rows of the diagonal block (tile i is finished once p > i), 8..15 = the
+        // CTA's rows below.  Static assignment balanced per sub-partition over the sweep.
+        int mt0, mt1, mt2;
+        switch (warp) {
+            case 1: mt0 = 8; mt1 = 9; mt2 = 0; break;
+            case 5: mt0 = 10; mt1 = 11; mt2 = 1; break;
+            case 2: mt0 = 12; mt1 = 2; mt2 = 6; break;
+            case 6: mt0 = 13; mt1 = 4; mt2 = -1; break;
+            case 3: mt0 = 14; mt1 = 3; mt2 = 7; break;
+            default: mt0 = 15; mt1 = 5; mt2 = -1; break;
+        }
+        const int mt[3] = {mt0, mt1, mt2};
+        const double* rowp[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
+            rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
+        }
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int c0 = p * 8;
+            bool on[3];
+            double cf[3][2];
+            double2 a0[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                on[i] = mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p);
+                cf[i][0] = 0.0; cf[i][1] = 0.0;
+                a0[i] = make_double2(0.0, 0.0);
+                if (on[i]) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
+            }
+            if (has_prev) {
+#pragma unroll 4
+                for (int kk = 0; kk < 64; kk += 4) {
+                    const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (on[i]) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
+                }
+            }
+#pragma unroll 2
+            for (int k = 0; k < c0 - 8; k += 4) {
+                const double nb = -Lc[(k + tq) * PL + c0 + gq];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PL + mt[i] * 8 + gq], nb);
+            }
+            if (p >= 1) {
+                named_bar_sync(2, WS_BAR_THREADS);           // columns [c0-8, c0) are in Lc
+#pragma unroll
+                for (int k8 = 0; k8 < 8; k8 += 4) {
+                    const int k = c0 - 8 + k8;
+                    const double nb = -Lc[(k + tq) * PL + c0 + gq];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PL + mt[i] * 8 + gq], nb);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (on[i])
+                    *reinterpret_cast<double2*>(Xr + (mt[i] * 8 + gq) * XP + 2 * tq) =
+                        make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+            if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
+            __threadfence_block();
+            named_bar_arrive(1, WS_BAR_THREADS);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- chain warp: lane owns rows lane + 32 g
+    double* Lt = Ltmp + (long long)k0 * ldt + k0;
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = p * 8;
+        named_bar_sync(1, WS_BAR_THREADS);
+        double D[8][8], rinv[8], acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) D[i][j] = Xr[(c0 + i) * XP + j];
+        bool gon[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            gon[g] = (32 * g + 31 >= c0) && (g < 2 || has_rows);          // warp-uniform
+            if (gon[g]) {
+                const double2* q = reinterpret_cast<const double2*>(Xr + (lane + 32 * g) * XP);
+                const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+                acc[g][0] = v0.x; acc[g][1] = v0.y; acc[g][2] = v1.x; acc[g][3] = v1.y;
+                acc[g][4] = v2.x; acc[g][5] = v2.y; acc[g][6] = v3.x; acc[g][7] = v3.y;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[g][c] = 0.0;
+            }
+        }
+        int badcol = 8;                       // first non-positive pivot of this block (8 = none)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double d = D[c][c];
+            const bool ok = d > 0.0;
+            badcol = (!ok && badcol == 8) ? c : badcol;
+            d = ok ? d : 1.0;
+            const double ri = rsqrt_pos(d);
+            rinv[c] = ri;
+            D[c][c] = d * ri;
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i)
+#pragma unroll
+                for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
+        }
+        if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (!gon[g]) continue;
+            const int row = lane + 32 * g;
+            const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double xc = acc[g][c] * rinv[c];
+                acc[g][c] = (c <= jrow) ? xc : 0.0;
+#pragma unroll
+                for (int cc = c + 1; cc < 8; ++cc) acc[g][cc] = fma(-xc, D[cc][c], acc[g][cc]);
+            }
+            if (jrow >= 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PL + row] = acc[g][c];
+                double* dst = nullptr;
+                if (g >= 2) dst = Ar + (long long)(row - 64) * lda + c0;
+                else if (b == 0) dst = Lt + (long long)row * ldt + c0;       // L_kk is parked: other CTAs still read A_kk
+                if (dst) {
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2)
+                        *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
+                }
+            }
+        }
+        if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
+        if (p < 7) {
+            __threadfence_block();
+            named_bar_arrive(2, WS_BAR_THREADS);
+        }
+    }
+    if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
 }
 
 // After the sweep, for every diagonal block at once: move L_kk from Ltmp into A, invert it by
@@ -537,14 +732,17 @@ __global__ void __launch_bounds__(256) diag_finish_kernel(double* __restrict__ A
 }
 
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
+// 1: warp-specialised panel step, 0: phase-alternating one (MOGP_PANEL_VARIANT overrides the default for A/B runs)
+static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 0;
+extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; return 0; }
 extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
     if (!g_panel_dbg) {
-        if (cudaMalloc(&g_panel_dbg, 32 * 8) != cudaSuccess) return -2;
-        cudaMemset(g_panel_dbg, 0, 32 * 8);
+        if (cudaMalloc(&g_panel_dbg, 64 * 8) != cudaSuccess) return -2;
+        cudaMemset(g_panel_dbg, 0, 64 * 8);
         return 1;
     }
     cudaDeviceSynchronize();
-    return cudaMemcpy(out_host, g_panel_dbg, 24 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    return cudaMemcpy(out_host, g_panel_dbg, 56 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 // ============================================================================ blocked Cholesky
@@ -563,8 +761,21 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     if (e != cudaSuccess) return e;
     const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
     const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
+    const size_t smem_w = (size_t)(128 * PZ + 64 * PL + 128 * XP) * sizeof(double);
+    if ((ld | ldt) & 1) return cudaErrorInvalidValue;          // 16-byte row accesses
     static bool attr_done = false;
+    auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
+        if (g_panel_variant == 1)
+            potrf_panel_ws_kernel<<<std::max(1, nrb), 256, smem_w, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
+        else
+            potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
+    };
     if (!attr_done) {
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -613,8 +824,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 const int ks = (int)(k / MOGP_NB);
                 // panel(k) reads its column updated by the inner update issued two steps earlier (third stream)
                 if (two3 && k >= K0 + 2 * MOGP_NB && (e = cudaStreamWaitEvent(st, ps->ev3[ks - 2], 0)) != cudaSuccess) return e;
-                potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, k > K0 ? 1 : 0,
-                                                                          info, nullptr);
+                launch_panel(k, nrb, k > K0 ? 1 : 0, nullptr, st);
                 MOGP_COUNT(1);
                 const int64_t c0 = k + 2 * MOGP_NB, Nc = Kend - c0, M = Np - c0;
                 if (Nc > 0 && M > 0) {                      // remaining columns of this outer panel
@@ -675,8 +885,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         const int64_t k = (int64_t)s * MOGP_NB;
         const int nrb = nb - s - 1;
         if (two && s >= 2 && (e = cudaStreamWaitEvent(st, ps->ev2[s - 2], 0)) != cudaSuccess) return e;
-        potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, st>>>(A, ld, Ltmp, ldt, (int)k, nrb, s > 0 ? 1 : 0, info,
-                                                                  (s == 1) ? g_panel_dbg : nullptr);
+        launch_panel(k, nrb, s > 0 ? 1 : 0, (s == 1) ? g_panel_dbg : nullptr, st);
         MOGP_COUNT(1);
         const int64_t c0 = k + 2 * MOGP_NB, M = Np - c0;                          // column blocks >= s+2
         if (M > 0) {
@@ -1036,4 +1245,87 @@ extern "C" int mogp_probe_latency(double* out_host /*16*/) {
     cudaError_t e = cudaMemcpy(out_host, d, 16 * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? 0 : -2;
+}
+
+// Contention probe: warps 0..3 run a dependent DFMA chain (the shape of the Cholesky pivot chain) while warps
+// 4..7 (one per SM sub-partition, sharing the fp64 pipe with them) stream DMMAs on `nacc` independent
+// accumulators.  out[0] = chain cycles per DFMA, out[1] = cycles per DMMA of one tensor warp.
+template <int NACC>
+__global__ void contention_probe_kernel(double* out, int chain_ops, int dmma_iters, double seed) {
+    const int warp = threadIdx.x >> 5;
+    double y = 1.0000001, z = 1e-9;
+    if (warp < 4) {
+        double x = seed + threadIdx.x * 1e-9;
+        __syncthreads();
+        const long long t0 = clock64();
+#pragma unroll 16
+        for (int i = 0; i < chain_ops; ++i) x = fma(x, y, z);
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / chain_ops; out[2] = x; }
+    } else {
+        double c[NACC > 0 ? NACC : 1][2];
+#pragma unroll
+        for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a) { c[a][0] = seed; c[a][1] = seed * 0.5; }
+        __syncthreads();
+        const long long t0 = clock64();
+        if (NACC > 0) {
+            for (int i = 0; i < dmma_iters; ++i) {
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) dmma884(c[a][0], c[a][1], y, z);
+            }
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 128) {
+            double s = 0;
+            for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a) s += c[a][0] + c[a][1];
+            out[1] = NACC > 0 ? (double)(t1 - t0) / ((double)dmma_iters * NACC) : 0.0;
+            out[3] = s;
+        }
+    }
+}
+// Same probe with the layout of the warp-specialised panel step: chain on warp 0 only, DMMA streams (3
+// accumulators) on warps 1,2,3,5,6,7, warp 4 idle.  out[0] = chain cycles per DFMA, out[1] = cycles per DMMA.
+__global__ void contention_split_kernel(double* out, int chain_ops, int dmma_iters, double seed) {
+    const int warp = threadIdx.x >> 5;
+    double y = 1.0000001, z = 1e-9;
+    __syncthreads();
+    if (warp == 0) {
+        double x = seed + threadIdx.x * 1e-9;
+        const long long t0 = clock64();
+#pragma unroll 16
+        for (int i = 0; i < chain_ops; ++i) x = fma(x, y, z);
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / chain_ops; out[2] = x; }
+    } else if (warp != 4) {
+        double c[3][2] = {{seed, seed}, {seed, seed}, {seed, seed}};
+        const long long t0 = clock64();
+        for (int i = 0; i < dmma_iters; ++i) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dmma884(c[a][0], c[a][1], y, z);
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 32) { out[1] = (double)(t1 - t0) / ((double)dmma_iters * 3); out[3] = c[0][0] + c[1][1] + c[2][0]; }
+    }
+}
+extern "C" int mogp_probe_contention(double* out_host /*15*/) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, 16 * 8) != cudaSuccess) return -2;
+    const int chain = 2048;
+    for (int mode = 0; mode < 5; ++mode) {
+        cudaMemset(d, 0, 16 * 8);
+        for (int rep = 0; rep < 2; ++rep) {
+            if (mode == 4) contention_split_kernel<<<1, 256>>>(d, chain, 1500, 1.5);
+            if (mode == 0) contention_probe_kernel<0><<<1, 256>>>(d, chain, 0, 1.5);
+            if (mode == 1) contention_probe_kernel<1><<<1, 256>>>(d, chain, 4000, 1.5);
+            if (mode == 2) contention_probe_kernel<2><<<1, 256>>>(d, chain, 2000, 1.5);
+            if (mode == 3) contention_probe_kernel<4><<<1, 256>>>(d, chain, 1000, 1.5);
+        }
+        double h[4];
+        if (cudaMemcpy(h, d, 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d); return -2; }
+        out_host[3 * mode] = h[0];
+        out_host[3 * mode + 1] = h[1];
+        out_host[3 * mode + 2] = 0.0;
+    }
+    cudaFree(d);
+    return 0;
 }

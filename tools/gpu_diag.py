@@ -46,6 +46,11 @@ def sec_peak(eng):
     eng.lib.mogp_probe_latency(lat)
     names = ["DFMA", "DMUL", "rsqrt+add", "sqrt+add", "div+add", "LDS->addr", "DMMA", "SHFL64+add", "BAR(1 warp)"]
     print("dependent-chain latency (cycles/op): " + "  ".join("%s %.1f" % (n, lat[i]) for i, n in enumerate(names)))
+    con = (C.c_double * 15)()
+    eng.lib.mogp_probe_contention(con)
+    print("DFMA chain latency with a DMMA stream on the same sub-partition (0/1/2/4 accumulators): " +
+          "  ".join("chain %.1f dmma %.1f" % (con[3 * m], con[3 * m + 1]) for m in range(4)) +
+          " | chain on warp 0, DMMA on warps 1,2,3,5,6,7: chain %.1f dmma %.1f (two warps share a sub-partition)" % (con[12], con[13]))
     print("8 dependent DMMAs after a scalar-fp64 gap of 0/64/256/1024 DFMAs: %.0f %.0f %.0f %.0f cycles" % (lat[10], lat[11], lat[12], lat[13]))
 
 
@@ -204,9 +209,11 @@ def sec_time(eng):
 
 def sec_panel(eng):
     import ctypes as C
-    buf = (C.c_longlong * 24)()
-    eng.lib.mogp_panel_debug(buf)          # arms the timestamps
-    for n in (2048, 8192):
+    buf = (C.c_longlong * 56)()
+    eng.lib.mogp_panel_debug(buf)          # arms the timestamps (second panel of the single-level sweep)
+    for variant in (1, 0):
+        eng.lib.mogp_set_panel_variant(variant)
+        n = 2048
         A = spd(n, 1).cuda()
         for _ in range(3):
             W = A.clone()
@@ -214,9 +221,15 @@ def sec_panel(eng):
         torch.cuda.synchronize()
         eng.lib.mogp_panel_debug(buf)
         t = [int(v) for v in buf]
-        print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
-        print("   p4 f-phase detail: start->loop end %d (from u-end %d), xr store %d, sync1 %d, rest(acc load, Dsm, sync2) %d" % (
-            t[20] - t[19], t[19] - t[9], t[21] - t[20], t[22] - t[21], t[10] - t[22]))
+        if variant == 1:
+            print("ws panel n=%d: prologue %d | chain done stamps (delta): %s | tensor Xr-ready (rel. start): %s | total %d cycles" % (
+                n, t[1] - t[0], [t[2 + p] - (t[1] if p == 0 else t[1 + p]) for p in range(8)],
+                [t[16 + p] - t[0] for p in range(8)], t[10] - t[0]))
+            print("   chain u(p) = done(p) - Xr-ready(p): %s ; exchange = Xr-ready(p+1) - done(p): %s" % (
+                [t[2 + p] - t[16 + p] for p in range(8)], [t[17 + p] - t[2 + p] for p in range(7)]))
+        else:
+            print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
+    eng.lib.mogp_set_panel_variant(1)
 
 
 def sec_gemmk(eng):
