@@ -58,6 +58,7 @@ _EXTRA = {
     "mogp_probe_latency": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_probe_contention": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_set_panel_variant": (C.c_int, [C.c_int]),
+    "mogp_set_trtri_pipe": (C.c_int, [C.c_int]),
     "mogp_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mogp_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mogp_host_pair_comps": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp]),

@@ -75,7 +75,10 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
         h->ps.ev1 = new cudaEvent_t[nev + 2]();
         h->ps.ev2 = new cudaEvent_t[nev + 2]();
         h->ps.ev3 = new cudaEvent_t[nev + 2]();
+        h->ps.evp = new cudaEvent_t[nev + 2]();
+        if ((e = cudaStreamCreateWithPriority(&h->ps.s4, cudaStreamNonBlocking, plo + (phi - plo) / 2)) != cudaSuccess) return fail(e);
         for (int i = 0; i < nev + 2; ++i) {
+            if ((e = cudaEventCreateWithFlags(&h->ps.evp[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
             if ((e = cudaEventCreateWithFlags(&h->ps.ev1[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
             if ((e = cudaEventCreateWithFlags(&h->ps.ev2[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
             if ((e = cudaEventCreateWithFlags(&h->ps.ev3[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -108,7 +111,9 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
             if (h->ps.ev1[i]) cudaEventDestroy(h->ps.ev1[i]);
             if (h->ps.ev2[i]) cudaEventDestroy(h->ps.ev2[i]);
             if (h->ps.ev3 && h->ps.ev3[i]) cudaEventDestroy(h->ps.ev3[i]);
+            if (h->ps.evp && h->ps.evp[i]) cudaEventDestroy(h->ps.evp[i]);
         }
+    delete[] h->ps.evp;
     delete[] h->ps.ev1;
     delete[] h->ps.ev2;
     delete[] h->ps.ev3;
@@ -120,6 +125,7 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
     if (h->ps.s2) cudaStreamDestroy(h->ps.s2);
     if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
     if (h->ps.s3) cudaStreamDestroy(h->ps.s3);
+    if (h->ps.s4) cudaStreamDestroy(h->ps.s4);
     void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
                     h->comps, h->comps2, h->chanbuf2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)
@@ -283,8 +289,9 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     MOGP_CHECK(h, cudaSetDevice(h->device));
     H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
-    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps));
-    MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
+    bool fused_inverse = false;
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
+    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
     MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
     h->have_factor = false;
@@ -333,10 +340,12 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     // K~ (lower) -> L, diag blocks of Linv
     MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, dv, 1, h->A, ld, N, Np, st));
     STAGE_MARK();
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps));
+    // (with the pipelined inverse the GEMMs of Linv = L^-1 are issued behind the panel chain, inside potrf_padded)
+    bool fused_inverse = false;
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
     STAGE_MARK();
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
-    MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
+    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
     STAGE_MARK();
     // K^-1 = Linv^T Linv does not need alpha: it runs on a second stream concurrently with the solves
     // (z = Linv y, alpha = Linv^T z, diag K^-1); the gradient kernel subtracts alpha alpha^T while loading.
@@ -450,7 +459,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
             h->graphs.push_back(sg);
         }
         const double* dvp = data_var_dev ? gdv : nullptr;
-        if (sg->exec && sg->epoch != h->realloc_epoch) {      // a workspace buffer moved since the capture
+        if (sg->exec && (sg->epoch != h->realloc_epoch || sg->cfg_epoch != g_mogp_cfg_epoch)) {   // a workspace buffer moved (or a tuning knob changed) since the capture
             cudaGraphExecDestroy(sg->exec);
             sg->exec = nullptr;
         }
@@ -475,6 +484,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
             }
             sg->launches = g_mogp_launches - l0;
             sg->epoch = h->realloc_epoch;
+            sg->cfg_epoch = g_mogp_cfg_epoch;
             ce = cudaGraphInstantiate(&sg->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) { sg->exec = nullptr; h->err = "cudaGraphInstantiate failed"; g_use_graphs = 0; return -2; }

@@ -79,7 +79,7 @@ struct StepGraph {             // one captured exact-GP step (see capi.cu)
     int kind = 0, C = 0, Q = 0, D = 0, want_grad = 0, has_dv = 0, uses = 0;
     int64_t N = 0;
     double jitter = 0.0;
-    long long launches = 0, epoch = 0;
+    long long launches = 0, epoch = 0, cfg_epoch = 0;
     std::vector<int32_t> off;
     cudaGraphExec_t exec = nullptr;
 };
@@ -90,6 +90,8 @@ struct PotrfStreams {          // look-ahead resources owned by the handle
     cudaEvent_t* ev3 = nullptr;   // [nev + 2] recorded on s3
     cudaEvent_t* ev1 = nullptr;   // [nev + 2] recorded on the caller's stream after panel steps
     cudaEvent_t* ev2 = nullptr;   // [nev + 2] recorded on s2 after bulk updates
+    cudaStream_t s4 = nullptr;    // medium priority: triangular inverse pipelined behind the panel chain
+    cudaEvent_t* evp = nullptr;   // [nev + 2] recorded on s1 after every panel step (pipelined inverse)
     int nev = 0;
 };
 struct mogp_handle_s {
@@ -143,6 +145,7 @@ struct mogp_handle_s {
 
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern long long g_mogp_launches;
+extern long long g_mogp_cfg_epoch;
 #define MOGP_COUNT(n) (g_mogp_launches += (n))
 
 // ------------------------------------------------------------------ covariance kernels (cov.cu)
@@ -167,8 +170,12 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
                             int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st);
 
 // ------------------------------------------------------------------ dense linear algebra (linalg.cu)
+// fused_inverse: NULL -> factor only (diagonal blocks of Linv get inv(L_kk)); else the triangular inverse may be
+// pipelined behind the panel chain (needs Ltmp == the scratch trtri_padded would use, ldt == ldi == lda); on return
+// *fused_inverse tells whether Linv is complete (true) or trtri_padded still has to run (false).
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
-                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps);
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
+                         bool* fused_inverse = nullptr);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
 // z = Linv * y (lower-triangular mat-vec), rows [0,Np)

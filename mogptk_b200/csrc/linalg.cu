@@ -200,12 +200,13 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
 }
 
 long long g_mogp_launches = 0;
+long long g_mogp_cfg_epoch = 0;      // bumped by the tuning setters: captured step graphs are re-captured
 // 0 (default): 64x64 tiles   1: force 128x128 tiles (256 threads)   3: force 128x64 tiles
 static int g_gemm_cfg = -1;
 static long long g_small_tile_threshold = 1400;
-extern "C" void mogp_set_small_tile_threshold(long long t) { g_small_tile_threshold = t; }
+extern "C" void mogp_set_small_tile_threshold(long long t) { g_small_tile_threshold = t; ++g_mogp_cfg_epoch; }
 
-extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
+extern "C" void mogp_set_gemm_config(int cfg) { g_gemm_cfg = cfg; ++g_mogp_cfg_epoch; }
 
 template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool TA, bool TB>
 static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s) {
@@ -481,34 +482,73 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
 // Same contract as potrf_panel_kernel, different schedule.  Measured on B200: a dependent DFMA chain slows from
 // 8.5 to 40 cycles per op when a DMMA stream runs on the same SM sub-partition (they share the fp64 pipe), so
 // tensor work cannot simply be overlapped with the pivot chain.  Here warp 0 alone (sub-partition 0) carries the
-// scalar chain for all 128 rows of the CTA (4 rows per lane: one redundant 8x8 pivot factorisation per lane
-// instead of one per row), warps 1,2,3,5,6,7 (sub-partitions 1..3, two warps each) do every DMMA, and warp 4 --
-// which would share sub-partition 0 with the chain -- retires after the prologue.  For sub-panel p the tensor warps
-// accumulate, while the chain is still busy with sub-panel p-1,
+// scalar chain for all rows of the CTA (one row per lane and 32-row group: one redundant 8x8 pivot factorisation
+// per lane instead of one per row), warps 1,2,3,5,6,7 (sub-partitions 1..3, two warps each) do every DMMA, and
+// warp 4 -- which would share sub-partition 0 with the chain -- retires after the prologue.  For sub-panel p the
+// tensor warps accumulate, while the chain is still busy with sub-panel p-1,
 //     E = -[previous panel rows] [previous panel rows of the pivots]^T - L[:, <c0-8] L[piv, <c0-8]^T
 // (the previous panel's rank-64 update is applied lazily, 8 columns at a time, instead of up front), then wait
 // for the chain, add the last 8 finished columns (two k-steps), add the matrix entries (read straight from
-// global memory, issued before the accumulation) and hand the 128 x 8 block to the chain through Xr.  Finished
+// global memory, issued before the accumulation) and hand the ROWS x 8 block to the chain through Xr.  Finished
 // values go from the chain's registers to global memory directly.  Named barriers: 1 = "Xr full" (tensor warps
 // arrive, chain waits), 2 = "columns done" (chain arrives, tensor warps wait).
+// OT = 8-row tiles of own rows per CTA: 8 (64 rows below the diagonal block per CTA) or 4 (32 rows: the tensor
+// work per CTA -- half of which is the redundant update of the diagonal block -- drops from 16 to 12 row tiles,
+// which brings it level with the chain; used while twice the CTAs still fit one wave).
 #define XP 10    // pitch of the exchange tile (16-byte aligned rows, conflict-free 128-bit row reads)
 #define WS_BAR_THREADS 224      // chain warp + six tensor warps
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+template <int OT>
+struct WsCfg {
+    static constexpr int ROWS = 64 + 8 * OT;        // diagonal block + own rows
+    static constexpr int NS = OT == 8 ? 3 : 2;      // row-tile slots per tensor warp
+    static constexpr int NG = ROWS / 32;            // 32-row groups of the chain warp
+    static constexpr int PLW = OT == 8 ? 132 : 100; // pitch of Lc (== 4 mod 16, >= ROWS)
+    static constexpr size_t SMEM = (size_t)(ROWS * PZ + 64 * PLW + ROWS * XP) * sizeof(double);
+};
+// Row tiles (8 rows each): 0..7 = rows of the diagonal block (tile i is finished once p > i), 8.. = the CTA's own
+// rows.  Static assignment, balanced per sub-partition over the sweep (warps w and w+4 share a sub-partition).
+template <int OT>
+__device__ __forceinline__ int ws_tile(int warp, int slot) {
+    if (OT == 8) {
+        switch (warp) {
+            case 1: return slot == 0 ? 8 : slot == 1 ? 9 : 0;
+            case 5: return slot == 0 ? 10 : slot == 1 ? 11 : 1;
+            case 2: return slot == 0 ? 12 : slot == 1 ? 2 : 6;
+            case 6: return slot == 0 ? 13 : slot == 1 ? 4 : -1;
+            case 3: return slot == 0 ? 14 : slot == 1 ? 3 : 7;
+            default: return slot == 0 ? 15 : slot == 1 ? 5 : -1;
+        }
+    } else {
+        switch (warp) {
+            case 1: return slot == 0 ? 8 : 0;
+            case 5: return slot == 0 ? 9 : 3;
+            case 2: return slot == 0 ? 10 : 1;
+            case 6: return slot == 0 ? 4 : 6;
+            case 3: return slot == 0 ? 11 : 2;
+            default: return slot == 0 ? 5 : 7;
+        }
+    }
+}
+
+template <int OT>
 __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restrict__ A, long long lda,
                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
                                                                 int has_prev, int32_t* info, long long* dbg) {
+    using Cfg = WsCfg<OT>;
+    constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
     extern __shared__ __align__(16) double sm[];
-    double* ZZ = sm;                 // [128][PZ] previous-panel values of the diagonal-block rows and of this CTA's rows
-    double* Lc = sm + 128 * PZ;      // [64][PL]  finished columns, column-major: Lc[col][row]
-    double* Xr = Lc + 64 * PL;       // [128][XP] tensor warps -> chain exchange
+    double* ZZ = sm;                 // [ROWS][PZ] previous-panel values of the diagonal-block rows and of this CTA's rows
+    double* Lc = sm + ROWS * PZ;     // [64][PLW]  finished columns, column-major: Lc[col][row]
+    double* Xr = Lc + 64 * PLW;      // [ROWS][XP] tensor warps -> chain exchange
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
-    const bool has_rows = b < nrb;
+    const bool has_rows = b < nrb;   // nrb counts blocks of 8*OT rows here
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const double* Ad = A + (long long)k0 * lda + k0;
-    double* Ar = A + (long long)(k0 + 64 + 64 * b) * lda + k0;
+    double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
     if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
     if (has_prev) {
 #pragma unroll
@@ -516,7 +556,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
             const int idx = tid + it * 256;              // 2048 16-byte chunks per 64 x 64 tile
             const int r = idx >> 5, cc = idx & 31;
             cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
-            if (has_rows) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
+            if (has_rows && it < OT) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -527,32 +567,22 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
 
     if (warp != 0) {
         // ------------------------------------------------------------------ tensor warps
-        // m-tiles (8 rows each): 0..7 = rows of the diagonal block (tile i is finished once p > i), 8..15 = the
-        // CTA's rows below.  Static assignment balanced per sub-partition over the sweep.
-        int mt0, mt1, mt2;
-        switch (warp) {
-            case 1: mt0 = 8; mt1 = 9; mt2 = 0; break;
-            case 5: mt0 = 10; mt1 = 11; mt2 = 1; break;
-            case 2: mt0 = 12; mt1 = 2; mt2 = 6; break;
-            case 6: mt0 = 13; mt1 = 4; mt2 = -1; break;
-            case 3: mt0 = 14; mt1 = 3; mt2 = 7; break;
-            default: mt0 = 15; mt1 = 5; mt2 = -1; break;
-        }
-        const int mt[3] = {mt0, mt1, mt2};
-        const double* rowp[3];
+        int mt[NS];
+        const double* rowp[NS];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NS; ++i) {
+            mt[i] = ws_tile<OT>(warp, i);
             const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
             rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
         }
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
             const int c0 = p * 8;
-            bool on[3];
-            double cf[3][2];
-            double2 a0[3];
+            bool on[NS];
+            double cf[NS][2];
+            double2 a0[NS];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < NS; ++i) {
                 on[i] = mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p);
                 cf[i][0] = 0.0; cf[i][1] = 0.0;
                 a0[i] = make_double2(0.0, 0.0);
@@ -563,30 +593,30 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
                 for (int kk = 0; kk < 64; kk += 4) {
                     const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
+                    for (int i = 0; i < NS; ++i)
                         if (on[i]) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
                 }
             }
 #pragma unroll 2
             for (int k = 0; k < c0 - 8; k += 4) {
-                const double nb = -Lc[(k + tq) * PL + c0 + gq];
+                const double nb = -Lc[(k + tq) * PLW + c0 + gq];
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PL + mt[i] * 8 + gq], nb);
+                for (int i = 0; i < NS; ++i)
+                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
             }
             if (p >= 1) {
                 named_bar_sync(2, WS_BAR_THREADS);           // columns [c0-8, c0) are in Lc
 #pragma unroll
                 for (int k8 = 0; k8 < 8; k8 += 4) {
                     const int k = c0 - 8 + k8;
-                    const double nb = -Lc[(k + tq) * PL + c0 + gq];
+                    const double nb = -Lc[(k + tq) * PLW + c0 + gq];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PL + mt[i] * 8 + gq], nb);
+                    for (int i = 0; i < NS; ++i)
+                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < NS; ++i)
                 if (on[i])
                     *reinterpret_cast<double2*>(Xr + (mt[i] * 8 + gq) * XP + 2 * tq) =
                         make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
@@ -603,14 +633,14 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
     for (int p = 0; p < 8; ++p) {
         const int c0 = p * 8;
         named_bar_sync(1, WS_BAR_THREADS);
-        double D[8][8], rinv[8], acc[4][8];
+        double D[8][8], rinv[8], acc[NG][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) D[i][j] = Xr[(c0 + i) * XP + j];
-        bool gon[4];
+        bool gon[NG];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
             gon[g] = (32 * g + 31 >= c0) && (g < 2 || has_rows);          // warp-uniform
             if (gon[g]) {
                 const double2* q = reinterpret_cast<const double2*>(Xr + (lane + 32 * g) * XP);
@@ -641,7 +671,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         }
         if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
             if (!gon[g]) continue;
             const int row = lane + 32 * g;
             const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
@@ -654,21 +684,27 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
             }
             if (jrow >= 0) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PL + row] = acc[g][c];
-                double* dst = nullptr;
-                if (g >= 2) dst = Ar + (long long)(row - 64) * lda + c0;
-                else if (b == 0) dst = Lt + (long long)row * ldt + c0;       // L_kk is parked: other CTAs still read A_kk
-                if (dst) {
-#pragma unroll
-                    for (int c = 0; c < 8; c += 2)
-                        *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
-                }
+                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[g][c];
             }
         }
         if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
         if (p < 7) {
-            __threadfence_block();
+            __threadfence_block();       // only shared-memory stores are outstanding here: the global ones follow
             named_bar_arrive(2, WS_BAR_THREADS);
+        }
+        // finished values to global memory, off the critical path (the tensor warps are already released)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int row = lane + 32 * g;
+            if (!gon[g] || row < c0) continue;
+            double* dst = nullptr;
+            if (g >= 2) dst = Ar + (long long)(row - 64) * lda + c0;
+            else if (b == 0) dst = Lt + (long long)row * ldt + c0;           // L_kk is parked: other CTAs still read A_kk
+            if (dst) {
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
+            }
         }
     }
     if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
@@ -731,10 +767,57 @@ __global__ void __launch_bounds__(256) diag_finish_kernel(double* __restrict__ A
     }
 }
 
+// Single-block version for the pipelined inverse (one launch per panel step, right behind it): 64 threads,
+// thread j owns column j of X = L_kk^-1 and solves L_kk X = I by forward substitution with the running sums
+// r_i = sum_{k<i} L_ik x_kj in registers (fully unrolled: every operand address is a compile-time constant, the
+// L entries are warp-uniform shared-memory broadcasts).  No divergence: for k < j the solution entry is an
+// explicit zero.  ~2000 DFMA per thread, a dependent chain of 64 x (DMUL + DFMA).
+#define DP 66    // pitch of the transposed block (even: 16-byte aligned pairs)
+__global__ void __launch_bounds__(64) diag_inv_kernel(double* __restrict__ A, long long lda,
+                                                      const double* __restrict__ Ltmp, long long ldt,
+                                                      double* __restrict__ Linv, long long ldi,
+                                                      double* __restrict__ logdet_part, int blk0) {
+    __shared__ __align__(16) double Lt[64 * DP];      // Lt[k][i] = L[i][k]
+    __shared__ double dinv[64];
+    const int j = threadIdx.x, blk = blk0 + blockIdx.x;
+    const double* Ls = Ltmp + (long long)blk * 64 * ldt + (long long)blk * 64;
+    double* Ab = A + (long long)blk * 64 * lda + (long long)blk * 64;
+    double* Lb = Linv + (long long)blk * 64 * ldi + (long long)blk * 64;
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) {
+        const double v = (j <= r) ? Ls[(long long)r * ldt + j] : 0.0;
+        Lt[j * DP + r] = v;
+        if (j <= r) Ab[(long long)r * lda + j] = v;
+    }
+    __syncthreads();
+    {
+        const double d = Lt[j * DP + j];
+        dinv[j] = 1.0 / d;
+        double lg = log(d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+        if ((j & 31) == 0) Lt[63 * DP + 64 + (j >> 5)] = lg;     // two spare slots of the last padded row
+    }
+    __syncthreads();
+    if (j == 0) logdet_part[blk] = Lt[63 * DP + 64] + Lt[63 * DP + 65];
+    double r[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        const double dk = dinv[k];
+        double x = -r[k] * dk;
+        x = (k == j) ? dk : ((k < j) ? 0.0 : x);
+        Lb[(long long)k * ldi + j] = x;
+#pragma unroll
+        for (int i = k + 1; i < 64; ++i) r[i] = fma(Lt[k * DP + i], x, r[i]);
+    }
+}
+
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
 // 1: warp-specialised panel step, 0: phase-alternating one (MOGP_PANEL_VARIANT overrides the default for A/B runs)
 static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 0;
-extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; return 0; }
+extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
     if (!g_panel_dbg) {
         if (cudaMalloc(&g_panel_dbg, 64 * 8) != cudaSuccess) return -2;
@@ -755,25 +838,58 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
 // panel(s+1) runs concurrently with bulk(s); panel(s+2) waits for bulk(s).  For small matrices
 // the step time is the panel chain, for large ones the chain hides behind the GEMMs.
 // Ltmp is an Np x Np scratch whose diagonal blocks are used; diagonal blocks of Linv get inv(L_kk).
+// Operations of the pipelined triangular inverse, in issue order (see build_inverse_plan).
+struct InvOp { int kind; int lo, mid, hi; int ready; };   // kind 0: inv of diagonal block lo; 1: T = L_BA Linv_AA; 2: Linv_BA = -Linv_BB T
+// Block doubling as a recursion over 64-row block ranges: A = [lo, mid), B = [mid, hi), mid - lo = the largest
+// power of two below hi - lo (the same pairs the level-batched trtri_padded forms).  `ready` = index of the last
+// panel step the operation depends on; depth-first order is both dependency order and non-decreasing in `ready`,
+// so one in-order stream that is released panel by panel can run it.
+static void build_inverse_plan(int lo, int hi, std::vector<InvOp>& ops) {
+    if (hi - lo == 1) { ops.push_back({0, lo, lo, hi, lo}); return; }
+    int s = 1;
+    while (2 * s < hi - lo) s *= 2;
+    const int mid = lo + s;
+    build_inverse_plan(lo, mid, ops);
+    ops.push_back({1, lo, mid, hi, mid - 1});        // needs Linv_AA and the columns of A below it: panel mid-1
+    build_inverse_plan(mid, hi, ops);
+    ops.push_back({2, lo, mid, hi, hi - 1});
+}
+static int g_trtri_pipe = std::getenv("MOGP_TRTRI_PIPE") ? std::atoi(std::getenv("MOGP_TRTRI_PIPE")) : 0;
+extern "C" int mogp_set_trtri_pipe(int v) { g_trtri_pipe = v; ++g_mogp_cfg_epoch; return 0; }
+
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
-                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps) {
+                         int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
+                         bool* fused_inverse) {
+    if (fused_inverse) *fused_inverse = false;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
     const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
-    const size_t smem_w = (size_t)(128 * PZ + 64 * PL + 128 * XP) * sizeof(double);
     if ((ld | ldt) & 1) return cudaErrorInvalidValue;          // 16-byte row accesses
     static bool attr_done = false;
+    static int n_sm = 148;
+    // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
+    // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
-        if (g_panel_variant == 1)
-            potrf_panel_ws_kernel<<<std::max(1, nrb), 256, smem_w, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
+        if (g_panel_variant == 2 && 2 * nrb <= n_sm)
+            potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp);
+        else if (g_panel_variant >= 1)
+            potrf_panel_ws_kernel<8><<<std::max(1, nrb), 256, WsCfg<8>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
     if (!attr_done) {
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<4>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
@@ -880,6 +996,48 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         }
         return finish(last);
     }
+    // Pipelined inverse (single-level sweep only): the diagonal-block inverses and the GEMMs of the block
+    // doubling are issued on a fourth stream as soon as the panel steps they depend on are done, so that only
+    // the last pair of every level is left when the factorisation ends.
+    const bool pipe = fused_inverse != nullptr && g_trtri_pipe != 0 && two && ps->s4 != nullptr && ps->evp != nullptr &&
+                      ldi == ld && ldt == ld;
+    std::vector<InvOp> plan;
+    size_t next_op = 0;
+    if (pipe) {
+        build_inverse_plan(0, nb, plan);
+        if ((e = cudaStreamWaitEvent(ps->s4, ps->ev1[0], 0)) != cudaSuccess) return e;
+    }
+    auto issue_inverse_ops = [&](int s) -> cudaError_t {
+        cudaError_t ee;
+        if ((ee = cudaEventRecord(ps->evp[s], st)) != cudaSuccess) return ee;
+        if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
+        for (; next_op < plan.size() && plan[next_op].ready <= s; ++next_op) {
+            const InvOp& op = plan[next_op];
+            if (op.kind == 0) {
+                diag_inv_kernel<<<1, 64, 0, ps->s4>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, op.lo);
+                MOGP_COUNT(1);
+                if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
+                continue;
+            }
+            const long long o = (long long)op.lo * 64, S = (long long)(op.mid - op.lo) * 64, MB = (long long)(op.hi - op.mid) * 64;
+            GemmArgs g{};
+            if (op.kind == 1) {          // T = L_BA * Linv_AA   (Linv_AA lower triangular: k starts at the column tile)
+                g.A = A + (o + S) * ld + o; g.lda = ld;
+                g.B = Linv + o * ld + o; g.ldb = ld;
+                g.C = Ltmp + (o + S) * ld + o; g.ldc = ld;
+                g.M = (int)MB; g.N = (int)S; g.K = (int)S;
+                g.klo_mode = 1; g.pair = 1; g.alpha = 1.0; g.beta = 0.0;
+            } else {                     // Linv_BA = -Linv_BB * T   (Linv_BB lower triangular: k ends at the row tile)
+                g.A = Linv + (o + S) * ld + (o + S); g.lda = ld;
+                g.B = Ltmp + (o + S) * ld + o; g.ldb = ld;
+                g.C = Linv + (o + S) * ld + o; g.ldc = ld;
+                g.M = (int)MB; g.N = (int)S; g.K = (int)MB;
+                g.khi_mode = 1; g.pair = 2; g.alpha = -1.0; g.beta = 0.0;
+            }
+            if ((ee = launch_gemm(0, 0, g, 1, ps->s4)) != cudaSuccess) return ee;
+        }
+        return cudaSuccess;
+    };
     int last_bulk = -1;
     for (int s = 0; s < nb; ++s) {
         const int64_t k = (int64_t)s * MOGP_NB;
@@ -887,6 +1045,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         if (two && s >= 2 && (e = cudaStreamWaitEvent(st, ps->ev2[s - 2], 0)) != cudaSuccess) return e;
         launch_panel(k, nrb, s > 0 ? 1 : 0, (s == 1) ? g_panel_dbg : nullptr, st);
         MOGP_COUNT(1);
+        if (pipe && (e = issue_inverse_ops(s)) != cudaSuccess) return e;
         const int64_t c0 = k + 2 * MOGP_NB, M = Np - c0;                          // column blocks >= s+2
         if (M > 0) {
             if (two) {
@@ -906,6 +1065,16 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 last_bulk = s;
             }
         }
+    }
+    if (pipe) {
+        // join: bulk stream, panel chain and the inverse stream back into the caller's stream; Linv is complete
+        if (last_bulk >= 0 && (e = cudaStreamWaitEvent(user, ps->ev2[last_bulk], 0)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ps->ev1[ps->nev + 1], st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return e;
+        *fused_inverse = true;
+        return cudaSuccess;
     }
     return finish(two && last_bulk >= 0 ? ps->ev2[last_bulk] : nullptr);
 }

@@ -87,16 +87,31 @@ def spd(n, seed=0, shift=0.5):
 
 
 def sec_potrf(eng):
-    for n in (64, 128, 200, 256, 640, 1024, 2048):
+    print("panel variant (env):", os.environ.get("MOGP_PANEL_VARIANT", "default"), " trtri pipe:", os.environ.get("MOGP_TRTRI_PIPE", "default"))
+    worst = 0.0
+    for n in (64, 128, 200, 256, 640, 1024, 2048, 2176, 4096):
         A = spd(n, n)
         Lref = torch.linalg.cholesky(A)
         Ad = A.cuda().clone()
         info = eng.potrf_(Ad)
         L = torch.tril(Ad).cpu()
-        print("potrf n=%4d info=%d  relerr(L) %.2e  relerr(LL^T) %.2e" % (n, info, rel(L, Lref), rel(L @ L.T, A)))
+        e1, e2 = rel(L, Lref), rel(L @ L.T, A)
+        worst = max(worst, e1, e2) if info == 0 else float("inf")
+        print("potrf n=%4d info=%d  relerr(L) %.2e  relerr(LL^T) %.2e" % (n, info, e1, e2))
     A = spd(300, 5)
     A[150, 150] = -1.0
-    print("potrf bad pivot -> info", eng.potrf_(A.cuda().clone()), "(expect 151)")
+    bad = eng.potrf_(A.cuda().clone())
+    print("potrf bad pivot -> info", bad, "(expect 151)")
+    for n in (128, 384, 1024, 2048, 2176):
+        A = spd(n, n + 1, 0.3)
+        Ad = A.cuda().clone()
+        Linv, Kinv, info = eng.trtri_kinv_(Ad)
+        Lref = torch.linalg.cholesky(A)
+        e = (rel(torch.tril(Ad).cpu(), Lref), rel(torch.tril(Linv).cpu(), torch.linalg.inv(Lref)),
+             rel(torch.tril(Kinv).cpu(), torch.tril(torch.linalg.inv(A))))
+        worst = max(worst, *e) if info == 0 else float("inf")
+        print("trtri n=%4d info=%d relerr(L) %.2e relerr(Linv) %.2e relerr(Kinv) %.2e" % ((n, info) + e))
+    print("POTRF_VERDICT %s worst %.2e" % ("OK" if worst < 1e-9 and bad == 151 else "FAIL", worst))
     for cfg in (0,):
         eng.lib.mogp_set_gemm_config(cfg)
         for n in (2048, 4096, 8192):
@@ -112,7 +127,7 @@ def sec_potrf(eng):
             t_cp, _ = ev_time(cp, reps=3, warm=1)
             t = t_all - t_cp
             print("potrf cfg%d n=%d: %.3f ms  %.2f TFLOP/s" % (cfg, n, t, n ** 3 / 3.0 / t / 1e9))
-            if cfg == 0:
+            if cfg == 0 and os.environ.get("MOGP_PANEL_VARIANT", "0") == "0":
                 def cus():
                     torch.linalg.cholesky(A, out=W)
                 t2, _ = ev_time(cus, reps=3, warm=1)
@@ -185,7 +200,7 @@ def sec_time(eng):
     from mogptk_b200.engine import pack_params
     for cfg in (0,):
         eng.lib.mogp_set_gemm_config(cfg)
-        for name in ("cfg1", "cfg2", "cfg4", "cfg3"):
+        for name in os.environ.get("DIAG_CFGS", "cfg1,cfg2,cfg4,cfg3").split(","):
             g = load_golden(name)
             rows = eng.prepare(g["kind"], g["params"], g["X"], g["y"])
             p = pack_params(g["kind"], g["params"], eng.device)
@@ -197,6 +212,19 @@ def sec_time(eng):
             t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=9, warm=3)
             t0, m0 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], False, check=False), reps=9, warm=3)
             print("   graphs off: loss+grad %.3f ms (min %.3f)" % (tn, mn_))
+            import ctypes as C
+            eng.lib.mogp_set_profile(eng.h, 1)
+            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            st = (C.c_float * 8)()
+            ns = eng.lib.mogp_stage_times(eng.h, st)
+            eng.lib.mogp_set_profile(eng.h, 0)
+            print("   stages (sequential, profile mode): " + " ".join("%s %.3f" % (nm, st[i]) for i, nm in enumerate(
+                ["kbuild", "potrf", "trtri", "solves", "kinv", "grad"][:ns])))
+            lml_ref = float(g["lml"])
+            r = eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=True)
+            lml_got = float(r[0].item())
+            print("   lml %.10f ref %.10f rel %.2e %s" % (lml_got, lml_ref, abs(lml_got - lml_ref) / abs(lml_ref),
+                                                        "LML_OK" if abs(lml_got - lml_ref) <= 1e-8 * abs(lml_ref) else "LML_FAIL"))
             Kout = torch.empty((N, N), dtype=torch.float64, device=eng.device)
             def kb():
                 eng.lib.mogp_kbuild(eng.h, {"MOSM": 0, "SM": 1, "CONV": 2}[g["kind"]], *rows.dims, eng._p(p), eng._p(rows.x),
@@ -211,7 +239,7 @@ def sec_panel(eng):
     import ctypes as C
     buf = (C.c_longlong * 56)()
     eng.lib.mogp_panel_debug(buf)          # arms the timestamps (second panel of the single-level sweep)
-    for variant in (1, 0):
+    for variant in (2, 1, 0):
         eng.lib.mogp_set_panel_variant(variant)
         n = 2048
         A = spd(n, 1).cuda()
@@ -221,15 +249,96 @@ def sec_panel(eng):
         torch.cuda.synchronize()
         eng.lib.mogp_panel_debug(buf)
         t = [int(v) for v in buf]
-        if variant == 1:
-            print("ws panel n=%d: prologue %d | chain done stamps (delta): %s | tensor Xr-ready (rel. start): %s | total %d cycles" % (
-                n, t[1] - t[0], [t[2 + p] - (t[1] if p == 0 else t[1 + p]) for p in range(8)],
+        if variant >= 1:
+            print("ws%d panel n=%d: prologue %d | chain done stamps (delta): %s | tensor Xr-ready (rel. start): %s | total %d cycles" % (
+                variant, n, t[1] - t[0], [t[2 + p] - (t[1] if p == 0 else t[1 + p]) for p in range(8)],
                 [t[16 + p] - t[0] for p in range(8)], t[10] - t[0]))
             print("   chain u(p) = done(p) - Xr-ready(p): %s ; exchange = Xr-ready(p+1) - done(p): %s" % (
                 [t[2 + p] - t[16 + p] for p in range(8)], [t[17 + p] - t[2 + p] for p in range(7)]))
         else:
             print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
-    eng.lib.mogp_set_panel_variant(1)
+    eng.lib.mogp_set_panel_variant(int(os.environ.get("MOGP_PANEL_VARIANT", "0")))
+
+
+def sec_exp(eng):
+    """A/B of the Cholesky panel variants and the pipelined inverse in one process.
+    EXP_COMBOS="variant:pipe,..." (default 0:0); prints a verdict line per combination."""
+    import ctypes as C
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params
+    combos = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("EXP_COMBOS", "0:0").split(",")]
+    names = os.environ.get("DIAG_CFGS", "cfg2,cfg4,cfg3").split(",")
+    prepared = {}
+    for name in names:
+        g = load_golden(name)
+        prepared[name] = (g, eng.prepare(g["kind"], g["params"], g["X"], g["y"]), pack_params(g["kind"], g["params"], eng.device),
+                          torch.tensor(g["sigma"], device=eng.device))
+    mats = {n: spd(n, n) for n in (128, 200, 640, 2048, 2176)}
+    refs = {n: torch.linalg.cholesky(A) for n, A in mats.items()}
+    invs = {n: torch.linalg.inv(refs[n]) for n in (128, 640, 2048, 2176)}
+    for (v, pipe) in combos:
+        eng.lib.mogp_set_panel_variant(v)
+        eng.lib.mogp_set_trtri_pipe(pipe)
+        tag = "v%d pipe%d" % (v, pipe)
+        worst = 0.0
+        for n, A in mats.items():
+            Ad = A.cuda().clone()
+            info = eng.potrf_(Ad)
+            e1 = rel(torch.tril(Ad).cpu(), refs[n])
+            worst = max(worst, e1) if info == 0 else float("inf")
+            print("[%s] potrf n=%4d info=%d relerr(L) %.2e" % (tag, n, info, e1))
+        Ab = spd(300, 5)
+        Ab[150, 150] = -1.0
+        bad = eng.potrf_(Ab.cuda().clone())
+        for n in invs:
+            Ad = mats[n].cuda().clone()
+            Linv, Kinv, info = eng.trtri_kinv_(Ad)
+            e = (rel(torch.tril(Ad).cpu(), refs[n]), rel(torch.tril(Linv).cpu(), invs[n]),
+                 rel(torch.tril(Kinv).cpu(), torch.tril(invs[n].T @ invs[n])))
+            worst = max(worst, *e) if info == 0 else float("inf")
+            print("[%s] trtri n=%4d info=%d relerr(L) %.2e relerr(Linv) %.2e relerr(Kinv) %.2e" % ((tag, n, info) + e))
+        print("[%s] VERDICT %s worst %.2e bad-pivot info %d (expect 151)" % (tag, "OK" if worst < 1e-9 and bad == 151 else "FAIL", worst, bad))
+        for n in (2048, 4096, 8192):
+            A = spd(n, 1).cuda()
+            W = A.clone()
+
+            def run():
+                W.copy_(A)
+                eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+
+            def cp():
+                W.copy_(A)
+            t_all, _ = ev_time(run, reps=5, warm=2)
+            t_cp, _ = ev_time(cp, reps=5, warm=2)
+            t = t_all - t_cp
+            print("[%s] potrf n=%d: %.3f ms  %.2f TFLOP/s" % (tag, n, t, n ** 3 / 3.0 / t / 1e9))
+        for name in names:
+            g, rows, p, sig = prepared[name]
+            N = g["X"].shape[0]
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=11, warm=4)
+            eng.lib.mogp_set_profile(eng.h, 1)
+            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            st = (C.c_float * 8)()
+            ns = eng.lib.mogp_stage_times(eng.h, st)
+            eng.lib.mogp_set_profile(eng.h, 0)
+            r = eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            lml_got, lml_ref = float(r[0].item()), float(g["lml"])
+            gerr = 0.0
+            P = p.numel()
+            from mogptk_b200.engine import unpack_grads
+            C_, Q, D = rows.dims
+            gd = unpack_grads(g["kind"], C_, Q, D, r[2:2 + P].cpu())
+            for k, got in gd.items():
+                ref = g["gc_" + k]
+                gerr = max(gerr, float(np.abs(got.numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-12)))
+            ok = abs(lml_got - lml_ref) <= 1e-8 * abs(lml_ref) and gerr <= 1e-6 and int(r[1].item()) == 0
+            print("[%s] step %-5s N=%d: %.3f ms (min %.3f) -> %.1f it/s | stages %s | lml rel %.1e grad %.1e %s" % (
+                tag, name, N, t1, m1, 1e3 / t1, " ".join("%s %.3f" % (nm, st[i]) for i, nm in enumerate(
+                    ["kbuild", "potrf", "trtri", "solves", "kinv", "grad"][:ns])),
+                abs(lml_got - lml_ref) / abs(lml_ref), gerr, "STEP_OK" if ok else "STEP_FAIL"))
+        sys.stdout.flush()
+    eng.lib.mogp_set_panel_variant(0)
+    eng.lib.mogp_set_trtri_pipe(0)
 
 
 def sec_gemmk(eng):
@@ -302,7 +411,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
