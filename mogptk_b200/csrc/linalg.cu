@@ -815,8 +815,10 @@ __global__ void __launch_bounds__(64) diag_inv_kernel(double* __restrict__ A, lo
 }
 
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
-// 1: warp-specialised panel step, 0: phase-alternating one (MOGP_PANEL_VARIANT overrides the default for A/B runs)
-static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 0;
+// 0: phase-alternating panel step; 1: warp-specialised, 64 own rows per CTA; 2 (default): warp-specialised with 32 own
+// rows per CTA while twice the CTAs fit one wave.  Measured on B200 (profiles/r01_panel_variants.txt): potrf N=2048
+// 0.721 / 0.657 / 0.538 ms, N=8192 7.88 / 7.72 / 7.68 ms.  MOGP_PANEL_VARIANT overrides the default for A/B runs.
+static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 2;
 extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
     if (!g_panel_dbg) {
