@@ -710,6 +710,229 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
     if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
 }
 
+// ---------------------------------------------------------------------------- decoupled warp-specialised panel step
+// Second generation of the schedule above (measured there: per 8-column sub-panel the chain took ~2000 cycles and
+// then waited ~800 more for the tensor warps to fold the just-finished columns into the next block -- the two
+// sides still alternated).  Here the tensor warps run one full sub-panel AHEAD of the chain: for sub-panel p they
+// only accumulate the previous panel's update and the columns finished through sub-panel p-2, into a double-
+// buffered exchange tile.  The chain warp applies the remaining rank-8 update (the columns it finished itself one
+// iteration earlier) with scalar FMAs that fill the latency shadows of the pivot chain; the 8x8 pivot block gets
+// that update cooperatively (two entries per lane) so the pivot chain can start after ~150 cycles.  No barrier
+// round trip is left on the critical path.  Barriers: 1,2 = "Xr[parity] full" (tensor arrive, chain sync);
+// 3,4 = "sub-panel of this parity done" (chain arrives, tensor warps sync two iterations later).
+// Lc carries 8 zero columns in front so that sub-panel 0 runs the same straight-line code (no p == 0 branch);
+// row groups are never skipped (finished rows compute garbage that is masked at the stores) so that the whole
+// chain iteration is one basic block for the instruction scheduler.
+template <int OT>
+struct Ws2Cfg {
+    static constexpr int ROWS = 64 + 8 * OT;
+    static constexpr int NS = OT == 8 ? 3 : 2;
+    static constexpr int NG = ROWS / 32;
+    static constexpr int PLW = OT == 8 ? 132 : 100;
+    static constexpr size_t SMEM = (size_t)(ROWS * PZ + 72 * PLW + 2 * ROWS * XP + 64) * sizeof(double);
+};
+
+template <int OT>
+__global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restrict__ A, long long lda,
+                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
+                                                                 int has_prev, int32_t* info, long long* dbg) {
+    using Cfg = Ws2Cfg<OT>;
+    constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
+    extern __shared__ __align__(16) double sm[];
+    double* ZZ = sm;                        // [ROWS][PZ]   previous-panel values (diagonal-block rows, own rows)
+    double* Lc = sm + ROWS * PZ + 8 * PLW;  // [-8..64][PLW] finished columns, column-major; columns -8..-1 are zero
+    double* Xr = Lc + 64 * PLW;             // [2][ROWS][XP] tensor warps -> chain exchange, double buffered
+    double* Dsm = Xr + 2 * ROWS * XP;       // [8][8]        updated pivot block
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const bool has_rows = b < nrb;          // nrb counts blocks of 8*OT rows here
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const double* Ad = A + (long long)k0 * lda + k0;
+    double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
+    if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
+    if (has_prev) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = tid + it * 256;              // 2048 16-byte chunks per 64 x 64 tile
+            const int r = idx >> 5, cc = idx & 31;
+            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
+            if (has_rows && it < OT) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
+        }
+        cp_async_commit();
+    }
+    for (int i = tid; i < 8 * PLW; i += 256) Lc[i - 8 * PLW] = 0.0;
+    if (has_prev) cp_async_wait<0>();
+    __syncthreads();
+    if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
+    if (warp == 4) return;
+
+    if (warp != 0) {
+        // ------------------------------------------------------------------ tensor warps (one sub-panel ahead)
+        int mt[NS];
+        const double* rowp[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            mt[i] = ws_tile<OT>(warp, i);
+            const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
+            rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
+        }
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int c0 = p * 8;
+            double* Xp = Xr + (p & 1) * ROWS * XP;
+            bool on[NS];
+            double cf[NS][2];
+            double2 a0[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                on[i] = mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p);
+                cf[i][0] = 0.0; cf[i][1] = 0.0;
+                a0[i] = make_double2(0.0, 0.0);
+                if (on[i]) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
+            }
+            if (has_prev) {
+#pragma unroll 4
+                for (int kk = 0; kk < 64; kk += 4) {
+                    const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
+#pragma unroll
+                    for (int i = 0; i < NS; ++i)
+                        if (on[i]) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
+                }
+            }
+            // columns finished through sub-panel p-3 were published before this warp's previous barrier wait
+#pragma unroll 2
+            for (int k = 0; k < c0 - 16; k += 4) {
+                const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+            }
+            if (p >= 2) {
+                named_bar_sync(3 + (p & 1), WS_BAR_THREADS);       // sub-panel p-2 is in Lc (and Xr[p&1] has been consumed)
+#pragma unroll
+                for (int k8 = 0; k8 < 8; k8 += 4) {
+                    const int k = c0 - 16 + k8;
+                    const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+                    for (int i = 0; i < NS; ++i)
+                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if (on[i])
+                    *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
+                        make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+            if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
+            __threadfence_block();
+            named_bar_arrive(1 + (p & 1), WS_BAR_THREADS);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- chain warp: lane owns rows lane + 32 g
+    double* Lt = Ltmp + (long long)k0 * ldt + k0;
+    const int pi = lane >> 3, pj = lane & 7;      // cooperative pivot-block update: entries (pi, pj) and (pi + 4, pj)
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = p * 8;
+        const double* Xp = Xr + (p & 1) * ROWS * XP;
+        const double* Lprev = Lc + (c0 - 8) * PLW;          // the 8 columns finished in the previous iteration (zeros for p = 0)
+        named_bar_sync(1 + (p & 1), WS_BAR_THREADS);
+        {   // pivot block: D = Xr block - Lp Lp^T with Lp = L[c0..c0+8)[c0-8..c0)
+            double d0 = Xp[(c0 + pi) * XP + pj], d1 = Xp[(c0 + pi + 4) * XP + pj];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double lj = Lprev[c * PLW + c0 + pj];
+                d0 = fma(-Lprev[c * PLW + c0 + pi], lj, d0);
+                d1 = fma(-Lprev[c * PLW + c0 + pi + 4], lj, d1);
+            }
+            Dsm[pi * 8 + pj] = d0;
+            Dsm[(pi + 4) * 8 + pj] = d1;
+        }
+        double acc[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const double2* q = reinterpret_cast<const double2*>(Xp + (lane + 32 * g) * XP);
+            const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+            acc[g][0] = v0.x; acc[g][1] = v0.y; acc[g][2] = v1.x; acc[g][3] = v1.y;
+            acc[g][4] = v2.x; acc[g][5] = v2.y; acc[g][6] = v3.x; acc[g][7] = v3.y;
+        }
+        __syncwarp();
+        double D[8][8], rinv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
+        // rank-8 update of every row with the columns of the previous iteration (independent of the pivot chain)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2* bp = reinterpret_cast<const double2*>(Lprev + c * PLW + c0);
+            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double pv = -Lprev[c * PLW + lane + 32 * g];
+                acc[g][0] = fma(pv, b0.x, acc[g][0]); acc[g][1] = fma(pv, b0.y, acc[g][1]);
+                acc[g][2] = fma(pv, b1.x, acc[g][2]); acc[g][3] = fma(pv, b1.y, acc[g][3]);
+                acc[g][4] = fma(pv, b2.x, acc[g][4]); acc[g][5] = fma(pv, b2.y, acc[g][5]);
+                acc[g][6] = fma(pv, b3.x, acc[g][6]); acc[g][7] = fma(pv, b3.y, acc[g][7]);
+            }
+        }
+        int badcol = 8;                       // first non-positive pivot of this block (8 = none)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double d = D[c][c];
+            const bool ok = d > 0.0;
+            badcol = (!ok && badcol == 8) ? c : badcol;
+            d = ok ? d : 1.0;
+            const double ri = rsqrt_pos(d);
+            rinv[c] = ri;
+            D[c][c] = d * ri;
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
+#pragma unroll
+            for (int i = c + 1; i < 8; ++i)
+#pragma unroll
+                for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
+        }
+        if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int row = lane + 32 * g;
+            const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double xc = acc[g][c] * rinv[c];
+                acc[g][c] = (c <= jrow) ? xc : 0.0;
+#pragma unroll
+                for (int cc = c + 1; cc < 8; ++cc) acc[g][cc] = fma(-xc, D[cc][c], acc[g][cc]);
+            }
+            if (jrow >= 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[g][c];
+            }
+        }
+        if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
+        __threadfence_block();           // only shared-memory stores are outstanding here: the global ones follow
+        if (p < 6) named_bar_arrive(3 + (p & 1), WS_BAR_THREADS);
+        // finished values to global memory, off the critical path
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int row = lane + 32 * g;
+            if (row < c0 || (g >= 2 && !has_rows)) continue;
+            double* dst = nullptr;
+            if (g >= 2) dst = Ar + (long long)(row - 64) * lda + c0;
+            else if (b == 0) dst = Lt + (long long)row * ldt + c0;           // L_kk is parked: other CTAs still read A_kk
+            if (dst) {
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
+            }
+        }
+    }
+    if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
+}
+
 // After the sweep, for every diagonal block at once: move L_kk from Ltmp into A, invert it by
 // recursive doubling  inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]]  (s = 1,2,..,32) into
 // the diagonal block of Linv (explicit zeros above the diagonal), and emit sum(log diag).
@@ -873,7 +1096,9 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
     // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
-        if (g_panel_variant == 2 && 2 * nrb <= n_sm)
+        if (g_panel_variant == 3 && 2 * nrb <= n_sm)
+            potrf_panel_ws2_kernel<4><<<std::max(1, 2 * nrb), 256, Ws2Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp);
+        else if (g_panel_variant >= 2 && 2 * nrb <= n_sm)
             potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp);
         else if (g_panel_variant >= 1)
             potrf_panel_ws_kernel<8><<<std::max(1, nrb), 256, WsCfg<8>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
@@ -887,6 +1112,11 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ws2Cfg<4>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws2_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<4>::SMEM);
