@@ -52,13 +52,20 @@ _SIGNATURES = {
 _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
     "mogp_set_graphs": (None, [C.c_int]),
+    "mogp_set_graph_max_np": (None, [C.c_longlong]),
     "mogp_set_small_tile_threshold": (None, [C.c_longlong]),
     "mogp_launch_count": (C.c_longlong, []),
     "mogp_panel_debug": (C.c_int, [C.POINTER(C.c_longlong)]),
     "mogp_probe_latency": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_probe_contention": (C.c_int, [C.POINTER(C.c_double)]),
+    "mogp_probe_issue": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_set_panel_variant": (C.c_int, [C.c_int]),
     "mogp_set_trtri_pipe": (C.c_int, [C.c_int]),
+    "mogp_set_panel_nofence": (C.c_int, [C.c_int]),
+    "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
+    "mogp_set_panel_pdl": (C.c_int, [C.c_int]),
+    "mogp_get_panel_pdl": (C.c_int, []),
+    "mogp_panel_spans": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "mogp_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mogp_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mogp_host_pair_comps": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp]),

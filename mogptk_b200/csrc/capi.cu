@@ -77,6 +77,12 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
         h->ps.ev3 = new cudaEvent_t[nev + 2]();
         h->ps.evp = new cudaEvent_t[nev + 2]();
         if ((e = cudaStreamCreateWithPriority(&h->ps.s4, cudaStreamNonBlocking, plo + (phi - plo) / 2)) != cudaSuccess) return fail(e);
+        for (int i = 0; i < 8; ++i)
+            if ((e = cudaStreamCreateWithPriority(&h->ps.sl[i], cudaStreamNonBlocking, plo + (phi - plo) / 2)) != cudaSuccess) return fail(e);
+        h->ps.nevq = 3 * nev + 16;
+        h->ps.evq = new cudaEvent_t[h->ps.nevq]();
+        for (int i = 0; i < h->ps.nevq; ++i)
+            if ((e = cudaEventCreateWithFlags(&h->ps.evq[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
         for (int i = 0; i < nev + 2; ++i) {
             if ((e = cudaEventCreateWithFlags(&h->ps.evp[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
             if ((e = cudaEventCreateWithFlags(&h->ps.ev1[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -114,6 +120,12 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
             if (h->ps.evp && h->ps.evp[i]) cudaEventDestroy(h->ps.evp[i]);
         }
     delete[] h->ps.evp;
+    if (h->ps.evq)
+        for (int i = 0; i < h->ps.nevq; ++i)
+            if (h->ps.evq[i]) cudaEventDestroy(h->ps.evq[i]);
+    delete[] h->ps.evq;
+    for (int i = 0; i < 8; ++i)
+        if (h->ps.sl[i]) cudaStreamDestroy(h->ps.sl[i]);
     delete[] h->ps.ev1;
     delete[] h->ps.ev2;
     delete[] h->ps.ev3;
@@ -375,6 +387,10 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
 }
 
 static int g_use_graphs = -1;
+// Largest padded size whose step is replayed as a CUDA graph.  With programmatic dependent launches between the panel steps
+// the replayed graph wins at every size we run (cfg4 N=4096: 3.34 ms against 3.53 ms eagerly; cfg3 N=8192: equal).
+static long long g_graph_max_np = std::getenv("MOGP_GRAPH_MAX_NP") ? std::atoll(std::getenv("MOGP_GRAPH_MAX_NP")) : (1ll << 20);
+extern "C" void mogp_set_graph_max_np(long long v) { g_graph_max_np = v; }
 extern "C" void mogp_set_graphs(int on) { g_use_graphs = on ? 1 : 0; }
 
 extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
@@ -420,9 +436,9 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     double* gdv = gy + N;
     double* gout = gdv + N;
 
-    // Replayed graphs lose the stream priorities the Cholesky look-ahead relies on (measured: 7% slower at
-    // N=4096, 2% at N=8192) while the launch-latency savings only matter for small problems.
-    const bool graphs = g_use_graphs == 1 && !h->profile && Np <= 3072;
+    // (Before the panel steps were chained with programmatic dependent launches, graphs were only used up to Np = 3072:
+    // a replayed graph loses the stream priorities of the look-ahead, which cost 7% at N = 4096.)
+    const bool graphs = g_use_graphs == 1 && !h->profile && Np <= g_graph_max_np;
     if (!graphs) {
         if (x_dev != h->xbuf)
             MOGP_CHECK(h, cudaMemcpyAsync(h->xbuf, x_dev, (size_t)N * D * 8, cudaMemcpyDeviceToDevice, st));

@@ -92,6 +92,9 @@ struct PotrfStreams {          // look-ahead resources owned by the handle
     cudaEvent_t* ev2 = nullptr;   // [nev + 2] recorded on s2 after bulk updates
     cudaStream_t s4 = nullptr;    // medium priority: triangular inverse pipelined behind the panel chain
     cudaEvent_t* evp = nullptr;   // [nev + 2] recorded on s1 after every panel step (pipelined inverse)
+    cudaStream_t sl[8] = {};      // medium priority: one stream per doubling level of the pipelined inverse
+    cudaEvent_t* evq = nullptr;   // [nevq] completion events of the pipelined inverse's operations (+ 8 join events)
+    int nevq = 0;
     int nev = 0;
 };
 struct mogp_handle_s {

@@ -497,8 +497,111 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
 // which brings it level with the chain; used while twice the CTAs still fit one wave).
 #define XP 10    // pitch of the exchange tile (16-byte aligned rows, conflict-free 128-bit row reads)
 #define WS_BAR_THREADS 224      // chain warp + six tensor warps
+// Programmatic dependent launch: a panel step launched with the programmatic-serialization attribute may start while
+// the previous step is still running (its launch latency, ~4 us measured, is what this hides); it must not touch
+// anything the previous step produces before pdl_wait() returns.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Kernel spans as seen from inside (all CTAs), one slot per panel step: g_span[2 s] = earliest entry, g_span[2 s + 1] =
+// latest warp exit (ns, global timer).  Off unless armed through mogp_panel_spans (a constant-bank flag).
+__constant__ int c_span_on = 0;
+__device__ unsigned long long g_span[2 * 136];
+__device__ __forceinline__ void span_enter(int k0) {
+    if (c_span_on && threadIdx.x == 0) atomicMin(&g_span[2 * (k0 >> 6)], global_ns());
+}
+__device__ __forceinline__ void span_exit(int k0) {
+    if (c_span_on && (threadIdx.x & 31) == 0) atomicMax(&g_span[2 * (k0 >> 6) + 1], global_ns());
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// One sub-panel of a tensor warp, with the set of live row tiles fixed at compile time (MASK bit i = slot i live).
+// A DMMA under a run-time predicate gets a WARPSYNC in front of it, which serialises it behind the previous
+// one (measured: ~65 cycles per DMMA and warp instead of 32, i.e. half the tensor rate); with the predicate
+// resolved at compile time the DMMAs of a k-step issue back to back.
+//   E = [A entries] - Z Zpiv^T (previous panel, if any) - L[:, 0:k_all) L[piv, 0:k_all)^T,
+// columns [0, k_pre) of Lc are already published, columns [k_pre, k_all) only after barrier `wait_id` (skipped when
+// wait_id < 0).  The 8-column block goes to Xp, then barrier `arrive_id` is signalled.
+template <int NS, int MASK, int PLW>
+__device__ __forceinline__ void ws_tensor_subpanel(const double* ZZ, const double* Lc, double* Xp, const int (&mt)[NS],
+                                                   const double* const (&rowp)[NS], int c0, int has_prev, int k_pre,
+                                                   int k_all, int wait_id, int arrive_id, int bar_threads, bool use_fence,
+                                                   int gq, int tq, long long* ts, int wait_threads = 0, int arrive_id2 = -1) {
+    if (wait_threads == 0) wait_threads = bar_threads;
+    if (ts) ts[0] = clock64();
+    double cf[NS][2];
+    double2 a0[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        cf[i][0] = 0.0; cf[i][1] = 0.0;
+        a0[i] = make_double2(0.0, 0.0);
+        if ((MASK >> i) & 1) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
+    }
+    if (has_prev) {
+#pragma unroll 4
+        for (int kk = 0; kk < 64; kk += 4) {
+            const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
+        }
+    }
+    if (ts) ts[1] = clock64() + (cf[0][0] == 1.2345e300 ? 1 : 0);      // (data dependence: after the accumulation)
+#pragma unroll 2
+    for (int k = 0; k < k_pre; k += 4) {
+        const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+            if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+    }
+    if (ts) ts[2] = clock64() + (cf[0][0] == 1.2345e300 ? 1 : 0);
+    if (wait_id >= 0) {
+        named_bar_sync(wait_id, wait_threads);
+        if (ts) ts[3] = clock64();
+#pragma unroll 2
+        for (int k = k_pre; k < k_all; k += 4) {
+            const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+        if ((MASK >> i) & 1)
+            *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
+                make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+    if (ts) ts[4] = clock64() + (cf[0][0] == 1.2345e300 ? 1 : 0);
+    if (use_fence) __threadfence_block();
+    named_bar_arrive(arrive_id, bar_threads);
+    if (arrive_id2 >= 0) named_bar_arrive(arrive_id2, bar_threads);
+    if (ts) ts[5] = clock64();
+}
+#define WS_TENSOR_CASE(M)                                                                                          \
+    case M:                                                                                                        \
+        ws_tensor_subpanel<NS, (M) & ((1 << NS) - 1), PLW>(ZZ, Lc, Xp, mt, rowp, c0, has_prev, k_pre, k_all, wait_id,  \
+                                                           arrive_id, bar_threads, use_fence, gq, tq, ts, wait_threads, arrive_id2); \
+        break;
+template <int NS, int PLW>
+__device__ __forceinline__ void ws_tensor_dispatch(int mask, const double* ZZ, const double* Lc, double* Xp,
+                                                   const int (&mt)[NS], const double* const (&rowp)[NS], int c0,
+                                                   int has_prev, int k_pre, int k_all, int wait_id, int arrive_id,
+                                                   int bar_threads, bool use_fence, int gq, int tq, long long* ts,
+                                                   int wait_threads = 0, int arrive_id2 = -1) {
+    switch (mask) {
+        WS_TENSOR_CASE(0) WS_TENSOR_CASE(1) WS_TENSOR_CASE(2) WS_TENSOR_CASE(3)
+        default:
+            if (NS == 3) {
+                switch (mask) { WS_TENSOR_CASE(4) WS_TENSOR_CASE(5) WS_TENSOR_CASE(6) WS_TENSOR_CASE(7) default: break; }
+            }
+            break;
+    }
+}
 
 template <int OT>
 struct WsCfg {
@@ -536,7 +639,9 @@ __device__ __forceinline__ int ws_tile(int warp, int slot) {
 template <int OT>
 __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restrict__ A, long long lda,
                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                                int has_prev, int32_t* info, long long* dbg) {
+                                                                int flags, int32_t* info, long long* dbg) {
+    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
+    const bool use_fence = (flags & 2) == 0;
     using Cfg = WsCfg<OT>;
     constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
     extern __shared__ __align__(16) double sm[];
@@ -549,6 +654,8 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const double* Ad = A + (long long)k0 * lda + k0;
     double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
+    span_enter(k0);
+    pdl_wait();                       // everything below reads what the previous panel step (and the updates before it) wrote
     if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
     if (has_prev) {
 #pragma unroll
@@ -562,8 +669,9 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         cp_async_wait<0>();
     }
     __syncthreads();
+    pdl_launch_dependents();          // the next panel step may be scheduled now (it parks in pdl_wait until this grid is done)
     if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
-    if (warp == 4) return;
+    if (warp == 4) { span_exit(k0); return; }
 
     if (warp != 0) {
         // ------------------------------------------------------------------ tensor warps
@@ -578,52 +686,18 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
             const int c0 = p * 8;
-            bool on[NS];
-            double cf[NS][2];
-            double2 a0[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                on[i] = mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p);
-                cf[i][0] = 0.0; cf[i][1] = 0.0;
-                a0[i] = make_double2(0.0, 0.0);
-                if (on[i]) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
-            }
-            if (has_prev) {
-#pragma unroll 4
-                for (int kk = 0; kk < 64; kk += 4) {
-                    const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        if (on[i]) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
-                }
-            }
-#pragma unroll 2
-            for (int k = 0; k < c0 - 8; k += 4) {
-                const double nb = -Lc[(k + tq) * PLW + c0 + gq];
-#pragma unroll
-                for (int i = 0; i < NS; ++i)
-                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
-            }
-            if (p >= 1) {
-                named_bar_sync(2, WS_BAR_THREADS);           // columns [c0-8, c0) are in Lc
-#pragma unroll
-                for (int k8 = 0; k8 < 8; k8 += 4) {
-                    const int k = c0 - 8 + k8;
-                    const double nb = -Lc[(k + tq) * PLW + c0 + gq];
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
-                }
-            }
+            int mask = 0;
 #pragma unroll
             for (int i = 0; i < NS; ++i)
-                if (on[i])
-                    *reinterpret_cast<double2*>(Xr + (mt[i] * 8 + gq) * XP + 2 * tq) =
-                        make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+                if (mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p)) mask |= 1 << i;
+            double* Xp = Xr;
+            // columns [0, c0-8) were published before this warp's previous barrier wait; [c0-8, c0) follow barrier 2
+            long long* ts = (dbg && warp == 1 && lane == 0 && b == 0 && (p == 0 || p == 3)) ? dbg + (p == 0 ? 40 : 48) : nullptr;
+            ws_tensor_dispatch<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 8, c0, p >= 1 ? 2 : -1, 1,
+                                        WS_BAR_THREADS, use_fence, gq, tq, ts);
             if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
-            __threadfence_block();
-            named_bar_arrive(1, WS_BAR_THREADS);
         }
+        span_exit(k0);
         return;
     }
 
@@ -689,7 +763,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         }
         if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
         if (p < 7) {
-            __threadfence_block();       // only shared-memory stores are outstanding here: the global ones follow
+            if (use_fence) __threadfence_block();       // only shared-memory stores are outstanding here: the global ones follow
             named_bar_arrive(2, WS_BAR_THREADS);
         }
         // finished values to global memory, off the critical path (the tensor warps are already released)
@@ -708,6 +782,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         }
     }
     if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
+    span_exit(k0);
 }
 
 // ---------------------------------------------------------------------------- decoupled warp-specialised panel step
@@ -735,7 +810,9 @@ struct Ws2Cfg {
 template <int OT>
 __global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restrict__ A, long long lda,
                                                                  double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                                 int has_prev, int32_t* info, long long* dbg) {
+                                                                 int flags, int32_t* info, long long* dbg) {
+    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
+    const bool use_fence = (flags & 2) == 0;
     using Cfg = Ws2Cfg<OT>;
     constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
     extern __shared__ __align__(16) double sm[];
@@ -824,7 +901,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restr
                     *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
                         make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
             if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
-            __threadfence_block();
+            if (use_fence) __threadfence_block();
             named_bar_arrive(1 + (p & 1), WS_BAR_THREADS);
         }
         return;
@@ -913,7 +990,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restr
             }
         }
         if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
-        __threadfence_block();           // only shared-memory stores are outstanding here: the global ones follow
+        if (use_fence) __threadfence_block();           // only shared-memory stores are outstanding here: the global ones follow
         if (p < 6) named_bar_arrive(3 + (p & 1), WS_BAR_THREADS);
         // finished values to global memory, off the critical path
 #pragma unroll
@@ -931,6 +1008,280 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restr
         }
     }
     if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
+}
+
+// ---------------------------------------------------------------------------- two scalar warps (pivot + rows)
+// Third generation.  Measured on the decoupled kernel above: with the tensor warps out of the way the chain warp
+// still needed ~2800 cycles per sub-panel for ~500 fp64 instructions, i.e. ~5.5 cycles per instruction although
+// 24 independent FMA chains were available -- a lone warp reaches only about half of its sub-partition's fp64
+// issue rate (the same holds for DMMA).  Here the scalar work is split over the two warps of sub-partition 0:
+//   warp 0 (pivot warp): cooperative update of the 8x8 pivot block, its factorisation, and the 32-row group that
+//                        holds the current and next pivot rows (group p/4 of the diagonal block);
+//   warp 4 (row warp):   every other live row (the other diagonal-block group while p < 4, and the own rows).
+// The pivot warp publishes the factored block (double buffered) and moves on; the row warp trails it by about
+// one pivot phase and is only waited for by the tensor warps two sub-panels later (and by the pivot warp once,
+// when the pivot rows move from group 0 to group 1 at p = 4).
+// Barriers (named, counts in threads): 1,2 and 8,9 "Xr[parity] full" for the pivot warp and for the row warp (192
+// tensor arrive + 32 sync each: one shared barrier would hold the pivot warp back until the row warp got there);
+// 3,4 "sub-panel of this parity in Lc" (64 scalar arrive, 192 tensor sync); 5,6 "factored pivot block
+// published" (32 arrive, 32 sync); 7 "row warp finished sub-panel 3" (32 arrive, 32 sync).
+template <int OT>
+struct Ws3Cfg {
+    static constexpr int ROWS = 64 + 8 * OT;
+    static constexpr int NS = OT == 8 ? 3 : 2;
+    static constexpr int NG = ROWS / 32;
+    static constexpr int PLW = OT == 8 ? 132 : 100;
+    static constexpr size_t SMEM = (size_t)(ROWS * PZ + 72 * PLW + 2 * ROWS * XP + 64 + 2 * 48) * sizeof(double);
+};
+
+// acc[0..8) -= sum_c L[row][c0-8+c] * L[c0+.][c0-8+c]   (the columns of the previous sub-panel; zeros for p = 0)
+__device__ __forceinline__ void rank8_update(double (&acc)[8], const double* Lprev, int plw, int c0, int row) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double2* bp = reinterpret_cast<const double2*>(Lprev + c * plw + c0);
+        const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+        const double pv = -Lprev[c * plw + row];
+        acc[0] = fma(pv, b0.x, acc[0]); acc[1] = fma(pv, b0.y, acc[1]);
+        acc[2] = fma(pv, b1.x, acc[2]); acc[3] = fma(pv, b1.y, acc[3]);
+        acc[4] = fma(pv, b2.x, acc[4]); acc[5] = fma(pv, b2.y, acc[5]);
+        acc[6] = fma(pv, b3.x, acc[6]); acc[7] = fma(pv, b3.y, acc[7]);
+    }
+}
+__device__ __forceinline__ void load_row8(double (&acc)[8], const double* src) {
+    const double2* q = reinterpret_cast<const double2*>(src);
+    const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+    acc[0] = v0.x; acc[1] = v0.y; acc[2] = v1.x; acc[3] = v1.y;
+    acc[4] = v2.x; acc[5] = v2.y; acc[6] = v3.x; acc[7] = v3.y;
+}
+// forward substitution of one row against the factored pivot block; entries right of the diagonal of a pivot row
+// are masked (jrow = row - c0; >= 8 for rows below the block)
+__device__ __forceinline__ void subst_row8(double (&acc)[8], const double (&D)[8][8], const double (&rinv)[8], int jrow) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double xc = acc[c] * rinv[c];
+        acc[c] = (c <= jrow) ? xc : 0.0;
+#pragma unroll
+        for (int cc = c + 1; cc < 8; ++cc) acc[cc] = fma(-xc, D[cc][c], acc[cc]);
+    }
+}
+
+template <int OT>
+__global__ void __launch_bounds__(256, 1) potrf_panel_ws3_kernel(double* __restrict__ A, long long lda,
+                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
+                                                                 int flags, int32_t* info, long long* dbg) {
+    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
+    const bool use_fence = (flags & 2) == 0;
+    using Cfg = Ws3Cfg<OT>;
+    constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
+    extern __shared__ __align__(16) double sm[];
+    double* ZZ = sm;                        // [ROWS][PZ]   previous-panel values (diagonal-block rows, own rows)
+    double* Lc = sm + ROWS * PZ + 8 * PLW;  // [-8..64][PLW] finished columns, column-major; columns -8..-1 are zero
+    double* Xr = Lc + 64 * PLW;             // [2][ROWS][XP] tensor warps -> scalar warps exchange, double buffered
+    double* Dsm = Xr + 2 * ROWS * XP;       // [8][8]        updated pivot block (pivot warp only)
+    double* Dfac = Dsm + 64;                // [2][48]       factored pivot block: row-major 8x8 lower | rinv at +40 (per parity)
+    // (The matrix entries are read per sub-panel straight from global memory, issued before the accumulation so that
+    // the L2 latency is covered.  Staging the block in shared memory was measured: no gain in the kernel, and at 182 KB
+    // per CTA the panel step can no longer share an SM with the trailing-update GEMM CTAs, which cost ~5 us per step.)
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const bool has_rows = b < nrb;          // nrb counts blocks of 8*OT rows here
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const double* Ad = A + (long long)k0 * lda + k0;
+    double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
+    double* Lt = Ltmp + (long long)k0 * ldt + k0;
+    span_enter(k0);
+    if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
+    if (dbg && tid == 0 && b == 1) dbg[14] = clock64();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = tid + it * 256;                  // 2048 16-byte chunks per 64 x 64 tile
+        const int r = idx >> 5, cc = idx & 31;
+        if (has_prev) {
+            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
+            if (has_rows && it < OT) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
+        }
+    }
+    cp_async_commit();
+    for (int i = tid; i < 8 * PLW; i += 256) Lc[i - 8 * PLW] = 0.0;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
+
+    if (warp != 0 && warp != 4) {
+        // ------------------------------------------------------------------ tensor warps (one sub-panel ahead)
+        int mt[NS];
+        const double* rowp[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            mt[i] = ws_tile<OT>(warp, i);
+            const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
+            rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
+        }
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int c0 = p * 8;
+            int mask = 0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if (mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p)) mask |= 1 << i;
+            double* Xp = Xr + (p & 1) * ROWS * XP;
+            // columns through sub-panel p-3 were published before this warp's previous barrier wait; sub-panel p-2
+            // follows barrier 3/4 (which also says Xr[p&1] has been consumed); sub-panel p-1 is the scalar warps' job
+            long long* ts = (dbg && warp == 1 && lane == 0 && b == 0 && (p == 0 || p == 3)) ? dbg + (p == 0 ? 40 : 48) : nullptr;
+            ws_tensor_dispatch<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 16, c0 - 8, p >= 2 ? 3 + (p & 1) : -1,
+                                        1 + (p & 1), 224, use_fence, gq, tq, ts, 256, 8 + (p & 1));
+            if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
+        }
+        if (dbg && lane == 0 && b == 0) dbg[56 + warp] = clock64();
+        span_exit(k0);
+        return;
+    }
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ pivot warp
+        const int pi = lane >> 3, pj = lane & 7;      // cooperative pivot-block update: entries (pi, pj) and (pi + 4, pj)
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int c0 = p * 8, par = p & 1;
+            const int row = lane + 32 * (p >> 2);               // the group that holds the pivot rows
+            const double* Xp = Xr + par * ROWS * XP;
+            const double* Lprev = Lc + (c0 - 8) * PLW;          // the 8 columns of the previous sub-panel (zeros for p = 0)
+            named_bar_sync(1 + par, 224);
+            if (p == 4) named_bar_sync(7, 64);                  // rows 32..63 of sub-panel 3 come from the row warp
+            const bool stamp = dbg && lane == 0 && b == 0 && (p == 2 || p == 5);
+            long long* ds = dbg + (p == 2 ? 24 : 32);
+            if (stamp) ds[0] = clock64();
+            {   // pivot block: D = Xr block - Lp Lp^T with Lp = L[c0..c0+8)[c0-8..c0)
+                double d0 = Xp[(c0 + pi) * XP + pj], d1 = Xp[(c0 + pi + 4) * XP + pj];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double lj = Lprev[c * PLW + c0 + pj];
+                    d0 = fma(-Lprev[c * PLW + c0 + pi], lj, d0);
+                    d1 = fma(-Lprev[c * PLW + c0 + pi + 4], lj, d1);
+                }
+                Dsm[pi * 8 + pj] = d0;
+                Dsm[(pi + 4) * 8 + pj] = d1;
+            }
+            double acc[8];
+            load_row8(acc, Xp + row * XP);
+            __syncwarp();
+            if (stamp) ds[1] = clock64();
+            double D[8][8], rinv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
+            rank8_update(acc, Lprev, PLW, c0, row);
+            int badcol = 8;                       // first non-positive pivot of this block (8 = none)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double d = D[c][c];
+                const bool ok = d > 0.0;
+                badcol = (!ok && badcol == 8) ? c : badcol;
+                d = ok ? d : 1.0;
+                const double ri = rsqrt_pos(d);
+                rinv[c] = ri;
+                D[c][c] = d * ri;
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i)
+#pragma unroll
+                    for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
+            }
+            {   // publish the factored block (every lane holds the same values: same-value stores)
+                double* F = Dfac + par * 48;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) F[i * (i + 1) / 2 + j] = D[i][j];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) F[40 + c] = rinv[c];
+            }
+            if (stamp) ds[2] = clock64();
+            if (use_fence) __threadfence_block();
+            if (stamp) ds[3] = clock64();
+            named_bar_arrive(5 + par, 64);
+            if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
+            const int jrow = row - c0;
+            subst_row8(acc, D, rinv, jrow);
+            if (jrow >= 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[c];
+            }
+            if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
+            if (stamp) ds[4] = clock64();
+            if (use_fence) __threadfence_block();
+            if (stamp) ds[5] = clock64();
+            if (p < 6) named_bar_arrive(3 + par, 256);
+            if (jrow >= 0 && b == 0) {                          // L_kk is parked: other CTAs still read A_kk
+                double* dst = Lt + (long long)row * ldt + c0;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
+            }
+        }
+        if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
+        if (dbg && lane == 0 && b == 1) { dbg[13] = clock64(); }
+        span_exit(k0);
+        return;
+    }
+
+    // ---------------------------------------------------------------------- row warp (warp 4)
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = p * 8, par = p & 1;
+        const double* Xp = Xr + par * ROWS * XP;
+        const double* Lprev = Lc + (c0 - 8) * PLW;
+        const bool on1 = p < 4;                                 // rows 32..63 while the pivot rows are in group 0
+        named_bar_sync(8 + par, 224);
+        double acc[NG - 1][8];
+        int rows[NG - 1];
+        bool act[NG - 1];
+        rows[0] = lane + 32; act[0] = on1;
+#pragma unroll
+        for (int g = 1; g < NG - 1; ++g) { rows[g] = lane + 32 * (g + 1); act[g] = has_rows; }
+#pragma unroll
+        for (int g = 0; g < NG - 1; ++g) load_row8(acc[g], Xp + rows[g] * XP);
+        named_bar_sync(5 + par, 64);                            // factored pivot block of this sub-panel (and the pivot warp's
+                                                                // stores of the previous one) are visible
+        double D[8][8], rinv[8];
+        {
+            const double* F = Dfac + par * 48;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) D[i][j] = F[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rinv[c] = F[40 + c];
+        }
+#pragma unroll
+        for (int g = 0; g < NG - 1; ++g) {
+            if (!act[g]) continue;                              // warp-uniform
+            rank8_update(acc[g], Lprev, PLW, c0, rows[g]);
+            subst_row8(acc[g], D, rinv, rows[g] - c0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + rows[g]] = acc[g][c];
+        }
+        if (use_fence) __threadfence_block();
+        if (p < 6) named_bar_arrive(3 + par, 256);
+        if (p == 3) named_bar_arrive(7, 64);
+#pragma unroll
+        for (int g = 0; g < NG - 1; ++g) {
+            if (!act[g]) continue;
+            double* dst = nullptr;
+            if (g >= 1) dst = Ar + (long long)(rows[g] - 64) * lda + c0;
+            else if (b == 0) dst = Lt + (long long)rows[g] * ldt + c0;
+            if (dst) {
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
+            }
+        }
+    }
+    if (dbg && lane == 0 && b == 0) dbg[11] = clock64();
+    if (dbg && lane == 0 && b == 1) dbg[12] = clock64();
+    span_exit(k0);
 }
 
 // After the sweep, for every diagonal block at once: move L_kk from Ltmp into A, invert it by
@@ -1037,10 +1388,33 @@ __global__ void __launch_bounds__(64) diag_inv_kernel(double* __restrict__ A, lo
     }
 }
 
+// on = 1: arm (resets the slots); on = 0: disarm and copy 2 * n values out (ns)
+extern "C" int mogp_panel_spans(int on, unsigned long long* out_host, int n) {
+    if (on) {
+        std::vector<unsigned long long> init(2 * 136);
+        for (int i = 0; i < 136; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+        if (cudaMemcpyToSymbol(g_span, init.data(), init.size() * 8) != cudaSuccess) return -2;
+        const int one = 1;
+        return cudaMemcpyToSymbol(c_span_on, &one, 4) == cudaSuccess ? 0 : -2;
+    }
+    cudaDeviceSynchronize();
+    const int zero = 0;
+    cudaMemcpyToSymbol(c_span_on, &zero, 4);
+    if (n > 136) n = 136;
+    return cudaMemcpyFromSymbol(out_host, g_span, (size_t)2 * n * 8) == cudaSuccess ? 0 : -2;
+}
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
 // 0: phase-alternating panel step; 1: warp-specialised, 64 own rows per CTA; 2 (default): warp-specialised with 32 own
 // rows per CTA while twice the CTAs fit one wave.  Measured on B200 (profiles/r01_panel_variants.txt): potrf N=2048
 // 0.721 / 0.657 / 0.538 ms, N=8192 7.88 / 7.72 / 7.68 ms.  MOGP_PANEL_VARIANT overrides the default for A/B runs.
+// Programmatic dependent launch of the panel steps: 0 off, 1 (default) inside graph capture only, 2 always.  Measured on B200
+// (profiles/r01_pdl_graphs.txt): inside a replayed graph it hides ~2 us of the ~4 us launch gap between consecutive panel
+// steps (cfg2 0.902 -> 0.846 ms, cfg4 3.47 -> 3.34 ms); eagerly the event waits between the steps cancel it.
+static int g_panel_pdl = std::getenv("MOGP_PANEL_PDL") ? std::atoi(std::getenv("MOGP_PANEL_PDL")) : 1;
+extern "C" int mogp_set_panel_pdl(int v) { g_panel_pdl = v; ++g_mogp_cfg_epoch; return 0; }
+extern "C" int mogp_get_panel_pdl(void) { return g_panel_pdl; }
+static int g_panel_nofence = std::getenv("MOGP_PANEL_NOFENCE") ? std::atoi(std::getenv("MOGP_PANEL_NOFENCE")) : 0;
+extern "C" int mogp_set_panel_nofence(int v) { g_panel_nofence = v; ++g_mogp_cfg_epoch; return 0; }
 static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 2;
 extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
@@ -1050,7 +1424,8 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
         return 1;
     }
     cudaDeviceSynchronize();
-    return cudaMemcpy(out_host, g_panel_dbg, 56 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    cudaError_t ce = cudaMemcpy(out_host, g_panel_dbg, 64 * 8, cudaMemcpyDeviceToHost);
+    return ce == cudaSuccess ? 0 : -2;
 }
 
 // ============================================================================ blocked Cholesky
@@ -1064,22 +1439,31 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
 // the step time is the panel chain, for large ones the chain hides behind the GEMMs.
 // Ltmp is an Np x Np scratch whose diagonal blocks are used; diagonal blocks of Linv get inv(L_kk).
 // Operations of the pipelined triangular inverse, in issue order (see build_inverse_plan).
-struct InvOp { int kind; int lo, mid, hi; int ready; };   // kind 0: inv of diagonal block lo; 1: T = L_BA Linv_AA; 2: Linv_BA = -Linv_BB T
-// Block doubling as a recursion over 64-row block ranges: A = [lo, mid), B = [mid, hi), mid - lo = the largest
-// power of two below hi - lo (the same pairs the level-batched trtri_padded forms).  `ready` = index of the last
-// panel step the operation depends on; depth-first order is both dependency order and non-decreasing in `ready`,
-// so one in-order stream that is released panel by panel can run it.
-static void build_inverse_plan(int lo, int hi, std::vector<InvOp>& ops) {
-    if (hi - lo == 1) { ops.push_back({0, lo, lo, hi, lo}); return; }
-    int s = 1;
-    while (2 * s < hi - lo) s *= 2;
+// kind 0: inverse of diagonal block lo; 1: T = L_BA Linv_AA; 2: Linv_BA = -Linv_BB T  (A = [lo, mid), B = [mid, hi)).
+// `ready` = index of the last panel step the operation depends on; `wait` = completion event of the operation that
+// finishes the sub-range it needs (-1: none), `done` = its own completion event, `level` = log2 of the pair size.
+struct InvOp { int kind, lo, mid, hi, ready, wait, done, level; };
+// Block doubling as a recursion over 64-row block ranges: mid - lo = the largest power of two below hi - lo (the
+// same pairs the level-batched trtri_padded forms).  Depth-first order is dependency order and non-decreasing in
+// `ready`, so the operations can be released panel by panel; every doubling level gets its own stream (its pairs
+// are ordered by readiness anyway) so that independent levels do not serialise.  Returns the completion event of
+// the whole range.
+static int build_inverse_plan(int lo, int hi, std::vector<InvOp>& ops, int& nev) {
+    if (hi - lo == 1) { ops.push_back({0, lo, lo, hi, lo, -1, nev, 0}); return nev++; }
+    int s = 1, lvl = 0;
+    while (2 * s < hi - lo) { s *= 2; ++lvl; }
     const int mid = lo + s;
-    build_inverse_plan(lo, mid, ops);
-    ops.push_back({1, lo, mid, hi, mid - 1});        // needs Linv_AA and the columns of A below it: panel mid-1
-    build_inverse_plan(mid, hi, ops);
-    ops.push_back({2, lo, mid, hi, hi - 1});
+    const int ea = build_inverse_plan(lo, mid, ops, nev);
+    ops.push_back({1, lo, mid, hi, mid - 1, ea, nev++, lvl});      // needs Linv_AA (which implies panel mid-1)
+    const int eb = build_inverse_plan(mid, hi, ops, nev);
+    ops.push_back({2, lo, mid, hi, hi - 1, eb, nev, lvl});         // follows its own T on the level's stream
+    return nev++;
 }
-static int g_trtri_pipe = std::getenv("MOGP_TRTRI_PIPE") ? std::atoi(std::getenv("MOGP_TRTRI_PIPE")) : 0;
+// timing experiments only: skip the bulk trailing updates (wrong factor, shows the bare panel chain)
+static int g_skip_bulk = std::getenv("MOGP_SKIP_BULK") ? std::atoi(std::getenv("MOGP_SKIP_BULK")) : 0;
+extern "C" int mogp_set_skip_bulk(int v) { g_skip_bulk = v; ++g_mogp_cfg_epoch; return 0; }
+// Pipelined inverse on by default (measured: cfg2 0.938 -> 0.899 ms, cfg4 3.62 -> 3.55 ms; profiles/r01_panel_variants.txt).
+static int g_trtri_pipe = std::getenv("MOGP_TRTRI_PIPE") ? std::atoi(std::getenv("MOGP_TRTRI_PIPE")) : 1;
 extern "C" int mogp_set_trtri_pipe(int v) { g_trtri_pipe = v; ++g_mogp_cfg_epoch; return 0; }
 
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
@@ -1096,12 +1480,34 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
     // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
-        if (g_panel_variant == 3 && 2 * nrb <= n_sm)
-            potrf_panel_ws2_kernel<4><<<std::max(1, 2 * nrb), 256, Ws2Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp);
-        else if (g_panel_variant >= 2 && 2 * nrb <= n_sm)
-            potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp);
+        if (g_panel_variant == 4 && 2 * nrb <= n_sm)
+            potrf_panel_ws3_kernel<4><<<std::max(1, 2 * nrb), 256, Ws3Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
+        else if (g_panel_variant == 3 && 2 * nrb <= n_sm)
+            potrf_panel_ws2_kernel<4><<<std::max(1, 2 * nrb), 256, Ws2Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
+        else if (g_panel_variant >= 2 && 2 * nrb <= n_sm) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (g_panel_pdl == 1) cudaStreamIsCapturing(s_, &cap);       // 1: only inside graph capture (measured: no gain eagerly,
+                                                                         // the event waits between the steps cancel it); 2: always
+            if (has_prev && (g_panel_pdl == 2 || (g_panel_pdl == 1 && cap == cudaStreamCaptureStatusActive))) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)std::max(1, 2 * nrb)); cfg.blockDim = dim3(256);
+                cfg.dynamicSmemBytes = WsCfg<4>::SMEM; cfg.stream = s_;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaError_t le = cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<4>, A, (long long)ld, Ltmp, (long long)ldt, (int)k, 2 * nrb,
+                                                    (int)(has_prev | (g_panel_nofence << 1)), info, dbgp);
+                if (le != cudaSuccess) {          // not supported in this context: plain launches from now on
+                    cudaGetLastError();
+                    g_panel_pdl = 0;
+                    potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
+                }
+            } else
+                potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
+        }
         else if (g_panel_variant >= 1)
-            potrf_panel_ws_kernel<8><<<std::max(1, nrb), 256, WsCfg<8>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
+            potrf_panel_ws_kernel<8><<<std::max(1, nrb), 256, WsCfg<8>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
@@ -1112,6 +1518,11 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ws3Cfg<4>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(potrf_panel_ws3_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ws2Cfg<4>::SMEM);
@@ -1232,25 +1643,30 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     // doubling are issued on a fourth stream as soon as the panel steps they depend on are done, so that only
     // the last pair of every level is left when the factorisation ends.
     const bool pipe = fused_inverse != nullptr && g_trtri_pipe != 0 && two && ps->s4 != nullptr && ps->evp != nullptr &&
-                      ldi == ld && ldt == ld;
+                      ps->evq != nullptr && ldi == ld && ldt == ld && 3 * nb + 16 <= ps->nevq && nb <= 128;
     std::vector<InvOp> plan;
     size_t next_op = 0;
+    bool level_used[8] = {};
     if (pipe) {
-        build_inverse_plan(0, nb, plan);
-        if ((e = cudaStreamWaitEvent(ps->s4, ps->ev1[0], 0)) != cudaSuccess) return e;
+        int ne = 0;
+        build_inverse_plan(0, nb, plan, ne);
     }
     auto issue_inverse_ops = [&](int s) -> cudaError_t {
         cudaError_t ee;
         if ((ee = cudaEventRecord(ps->evp[s], st)) != cudaSuccess) return ee;
-        if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
         for (; next_op < plan.size() && plan[next_op].ready <= s; ++next_op) {
             const InvOp& op = plan[next_op];
             if (op.kind == 0) {
+                if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
                 diag_inv_kernel<<<1, 64, 0, ps->s4>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, op.lo);
                 MOGP_COUNT(1);
                 if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
+                if ((ee = cudaEventRecord(ps->evq[op.done], ps->s4)) != cudaSuccess) return ee;
                 continue;
             }
+            cudaStream_t sv = ps->sl[op.level];
+            level_used[op.level] = true;
+            if ((ee = cudaStreamWaitEvent(sv, ps->evq[op.wait], 0)) != cudaSuccess) return ee;
             const long long o = (long long)op.lo * 64, S = (long long)(op.mid - op.lo) * 64, MB = (long long)(op.hi - op.mid) * 64;
             GemmArgs g{};
             if (op.kind == 1) {          // T = L_BA * Linv_AA   (Linv_AA lower triangular: k starts at the column tile)
@@ -1266,7 +1682,8 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 g.M = (int)MB; g.N = (int)S; g.K = (int)MB;
                 g.khi_mode = 1; g.pair = 2; g.alpha = -1.0; g.beta = 0.0;
             }
-            if ((ee = launch_gemm(0, 0, g, 1, ps->s4)) != cudaSuccess) return ee;
+            if ((ee = launch_gemm(0, 0, g, 1, sv)) != cudaSuccess) return ee;
+            if ((ee = cudaEventRecord(ps->evq[op.done], sv)) != cudaSuccess) return ee;
         }
         return cudaSuccess;
     };
@@ -1290,7 +1707,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
             u.C = A + c0 * ld + c0; u.ldc = ld;
             u.M = (int)M; u.N = (int)M; u.K = MOGP_NB;
             u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
-            e = launch_gemm(0, 1, u, 1, s2);
+            e = g_skip_bulk ? cudaSuccess : launch_gemm(0, 1, u, 1, s2);
             if (e != cudaSuccess) return e;
             if (two) {
                 if ((e = cudaEventRecord(ps->ev2[s], s2)) != cudaSuccess) return e;
@@ -1305,6 +1722,12 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         if ((e = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return e;
+        for (int l = 0; l < 8; ++l) {
+            if (!level_used[l]) continue;
+            cudaEvent_t ej = ps->evq[ps->nevq - 8 + l];
+            if ((e = cudaEventRecord(ej, ps->sl[l])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(user, ej, 0)) != cudaSuccess) return e;
+        }
         *fused_inverse = true;
         return cudaSuccess;
     }
@@ -1646,6 +2069,40 @@ extern "C" int mogp_probe_latency(double* out_host /*16*/) {
     cudaError_t e = cudaMemcpy(out_host, d, 16 * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? 0 : -2;
+}
+
+// Issue-rate probe: `nw` warps of sub-partition 0 (warps 0, 4, 8, ...) each run 8 independent DFMA chains.
+// out[0] = cycles per DFMA instruction seen by warp 0 (a lone warp reaches about half of the pipe's rate).
+__global__ void issue_probe_kernel(double* out, int iters, int nw, double seed) {
+    const int warp = threadIdx.x >> 5;
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = seed + i + threadIdx.x * 1e-9;
+    const double a = 1.0000001, bb = 1e-9;
+    __syncthreads();
+    if ((warp & 3) == 0 && (warp >> 2) < nw) {
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, bb);
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) out[0] = (double)(t1 - t0) / ((double)iters * 8);
+    }
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += c[i];
+    if (sum == 123.456) out[1] = sum;
+}
+extern "C" int mogp_probe_issue(double* out_host /*4*/) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, 4 * 8) != cudaSuccess) return -2;
+    for (int nw = 1; nw <= 4; ++nw) {
+        for (int rep = 0; rep < 2; ++rep) issue_probe_kernel<<<1, 512>>>(d, 512, nw, 1.5);
+        if (cudaMemcpy(out_host + (nw - 1), d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d); return -2; }
+    }
+    cudaFree(d);
+    return 0;
 }
 
 // Contention probe: warps 0..3 run a dependent DFMA chain (the shape of the Cholesky pivot chain) while warps

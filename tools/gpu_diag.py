@@ -51,6 +51,9 @@ def sec_peak(eng):
     print("DFMA chain latency with a DMMA stream on the same sub-partition (0/1/2/4 accumulators): " +
           "  ".join("chain %.1f dmma %.1f" % (con[3 * m], con[3 * m + 1]) for m in range(4)) +
           " | chain on warp 0, DMMA on warps 1,2,3,5,6,7: chain %.1f dmma %.1f (two warps share a sub-partition)" % (con[12], con[13]))
+    iss = (C.c_double * 4)()
+    eng.lib.mogp_probe_issue(iss)
+    print("independent DFMA issue (8 chains per thread), cycles per instruction seen by warp 0 with 1/2/3/4 warps on its sub-partition: %.2f %.2f %.2f %.2f" % tuple(iss))
     print("8 dependent DMMAs after a scalar-fp64 gap of 0/64/256/1024 DFMAs: %.0f %.0f %.0f %.0f cycles" % (lat[10], lat[11], lat[12], lat[13]))
 
 
@@ -237,27 +240,46 @@ def sec_time(eng):
 
 def sec_panel(eng):
     import ctypes as C
-    buf = (C.c_longlong * 56)()
+    buf = (C.c_longlong * 64)()
     eng.lib.mogp_panel_debug(buf)          # arms the timestamps (second panel of the single-level sweep)
-    for variant in (2, 1, 0):
+    for variant, nofence in ((4, 0), (2, 0)):
         eng.lib.mogp_set_panel_variant(variant)
+        eng.lib.mogp_set_panel_nofence(nofence)
+        print("--- variant %d nofence %d" % (variant, nofence))
         n = 2048
         A = spd(n, 1).cuda()
         for _ in range(3):
             W = A.clone()
             eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
         torch.cuda.synchronize()
+        eng.lib.mogp_panel_debug(buf)          # (also re-arms the span stamps)
+        W = A.clone()
+        eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+        torch.cuda.synchronize()
         eng.lib.mogp_panel_debug(buf)
         t = [int(v) for v in buf]
+
         if variant >= 1:
             print("ws%d panel n=%d: prologue %d | chain done stamps (delta): %s | tensor Xr-ready (rel. start): %s | total %d cycles" % (
                 variant, n, t[1] - t[0], [t[2 + p] - (t[1] if p == 0 else t[1 + p]) for p in range(8)],
                 [t[16 + p] - t[0] for p in range(8)], t[10] - t[0]))
             print("   chain u(p) = done(p) - Xr-ready(p): %s ; exchange = Xr-ready(p+1) - done(p): %s" % (
                 [t[2 + p] - t[16 + p] for p in range(8)], [t[17 + p] - t[2 + p] for p in range(7)]))
+            for base, pp in ((40, 0), (48, 3)):
+                d = t[base:base + 6]
+                print("   tensor warp 1 p=%d (start rel. kernel %d): prev-panel accumulation %d | published columns %d | barrier wait %d | tail+store %d | fence+arrive %d" % (
+                    pp, d[0] - t[0], d[1] - d[0], d[2] - d[1], (d[3] - d[2]) if pp else 0, d[4] - (d[3] if pp else d[2]), d[5] - d[4]))
+            if variant == 4:
+                print("   ends rel. kernel start: pivot %d | row warp %d | tensor warps %s | CTA 1: pivot %d row %d (its own start)" % (
+                    t[10] - t[0], t[11] - t[0], [t[56 + w] - t[0] for w in (1, 2, 3, 5, 6, 7)], t[13] - t[14], t[12] - t[14]))
+                for base, pp in ((24, 2), (32, 5)):
+                    d = t[base:base + 6]
+                    print("   pivot warp p=%d: coop+exchange %d | pivot chain+rank8+publish %d | fence %d | subst+store %d | fence %d" % (
+                        pp, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4]))
         else:
             print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
-    eng.lib.mogp_set_panel_variant(int(os.environ.get("MOGP_PANEL_VARIANT", "0")))
+    eng.lib.mogp_set_panel_variant(int(os.environ.get("MOGP_PANEL_VARIANT", "2")))
+    eng.lib.mogp_set_panel_nofence(0)
 
 
 def sec_exp(eng):
@@ -267,6 +289,11 @@ def sec_exp(eng):
     from conftest import load_golden
     from mogptk_b200.engine import pack_params
     combos = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("EXP_COMBOS", "0:0").split(",")]
+    nofence = int(os.environ.get("EXP_NOFENCE", "0"))
+    eng.lib.mogp_set_panel_nofence(nofence)
+    eng.lib.mogp_set_panel_pdl(int(os.environ.get("EXP_PDL", "0")))
+    eng.lib.mogp_set_graph_max_np(int(os.environ.get("EXP_GRAPH_MAX_NP", "3072")))
+    print("nofence =", nofence, "pdl =", os.environ.get("EXP_PDL", "0"))
     names = os.environ.get("DIAG_CFGS", "cfg2,cfg4,cfg3").split(",")
     prepared = {}
     for name in names:
@@ -341,6 +368,66 @@ def sec_exp(eng):
     eng.lib.mogp_set_trtri_pipe(0)
 
 
+def sec_gaps(eng):
+    """Panel chain versus interference from the concurrent trailing updates (timing only: skip_bulk gives a wrong factor)."""
+    for n in (2048, 4096):
+        A = spd(n, 1).cuda()
+        W = A.clone()
+
+        def run():
+            W.copy_(A)
+            eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+
+        def cp():
+            W.copy_(A)
+        t_cp, _ = ev_time(cp, reps=5, warm=2)
+        for v in (2, 4, 0):
+            eng.lib.mogp_set_panel_variant(v)
+            line = "gaps n=%d variant %d:" % (n, v)
+            for skip in (0, 1):
+                eng.lib.mogp_set_skip_bulk(skip)
+                for cfg in (0, 2):
+                    eng.lib.mogp_set_gemm_config(cfg)
+                    t_all, _ = ev_time(run, reps=7, warm=2)
+                    line += "  %s/%s %.3f ms" % ("no-bulk" if skip else "bulk", "32x64" if cfg == 0 else "64x64", t_all - t_cp)
+            print(line)
+    eng.lib.mogp_set_skip_bulk(0)
+    eng.lib.mogp_set_gemm_config(0)
+    eng.lib.mogp_set_panel_variant(2)
+
+
+def sec_spans(eng):
+    """Per panel step: kernel span seen from inside (global timer over all CTAs) and the gap to the next step."""
+    import ctypes as C
+    n = int(os.environ.get("SPAN_N", "2048"))
+    nb = n // 64
+    A = spd(n, 1).cuda()
+    out = (C.c_ulonglong * (2 * nb))()
+    for v, pdl in ((2, 0), (2, 1)):
+        eng.lib.mogp_set_panel_variant(v)
+        eng.lib.mogp_set_panel_pdl(pdl)
+        for skip in (0, 1):
+            eng.lib.mogp_set_skip_bulk(skip)
+            for _ in range(3):
+                W = A.clone()
+                eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+            torch.cuda.synchronize()
+            eng.lib.mogp_panel_spans(1, out, nb)
+            W = A.clone()
+            eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+            torch.cuda.synchronize()
+            eng.lib.mogp_panel_spans(0, out, nb)
+            t = [int(x) for x in out]
+            spans = [(t[2 * s + 1] - t[2 * s]) / 1e3 for s in range(nb)]
+            gaps = [(t[2 * s + 2] - t[2 * s + 1]) / 1e3 for s in range(nb - 1)]
+            print("pdl requested %d active %d" % (pdl, eng.lib.mogp_get_panel_pdl()))
+            print("spans n=%d variant %d %s: kernel span mean %.2f us (first 6: %s), gap to next step mean %.2f us (first 6: %s), chain total %.1f us" % (
+                n, v, "no-bulk" if skip else "bulk", float(np.mean(spans)), " ".join("%.1f" % x for x in spans[:6]),
+                float(np.mean(gaps)), " ".join("%.1f" % x for x in gaps[:6]), (t[2 * nb - 1] - t[0]) / 1e3))
+    eng.lib.mogp_set_skip_bulk(0)
+    eng.lib.mogp_set_panel_variant(2)
+
+
 def sec_gemmk(eng):
     """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
     for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
@@ -411,7 +498,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
