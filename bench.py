@@ -280,6 +280,12 @@ def run_b200(args):
                         "dram read+write of the same launch from profiles/r01_ncu_full_kinv_gemm.txt (cfg3 only). The GEMM "
                         "kernel family is %.0f%% of the step's kernel time at cfg3 and ~40%% at cfg2, where the latency-bound "
                         "Cholesky panel kernel (no roofline) takes ~50%%." % (dfma or 0.0, 84.0),
+                "potrf_inverse": {
+                    "achieved": ((2.0 if stages.get("trtri", 1.0) < 0.02 else 1.0) * float(N) ** 3 / 3.0)
+                                / (stages["potrf"] * 1e-3) / 1e12 if stages.get("potrf") else None,
+                    "what": "stage 'potrf' of the profiled step: Cholesky (N^3/3) and, when the triangular inverse is pipelined "
+                            "behind the panel chain (N <= 4096; stage 'trtri' ~ 0), also L^-1 (N^3/3), over its CUDA-event time; "
+                            "at cfg2 this stage is bound by the latency of the 32-step panel chain, not by the tensor pipe"},
                 "step": {"achieved": ach, "frac": ach / dmma,
                          "what": "whole step: N^3 algorithmic flop (potrf N^3/3 + inverse 2N^3/3) / CUDA-event step time"},
                 "stage_ms": stages},

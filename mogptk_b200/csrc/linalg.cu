@@ -1567,6 +1567,73 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         MOGP_COUNT(1);
         return cudaGetLastError();
     };
+    // Pipelined inverse: the diagonal-block inverses and the GEMMs of the block
+    // doubling are issued on a fourth stream as soon as the panel steps they depend on are done, so that only
+    // the last pair of every level is left when the factorisation ends.
+    const bool pipe = fused_inverse != nullptr && g_trtri_pipe != 0 && two && ps->s4 != nullptr && ps->evp != nullptr &&
+                      ps->evq != nullptr && ldi == ld && ldt == ld && 3 * nb + 16 <= ps->nevq && nb <= 128 &&
+                      (Np <= 4096 || g_trtri_pipe >= 2);      // measured at N = 8192: no gain over the level-batched trtri_padded
+                                                              // (13.33 ms against 7.71 + 5.80 ms): the machine is already full
+    std::vector<InvOp> plan;
+    size_t next_op = 0;
+    bool level_used[8] = {};
+    if (pipe) {
+        int ne = 0;
+        build_inverse_plan(0, nb, plan, ne);
+    }
+    auto issue_inverse_ops = [&](int s) -> cudaError_t {
+        cudaError_t ee;
+        if ((ee = cudaEventRecord(ps->evp[s], st)) != cudaSuccess) return ee;
+        for (; next_op < plan.size() && plan[next_op].ready <= s; ++next_op) {
+            const InvOp& op = plan[next_op];
+            if (op.kind == 0) {
+                if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
+                diag_inv_kernel<<<1, 64, 0, ps->s4>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, op.lo);
+                MOGP_COUNT(1);
+                if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
+                if ((ee = cudaEventRecord(ps->evq[op.done], ps->s4)) != cudaSuccess) return ee;
+                continue;
+            }
+            cudaStream_t sv = ps->sl[op.level];
+            level_used[op.level] = true;
+            if ((ee = cudaStreamWaitEvent(sv, ps->evq[op.wait], 0)) != cudaSuccess) return ee;
+            const long long o = (long long)op.lo * 64, S = (long long)(op.mid - op.lo) * 64, MB = (long long)(op.hi - op.mid) * 64;
+            GemmArgs g{};
+            if (op.kind == 1) {          // T = L_BA * Linv_AA   (Linv_AA lower triangular: k starts at the column tile)
+                g.A = A + (o + S) * ld + o; g.lda = ld;
+                g.B = Linv + o * ld + o; g.ldb = ld;
+                g.C = Ltmp + (o + S) * ld + o; g.ldc = ld;
+                g.M = (int)MB; g.N = (int)S; g.K = (int)S;
+                g.klo_mode = 1; g.pair = 1; g.alpha = 1.0; g.beta = 0.0;
+            } else {                     // Linv_BA = -Linv_BB * T   (Linv_BB lower triangular: k ends at the row tile)
+                g.A = Linv + (o + S) * ld + (o + S); g.lda = ld;
+                g.B = Ltmp + (o + S) * ld + o; g.ldb = ld;
+                g.C = Linv + (o + S) * ld + o; g.ldc = ld;
+                g.M = (int)MB; g.N = (int)S; g.K = (int)MB;
+                g.khi_mode = 1; g.pair = 2; g.alpha = -1.0; g.beta = 0.0;
+            }
+            if ((ee = launch_gemm(0, 0, g, 1, sv)) != cudaSuccess) return ee;
+            if ((ee = cudaEventRecord(ps->evq[op.done], sv)) != cudaSuccess) return ee;
+        }
+        return cudaSuccess;
+    };
+    // join of the pipelined inverse: bulk stream, panel chain and every inverse stream back into the caller's stream
+    auto finish_pipe = [&](cudaEvent_t last_bulk_ev) -> cudaError_t {
+        cudaError_t ee;
+        if (last_bulk_ev && (ee = cudaStreamWaitEvent(user, last_bulk_ev, 0)) != cudaSuccess) return ee;
+        if ((ee = cudaEventRecord(ps->ev1[ps->nev + 1], st)) != cudaSuccess) return ee;
+        if ((ee = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return ee;
+        if ((ee = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return ee;
+        if ((ee = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return ee;
+        for (int l = 0; l < 8; ++l) {
+            if (!level_used[l]) continue;
+            cudaEvent_t ej = ps->evq[ps->nevq - 8 + l];
+            if ((ee = cudaEventRecord(ej, ps->sl[l])) != cudaSuccess) return ee;
+            if ((ee = cudaStreamWaitEvent(user, ej, 0)) != cudaSuccess) return ee;
+        }
+        *fused_inverse = true;
+        return cudaSuccess;
+    };
     if (Np > 4096) {
         // Large matrices: two-level updates (K = 64 inside a 256-column outer panel, one K = 256 SYRK per
         // outer panel) keep the trailing-matrix traffic down.  The SYRK is split into the next outer
@@ -1585,6 +1652,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 if (two3 && k >= K0 + 2 * MOGP_NB && (e = cudaStreamWaitEvent(st, ps->ev3[ks - 2], 0)) != cudaSuccess) return e;
                 launch_panel(k, nrb, k > K0 ? 1 : 0, nullptr, st);
                 MOGP_COUNT(1);
+                if (pipe && (e = issue_inverse_ops(ks)) != cudaSuccess) return e;
                 const int64_t c0 = k + 2 * MOGP_NB, Nc = Kend - c0, M = Np - c0;
                 if (Nc > 0 && M > 0) {                      // remaining columns of this outer panel
                     cudaStream_t si = st;
@@ -1637,56 +1705,8 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 last = two ? ps->ev2[2 * J + 1] : nullptr;
             }
         }
-        return finish(last);
+        return pipe ? finish_pipe(last) : finish(last);
     }
-    // Pipelined inverse (single-level sweep only): the diagonal-block inverses and the GEMMs of the block
-    // doubling are issued on a fourth stream as soon as the panel steps they depend on are done, so that only
-    // the last pair of every level is left when the factorisation ends.
-    const bool pipe = fused_inverse != nullptr && g_trtri_pipe != 0 && two && ps->s4 != nullptr && ps->evp != nullptr &&
-                      ps->evq != nullptr && ldi == ld && ldt == ld && 3 * nb + 16 <= ps->nevq && nb <= 128;
-    std::vector<InvOp> plan;
-    size_t next_op = 0;
-    bool level_used[8] = {};
-    if (pipe) {
-        int ne = 0;
-        build_inverse_plan(0, nb, plan, ne);
-    }
-    auto issue_inverse_ops = [&](int s) -> cudaError_t {
-        cudaError_t ee;
-        if ((ee = cudaEventRecord(ps->evp[s], st)) != cudaSuccess) return ee;
-        for (; next_op < plan.size() && plan[next_op].ready <= s; ++next_op) {
-            const InvOp& op = plan[next_op];
-            if (op.kind == 0) {
-                if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
-                diag_inv_kernel<<<1, 64, 0, ps->s4>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, op.lo);
-                MOGP_COUNT(1);
-                if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
-                if ((ee = cudaEventRecord(ps->evq[op.done], ps->s4)) != cudaSuccess) return ee;
-                continue;
-            }
-            cudaStream_t sv = ps->sl[op.level];
-            level_used[op.level] = true;
-            if ((ee = cudaStreamWaitEvent(sv, ps->evq[op.wait], 0)) != cudaSuccess) return ee;
-            const long long o = (long long)op.lo * 64, S = (long long)(op.mid - op.lo) * 64, MB = (long long)(op.hi - op.mid) * 64;
-            GemmArgs g{};
-            if (op.kind == 1) {          // T = L_BA * Linv_AA   (Linv_AA lower triangular: k starts at the column tile)
-                g.A = A + (o + S) * ld + o; g.lda = ld;
-                g.B = Linv + o * ld + o; g.ldb = ld;
-                g.C = Ltmp + (o + S) * ld + o; g.ldc = ld;
-                g.M = (int)MB; g.N = (int)S; g.K = (int)S;
-                g.klo_mode = 1; g.pair = 1; g.alpha = 1.0; g.beta = 0.0;
-            } else {                     // Linv_BA = -Linv_BB * T   (Linv_BB lower triangular: k ends at the row tile)
-                g.A = Linv + (o + S) * ld + (o + S); g.lda = ld;
-                g.B = Ltmp + (o + S) * ld + o; g.ldb = ld;
-                g.C = Linv + (o + S) * ld + o; g.ldc = ld;
-                g.M = (int)MB; g.N = (int)S; g.K = (int)MB;
-                g.khi_mode = 1; g.pair = 2; g.alpha = -1.0; g.beta = 0.0;
-            }
-            if ((ee = launch_gemm(0, 0, g, 1, sv)) != cudaSuccess) return ee;
-            if ((ee = cudaEventRecord(ps->evq[op.done], sv)) != cudaSuccess) return ee;
-        }
-        return cudaSuccess;
-    };
     int last_bulk = -1;
     for (int s = 0; s < nb; ++s) {
         const int64_t k = (int64_t)s * MOGP_NB;
@@ -1715,22 +1735,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
             }
         }
     }
-    if (pipe) {
-        // join: bulk stream, panel chain and the inverse stream back into the caller's stream; Linv is complete
-        if (last_bulk >= 0 && (e = cudaStreamWaitEvent(user, ps->ev2[last_bulk], 0)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(ps->ev1[ps->nev + 1], st)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return e;
-        for (int l = 0; l < 8; ++l) {
-            if (!level_used[l]) continue;
-            cudaEvent_t ej = ps->evq[ps->nevq - 8 + l];
-            if ((e = cudaEventRecord(ej, ps->sl[l])) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(user, ej, 0)) != cudaSuccess) return e;
-        }
-        *fused_inverse = true;
-        return cudaSuccess;
-    }
+    if (pipe) return finish_pipe(last_bulk >= 0 ? ps->ev2[last_bulk] : nullptr);
     return finish(two && last_bulk >= 0 ? ps->ev2[last_bulk] : nullptr);
 }
 
