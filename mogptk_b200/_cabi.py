@@ -61,13 +61,13 @@ _EXTRA = {
     "mogp_probe_issue": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_set_panel_variant": (C.c_int, [C.c_int]),
     "mogp_set_trtri_pipe": (C.c_int, [C.c_int]),
-    "mogp_set_panel_nofence": (C.c_int, [C.c_int]),
     "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
     "mogp_set_panel_pdl": (C.c_int, [C.c_int]),
     "mogp_get_panel_pdl": (C.c_int, []),
     "mogp_panel_spans": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "mogp_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mogp_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mogp_host_inverse_plan": (C.c_int, [C.c_int, c_ip, C.c_int]),
     "mogp_host_pair_comps": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp]),
     "mogp_host_chain": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp, c_dp, c_dp]),
 }

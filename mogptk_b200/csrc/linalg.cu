@@ -520,6 +520,44 @@ __device__ __forceinline__ void span_exit(int k0) {
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// In-register Cholesky of the 8x8 pivot block (lower triangle of D in, L out; rinv[c] = 1 / L[c][c]); badcol = first
+// non-positive pivot (8 = none; such pivots are replaced by 1 so that everything stays finite).
+// Two columns at a time with the closed form of the 2x2 leading block [[a, b], [b, c]]: l11 = sqrt(a), l21 = b / l11,
+// l22 = sqrt(det / a) with det = a c - b^2, so rsqrt(a) and rsqrt(det) are independent and the sequential chain is 4
+// instead of 8 reciprocal square roots per block.  (det by one FMA: its rounding error eps b^2 / det is no larger than that
+// of the column-wise c - l21^2.)
+__device__ __forceinline__ void factor_pivot8_pairs(double (&D)[8][8], double (&rinv)[8], int& badcol) {
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        double a = D[c][c];
+        const double b = D[c + 1][c];
+        double det = fma(a, D[c + 1][c + 1], -(b * b));
+        const bool ok0 = a > 0.0, ok1 = det > 0.0;
+        badcol = (!ok0 && badcol == 8) ? c : badcol;
+        badcol = (ok0 && !ok1 && badcol == 8) ? c + 1 : badcol;
+        a = ok0 ? a : 1.0;
+        det = (ok0 && ok1) ? det : 1.0;
+        const double r1 = rsqrt_pos(a), rd = rsqrt_pos(det);
+        const double l11 = a * r1;
+        const double r2 = l11 * rd;                   // 1 / l22 = sqrt(a) / sqrt(det)
+        const double l21 = b * r1;
+        rinv[c] = r1;
+        rinv[c + 1] = r2;
+        D[c][c] = l11;
+        D[c + 1][c] = l21;
+        D[c + 1][c + 1] = (det * rd) * r1;            // sqrt(det) / sqrt(a)
+#pragma unroll
+        for (int i = c + 2; i < 8; ++i) {
+            D[i][c] *= r1;
+            D[i][c + 1] = fma(-D[i][c], l21, D[i][c + 1]) * r2;
+        }
+#pragma unroll
+        for (int i = c + 2; i < 8; ++i)
+#pragma unroll
+            for (int j = c + 2; j <= i; ++j) D[i][j] = fma(-D[i][c + 1], D[j][c + 1], fma(-D[i][c], D[j][c], D[i][j]));
+    }
+}
+
 // One sub-panel of a tensor warp, with the set of live row tiles fixed at compile time (MASK bit i = slot i live).
 // A DMMA under a run-time predicate gets a WARPSYNC in front of it, which serialises it behind the previous
 // one (measured: ~65 cycles per DMMA and warp instead of 32, i.e. half the tensor rate); with the predicate
@@ -530,9 +568,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("
 template <int NS, int MASK, int PLW>
 __device__ __forceinline__ void ws_tensor_subpanel(const double* ZZ, const double* Lc, double* Xp, const int (&mt)[NS],
                                                    const double* const (&rowp)[NS], int c0, int has_prev, int k_pre,
-                                                   int k_all, int wait_id, int arrive_id, int bar_threads, bool use_fence,
-                                                   int gq, int tq, long long* ts, int wait_threads = 0, int arrive_id2 = -1) {
-    if (wait_threads == 0) wait_threads = bar_threads;
+                                                   int k_all, int wait_id, int arrive_id, int bar_threads, int gq, int tq,
+                                                   long long* ts) {
     if (ts) ts[0] = clock64();
     double cf[NS][2];
     double2 a0[NS];
@@ -561,7 +598,7 @@ __device__ __forceinline__ void ws_tensor_subpanel(const double* ZZ, const doubl
     }
     if (ts) ts[2] = clock64() + (cf[0][0] == 1.2345e300 ? 1 : 0);
     if (wait_id >= 0) {
-        named_bar_sync(wait_id, wait_threads);
+        named_bar_sync(wait_id, bar_threads);
         if (ts) ts[3] = clock64();
 #pragma unroll 2
         for (int k = k_pre; k < k_all; k += 4) {
@@ -577,22 +614,20 @@ __device__ __forceinline__ void ws_tensor_subpanel(const double* ZZ, const doubl
             *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
                 make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
     if (ts) ts[4] = clock64() + (cf[0][0] == 1.2345e300 ? 1 : 0);
-    if (use_fence) __threadfence_block();
+    __threadfence_block();
     named_bar_arrive(arrive_id, bar_threads);
-    if (arrive_id2 >= 0) named_bar_arrive(arrive_id2, bar_threads);
     if (ts) ts[5] = clock64();
 }
 #define WS_TENSOR_CASE(M)                                                                                          \
     case M:                                                                                                        \
         ws_tensor_subpanel<NS, (M) & ((1 << NS) - 1), PLW>(ZZ, Lc, Xp, mt, rowp, c0, has_prev, k_pre, k_all, wait_id,  \
-                                                           arrive_id, bar_threads, use_fence, gq, tq, ts, wait_threads, arrive_id2); \
+                                                           arrive_id, bar_threads, gq, tq, ts);                     \
         break;
 template <int NS, int PLW>
 __device__ __forceinline__ void ws_tensor_dispatch(int mask, const double* ZZ, const double* Lc, double* Xp,
                                                    const int (&mt)[NS], const double* const (&rowp)[NS], int c0,
                                                    int has_prev, int k_pre, int k_all, int wait_id, int arrive_id,
-                                                   int bar_threads, bool use_fence, int gq, int tq, long long* ts,
-                                                   int wait_threads = 0, int arrive_id2 = -1) {
+                                                   int bar_threads, int gq, int tq, long long* ts) {
     switch (mask) {
         WS_TENSOR_CASE(0) WS_TENSOR_CASE(1) WS_TENSOR_CASE(2) WS_TENSOR_CASE(3)
         default:
@@ -639,9 +674,7 @@ __device__ __forceinline__ int ws_tile(int warp, int slot) {
 template <int OT>
 __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restrict__ A, long long lda,
                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                                int flags, int32_t* info, long long* dbg) {
-    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
-    const bool use_fence = (flags & 2) == 0;
+                                                                int has_prev, int32_t* info, long long* dbg) {
     using Cfg = WsCfg<OT>;
     constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
     extern __shared__ __align__(16) double sm[];
@@ -694,7 +727,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
             // columns [0, c0-8) were published before this warp's previous barrier wait; [c0-8, c0) follow barrier 2
             long long* ts = (dbg && warp == 1 && lane == 0 && b == 0 && (p == 0 || p == 3)) ? dbg + (p == 0 ? 40 : 48) : nullptr;
             ws_tensor_dispatch<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 8, c0, p >= 1 ? 2 : -1, 1,
-                                        WS_BAR_THREADS, use_fence, gq, tq, ts);
+                                        WS_BAR_THREADS, gq, tq, ts);
             if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
         }
         span_exit(k0);
@@ -727,22 +760,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
             }
         }
         int badcol = 8;                       // first non-positive pivot of this block (8 = none)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            double d = D[c][c];
-            const bool ok = d > 0.0;
-            badcol = (!ok && badcol == 8) ? c : badcol;
-            d = ok ? d : 1.0;
-            const double ri = rsqrt_pos(d);
-            rinv[c] = ri;
-            D[c][c] = d * ri;
-#pragma unroll
-            for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
-#pragma unroll
-            for (int i = c + 1; i < 8; ++i)
-#pragma unroll
-                for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
-        }
+        factor_pivot8_pairs(D, rinv, badcol);
         if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -763,7 +781,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         }
         if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
         if (p < 7) {
-            if (use_fence) __threadfence_block();       // only shared-memory stores are outstanding here: the global ones follow
+            __threadfence_block();       // only shared-memory stores are outstanding here: the global ones follow
             named_bar_arrive(2, WS_BAR_THREADS);
         }
         // finished values to global memory, off the critical path (the tensor warps are already released)
@@ -782,505 +800,6 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
         }
     }
     if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
-    span_exit(k0);
-}
-
-// ---------------------------------------------------------------------------- decoupled warp-specialised panel step
-// Second generation of the schedule above (measured there: per 8-column sub-panel the chain took ~2000 cycles and
-// then waited ~800 more for the tensor warps to fold the just-finished columns into the next block -- the two
-// sides still alternated).  Here the tensor warps run one full sub-panel AHEAD of the chain: for sub-panel p they
-// only accumulate the previous panel's update and the columns finished through sub-panel p-2, into a double-
-// buffered exchange tile.  The chain warp applies the remaining rank-8 update (the columns it finished itself one
-// iteration earlier) with scalar FMAs that fill the latency shadows of the pivot chain; the 8x8 pivot block gets
-// that update cooperatively (two entries per lane) so the pivot chain can start after ~150 cycles.  No barrier
-// round trip is left on the critical path.  Barriers: 1,2 = "Xr[parity] full" (tensor arrive, chain sync);
-// 3,4 = "sub-panel of this parity done" (chain arrives, tensor warps sync two iterations later).
-// Lc carries 8 zero columns in front so that sub-panel 0 runs the same straight-line code (no p == 0 branch);
-// row groups are never skipped (finished rows compute garbage that is masked at the stores) so that the whole
-// chain iteration is one basic block for the instruction scheduler.
-template <int OT>
-struct Ws2Cfg {
-    static constexpr int ROWS = 64 + 8 * OT;
-    static constexpr int NS = OT == 8 ? 3 : 2;
-    static constexpr int NG = ROWS / 32;
-    static constexpr int PLW = OT == 8 ? 132 : 100;
-    static constexpr size_t SMEM = (size_t)(ROWS * PZ + 72 * PLW + 2 * ROWS * XP + 64) * sizeof(double);
-};
-
-template <int OT>
-__global__ void __launch_bounds__(256, 1) potrf_panel_ws2_kernel(double* __restrict__ A, long long lda,
-                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                                 int flags, int32_t* info, long long* dbg) {
-    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
-    const bool use_fence = (flags & 2) == 0;
-    using Cfg = Ws2Cfg<OT>;
-    constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
-    extern __shared__ __align__(16) double sm[];
-    double* ZZ = sm;                        // [ROWS][PZ]   previous-panel values (diagonal-block rows, own rows)
-    double* Lc = sm + ROWS * PZ + 8 * PLW;  // [-8..64][PLW] finished columns, column-major; columns -8..-1 are zero
-    double* Xr = Lc + 64 * PLW;             // [2][ROWS][XP] tensor warps -> chain exchange, double buffered
-    double* Dsm = Xr + 2 * ROWS * XP;       // [8][8]        updated pivot block
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x;
-    const bool has_rows = b < nrb;          // nrb counts blocks of 8*OT rows here
-    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const double* Ad = A + (long long)k0 * lda + k0;
-    double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
-    if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
-    if (has_prev) {
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int idx = tid + it * 256;              // 2048 16-byte chunks per 64 x 64 tile
-            const int r = idx >> 5, cc = idx & 31;
-            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
-            if (has_rows && it < OT) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
-        }
-        cp_async_commit();
-    }
-    for (int i = tid; i < 8 * PLW; i += 256) Lc[i - 8 * PLW] = 0.0;
-    if (has_prev) cp_async_wait<0>();
-    __syncthreads();
-    if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
-    if (warp == 4) return;
-
-    if (warp != 0) {
-        // ------------------------------------------------------------------ tensor warps (one sub-panel ahead)
-        int mt[NS];
-        const double* rowp[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            mt[i] = ws_tile<OT>(warp, i);
-            const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
-            rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
-        }
-#pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
-            const int c0 = p * 8;
-            double* Xp = Xr + (p & 1) * ROWS * XP;
-            bool on[NS];
-            double cf[NS][2];
-            double2 a0[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                on[i] = mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p);
-                cf[i][0] = 0.0; cf[i][1] = 0.0;
-                a0[i] = make_double2(0.0, 0.0);
-                if (on[i]) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
-            }
-            if (has_prev) {
-#pragma unroll 4
-                for (int kk = 0; kk < 64; kk += 4) {
-                    const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        if (on[i]) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
-                }
-            }
-            // columns finished through sub-panel p-3 were published before this warp's previous barrier wait
-#pragma unroll 2
-            for (int k = 0; k < c0 - 16; k += 4) {
-                const double nb = -Lc[(k + tq) * PLW + c0 + gq];
-#pragma unroll
-                for (int i = 0; i < NS; ++i)
-                    if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
-            }
-            if (p >= 2) {
-                named_bar_sync(3 + (p & 1), WS_BAR_THREADS);       // sub-panel p-2 is in Lc (and Xr[p&1] has been consumed)
-#pragma unroll
-                for (int k8 = 0; k8 < 8; k8 += 4) {
-                    const int k = c0 - 16 + k8;
-                    const double nb = -Lc[(k + tq) * PLW + c0 + gq];
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        if (on[i]) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-                if (on[i])
-                    *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
-                        make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
-            if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
-            if (use_fence) __threadfence_block();
-            named_bar_arrive(1 + (p & 1), WS_BAR_THREADS);
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- chain warp: lane owns rows lane + 32 g
-    double* Lt = Ltmp + (long long)k0 * ldt + k0;
-    const int pi = lane >> 3, pj = lane & 7;      // cooperative pivot-block update: entries (pi, pj) and (pi + 4, pj)
-#pragma unroll 1
-    for (int p = 0; p < 8; ++p) {
-        const int c0 = p * 8;
-        const double* Xp = Xr + (p & 1) * ROWS * XP;
-        const double* Lprev = Lc + (c0 - 8) * PLW;          // the 8 columns finished in the previous iteration (zeros for p = 0)
-        named_bar_sync(1 + (p & 1), WS_BAR_THREADS);
-        {   // pivot block: D = Xr block - Lp Lp^T with Lp = L[c0..c0+8)[c0-8..c0)
-            double d0 = Xp[(c0 + pi) * XP + pj], d1 = Xp[(c0 + pi + 4) * XP + pj];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double lj = Lprev[c * PLW + c0 + pj];
-                d0 = fma(-Lprev[c * PLW + c0 + pi], lj, d0);
-                d1 = fma(-Lprev[c * PLW + c0 + pi + 4], lj, d1);
-            }
-            Dsm[pi * 8 + pj] = d0;
-            Dsm[(pi + 4) * 8 + pj] = d1;
-        }
-        double acc[NG][8];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const double2* q = reinterpret_cast<const double2*>(Xp + (lane + 32 * g) * XP);
-            const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
-            acc[g][0] = v0.x; acc[g][1] = v0.y; acc[g][2] = v1.x; acc[g][3] = v1.y;
-            acc[g][4] = v2.x; acc[g][5] = v2.y; acc[g][6] = v3.x; acc[g][7] = v3.y;
-        }
-        __syncwarp();
-        double D[8][8], rinv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
-        // rank-8 update of every row with the columns of the previous iteration (independent of the pivot chain)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const double2* bp = reinterpret_cast<const double2*>(Lprev + c * PLW + c0);
-            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const double pv = -Lprev[c * PLW + lane + 32 * g];
-                acc[g][0] = fma(pv, b0.x, acc[g][0]); acc[g][1] = fma(pv, b0.y, acc[g][1]);
-                acc[g][2] = fma(pv, b1.x, acc[g][2]); acc[g][3] = fma(pv, b1.y, acc[g][3]);
-                acc[g][4] = fma(pv, b2.x, acc[g][4]); acc[g][5] = fma(pv, b2.y, acc[g][5]);
-                acc[g][6] = fma(pv, b3.x, acc[g][6]); acc[g][7] = fma(pv, b3.y, acc[g][7]);
-            }
-        }
-        int badcol = 8;                       // first non-positive pivot of this block (8 = none)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            double d = D[c][c];
-            const bool ok = d > 0.0;
-            badcol = (!ok && badcol == 8) ? c : badcol;
-            d = ok ? d : 1.0;
-            const double ri = rsqrt_pos(d);
-            rinv[c] = ri;
-            D[c][c] = d * ri;
-#pragma unroll
-            for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
-#pragma unroll
-            for (int i = c + 1; i < 8; ++i)
-#pragma unroll
-                for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
-        }
-        if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int row = lane + 32 * g;
-            const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double xc = acc[g][c] * rinv[c];
-                acc[g][c] = (c <= jrow) ? xc : 0.0;
-#pragma unroll
-                for (int cc = c + 1; cc < 8; ++cc) acc[g][cc] = fma(-xc, D[cc][c], acc[g][cc]);
-            }
-            if (jrow >= 0) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[g][c];
-            }
-        }
-        if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
-        if (use_fence) __threadfence_block();           // only shared-memory stores are outstanding here: the global ones follow
-        if (p < 6) named_bar_arrive(3 + (p & 1), WS_BAR_THREADS);
-        // finished values to global memory, off the critical path
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int row = lane + 32 * g;
-            if (row < c0 || (g >= 2 && !has_rows)) continue;
-            double* dst = nullptr;
-            if (g >= 2) dst = Ar + (long long)(row - 64) * lda + c0;
-            else if (b == 0) dst = Lt + (long long)row * ldt + c0;           // L_kk is parked: other CTAs still read A_kk
-            if (dst) {
-#pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
-            }
-        }
-    }
-    if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
-}
-
-// ---------------------------------------------------------------------------- two scalar warps (pivot + rows)
-// Third generation.  Measured on the decoupled kernel above: with the tensor warps out of the way the chain warp
-// still needed ~2800 cycles per sub-panel for ~500 fp64 instructions, i.e. ~5.5 cycles per instruction although
-// 24 independent FMA chains were available -- a lone warp reaches only about half of its sub-partition's fp64
-// issue rate (the same holds for DMMA).  Here the scalar work is split over the two warps of sub-partition 0:
-//   warp 0 (pivot warp): cooperative update of the 8x8 pivot block, its factorisation, and the 32-row group that
-//                        holds the current and next pivot rows (group p/4 of the diagonal block);
-//   warp 4 (row warp):   every other live row (the other diagonal-block group while p < 4, and the own rows).
-// The pivot warp publishes the factored block (double buffered) and moves on; the row warp trails it by about
-// one pivot phase and is only waited for by the tensor warps two sub-panels later (and by the pivot warp once,
-// when the pivot rows move from group 0 to group 1 at p = 4).
-// Barriers (named, counts in threads): 1,2 and 8,9 "Xr[parity] full" for the pivot warp and for the row warp (192
-// tensor arrive + 32 sync each: one shared barrier would hold the pivot warp back until the row warp got there);
-// 3,4 "sub-panel of this parity in Lc" (64 scalar arrive, 192 tensor sync); 5,6 "factored pivot block
-// published" (32 arrive, 32 sync); 7 "row warp finished sub-panel 3" (32 arrive, 32 sync).
-template <int OT>
-struct Ws3Cfg {
-    static constexpr int ROWS = 64 + 8 * OT;
-    static constexpr int NS = OT == 8 ? 3 : 2;
-    static constexpr int NG = ROWS / 32;
-    static constexpr int PLW = OT == 8 ? 132 : 100;
-    static constexpr size_t SMEM = (size_t)(ROWS * PZ + 72 * PLW + 2 * ROWS * XP + 64 + 2 * 48) * sizeof(double);
-};
-
-// acc[0..8) -= sum_c L[row][c0-8+c] * L[c0+.][c0-8+c]   (the columns of the previous sub-panel; zeros for p = 0)
-__device__ __forceinline__ void rank8_update(double (&acc)[8], const double* Lprev, int plw, int c0, int row) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const double2* bp = reinterpret_cast<const double2*>(Lprev + c * plw + c0);
-        const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-        const double pv = -Lprev[c * plw + row];
-        acc[0] = fma(pv, b0.x, acc[0]); acc[1] = fma(pv, b0.y, acc[1]);
-        acc[2] = fma(pv, b1.x, acc[2]); acc[3] = fma(pv, b1.y, acc[3]);
-        acc[4] = fma(pv, b2.x, acc[4]); acc[5] = fma(pv, b2.y, acc[5]);
-        acc[6] = fma(pv, b3.x, acc[6]); acc[7] = fma(pv, b3.y, acc[7]);
-    }
-}
-__device__ __forceinline__ void load_row8(double (&acc)[8], const double* src) {
-    const double2* q = reinterpret_cast<const double2*>(src);
-    const double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
-    acc[0] = v0.x; acc[1] = v0.y; acc[2] = v1.x; acc[3] = v1.y;
-    acc[4] = v2.x; acc[5] = v2.y; acc[6] = v3.x; acc[7] = v3.y;
-}
-// forward substitution of one row against the factored pivot block; entries right of the diagonal of a pivot row
-// are masked (jrow = row - c0; >= 8 for rows below the block)
-__device__ __forceinline__ void subst_row8(double (&acc)[8], const double (&D)[8][8], const double (&rinv)[8], int jrow) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const double xc = acc[c] * rinv[c];
-        acc[c] = (c <= jrow) ? xc : 0.0;
-#pragma unroll
-        for (int cc = c + 1; cc < 8; ++cc) acc[cc] = fma(-xc, D[cc][c], acc[cc]);
-    }
-}
-
-template <int OT>
-__global__ void __launch_bounds__(256, 1) potrf_panel_ws3_kernel(double* __restrict__ A, long long lda,
-                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
-                                                                 int flags, int32_t* info, long long* dbg) {
-    const int has_prev = flags & 1;              // bit 1: skip the block-scope fences before the named-barrier arrivals
-    const bool use_fence = (flags & 2) == 0;
-    using Cfg = Ws3Cfg<OT>;
-    constexpr int ROWS = Cfg::ROWS, NS = Cfg::NS, NG = Cfg::NG, PLW = Cfg::PLW;
-    extern __shared__ __align__(16) double sm[];
-    double* ZZ = sm;                        // [ROWS][PZ]   previous-panel values (diagonal-block rows, own rows)
-    double* Lc = sm + ROWS * PZ + 8 * PLW;  // [-8..64][PLW] finished columns, column-major; columns -8..-1 are zero
-    double* Xr = Lc + 64 * PLW;             // [2][ROWS][XP] tensor warps -> scalar warps exchange, double buffered
-    double* Dsm = Xr + 2 * ROWS * XP;       // [8][8]        updated pivot block (pivot warp only)
-    double* Dfac = Dsm + 64;                // [2][48]       factored pivot block: row-major 8x8 lower | rinv at +40 (per parity)
-    // (The matrix entries are read per sub-panel straight from global memory, issued before the accumulation so that
-    // the L2 latency is covered.  Staging the block in shared memory was measured: no gain in the kernel, and at 182 KB
-    // per CTA the panel step can no longer share an SM with the trailing-update GEMM CTAs, which cost ~5 us per step.)
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x;
-    const bool has_rows = b < nrb;          // nrb counts blocks of 8*OT rows here
-    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const double* Ad = A + (long long)k0 * lda + k0;
-    double* Ar = A + (long long)(k0 + 64 + 8 * OT * b) * lda + k0;
-    double* Lt = Ltmp + (long long)k0 * ldt + k0;
-    span_enter(k0);
-    if (dbg && tid == 0 && b == 0) dbg[0] = clock64();
-    if (dbg && tid == 0 && b == 1) dbg[14] = clock64();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int idx = tid + it * 256;                  // 2048 16-byte chunks per 64 x 64 tile
-        const int r = idx >> 5, cc = idx & 31;
-        if (has_prev) {
-            cp_async16(ZZ + r * PZ + cc * 2, Ad + (long long)r * lda - 64 + cc * 2, true);
-            if (has_rows && it < OT) cp_async16(ZZ + (64 + r) * PZ + cc * 2, Ar + (long long)r * lda - 64 + cc * 2, true);
-        }
-    }
-    cp_async_commit();
-    for (int i = tid; i < 8 * PLW; i += 256) Lc[i - 8 * PLW] = 0.0;
-    cp_async_wait<0>();
-    __syncthreads();
-    if (dbg && tid == 0 && b == 0) dbg[1] = clock64();
-
-    if (warp != 0 && warp != 4) {
-        // ------------------------------------------------------------------ tensor warps (one sub-panel ahead)
-        int mt[NS];
-        const double* rowp[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            mt[i] = ws_tile<OT>(warp, i);
-            const int r = (mt[i] < 0 ? 0 : mt[i]) * 8 + gq;
-            rowp[i] = (r < 64) ? (Ad + (long long)r * lda) : (Ar + (long long)(r - 64) * lda);
-        }
-#pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
-            const int c0 = p * 8;
-            int mask = 0;
-#pragma unroll
-            for (int i = 0; i < NS; ++i)
-                if (mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p)) mask |= 1 << i;
-            double* Xp = Xr + (p & 1) * ROWS * XP;
-            // columns through sub-panel p-3 were published before this warp's previous barrier wait; sub-panel p-2
-            // follows barrier 3/4 (which also says Xr[p&1] has been consumed); sub-panel p-1 is the scalar warps' job
-            long long* ts = (dbg && warp == 1 && lane == 0 && b == 0 && (p == 0 || p == 3)) ? dbg + (p == 0 ? 40 : 48) : nullptr;
-            ws_tensor_dispatch<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 16, c0 - 8, p >= 2 ? 3 + (p & 1) : -1,
-                                        1 + (p & 1), 224, use_fence, gq, tq, ts, 256, 8 + (p & 1));
-            if (dbg && warp == 1 && lane == 0 && b == 0) dbg[16 + p] = clock64();
-        }
-        if (dbg && lane == 0 && b == 0) dbg[56 + warp] = clock64();
-        span_exit(k0);
-        return;
-    }
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ pivot warp
-        const int pi = lane >> 3, pj = lane & 7;      // cooperative pivot-block update: entries (pi, pj) and (pi + 4, pj)
-#pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
-            const int c0 = p * 8, par = p & 1;
-            const int row = lane + 32 * (p >> 2);               // the group that holds the pivot rows
-            const double* Xp = Xr + par * ROWS * XP;
-            const double* Lprev = Lc + (c0 - 8) * PLW;          // the 8 columns of the previous sub-panel (zeros for p = 0)
-            named_bar_sync(1 + par, 224);
-            if (p == 4) named_bar_sync(7, 64);                  // rows 32..63 of sub-panel 3 come from the row warp
-            const bool stamp = dbg && lane == 0 && b == 0 && (p == 2 || p == 5);
-            long long* ds = dbg + (p == 2 ? 24 : 32);
-            if (stamp) ds[0] = clock64();
-            {   // pivot block: D = Xr block - Lp Lp^T with Lp = L[c0..c0+8)[c0-8..c0)
-                double d0 = Xp[(c0 + pi) * XP + pj], d1 = Xp[(c0 + pi + 4) * XP + pj];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double lj = Lprev[c * PLW + c0 + pj];
-                    d0 = fma(-Lprev[c * PLW + c0 + pi], lj, d0);
-                    d1 = fma(-Lprev[c * PLW + c0 + pi + 4], lj, d1);
-                }
-                Dsm[pi * 8 + pj] = d0;
-                Dsm[(pi + 4) * 8 + pj] = d1;
-            }
-            double acc[8];
-            load_row8(acc, Xp + row * XP);
-            __syncwarp();
-            if (stamp) ds[1] = clock64();
-            double D[8][8], rinv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) D[i][j] = Dsm[i * 8 + j];
-            rank8_update(acc, Lprev, PLW, c0, row);
-            int badcol = 8;                       // first non-positive pivot of this block (8 = none)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double d = D[c][c];
-                const bool ok = d > 0.0;
-                badcol = (!ok && badcol == 8) ? c : badcol;
-                d = ok ? d : 1.0;
-                const double ri = rsqrt_pos(d);
-                rinv[c] = ri;
-                D[c][c] = d * ri;
-#pragma unroll
-                for (int i = c + 1; i < 8; ++i) D[i][c] *= ri;
-#pragma unroll
-                for (int i = c + 1; i < 8; ++i)
-#pragma unroll
-                    for (int j = c + 1; j <= i; ++j) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
-            }
-            {   // publish the factored block (every lane holds the same values: same-value stores)
-                double* F = Dfac + par * 48;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) F[i * (i + 1) / 2 + j] = D[i][j];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) F[40 + c] = rinv[c];
-            }
-            if (stamp) ds[2] = clock64();
-            if (use_fence) __threadfence_block();
-            if (stamp) ds[3] = clock64();
-            named_bar_arrive(5 + par, 64);
-            if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
-            const int jrow = row - c0;
-            subst_row8(acc, D, rinv, jrow);
-            if (jrow >= 0) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[c];
-            }
-            if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
-            if (stamp) ds[4] = clock64();
-            if (use_fence) __threadfence_block();
-            if (stamp) ds[5] = clock64();
-            if (p < 6) named_bar_arrive(3 + par, 256);
-            if (jrow >= 0 && b == 0) {                          // L_kk is parked: other CTAs still read A_kk
-                double* dst = Lt + (long long)row * ldt + c0;
-#pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
-            }
-        }
-        if (dbg && lane == 0 && b == 0) dbg[10] = clock64();
-        if (dbg && lane == 0 && b == 1) { dbg[13] = clock64(); }
-        span_exit(k0);
-        return;
-    }
-
-    // ---------------------------------------------------------------------- row warp (warp 4)
-#pragma unroll 1
-    for (int p = 0; p < 8; ++p) {
-        const int c0 = p * 8, par = p & 1;
-        const double* Xp = Xr + par * ROWS * XP;
-        const double* Lprev = Lc + (c0 - 8) * PLW;
-        const bool on1 = p < 4;                                 // rows 32..63 while the pivot rows are in group 0
-        named_bar_sync(8 + par, 224);
-        double acc[NG - 1][8];
-        int rows[NG - 1];
-        bool act[NG - 1];
-        rows[0] = lane + 32; act[0] = on1;
-#pragma unroll
-        for (int g = 1; g < NG - 1; ++g) { rows[g] = lane + 32 * (g + 1); act[g] = has_rows; }
-#pragma unroll
-        for (int g = 0; g < NG - 1; ++g) load_row8(acc[g], Xp + rows[g] * XP);
-        named_bar_sync(5 + par, 64);                            // factored pivot block of this sub-panel (and the pivot warp's
-                                                                // stores of the previous one) are visible
-        double D[8][8], rinv[8];
-        {
-            const double* F = Dfac + par * 48;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) D[i][j] = F[i * (i + 1) / 2 + j];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) rinv[c] = F[40 + c];
-        }
-#pragma unroll
-        for (int g = 0; g < NG - 1; ++g) {
-            if (!act[g]) continue;                              // warp-uniform
-            rank8_update(acc[g], Lprev, PLW, c0, rows[g]);
-            subst_row8(acc[g], D, rinv, rows[g] - c0);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + rows[g]] = acc[g][c];
-        }
-        if (use_fence) __threadfence_block();
-        if (p < 6) named_bar_arrive(3 + par, 256);
-        if (p == 3) named_bar_arrive(7, 64);
-#pragma unroll
-        for (int g = 0; g < NG - 1; ++g) {
-            if (!act[g]) continue;
-            double* dst = nullptr;
-            if (g >= 1) dst = Ar + (long long)(rows[g] - 64) * lda + c0;
-            else if (b == 0) dst = Lt + (long long)rows[g] * ldt + c0;
-            if (dst) {
-#pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2*>(dst + c) = make_double2(acc[g][c], acc[g][c + 1]);
-            }
-        }
-    }
-    if (dbg && lane == 0 && b == 0) dbg[11] = clock64();
-    if (dbg && lane == 0 && b == 1) dbg[12] = clock64();
     span_exit(k0);
 }
 
@@ -1405,7 +924,8 @@ extern "C" int mogp_panel_spans(int on, unsigned long long* out_host, int n) {
 }
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
 // 0: phase-alternating panel step; 1: warp-specialised, 64 own rows per CTA; 2 (default): warp-specialised with 32 own
-// rows per CTA while twice the CTAs fit one wave.  Measured on B200 (profiles/r01_panel_variants.txt): potrf N=2048
+// rows per CTA while twice the CTAs fit one wave.  (Two further schedules -- tensor warps a full sub-panel ahead of the
+// chain, and two scalar warps -- were measured and removed: DESIGN.md section 4.)  Measured on B200 (profiles/r01_panel_variants.txt): potrf N=2048
 // 0.721 / 0.657 / 0.538 ms, N=8192 7.88 / 7.72 / 7.68 ms.  MOGP_PANEL_VARIANT overrides the default for A/B runs.
 // Programmatic dependent launch of the panel steps: 0 off, 1 (default) inside graph capture only, 2 always.  Measured on B200
 // (profiles/r01_pdl_graphs.txt): inside a replayed graph it hides ~2 us of the ~4 us launch gap between consecutive panel
@@ -1413,8 +933,6 @@ static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the f
 static int g_panel_pdl = std::getenv("MOGP_PANEL_PDL") ? std::atoi(std::getenv("MOGP_PANEL_PDL")) : 1;
 extern "C" int mogp_set_panel_pdl(int v) { g_panel_pdl = v; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_get_panel_pdl(void) { return g_panel_pdl; }
-static int g_panel_nofence = std::getenv("MOGP_PANEL_NOFENCE") ? std::atoi(std::getenv("MOGP_PANEL_NOFENCE")) : 0;
-extern "C" int mogp_set_panel_nofence(int v) { g_panel_nofence = v; ++g_mogp_cfg_epoch; return 0; }
 static int g_panel_variant = std::getenv("MOGP_PANEL_VARIANT") ? std::atoi(std::getenv("MOGP_PANEL_VARIANT")) : 2;
 extern "C" int mogp_set_panel_variant(int v) { g_panel_variant = v; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
@@ -1438,6 +956,30 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
 // panel(s+1) runs concurrently with bulk(s); panel(s+2) waits for bulk(s).  For small matrices
 // the step time is the panel chain, for large ones the chain hides behind the GEMMs.
 // Ltmp is an Np x Np scratch whose diagonal blocks are used; diagonal blocks of Linv get inv(L_kk).
+// One warp-specialised panel step; n_cta_rows = number of 8*OT-row blocks below the diagonal block.  Steps that consume a
+// previous panel are launched with the programmatic-serialization attribute when g_panel_pdl asks for it (see above).
+template <int OT>
+static void launch_panel_ws(double* A, long long ld, double* Ltmp, long long ldt, int k, int n_cta_rows, int has_prev,
+                            int32_t* info, long long* dbgp, cudaStream_t s_) {
+    const unsigned grid = (unsigned)std::max(1, n_cta_rows);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (g_panel_pdl == 1) cudaStreamIsCapturing(s_, &cap);
+    if (has_prev && (g_panel_pdl == 2 || (g_panel_pdl == 1 && cap == cudaStreamCaptureStatusActive))) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = WsCfg<OT>::SMEM; cfg.stream = s_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
+            return;
+        cudaGetLastError();               // not supported in this context: plain launches from now on
+        g_panel_pdl = 0;
+    }
+    potrf_panel_ws_kernel<OT><<<grid, 256, WsCfg<OT>::SMEM, s_>>>(A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp);
+}
+
 // Operations of the pipelined triangular inverse, in issue order (see build_inverse_plan).
 // kind 0: inverse of diagonal block lo; 1: T = L_BA Linv_AA; 2: Linv_BA = -Linv_BB T  (A = [lo, mid), B = [mid, hi)).
 // `ready` = index of the last panel step the operation depends on; `wait` = completion event of the operation that
@@ -1462,6 +1004,21 @@ static int build_inverse_plan(int lo, int hi, std::vector<InvOp>& ops, int& nev)
 // timing experiments only: skip the bulk trailing updates (wrong factor, shows the bare panel chain)
 static int g_skip_bulk = std::getenv("MOGP_SKIP_BULK") ? std::atoi(std::getenv("MOGP_SKIP_BULK")) : 0;
 extern "C" int mogp_set_skip_bulk(int v) { g_skip_bulk = v; ++g_mogp_cfg_epoch; return 0; }
+// Host self-check hook (tests/test_host_math.py): the plan for nb blocks, 8 int32 per operation
+// [kind, lo, mid, hi, ready, wait, done, level]; returns the number of operations (or -1 if cap is too small).
+extern "C" int mogp_host_inverse_plan(int nb, int32_t* out, int cap) {
+    if (nb < 1) return -1;
+    std::vector<InvOp> ops;
+    int ne = 0;
+    build_inverse_plan(0, nb, ops, ne);
+    if ((int)ops.size() > cap) return -1;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const InvOp& o = ops[i];
+        const int32_t v[8] = {o.kind, o.lo, o.mid, o.hi, o.ready, o.wait, o.done, o.level};
+        for (int j = 0; j < 8; ++j) out[8 * i + j] = v[j];
+    }
+    return (int)ops.size();
+}
 // Pipelined inverse on by default (measured: cfg2 0.938 -> 0.899 ms, cfg4 3.62 -> 3.55 ms; profiles/r01_panel_variants.txt).
 static int g_trtri_pipe = std::getenv("MOGP_TRTRI_PIPE") ? std::atoi(std::getenv("MOGP_TRTRI_PIPE")) : 1;
 extern "C" int mogp_set_trtri_pipe(int v) { g_trtri_pipe = v; ++g_mogp_cfg_epoch; return 0; }
@@ -1480,34 +1037,10 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
     // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
-        if (g_panel_variant == 4 && 2 * nrb <= n_sm)
-            potrf_panel_ws3_kernel<4><<<std::max(1, 2 * nrb), 256, Ws3Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
-        else if (g_panel_variant == 3 && 2 * nrb <= n_sm)
-            potrf_panel_ws2_kernel<4><<<std::max(1, 2 * nrb), 256, Ws2Cfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
-        else if (g_panel_variant >= 2 && 2 * nrb <= n_sm) {
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            if (g_panel_pdl == 1) cudaStreamIsCapturing(s_, &cap);       // 1: only inside graph capture (measured: no gain eagerly,
-                                                                         // the event waits between the steps cancel it); 2: always
-            if (has_prev && (g_panel_pdl == 2 || (g_panel_pdl == 1 && cap == cudaStreamCaptureStatusActive))) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)std::max(1, 2 * nrb)); cfg.blockDim = dim3(256);
-                cfg.dynamicSmemBytes = WsCfg<4>::SMEM; cfg.stream = s_;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                at[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
-                cudaError_t le = cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<4>, A, (long long)ld, Ltmp, (long long)ldt, (int)k, 2 * nrb,
-                                                    (int)(has_prev | (g_panel_nofence << 1)), info, dbgp);
-                if (le != cudaSuccess) {          // not supported in this context: plain launches from now on
-                    cudaGetLastError();
-                    g_panel_pdl = 0;
-                    potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
-                }
-            } else
-                potrf_panel_ws_kernel<4><<<std::max(1, 2 * nrb), 256, WsCfg<4>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
-        }
+        if (g_panel_variant >= 2 && 2 * nrb <= n_sm)
+            launch_panel_ws<4>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp, s_);
         else if (g_panel_variant >= 1)
-            potrf_panel_ws_kernel<8><<<std::max(1, nrb), 256, WsCfg<8>::SMEM, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev | (g_panel_nofence << 1), info, dbgp);
+            launch_panel_ws<8>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp, s_);
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
@@ -1518,16 +1051,6 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ws3Cfg<4>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws3_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ws2Cfg<4>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws2_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<4>::SMEM);

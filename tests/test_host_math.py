@@ -111,3 +111,58 @@ def test_chain_rule_matches_autograd(lib, name):
     sig = g["sigma"]
     gs = np.array([2 * sig[c] * (np.trace(W[off[c]:off[c + 1], off[c]:off[c + 1]]) + adj[c]) for c in range(Cn)])
     assert np.abs(gs - ref["sigma"].numpy()).max() <= 1e-7 * max(np.abs(ref["sigma"].numpy()).max(), 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pipelined triangular inverse: the host-side plan (csrc/linalg.cu::build_inverse_plan) that potrf_padded releases
+# panel by panel.  Replaces the level-batched loop of trtri_padded for N <= 4096; the arithmetic it schedules is
+# torch.linalg.solve_triangular / cholesky_solve of the reference (mogptk/gpr/model.py:452,470).
+def _inverse_plan(lib, nb):
+    import ctypes as C
+    cap = 3 * nb + 8
+    buf = (C.c_int32 * (8 * cap))()
+    n = lib.mogp_host_inverse_plan(nb, buf, cap)
+    assert n > 0
+    return [tuple(buf[8 * i + j] for j in range(8)) for i in range(n)]
+
+
+@pytest.mark.parametrize("nb", [1, 2, 3, 4, 6, 8, 10, 32, 34, 64, 128])
+def test_inverse_plan_is_a_valid_schedule(lib, nb):
+    ops = _inverse_plan(lib, nb)
+    assert len(ops) == nb + 2 * (nb - 1)
+    ready = [o[4] for o in ops]
+    assert ready == sorted(ready), "operations must be releasable panel by panel"
+    assert ready[-1] == nb - 1
+    done_at = {}
+    for idx, (kind, lo, mid, hi, rdy, wait, done, level) in enumerate(ops):
+        assert done not in done_at
+        done_at[done] = idx
+        if kind == 0:
+            assert hi == lo + 1 and rdy == lo and wait == -1
+        else:
+            assert lo < mid < hi <= nb and (mid - lo) == 1 << level and (mid - lo) >= (hi - mid)
+            assert wait in done_at and done_at[wait] < idx, "a dependency is issued before its consumer"
+            assert rdy == (mid - 1 if kind == 1 else hi - 1)
+    # the T product of a pair is issued before its second GEMM, on the same level
+    for idx, o in enumerate(ops):
+        if o[0] == 2:
+            assert any(p[0] == 1 and p[1:4] == o[1:4] and p[7] == o[7] for p in ops[:idx])
+
+
+@pytest.mark.parametrize("nb", [1, 2, 5, 8, 13])
+def test_inverse_plan_computes_the_inverse(lib, nb):
+    """Run the plan with numpy blocks (block size 3) in issue order, only ever touching what an operation may touch."""
+    rng = np.random.default_rng(nb)
+    bs, n = 3, 3 * nb
+    L = np.tril(rng.standard_normal((n, n))) + 4.0 * np.eye(n)
+    Linv = np.zeros((n, n))
+    T = np.zeros((n, n))
+    for kind, lo, mid, hi, rdy, wait, done, level in _inverse_plan(lib, nb):
+        a, m, h = lo * bs, mid * bs, hi * bs
+        if kind == 0:
+            Linv[a:h, a:h] = np.linalg.inv(L[a:h, a:h])
+        elif kind == 1:
+            T[m:h, a:m] = L[m:h, a:m] @ Linv[a:m, a:m]
+        else:
+            Linv[m:h, a:m] = -Linv[m:h, m:h] @ T[m:h, a:m]
+    assert np.allclose(Linv, np.linalg.inv(L), rtol=1e-10, atol=1e-12)

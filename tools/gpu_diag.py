@@ -239,26 +239,21 @@ def sec_time(eng):
 
 
 def sec_panel(eng):
+    """Phase stamps (clock64) of the second panel step of an N=2048 factorisation, per panel variant.  The stamps and their
+    stores perturb the kernel (the warp-specialised one more than the others): use `spans` for absolute kernel times."""
     import ctypes as C
     buf = (C.c_longlong * 64)()
     eng.lib.mogp_panel_debug(buf)          # arms the timestamps (second panel of the single-level sweep)
-    for variant, nofence in ((4, 0), (2, 0)):
+    n = 2048
+    A = spd(n, 1).cuda()
+    for variant in (2, 1, 0):
         eng.lib.mogp_set_panel_variant(variant)
-        eng.lib.mogp_set_panel_nofence(nofence)
-        print("--- variant %d nofence %d" % (variant, nofence))
-        n = 2048
-        A = spd(n, 1).cuda()
         for _ in range(3):
             W = A.clone()
             eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
         torch.cuda.synchronize()
-        eng.lib.mogp_panel_debug(buf)          # (also re-arms the span stamps)
-        W = A.clone()
-        eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
-        torch.cuda.synchronize()
         eng.lib.mogp_panel_debug(buf)
         t = [int(v) for v in buf]
-
         if variant >= 1:
             print("ws%d panel n=%d: prologue %d | chain done stamps (delta): %s | tensor Xr-ready (rel. start): %s | total %d cycles" % (
                 variant, n, t[1] - t[0], [t[2 + p] - (t[1] if p == 0 else t[1 + p]) for p in range(8)],
@@ -269,131 +264,9 @@ def sec_panel(eng):
                 d = t[base:base + 6]
                 print("   tensor warp 1 p=%d (start rel. kernel %d): prev-panel accumulation %d | published columns %d | barrier wait %d | tail+store %d | fence+arrive %d" % (
                     pp, d[0] - t[0], d[1] - d[0], d[2] - d[1], (d[3] - d[2]) if pp else 0, d[4] - (d[3] if pp else d[2]), d[5] - d[4]))
-            if variant == 4:
-                print("   ends rel. kernel start: pivot %d | row warp %d | tensor warps %s | CTA 1: pivot %d row %d (its own start)" % (
-                    t[10] - t[0], t[11] - t[0], [t[56 + w] - t[0] for w in (1, 2, 3, 5, 6, 7)], t[13] - t[14], t[12] - t[14]))
-                for base, pp in ((24, 2), (32, 5)):
-                    d = t[base:base + 6]
-                    print("   pivot warp p=%d: coop+exchange %d | pivot chain+rank8+publish %d | fence %d | subst+store %d | fence %d" % (
-                        pp, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4]))
         else:
             print("panel n=%d: load %d | " % (n, t[1] - t[0]) + " ".join("p%d: f%d u%d" % (p, t[2 + 2 * p] - (t[1] if p == 0 else t[1 + 2 * p]), t[3 + 2 * p] - t[2 + 2 * p]) for p in range(8)) + " | store %d | total %d cycles" % (t[18] - t[17], t[18] - t[0]))
     eng.lib.mogp_set_panel_variant(int(os.environ.get("MOGP_PANEL_VARIANT", "2")))
-    eng.lib.mogp_set_panel_nofence(0)
-
-
-def sec_exp(eng):
-    """A/B of the Cholesky panel variants and the pipelined inverse in one process.
-    EXP_COMBOS="variant:pipe,..." (default 0:0); prints a verdict line per combination."""
-    import ctypes as C
-    from conftest import load_golden
-    from mogptk_b200.engine import pack_params
-    combos = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("EXP_COMBOS", "0:0").split(",")]
-    nofence = int(os.environ.get("EXP_NOFENCE", "0"))
-    eng.lib.mogp_set_panel_nofence(nofence)
-    eng.lib.mogp_set_panel_pdl(int(os.environ.get("EXP_PDL", "0")))
-    eng.lib.mogp_set_graph_max_np(int(os.environ.get("EXP_GRAPH_MAX_NP", "3072")))
-    print("nofence =", nofence, "pdl =", os.environ.get("EXP_PDL", "0"))
-    names = os.environ.get("DIAG_CFGS", "cfg2,cfg4,cfg3").split(",")
-    prepared = {}
-    for name in names:
-        g = load_golden(name)
-        prepared[name] = (g, eng.prepare(g["kind"], g["params"], g["X"], g["y"]), pack_params(g["kind"], g["params"], eng.device),
-                          torch.tensor(g["sigma"], device=eng.device))
-    mats = {n: spd(n, n) for n in (128, 200, 640, 2048, 2176)}
-    refs = {n: torch.linalg.cholesky(A) for n, A in mats.items()}
-    invs = {n: torch.linalg.inv(refs[n]) for n in (128, 640, 2048, 2176)}
-    for (v, pipe) in combos:
-        eng.lib.mogp_set_panel_variant(v)
-        eng.lib.mogp_set_trtri_pipe(pipe)
-        tag = "v%d pipe%d" % (v, pipe)
-        worst = 0.0
-        for n, A in mats.items():
-            Ad = A.cuda().clone()
-            info = eng.potrf_(Ad)
-            e1 = rel(torch.tril(Ad).cpu(), refs[n])
-            worst = max(worst, e1) if info == 0 else float("inf")
-            print("[%s] potrf n=%4d info=%d relerr(L) %.2e" % (tag, n, info, e1))
-        Ab = spd(300, 5)
-        Ab[150, 150] = -1.0
-        bad = eng.potrf_(Ab.cuda().clone())
-        for n in invs:
-            Ad = mats[n].cuda().clone()
-            Linv, Kinv, info = eng.trtri_kinv_(Ad)
-            e = (rel(torch.tril(Ad).cpu(), refs[n]), rel(torch.tril(Linv).cpu(), invs[n]),
-                 rel(torch.tril(Kinv).cpu(), torch.tril(invs[n].T @ invs[n])))
-            worst = max(worst, *e) if info == 0 else float("inf")
-            print("[%s] trtri n=%4d info=%d relerr(L) %.2e relerr(Linv) %.2e relerr(Kinv) %.2e" % ((tag, n, info) + e))
-        print("[%s] VERDICT %s worst %.2e bad-pivot info %d (expect 151)" % (tag, "OK" if worst < 1e-9 and bad == 151 else "FAIL", worst, bad))
-        for n in (2048, 4096, 8192):
-            A = spd(n, 1).cuda()
-            W = A.clone()
-
-            def run():
-                W.copy_(A)
-                eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
-
-            def cp():
-                W.copy_(A)
-            t_all, _ = ev_time(run, reps=5, warm=2)
-            t_cp, _ = ev_time(cp, reps=5, warm=2)
-            t = t_all - t_cp
-            print("[%s] potrf n=%d: %.3f ms  %.2f TFLOP/s" % (tag, n, t, n ** 3 / 3.0 / t / 1e9))
-        for name in names:
-            g, rows, p, sig = prepared[name]
-            N = g["X"].shape[0]
-            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=11, warm=4)
-            eng.lib.mogp_set_profile(eng.h, 1)
-            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
-            st = (C.c_float * 8)()
-            ns = eng.lib.mogp_stage_times(eng.h, st)
-            eng.lib.mogp_set_profile(eng.h, 0)
-            r = eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
-            lml_got, lml_ref = float(r[0].item()), float(g["lml"])
-            gerr = 0.0
-            P = p.numel()
-            from mogptk_b200.engine import unpack_grads
-            C_, Q, D = rows.dims
-            gd = unpack_grads(g["kind"], C_, Q, D, r[2:2 + P].cpu())
-            for k, got in gd.items():
-                ref = g["gc_" + k]
-                gerr = max(gerr, float(np.abs(got.numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-12)))
-            ok = abs(lml_got - lml_ref) <= 1e-8 * abs(lml_ref) and gerr <= 1e-6 and int(r[1].item()) == 0
-            print("[%s] step %-5s N=%d: %.3f ms (min %.3f) -> %.1f it/s | stages %s | lml rel %.1e grad %.1e %s" % (
-                tag, name, N, t1, m1, 1e3 / t1, " ".join("%s %.3f" % (nm, st[i]) for i, nm in enumerate(
-                    ["kbuild", "potrf", "trtri", "solves", "kinv", "grad"][:ns])),
-                abs(lml_got - lml_ref) / abs(lml_ref), gerr, "STEP_OK" if ok else "STEP_FAIL"))
-        sys.stdout.flush()
-    eng.lib.mogp_set_panel_variant(0)
-    eng.lib.mogp_set_trtri_pipe(0)
-
-
-def sec_gaps(eng):
-    """Panel chain versus interference from the concurrent trailing updates (timing only: skip_bulk gives a wrong factor)."""
-    for n in (2048, 4096):
-        A = spd(n, 1).cuda()
-        W = A.clone()
-
-        def run():
-            W.copy_(A)
-            eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
-
-        def cp():
-            W.copy_(A)
-        t_cp, _ = ev_time(cp, reps=5, warm=2)
-        for v in (2, 4, 0):
-            eng.lib.mogp_set_panel_variant(v)
-            line = "gaps n=%d variant %d:" % (n, v)
-            for skip in (0, 1):
-                eng.lib.mogp_set_skip_bulk(skip)
-                for cfg in (0, 2):
-                    eng.lib.mogp_set_gemm_config(cfg)
-                    t_all, _ = ev_time(run, reps=7, warm=2)
-                    line += "  %s/%s %.3f ms" % ("no-bulk" if skip else "bulk", "32x64" if cfg == 0 else "64x64", t_all - t_cp)
-            print(line)
-    eng.lib.mogp_set_skip_bulk(0)
-    eng.lib.mogp_set_gemm_config(0)
-    eng.lib.mogp_set_panel_variant(2)
 
 
 def sec_spans(eng):
@@ -403,9 +276,10 @@ def sec_spans(eng):
     nb = n // 64
     A = spd(n, 1).cuda()
     out = (C.c_ulonglong * (2 * nb))()
-    for v, pdl in ((2, 0), (2, 1)):
+    for v, pdl in ((2, 0), (2, 2), (1, 0), (0, 0)):
         eng.lib.mogp_set_panel_variant(v)
         eng.lib.mogp_set_panel_pdl(pdl)
+        print("--- variant %d pdl %d" % (v, pdl))
         for skip in (0, 1):
             eng.lib.mogp_set_skip_bulk(skip)
             for _ in range(3):
