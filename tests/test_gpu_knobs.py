@@ -1,0 +1,68 @@
+"""GPU tests of the scheduling knobs of the Cholesky / inverse stage: every panel-step variant, the pipelined and
+the level-batched triangular inverse, programmatic dependent launch on and off, graph replay on and off must all
+reproduce the reference (same tolerances as test_gpu_parity.py: LML rtol 1e-8, gradients <= 1e-6 of the largest
+entry).  The defaults are what the rest of the suite runs; these keep the alternatives -- which are also the
+fallbacks when a launch attribute is not supported -- honest."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def knobs(engine):
+    lib = engine.lib
+
+    def set_(variant=2, pipe=1, pdl=1, graphs=1):
+        lib.mogp_set_panel_variant(variant)
+        lib.mogp_set_trtri_pipe(pipe)
+        lib.mogp_set_panel_pdl(pdl)
+        lib.mogp_set_graphs(graphs)
+    yield set_
+    set_()          # back to the defaults for the rest of the session
+
+
+def _check(engine, g, reps=3):
+    # three evaluations: plain run, graph capture, graph replay
+    for _ in range(reps):
+        res = engine.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], True,
+                              data_var=g.get("data_var"))
+    assert res["info"] == 0
+    assert abs(res["lml"] - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+    for k, got in res["grad"].items():
+        ref = g["gc_" + k]
+        scale = max(float(np.abs(ref).max()), 1e-12)
+        assert float(np.abs(got.numpy().reshape(ref.shape) - ref).max()) <= 1e-6 * scale, k
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("pipe", [0, 1])
+@pytest.mark.parametrize("name", ["mosm_mid", "cfg2"])
+def test_panel_variants_and_inverse_schedules(engine, knobs, name, variant, pipe):
+    knobs(variant=variant, pipe=pipe)
+    _check(engine, load_golden(name))
+
+
+@pytest.mark.parametrize("pdl,graphs", [(0, 1), (2, 1), (2, 0), (1, 0)])
+@pytest.mark.parametrize("name", ["cfg2", "cfg4"])
+def test_dependent_launch_and_graph_modes(engine, knobs, name, pdl, graphs):
+    knobs(pdl=pdl, graphs=graphs)
+    _check(engine, load_golden(name))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n", [64, 200, 1024, 4224, 4736])
+def test_potrf_variants_against_lapack(engine, knobs, variant, n):
+    """4224 / 4736 rows take the two-level sweep; at 4736 the early panel steps use 64 own rows per CTA and the late ones 32."""
+    knobs(variant=variant)
+    gen = torch.Generator().manual_seed(n)
+    B = torch.randn((n, n + 8), generator=gen, dtype=torch.float64)
+    A = B @ B.T / n + 0.5 * torch.eye(n, dtype=torch.float64)
+    Ad = A.cuda().clone()
+    assert engine.potrf_(Ad) == 0
+    L = torch.tril(Ad).cpu()
+    Lref = torch.linalg.cholesky(A)
+    assert float((L - Lref).abs().max() / Lref.abs().max()) < 1e-12
