@@ -62,6 +62,7 @@ _EXTRA = {
     "mogp_set_panel_variant": (C.c_int, [C.c_int]),
     "mogp_set_trtri_pipe": (C.c_int, [C.c_int]),
     "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
+    "mogp_set_two_level_above": (C.c_int, [C.c_longlong]),
     "mogp_set_panel_pdl": (C.c_int, [C.c_int]),
     "mogp_get_panel_pdl": (C.c_int, []),
     "mogp_panel_spans": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),

@@ -1001,6 +1001,10 @@ static int build_inverse_plan(int lo, int hi, std::vector<InvOp>& ops, int& nev)
     ops.push_back({2, lo, mid, hi, hi - 1, eb, nev, lvl});         // follows its own T on the level's stream
     return nev++;
 }
+// sizes above this take the two-level sweep (K = 256 trailing updates).  Measured (profiles/r01_two_level_threshold.txt):
+// N = 4096 potrf 1.73 ms single-level, 1.65 ms two-level; N = 2048 0.52 ms single-level, 0.61 ms two-level.
+static long long g_two_level_above = std::getenv("MOGP_TWO_LEVEL_ABOVE") ? std::atoll(std::getenv("MOGP_TWO_LEVEL_ABOVE")) : 2048;
+extern "C" int mogp_set_two_level_above(long long v) { g_two_level_above = v; ++g_mogp_cfg_epoch; return 0; }
 // timing experiments only: skip the bulk trailing updates (wrong factor, shows the bare panel chain)
 static int g_skip_bulk = std::getenv("MOGP_SKIP_BULK") ? std::atoi(std::getenv("MOGP_SKIP_BULK")) : 0;
 extern "C" int mogp_set_skip_bulk(int v) { g_skip_bulk = v; ++g_mogp_cfg_epoch; return 0; }
@@ -1157,7 +1161,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         *fused_inverse = true;
         return cudaSuccess;
     };
-    if (Np > 4096) {
+    if (Np > g_two_level_above) {
         // Large matrices: two-level updates (K = 64 inside a 256-column outer panel, one K = 256 SYRK per
         // outer panel) keep the trailing-matrix traffic down.  The SYRK is split into the next outer
         // panel's columns (priority) and the rest; both run on S2 while S1 factors the next outer panel.

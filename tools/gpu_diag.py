@@ -269,6 +269,121 @@ def sec_panel(eng):
     eng.lib.mogp_set_panel_variant(int(os.environ.get("MOGP_PANEL_VARIANT", "2")))
 
 
+def sec_exp(eng):
+    """A/B of the Cholesky panel variants and the pipelined inverse in one process.
+    EXP_COMBOS="variant:pipe,..." (default 0:0); prints a verdict line per combination."""
+    import ctypes as C
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params
+    combos = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("EXP_COMBOS", "0:0").split(",")]
+    eng.lib.mogp_set_panel_pdl(int(os.environ.get("EXP_PDL", "1")))
+    eng.lib.mogp_set_graph_max_np(int(os.environ.get("EXP_GRAPH_MAX_NP", "1000000")))
+    eng.lib.mogp_set_two_level_above(int(os.environ.get("EXP_TWO_LEVEL_ABOVE", "2048")))
+    print("pdl =", os.environ.get("EXP_PDL", "1"), "two-level above", os.environ.get("EXP_TWO_LEVEL_ABOVE", "2048"))
+    names = os.environ.get("DIAG_CFGS", "cfg2,cfg4,cfg3").split(",")
+    prepared = {}
+    for name in names:
+        g = load_golden(name)
+        prepared[name] = (g, eng.prepare(g["kind"], g["params"], g["X"], g["y"]), pack_params(g["kind"], g["params"], eng.device),
+                          torch.tensor(g["sigma"], device=eng.device))
+    mats = {n: spd(n, n) for n in (128, 200, 640, 2048, 2176)}
+    refs = {n: torch.linalg.cholesky(A) for n, A in mats.items()}
+    invs = {n: torch.linalg.inv(refs[n]) for n in (128, 640, 2048, 2176)}
+    for (v, pipe) in combos:
+        eng.lib.mogp_set_panel_variant(v)
+        eng.lib.mogp_set_trtri_pipe(pipe)
+        tag = "v%d pipe%d" % (v, pipe)
+        worst = 0.0
+        for n, A in mats.items():
+            Ad = A.cuda().clone()
+            info = eng.potrf_(Ad)
+            e1 = rel(torch.tril(Ad).cpu(), refs[n])
+            worst = max(worst, e1) if info == 0 else float("inf")
+            print("[%s] potrf n=%4d info=%d relerr(L) %.2e" % (tag, n, info, e1))
+        Ab = spd(300, 5)
+        Ab[150, 150] = -1.0
+        bad = eng.potrf_(Ab.cuda().clone())
+        for n in invs:
+            Ad = mats[n].cuda().clone()
+            Linv, Kinv, info = eng.trtri_kinv_(Ad)
+            e = (rel(torch.tril(Ad).cpu(), refs[n]), rel(torch.tril(Linv).cpu(), invs[n]),
+                 rel(torch.tril(Kinv).cpu(), torch.tril(invs[n].T @ invs[n])))
+            worst = max(worst, *e) if info == 0 else float("inf")
+            print("[%s] trtri n=%4d info=%d relerr(L) %.2e relerr(Linv) %.2e relerr(Kinv) %.2e" % ((tag, n, info) + e))
+        print("[%s] VERDICT %s worst %.2e bad-pivot info %d (expect 151)" % (tag, "OK" if worst < 1e-9 and bad == 151 else "FAIL", worst, bad))
+        for n in (2048, 4096, 8192):
+            A = spd(n, 1).cuda()
+            W = A.clone()
+
+            def run():
+                W.copy_(A)
+                eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+
+            def cp():
+                W.copy_(A)
+            t_all, _ = ev_time(run, reps=5, warm=2)
+            t_cp, _ = ev_time(cp, reps=5, warm=2)
+            t = t_all - t_cp
+            print("[%s] potrf n=%d: %.3f ms  %.2f TFLOP/s" % (tag, n, t, n ** 3 / 3.0 / t / 1e9))
+        for name in names:
+            g, rows, p, sig = prepared[name]
+            N = g["X"].shape[0]
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=11, warm=4)
+            eng.lib.mogp_set_profile(eng.h, 1)
+            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            st = (C.c_float * 8)()
+            ns = eng.lib.mogp_stage_times(eng.h, st)
+            eng.lib.mogp_set_profile(eng.h, 0)
+            r = eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            lml_got, lml_ref = float(r[0].item()), float(g["lml"])
+            gerr = 0.0
+            P = p.numel()
+            from mogptk_b200.engine import unpack_grads
+            C_, Q, D = rows.dims
+            gd = unpack_grads(g["kind"], C_, Q, D, r[2:2 + P].cpu())
+            for k, got in gd.items():
+                ref = g["gc_" + k]
+                gerr = max(gerr, float(np.abs(got.numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-12)))
+            ok = abs(lml_got - lml_ref) <= 1e-8 * abs(lml_ref) and gerr <= 1e-6 and int(r[1].item()) == 0
+            print("[%s] step %-5s N=%d: %.3f ms (min %.3f) -> %.1f it/s | stages %s | lml rel %.1e grad %.1e %s" % (
+                tag, name, N, t1, m1, 1e3 / t1, " ".join("%s %.3f" % (nm, st[i]) for i, nm in enumerate(
+                    ["kbuild", "potrf", "trtri", "solves", "kinv", "grad"][:ns])),
+                abs(lml_got - lml_ref) / abs(lml_ref), gerr, "STEP_OK" if ok else "STEP_FAIL"))
+        sys.stdout.flush()
+    eng.lib.mogp_set_panel_variant(2)
+    eng.lib.mogp_set_trtri_pipe(1)
+    eng.lib.mogp_set_panel_pdl(1)
+    eng.lib.mogp_set_two_level_above(2048)
+
+
+def sec_gaps(eng):
+    """Panel chain versus interference from the concurrent trailing updates (timing only: skip_bulk gives a wrong factor)."""
+    for n in (2048, 4096):
+        A = spd(n, 1).cuda()
+        W = A.clone()
+
+        def run():
+            W.copy_(A)
+            eng.lib.mogp_potrf(eng.h, eng._p(W), n, n, None, eng._stream())
+
+        def cp():
+            W.copy_(A)
+        t_cp, _ = ev_time(cp, reps=5, warm=2)
+        for v in (2, 1, 0):
+            eng.lib.mogp_set_panel_variant(v)
+            line = "gaps n=%d variant %d:" % (n, v)
+            for skip in (0, 1):
+                eng.lib.mogp_set_skip_bulk(skip)
+                for cfg in (0, 2):
+                    eng.lib.mogp_set_gemm_config(cfg)
+                    t_all, _ = ev_time(run, reps=7, warm=2)
+                    line += "  %s/%s %.3f ms" % ("no-bulk" if skip else "bulk", "32x64" if cfg == 0 else "64x64", t_all - t_cp)
+            print(line)
+    eng.lib.mogp_set_skip_bulk(0)
+    eng.lib.mogp_set_gemm_config(0)
+    eng.lib.mogp_set_panel_variant(2)
+
+
 def sec_spans(eng):
     """Per panel step: kernel span seen from inside (global timer over all CTAs) and the gap to the next step."""
     import ctypes as C
