@@ -53,6 +53,7 @@ _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
     "mogp_set_graphs": (None, [C.c_int]),
     "mogp_set_graph_max_np": (None, [C.c_longlong]),
+    "mogp_test_fail_capture": (None, [C.c_int]),
     "mogp_set_small_tile_threshold": (None, [C.c_longlong]),
     "mogp_launch_count": (C.c_longlong, []),
     "mogp_panel_debug": (C.c_int, [C.POINTER(C.c_longlong)]),

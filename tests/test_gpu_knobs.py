@@ -66,3 +66,18 @@ def test_potrf_variants_against_lapack(engine, knobs, variant, n):
     L = torch.tril(Ad).cpu()
     Lref = torch.linalg.cholesky(A)
     assert float((L - Lref).abs().max() / Lref.abs().max()) < 1e-12
+
+
+def test_failed_graph_capture_falls_back_to_an_eager_run(engine, knobs):
+    """If the step cannot be captured (e.g. no programmatic-dependent-launch edges in graphs on an older driver) the
+    same call must still return the right numbers, and later calls run eagerly."""
+    knobs()
+    lib = engine.lib
+    g = load_golden("mosm_mid")
+    lib.mogp_test_fail_capture(1)
+    try:
+        _check(engine, g, reps=4)            # plain run, failed capture -> eager, eager, eager
+    finally:
+        lib.mogp_test_fail_capture(0)
+        knobs()                              # re-enables graphs and dependent launches
+    _check(engine, g, reps=3)                # and the replayed graph still agrees afterwards
