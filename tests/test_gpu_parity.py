@@ -51,14 +51,17 @@ def test_potrf_against_lapack(engine, n):
     assert rel(L @ L.T, A) < 1e-13
 
 
-def test_potrf_reports_first_bad_pivot(engine):
+@pytest.mark.parametrize("bad", [150, 151, 7, 64, 0, 299])
+def test_potrf_reports_first_bad_pivot(engine, bad):
+    """LAPACK convention: info = k means the leading minor of order k is not positive definite.  Even and odd
+    columns take different branches of the 2x2 pivot step; 64 is the first column of the second panel."""
     n = 300
     g = torch.Generator().manual_seed(5)
     B = torch.randn((n, n), generator=g, dtype=torch.float64)
     A = B @ B.T / n + 0.5 * torch.eye(n, dtype=torch.float64)
-    A[150, 150] = -1.0                      # leading minor 151 is not positive definite
+    A[bad, bad] = -1.0                      # leading minor bad + 1 is not positive definite
     info = engine.potrf_(A.cuda().clone())
-    assert info == 151
+    assert info == bad + 1
 
 
 @pytest.mark.parametrize("n", [128, 384, 1024])
