@@ -417,6 +417,17 @@ def sec_spans(eng):
     eng.lib.mogp_set_panel_variant(2)
 
 
+def sec_i8(eng):
+    """Experimental fp64-on-int8 tcgen05 GEMM (csrc/i8gemm.cu) against the DMMA GEMM: error and time per slice count."""
+    import ctypes as C
+    out = (C.c_double * 3)()
+    for (M, N, K) in [(128, 64, 64), (256, 128, 256), (1024, 1024, 1024), (4096, 4096, 4096)]:
+        for S in (6, 7, 8):
+            rc = eng.lib.mogp_i8gemm_selftest(M, N, K, S, out)
+            print("i8 gemm %5dx%5dx%5d S=%d rc=%d: rel. error %.2e | int8 path %.3f ms (%.1f TFLOP/s fp64-equivalent) | DMMA %.3f ms (%.1f TFLOP/s)" % (
+                M, N, K, S, rc, out[0], out[1], 2.0 * M * N * K / max(out[1], 1e-9) / 1e9, out[2], 2.0 * M * N * K / max(out[2], 1e-9) / 1e9))
+
+
 def sec_gemmk(eng):
     """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
     for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
@@ -487,7 +498,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"i8": sec_i8, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
