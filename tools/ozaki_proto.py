@@ -8,7 +8,9 @@ kind::i8 (dense int8 peak 4.5 POP/s on B200).  Ozaki-style slicing with a shared
 
 S slices -> S (S + 1) / 2 int8 GEMMs.  Reports the error of K^-1 = L^-T L^-1 for GP covariances of increasing
 condition number against an extended-precision reference, next to the error of the plain fp64 GEMM, as a function of
-S and b.  Usage: python tools/ozaki_proto.py [N]"""
+S and b; with --pipeline the whole O(N^3) structure of the step (blocked Cholesky updates, block-doubling inverse,
+K^-1) runs on the emulated GEMM and LML / gradient-like quantities are compared end to end.
+Usage: python tools/ozaki_proto.py [N] | --pipeline [N]"""
 import sys
 
 import numpy as np
@@ -59,7 +61,78 @@ def gp_covariance(n, noise, seed=0):
     return K
 
 
+def ozaki_gemm_fast(A, B, S, b):
+    """Same arithmetic as ozaki_gemm (pairs s + t < S) with the exact integer products done by the fp64 BLAS
+    (every partial sum is an integer below 2^53, so the float matmul is exact); anti-diagonals share an accumulator."""
+    da, ea = split_rows(A, S, b)
+    db, eb = split_rows(B.T, S, b)
+    da = da.astype(np.float64)
+    db = db.astype(np.float64)
+    C = np.zeros((A.shape[0], B.shape[1]))
+    for d in range(S - 1, -1, -1):                    # smallest weights first
+        P = np.zeros_like(C)
+        for s in range(d + 1):
+            P += da[s] @ db[d - s].T
+        C += P * 2.0 ** (-b * (d + 2))
+    return C * np.exp2(ea)[:, None] * np.exp2(eb)[None, :]
+
+
+def exact_gp_step(K, y, gemm, nb=64):
+    """The O(N^3) structure of the product path with a pluggable GEMM: blocked right-looking Cholesky (panel work in
+    fp64, trailing updates through `gemm`), L^-1 by block doubling, K^-1 = L^-T L^-1; returns (lml, tr W, W-weighted
+    probe) where W = (K^-1 - a a^T) / 2 is what the gradient kernel consumes."""
+    n = K.shape[0]
+    A = K.copy()
+    for k in range(0, n, nb):
+        e = min(k + nb, n)
+        A[k:e, k:e] = np.linalg.cholesky(A[k:e, k:e])
+        if e < n:
+            A[e:, k:e] = np.linalg.solve(A[k:e, k:e], A[e:, k:e].T).T
+            A[e:, e:] -= gemm(A[e:, k:e], A[e:, k:e].T)
+    L = np.tril(A)
+    Linv = np.zeros_like(L)
+    for k in range(0, n, nb):
+        e = min(k + nb, n)
+        Linv[k:e, k:e] = np.linalg.inv(L[k:e, k:e])
+    s = nb
+    while s < n:
+        for o in range(0, n, 2 * s):
+            m, h = o + s, min(o + 2 * s, n)
+            if m >= n:
+                continue
+            T = gemm(L[m:h, o:m], Linv[o:m, o:m])
+            Linv[m:h, o:m] = -gemm(Linv[m:h, m:h], T)
+        s *= 2
+    Kinv = gemm(np.ascontiguousarray(Linv.T), Linv)
+    z = Linv @ y
+    alpha = Linv.T @ z
+    lml = -0.5 * n * np.log(2 * np.pi) - np.log(np.diag(L)).sum() - 0.5 * float(z @ z)
+    W = 0.5 * (Kinv - np.outer(alpha, alpha))
+    idx = np.arange(n)
+    probe = float((W * np.cos(0.37 * (idx[:, None] - idx[None, :]))).sum())    # a dK/dtheta-like weighting
+    return lml, float(np.trace(W)), probe
+
+
+def pipeline(n):
+    rng = np.random.default_rng(1)
+    for noise in (1.0, 1e-2, 1e-4, 1e-6):
+        K = gp_covariance(n, noise)
+        y = rng.standard_normal(n)
+        ref = exact_gp_step(K.astype(np.longdouble).astype(np.float64), y, lambda a, b_: (a.astype(np.longdouble) @ b_.astype(np.longdouble)).astype(np.float64))
+        f64 = exact_gp_step(K, y, lambda a, b_: a @ b_)
+        print("N=%d noise=%.0e cond(K)=%.1e: fp64 GEMMs: lml rel %.1e  trW rel %.1e  probe rel %.1e" % (
+            n, noise, np.linalg.cond(K), abs(f64[0] - ref[0]) / abs(ref[0]), abs(f64[1] - ref[1]) / abs(ref[1]),
+            abs(f64[2] - ref[2]) / abs(ref[2])))
+        for S in (5, 6, 7, 8):
+            got = exact_gp_step(K, y, lambda a, b_: ozaki_gemm_fast(a, b_, S, 7))
+            print("   int8 slices S=%d (%2d GEMMs): lml rel %.1e  trW rel %.1e  probe rel %.1e" % (
+                S, S * (S + 1) // 2, abs(got[0] - ref[0]) / abs(ref[0]), abs(got[1] - ref[1]) / abs(ref[1]),
+                abs(got[2] - ref[2]) / abs(ref[2])))
+
+
 def main(argv):
+    if argv and argv[0] == "--pipeline":
+        return pipeline(int(argv[1]) if len(argv) > 1 else 1024)
     n = int(argv[0]) if argv else 768
     for noise in (1.0, 1e-2, 1e-4):
         K = gp_covariance(n, noise)
