@@ -70,10 +70,6 @@ _EXTRA = {
     "mogp_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mogp_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mogp_host_inverse_plan": (C.c_int, [C.c_int, c_ip, C.c_int]),
-    # experimental (round-2 groundwork): fp64 GEMM emulated on the int8 tensor pipe, csrc/i8gemm.cu
-    "mogp_i8gemm_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "mogp_dgemm_i8": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, C.c_longlong, C.c_longlong, c_dp, C.c_longlong,
-                                C.c_longlong, C.c_double, c_dp, C.c_longlong, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mogp_host_pair_comps": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp]),
     "mogp_host_chain": (C.c_int, [C.c_int] * 4 + [c_dp, c_dp, c_dp, c_dp]),
 }

@@ -1,4 +1,5 @@
-// EXPERIMENTAL (round-2 groundwork, NOT on the product path, not yet run on hardware): fp64 GEMM emulated on the
+// EXPERIMENTAL (round-2 groundwork; NOT linked into libmogp_b200.so -- only into libmogp_b200_exp.so, which nothing but
+// tools/gpu_diag.py i8 loads; not yet run on hardware): fp64 GEMM emulated on the
 // int8 tensor pipe of sm_100a (tcgen05.mma kind::i8, int32 accumulators in TMEM) by Ozaki-style slicing.
 //
 // Why: the O(N^3) stages of the exact-GP step (trailing updates of the Cholesky, L^-1, K^-1 = L^-T L^-1) run on

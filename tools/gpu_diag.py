@@ -420,10 +420,13 @@ def sec_spans(eng):
 def sec_i8(eng):
     """Experimental fp64-on-int8 tcgen05 GEMM (csrc/i8gemm.cu) against the DMMA GEMM: error and time per slice count."""
     import ctypes as C
+    explib = C.CDLL(os.path.join(ROOT, "mogptk_b200", "libmogp_b200_exp.so"))     # product objects + csrc/i8gemm.cu
+    explib.mogp_i8gemm_selftest.restype = C.c_int
+    explib.mogp_i8gemm_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     out = (C.c_double * 3)()
     for (M, N, K) in [(128, 64, 64), (256, 128, 256), (1024, 1024, 1024), (4096, 4096, 4096)]:
         for S in (6, 7, 8):
-            rc = eng.lib.mogp_i8gemm_selftest(M, N, K, S, out)
+            rc = explib.mogp_i8gemm_selftest(M, N, K, S, out)
             print("i8 gemm %5dx%5dx%5d S=%d rc=%d: rel. error %.2e | int8 path %.3f ms (%.1f TFLOP/s fp64-equivalent) | DMMA %.3f ms (%.1f TFLOP/s)" % (
                 M, N, K, S, rc, out[0], out[1], 2.0 * M * N * K / max(out[1], 1e-9) / 1e9, out[2], 2.0 * M * N * K / max(out[2], 1e-9) / 1e9))
 
