@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Pin oracle/next_kernels.py against the LIVE reference and write tests/golden/next_*.npz.  TEST INFRASTRUCTURE;
+runs only in the build container (needs /root/reference).  Usage: python oracle/make_golden_next.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.make_golden import import_reference, GOLDEN      # noqa: E402
+from oracle import next_kernels as nk                        # noqa: E402
+
+
+def main():
+    mogptk = import_reference()
+    gpr = mogptk.gpr
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    for kind, C, Q, Rq, D, ns in [("CSM", 3, 2, 2, 1, [17, 9, 12]), ("CSM", 2, 3, 1, 2, [11, 14]),
+                                  ("SMLMC", 3, 2, 2, 1, [13, 8, 10]), ("SMLMC", 2, 2, 3, 2, [9, 12])]:
+        xs = [torch.tensor(np.sort(rng.uniform(0, 4, (n, D)), axis=0)) for n in ns]
+        if kind == "CSM":
+            kernel = gpr.MixtureKernel(gpr.CrossSpectralKernel(output_dims=C, input_dims=D, Rq=Rq), Q)
+            p = {"amplitude": torch.rand(Q, C, Rq, dtype=torch.float64) + 0.2,
+                 "mean": torch.rand(Q, D, dtype=torch.float64) + 0.05,
+                 "variance": torch.rand(Q, D, dtype=torch.float64) + 0.1,
+                 "shift": 0.3 * torch.randn(Q, C, Rq, dtype=torch.float64)}
+            for q in range(Q):
+                kernel[q].amplitude.assign(p["amplitude"][q])
+                kernel[q].mean.assign(p["mean"][q])
+                kernel[q].variance.assign(p["variance"][q])
+                kernel[q].shift.assign(p["shift"][q])
+            # what the reference actually holds (constrained values after assign)
+            p = {"amplitude": torch.stack([kernel[q].amplitude().detach() for q in range(Q)]),
+                 "mean": torch.stack([kernel[q].mean().detach() for q in range(Q)]),
+                 "variance": torch.stack([kernel[q].variance().detach() for q in range(Q)]),
+                 "shift": torch.stack([kernel[q].shift().detach() for q in range(Q)])}
+        else:
+            kernel = gpr.LinearModelOfCoregionalizationKernel([gpr.SpectralKernel(D) for _ in range(Q)], output_dims=C,
+                                                              input_dims=D, Q=Q, Rq=Rq)
+            kernel.weight.assign(torch.rand(C, Q, Rq, dtype=torch.float64) + 0.1)
+            for q in range(Q):
+                kernel[q].magnitude.assign(torch.rand(1, dtype=torch.float64) + 0.2)
+                kernel[q].mean.assign(torch.rand(D, dtype=torch.float64) + 0.05)
+                kernel[q].variance.assign(torch.rand(D, dtype=torch.float64) * 0.2 + 0.02)
+            p = {"weight": kernel.weight().detach(),
+                 "magnitude": torch.stack([kernel[q].magnitude().detach().reshape(()) for q in range(Q)]),
+                 "mean": torch.stack([kernel[q].mean().detach() for q in range(Q)]),
+                 "variance": torch.stack([kernel[q].variance().detach() for q in range(Q)])}
+        X = torch.cat([torch.cat([torch.full((x.shape[0], 1), float(c), dtype=torch.float64), x], dim=1)
+                       for c, x in enumerate(xs)])
+        with torch.no_grad():
+            Kref = kernel.K(X).detach()
+            kd_ref = kernel.K_diag(X).detach()
+        # restatement == reference, block by block
+        off = np.cumsum([0] + ns)
+        worst = 0.0
+        for i in range(C):
+            for j in range(C):
+                blk = nk.KSUB[kind](i, j, xs[i], xs[j], p)
+                worst = max(worst, float((blk - Kref[off[i]:off[i + 1], off[j]:off[j + 1]]).abs().max()))
+        assert worst <= 1e-13 * float(Kref.abs().max()), (kind, worst)
+        kd_err = float((kd_ref - Kref.diagonal()).abs().max())
+        # reference quirk: SpectralKernel.K sums exp*cos over the input dimensions (singleoutput.py:556) while its K_diag
+        # returns the bare magnitude (:558-561), so K_diag != diag(K) for D > 1 (the SM kernel shares it)
+        assert kd_err < 1e-13 or (kind == "SMLMC" and D > 1), (kind, D, kd_err)
+        name = "next_%s_c%dq%dr%dd%d" % (kind.lower(), C, Q, Rq, D)
+        out = {"kind": kind, "C": C, "Q": Q, "Rq": Rq, "D": D, "X": X.numpy(), "K": Kref.numpy(), "K_diag": kd_ref.numpy()}
+        out.update({"p_" + k: v.numpy() for k, v in p.items()})
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print("%s: restatement == reference (max abs diff %.1e), |K_diag - diag K| = %.1e, wrote %s.npz" % (kind, worst, kd_err, name))
+
+
+if __name__ == "__main__":
+    main()
