@@ -1,0 +1,133 @@
+// ROUND-2 GROUNDWORK (compiled only into libmogp_b200_exp.so; CPU-tested through tests/test_next_kernels.py):
+// per channel-pair component tables and chain rules of the next two kernel families on the hot path, in the same
+// derived form and with the same record / owner conventions as covmath.cuh, so that they can be merged into
+// pair_comp() / chain_owner() once they have been run on hardware.
+//   CSM    MixtureKernel of Q CrossSpectralKernel (mogptk/gpr/multioutput.py:428-454):
+//          packed  amplitude (Q,C,Rq) | mean (Q,D) | variance (Q,D) | shift (Q,C,Rq);  R = Q*Rq components r = q*Rq + s
+//   SMLMC  LinearModelOfCoregionalizationKernel of Q SpectralKernel (gpr/multioutput.py:490-502, singleoutput.py:550-561):
+//          packed  weight (C,Q,Rq) | magnitude (Q) | mean (Q,D) | variance (Q,D);       R = Q*D  components r = q*D + d
+#pragma once
+#include "covmath.cuh"
+
+#define MOGP_KIND_CSM 3
+#define MOGP_KIND_SMLMC 4
+
+struct CsmOff { int amp, mu, var, sh; };
+__host__ __device__ inline CsmOff csm_off(int C, int Q, int Rq, int D) {
+    CsmOff o; o.amp = 0; o.mu = Q * C * Rq; o.var = o.mu + Q * D; o.sh = o.var + Q * D; return o;
+}
+struct LmcOff { int w, mag, mu, var; };
+__host__ __device__ inline LmcOff lmc_off(int C, int Q, int Rq, int D) {
+    LmcOff o; o.w = 0; o.mag = C * Q * Rq; o.mu = o.mag + Q; o.var = o.mu + Q * D; return o;
+}
+__host__ __device__ inline int next_num_params(int kind, int C, int Q, int Rq, int D) {
+    return kind == MOGP_KIND_CSM ? 2 * Q * C * Rq + 2 * Q * D : C * Q * Rq + Q + 2 * Q * D;
+}
+__host__ __device__ inline int next_num_comps(int kind, int Q, int Rq, int D) { return kind == MOGP_KIND_CSM ? Q * Rq : Q * D; }
+
+// comp record: [alpha, phi, v[D], m[D], theta[D]]
+__host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, int D, const double* __restrict__ p, int i,
+                                               int j, int r, double* __restrict__ out) {
+    double* v = out + 2;
+    double* m = out + 2 + D;
+    double* th = out + 2 + 2 * D;
+    for (int d = 0; d < D; ++d) v[d] = m[d] = th[d] = 0.0;
+    if (kind == MOGP_KIND_CSM) {                         // multioutput.py:432-447; i == j is the same formula
+        const CsmOff o = csm_off(C, Q, Rq, D);
+        const int q = r / Rq, s = r % Rq;
+        out[0] = sqrt(p[o.amp + (q * C + i) * Rq + s] * p[o.amp + (q * C + j) * Rq + s]);
+        out[1] = p[o.sh + (q * C + i) * Rq + s] - p[o.sh + (q * C + j) * Rq + s];
+        for (int d = 0; d < D; ++d) { v[d] = p[o.var + q * D + d]; m[d] = p[o.mu + q * D + d]; }
+    } else {                                             // multioutput.py:493-495 over singleoutput.py:554-556
+        const LmcOff o = lmc_off(C, Q, Rq, D);
+        const int q = r / D, d = r % D;
+        double w = 0.0;
+        for (int s = 0; s < Rq; ++s) w += p[o.w + (i * Q + q) * Rq + s] * p[o.w + (j * Q + q) * Rq + s];
+        out[0] = w * p[o.mag + q];
+        out[1] = 0.0;
+        v[d] = 4.0 * MOGP_PI * MOGP_PI * p[o.var + q * D + d];
+        m[d] = p[o.mu + q * D + d];
+    }
+}
+
+// owners: CSM: [0, Q*C*Rq) one (q, c, s) each (amplitude, shift), then Q owners (mean, variance of q);
+//         SMLMC: [0, C*Q*Rq) one (c, q, s) each (weight), then Q owners (magnitude, mean, variance of q)
+__host__ __device__ inline int n_chain_owners_next(int kind, int C, int Q, int Rq) {
+    return (kind == MOGP_KIND_CSM ? Q * C * Rq : C * Q * Rq) + Q;
+}
+
+__host__ __device__ inline void chain_owner_next(int kind, int C, int Q, int Rq, int D, const double* __restrict__ p,
+                                                 const double* __restrict__ comps, const double* __restrict__ gsum,
+                                                 const double* __restrict__ adj, int owner, double* __restrict__ g) {
+    const int st = comp_stride(D);
+    const int R = next_num_comps(kind, Q, Rq, D);
+    if (kind == MOGP_KIND_CSM) {
+        const CsmOff o = csm_off(C, Q, Rq, D);
+        if (owner < Q * C * Rq) {
+            const int q = owner / (C * Rq), c = (owner / Rq) % C, s = owner % Rq, r = q * Rq + s;
+            double ga = 0.0, gsh = 0.0;
+            for (int other = 0; other < C; ++other) {
+                const int i = c > other ? c : other, j = c > other ? other : c;
+                const double* S = gs_rec(gsum, i, j, R, st, r);
+                const double alpha = comps[(size_t)((i * C + j) * R + r) * st];
+                double S0 = S[0];
+                if (i == j) S0 += adj[c];
+                // alpha = sqrt(a_i a_j): d alpha / d a_c = alpha / (2 a_c), twice that on the diagonal pair (= 1)
+                ga += (i == j ? 2.0 : 1.0) * S0 * alpha / (2.0 * p[o.amp + (q * C + c) * Rq + s]);
+                if (i != j) gsh += (c == i ? 1.0 : -1.0) * (-2.0 * MOGP_PI * alpha * S[1]);
+            }
+            g[o.amp + (q * C + c) * Rq + s] = ga;
+            g[o.sh + (q * C + c) * Rq + s] = gsh;
+        } else {
+            const int q = owner - Q * C * Rq;
+            double gm[MOGP_MAX_D], gv[MOGP_MAX_D];
+            for (int d = 0; d < D; ++d) gm[d] = gv[d] = 0.0;
+            for (int i = 0; i < C; ++i)
+                for (int j = 0; j <= i; ++j)
+                    for (int s = 0; s < Rq; ++s) {
+                        const int r = q * Rq + s;
+                        const double* S = gs_rec(gsum, i, j, R, st, r);
+                        const double alpha = comps[(size_t)((i * C + j) * R + r) * st];
+                        for (int d = 0; d < D; ++d) {
+                            gv[d] += -0.5 * alpha * S[2 + d];
+                            gm[d] += -2.0 * MOGP_PI * alpha * S[2 + D + d];
+                        }
+                    }
+            for (int d = 0; d < D; ++d) { g[o.mu + q * D + d] = gm[d]; g[o.var + q * D + d] = gv[d]; }
+        }
+    } else {
+        const LmcOff o = lmc_off(C, Q, Rq, D);
+        if (owner < C * Q * Rq) {
+            const int c = owner / (Q * Rq), q = (owner / Rq) % Q, s = owner % Rq;
+            double gw = 0.0;
+            for (int other = 0; other < C; ++other) {
+                const int i = c > other ? c : other, j = c > other ? other : c;
+                double Ga = 0.0;                                         // d loss / d (sum_s w_i w_j) / magnitude
+                for (int d = 0; d < D; ++d) {
+                    const double* S = gs_rec(gsum, i, j, R, st, q * D + d);
+                    Ga += S[0] + (i == j ? adj[c] : 0.0);
+                }
+                gw += (i == j ? 2.0 : 1.0) * Ga * p[o.mag + q] * p[o.w + (other * Q + q) * Rq + s];
+            }
+            g[o.w + (c * Q + q) * Rq + s] = gw;
+        } else {
+            const int q = owner - C * Q * Rq;
+            double gmag = 0.0, gm[MOGP_MAX_D], gv[MOGP_MAX_D];
+            for (int d = 0; d < D; ++d) gm[d] = gv[d] = 0.0;
+            for (int i = 0; i < C; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double w = 0.0;
+                    for (int s = 0; s < Rq; ++s) w += p[o.w + (i * Q + q) * Rq + s] * p[o.w + (j * Q + q) * Rq + s];
+                    for (int d = 0; d < D; ++d) {
+                        const double* S = gs_rec(gsum, i, j, R, st, q * D + d);
+                        const double alpha = comps[(size_t)((i * C + j) * R + q * D + d) * st];
+                        gmag += (S[0] + (i == j ? adj[i] : 0.0)) * w;
+                        gv[d] += -0.5 * alpha * S[2 + d] * 4.0 * MOGP_PI * MOGP_PI;
+                        gm[d] += -2.0 * MOGP_PI * alpha * S[2 + D + d];
+                    }
+                }
+            g[o.mag + q] = gmag;
+            for (int d = 0; d < D; ++d) { g[o.mu + q * D + d] = gm[d]; g[o.var + q * D + d] = gv[d]; }
+        }
+    }
+}

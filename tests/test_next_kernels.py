@@ -49,3 +49,113 @@ def test_derived_component_form_matches_the_reference(name):
 
 def test_fixtures_exist():
     assert len(next_golden_names()) >= 4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# csrc/covmath_next.cuh through the host hooks of the experimental library: the component table reproduces the
+# reference's K, and the analytic chain rule reproduces autograd through the restatement (a synthetic symmetric
+# weight matrix W plays the role of (K^-1 - a a^T) / 2, adj the relative-jitter term on the diagonal pairs).
+import ctypes as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXP_LIB = os.path.join(ROOT, "mogptk_b200", "libmogp_b200_exp.so")
+KIND_ID = {"CSM": 3, "SMLMC": 4}
+ORDER = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance")}
+
+
+@pytest.fixture(scope="module")
+def explib():
+    if not os.path.exists(EXP_LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = C.CDLL(EXP_LIB)
+    lib.mogp_exp_host_pair_comps.restype = C.c_int
+    lib.mogp_exp_host_chain.restype = C.c_int
+    lib.mogp_exp_num_params.restype = C.c_int
+    return lib
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _pack(kind, p):
+    return np.concatenate([p[k].numpy().reshape(-1) for k in ORDER[kind]]).astype(np.float64)
+
+
+def _dims(kind, p):
+    if kind == "CSM":
+        Q, Cn, Rq = p["amplitude"].shape
+        return Cn, Q, Rq, p["mean"].shape[1]
+    Cn, Q, Rq = p["weight"].shape
+    return Cn, Q, Rq, p["mean"].shape[1]
+
+
+def _block_terms(comp, xa, xb, D):
+    alpha, phi = comp[0], comp[1]
+    v, m, th = comp[2:2 + D], comp[2 + D:2 + 2 * D], comp[2 + 2 * D:2 + 3 * D]
+    u = xa[:, None, :] - xb[None, :, :] + th[None, None, :]
+    E = np.exp(-0.5 * (u ** 2 * v).sum(-1))
+    ang = 2 * np.pi * ((u * m).sum(-1) + phi)
+    return alpha, E * np.cos(ang), E * np.sin(ang), u
+
+
+@pytest.mark.parametrize("name", next_golden_names())
+def test_component_table_and_chain_rule_of_the_next_families(explib, name):
+    kind, Cn, p, X, rows, K = _load(name)
+    Cn, Q, Rq, D = _dims(kind, p)
+    packed = _pack(kind, p)
+    assert explib.mogp_exp_num_params(KIND_ID[kind], Cn, Q, Rq, D) == packed.size
+    st = 2 + 3 * D
+    R = Q * Rq if kind == "CSM" else Q * D
+    comps = np.zeros(Cn * Cn * R * st)
+    assert explib.mogp_exp_host_pair_comps(KIND_ID[kind], Cn, Q, Rq, D, _ptr(packed), _ptr(comps)) == R
+    comps = comps.reshape(Cn, Cn, R, st)
+    xs = [X[rows[c], 1:].numpy() for c in range(Cn)]
+    Kn = K.numpy()
+    # 1. the table rebuilds K
+    for i in range(Cn):
+        for j in range(Cn):
+            blk = sum(a * EC for a, EC, _, _ in (_block_terms(comps[i, j, r], xs[i], xs[j], D) for r in range(R)))
+            ref = Kn[np.ix_(rows[i].numpy(), rows[j].numpy())]
+            assert np.abs(blk - ref).max() <= 1e-13 * np.abs(Kn).max()
+    # 2. chain rule against autograd: loss = sum_ab W_ab K_ab + sum_c adj_c * (diagonal value of pair (c, c))
+    rng = np.random.default_rng(7)
+    N = X.shape[0]
+    order = np.concatenate([rows[c].numpy() for c in range(Cn)])
+    off = np.concatenate([[0], np.cumsum([len(rows[c]) for c in range(Cn)])])
+    A = rng.standard_normal((N, N))
+    W = 0.5 * (A + A.T)                                   # in channel-sorted order
+    adj = rng.standard_normal(Cn)
+    gsum = np.zeros((Cn * (Cn + 1) // 2, R, st))
+    for i in range(Cn):
+        for j in range(i + 1):
+            Wb = W[off[i]:off[i + 1], off[j]:off[j + 1]] * (1.0 if i == j else 2.0)
+            for r in range(R):
+                _, EC, ES, u = _block_terms(comps[i, j, r], xs[i], xs[j], D)
+                rec = gsum[i * (i + 1) // 2 + j, r]
+                rec[0] = (Wb * EC).sum()
+                rec[1] = (Wb * ES).sum()
+                for d in range(D):
+                    rec[2 + d] = (Wb * EC * u[..., d] ** 2).sum()
+                    rec[2 + D + d] = (Wb * ES * u[..., d]).sum()
+                    rec[2 + 2 * D + d] = (Wb * EC * u[..., d]).sum()
+    grad = np.zeros(packed.size)
+    assert explib.mogp_exp_host_chain(KIND_ID[kind], Cn, Q, Rq, D, _ptr(packed), _ptr(gsum), _ptr(adj), _ptr(grad)) == packed.size
+    pt = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss = 0.0
+    xt = [torch.tensor(x) for x in xs]
+    Wt = torch.tensor(W)
+    for i in range(Cn):
+        for j in range(Cn):
+            loss = loss + (Wt[off[i]:off[i + 1], off[j]:off[j + 1]] * nk.KSUB[kind](i, j, xt[i], xt[j], pt)).sum()
+        zero = torch.zeros(1, D, dtype=torch.float64)
+        loss = loss + adj[i] * nk.KSUB[kind](i, i, zero, zero, pt).sum()      # K_rr of channel i (sum of the alphas)
+    loss.backward()
+    ref = np.concatenate([pt[k].grad.numpy().reshape(-1) for k in ORDER[kind]])
+    o = 0
+    for k in ORDER[kind]:
+        n = pt[k].numel()
+        scale = max(np.abs(ref[o:o + n]).max(), 1e-12)
+        assert np.abs(grad[o:o + n] - ref[o:o + n]).max() <= 1e-9 * scale, (k, grad[o:o + n], ref[o:o + n])
+        o += n
