@@ -70,6 +70,55 @@ def main():
         name = "next_%s_c%dq%dr%dd%d" % (kind.lower(), C, Q, Rq, D)
         out = {"kind": kind, "C": C, "Q": Q, "Rq": Rq, "D": D, "X": X.numpy(), "K": Kref.numpy(), "K_diag": kd_ref.numpy()}
         out.update({"p_" + k: v.numpy() for k, v in p.items()})
+        # the exact-GP step of the reference on this kernel: LML, gradients w.r.t. the constrained values, predictions
+        orc = nk.register()
+        y = torch.tensor(rng.standard_normal((X.shape[0], 1)))
+        sigma = torch.tensor(0.3 + 0.4 * rng.uniform(size=C))
+        jitter = 1e-8
+        model = gpr.Exact(kernel, X.numpy(), y.numpy(), variance=(sigma ** 2).tolist(), jitter=jitter)
+        sigma = model.likelihood.scale().detach().reshape(-1).clone()      # what the reference holds after its transform
+        lml_ref = float(model.log_marginal_likelihood().detach())
+        lml_orc = float(orc.lml(kind, p, sigma, X, y, jitter))
+        assert abs(lml_orc - lml_ref) <= 1e-12 * abs(lml_ref), (kind, lml_orc, lml_ref)
+        _, g_orc = orc.loss_and_grad(kind, p, sigma, X, y, jitter)
+        # reference gradients w.r.t. the constrained values: autograd through its own kernel objects
+        cons = {}
+        if kind == "CSM":
+            leaves = {k: [getattr(kernel[q], k) for q in range(Q)] for k in ("amplitude", "mean", "variance", "shift")}
+        else:
+            leaves = {"weight": [kernel.weight], "magnitude": [kernel[q].magnitude for q in range(Q)],
+                      "mean": [kernel[q].mean for q in range(Q)], "variance": [kernel[q].variance for q in range(Q)]}
+        model.zero_grad()
+        loss = -model.log_marginal_likelihood()
+        flat = [t for ts in leaves.values() for t in ts]
+        cvals = [t() for t in flat]                                   # constrained values (graph nodes)
+        grads = torch.autograd.grad(-model.log_marginal_likelihood(), flat, allow_unused=True)
+        # chain back from raw to constrained: d/d constrained = d/d raw / (d constrained / d raw)
+        gi = 0
+        for kname, ts in leaves.items():
+            parts = []
+            for t in ts:
+                c = t()
+                (dc,) = torch.autograd.grad(c.sum(), t, retain_graph=True)
+                g_raw = grads[gi] if grads[gi] is not None else torch.zeros_like(t)
+                parts.append((g_raw / dc).detach().reshape(c.shape))
+                gi += 1
+            ref = parts[0] if kname == "weight" else torch.stack([x.reshape(x.shape) for x in parts])
+            if kind == "SMLMC" and kname == "magnitude":
+                ref = ref.reshape(-1)
+            got = g_orc[kname]
+            scale = max(float(ref.abs().max()), 1e-12)
+            assert float((got.reshape(ref.shape) - ref).abs().max()) <= 2e-8 * scale, (kind, kname, got, ref)
+            out["gc_" + kname] = got.numpy()
+        out["gc_sigma"] = g_orc["sigma"].numpy()
+        Xs = torch.cat([torch.cat([torch.full((5, 1), float(c), dtype=torch.float64),
+                                   torch.tensor(rng.uniform(0, 4, (5, D)))], dim=1) for c in range(C)])
+        mu_ref, var_ref = model.predict_f(Xs.numpy())
+        mu_orc, var_orc = orc.predict_f(kind, p, sigma, X, y, Xs, jitter)
+        assert float((mu_orc - mu_ref).abs().max()) <= 1e-9 * max(float(mu_ref.abs().max()), 1e-12)
+        assert float((var_orc - var_ref).abs().max()) <= 1e-9 * max(float(var_ref.abs().max()), 1e-12)
+        out.update({"y": y.numpy().reshape(-1), "sigma": sigma.numpy(), "jitter": jitter, "lml": lml_ref, "Xs": Xs.numpy(),
+                    "pred_mu": mu_ref.detach().numpy().reshape(-1), "pred_var": var_ref.detach().numpy().reshape(-1)})
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
         print("%s: restatement == reference (max abs diff %.1e), |K_diag - diag K| = %.1e, wrote %s.npz" % (kind, worst, kd_err, name))
 

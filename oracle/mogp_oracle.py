@@ -155,8 +155,23 @@ _KSUB = {"MOSM": mosm_ksub, "SM": sm_ksub, "CONV": conv_ksub}
 _KSUB_DIAG = {"MOSM": mosm_ksub_diag, "SM": sm_ksub_diag, "CONV": conv_ksub_diag}
 
 
+_N_CHANNELS = {"CONV": lambda p: p["weight"].shape[1]}
+
+
 def n_channels(kind, p):
-    return p["weight"].shape[1] if kind == "CONV" else p[PARAM_NAMES[kind][0]].shape[0]
+    if kind in _N_CHANNELS:
+        return _N_CHANNELS[kind](p)
+    return p[PARAM_NAMES[kind][0]].shape[0]
+
+
+def register_kind(kind, param_names, ksub, ksub_diag, n_channels_fn=None):
+    """Let another test-infrastructure module (oracle/next_kernels.py) reuse the block assembly / LML / prediction
+    restatements above for a further kernel family."""
+    PARAM_NAMES[kind] = tuple(param_names)
+    _KSUB[kind] = ksub
+    _KSUB_DIAG[kind] = ksub_diag
+    if n_channels_fn is not None:
+        _N_CHANNELS[kind] = n_channels_fn
 
 
 # --------------------------------------------------------------------------------------

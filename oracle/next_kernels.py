@@ -91,4 +91,26 @@ def k_from_components(comps, x1, x2):
     return out
 
 
+def csm_ksub_diag(i, n, p):
+    """Sum over the mixture of CrossSpectralKernel.Ksub_diag (gpr/multioutput.py:451-454)."""
+    return p["amplitude"][:, i].sum().repeat(n)
+
+
+def smlmc_ksub_diag(i, n, p):
+    """LinearModelOfCoregionalizationKernel.Ksub_diag (gpr/multioutput.py:497-502) over SpectralKernel.K_diag
+    (singleoutput.py:558-561: the bare magnitude whatever D is)."""
+    magnitude = torch.sum(p["weight"][i] ** 2, dim=1)
+    return (magnitude * p["magnitude"]).sum().repeat(n)
+
+
 KSUB = {"CSM": csm_ksub, "SMLMC": smlmc_ksub}
+KSUB_DIAG = {"CSM": csm_ksub_diag, "SMLMC": smlmc_ksub_diag}
+PARAM_NAMES = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance")}
+
+
+def register():
+    """Plug both families into oracle.mogp_oracle's block assembly / LML / gradient / prediction restatements."""
+    from oracle import mogp_oracle as orc
+    orc.register_kind("CSM", PARAM_NAMES["CSM"], csm_ksub, csm_ksub_diag, lambda p: p["amplitude"].shape[1])
+    orc.register_kind("SMLMC", PARAM_NAMES["SMLMC"], smlmc_ksub, smlmc_ksub_diag)
+    return orc

@@ -159,3 +159,22 @@ def test_component_table_and_chain_rule_of_the_next_families(explib, name):
         scale = max(np.abs(ref[o:o + n]).max(), 1e-12)
         assert np.abs(grad[o:o + n] - ref[o:o + n]).max() <= 1e-9 * scale, (k, grad[o:o + n], ref[o:o + n])
         o += n
+
+
+@pytest.mark.parametrize("name", next_golden_names())
+def test_oracle_step_of_the_next_families_matches_the_reference(name):
+    """LML, gradients w.r.t. the constrained parameters and predictions of the reference's gpr.Exact on these kernels
+    (fixtures from the live reference) against the oracle restatement -- the parity target of the round-2 GPU path."""
+    orc = nk.register()
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    kind, C_, p, X, rows, K = _load(name)
+    y, sigma, jitter = torch.tensor(z["y"]), torch.tensor(z["sigma"]), float(z["jitter"])
+    lml = float(orc.lml(kind, p, sigma, X, y, jitter))
+    assert abs(lml - float(z["lml"])) <= 1e-10 * abs(float(z["lml"]))
+    _, g = orc.loss_and_grad(kind, p, sigma, X, y, jitter)
+    for k in list(nk.PARAM_NAMES[kind]) + ["sigma"]:
+        ref = z["gc_" + k]
+        assert np.abs(g[k].numpy().reshape(ref.shape) - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-12), k
+    mu, var = orc.predict_f(kind, p, sigma, X, y, torch.tensor(z["Xs"]), jitter)
+    assert np.abs(mu.numpy().reshape(-1) - z["pred_mu"]).max() <= 1e-9 * max(np.abs(z["pred_mu"]).max(), 1e-12)
+    assert np.abs(var.numpy().reshape(-1) - z["pred_var"]).max() <= 1e-9 * max(np.abs(z["pred_var"]).max(), 1e-12)
