@@ -12,6 +12,8 @@ tests/test_next_kernels.py.
 Parameter layouts (constrained values, fp64):
   CSM    amplitude (Q,C,Rq)  mean (Q,D)  variance (Q,D)  shift (Q,C,Rq)      MixtureKernel of Q CrossSpectralKernel
   SMLMC  weight (C,Q,Rq)  magnitude (Q,)  mean (Q,D)  variance (Q,D)          LMC of Q SpectralKernel
+  UMOSM  weight (Q,C,C) (lower triangle used)  mean/variance/delay (Q,C,D)  phase (Q,C)     mixture of Q uMOSM kernels
+  MOHSM  weight (Q,C)  mean/variance/delay (Q,C,D)  lengthscale (Q,C)  center (Q,D)  phase (Q,C)   (K only: non-stationary)
 """
 import math
 
@@ -57,6 +59,84 @@ def smlmc_ksub(i, j, x1, x2, p):
     return out
 
 
+def umosm_ksub(i, j, x1, x2, p):
+    """Sum over the Q mixture terms of UncoupledMultiOutputSpectralKernel.Ksub (gpr/multioutput.py:261-286).
+    Note the phase sits OUTSIDE the 2 pi factor here (:285), unlike the MOSM kernel (:203)."""
+    tau = _tau(x1, x2)
+    D = x1.shape[1]
+    twopi = (2.0 * PI) ** (D / 2.0)                                                                        # :258
+    out = 0.0
+    for q in range(p["weight"].shape[0]):
+        w = p["weight"][q].tril()
+        magnitude = w.mm(w.T)                                                                              # :265
+        if i == j:
+            variance = p["variance"][q, i]
+            alpha = magnitude[i, i] * twopi * variance.prod().sqrt()                                       # :268
+            exp = torch.exp(-0.5 * torch.tensordot(tau ** 2, variance, dims=1))
+            cos = torch.cos(2.0 * PI * torch.tensordot(tau, p["mean"][q, i], dims=1))
+            out = out + alpha * exp * cos
+        else:
+            iv = 1.0 / (p["variance"][q, i] + p["variance"][q, j])                                         # :273
+            dm = p["mean"][q, i] - p["mean"][q, j]
+            mag = magnitude[i, j] * torch.exp(-PI ** 2 * dm.dot(iv * dm))                                  # :276
+            mean = iv * (p["variance"][q, i] * p["mean"][q, j] + p["variance"][q, j] * p["mean"][q, i])
+            variance = 2.0 * p["variance"][q, i] * iv * p["variance"][q, j]
+            delay = p["delay"][q, i] - p["delay"][q, j]
+            phase = p["phase"][q, i] - p["phase"][q, j]
+            alpha = mag * twopi * variance.prod().sqrt()                                                   # :283
+            exp = torch.exp(-0.5 * torch.tensordot((tau + delay) ** 2, variance, dims=1))
+            cos = torch.cos(2.0 * PI * torch.tensordot(tau + delay, mean, dims=1) + phase)                 # :285
+            out = out + alpha * exp * cos
+    return out
+
+
+def umosm_ksub_diag(i, n, p):
+    """gpr/multioutput.py:288-293 summed over the mixture."""
+    D = p["mean"].shape[2]
+    out = 0.0
+    for q in range(p["weight"].shape[0]):
+        w = p["weight"][q].tril()
+        out = out + w.mm(w.T)[i, i] * (2.0 * PI) ** (D / 2.0) * p["variance"][q, i].prod().sqrt()
+    return out.repeat(n)
+
+
+def mohsm_ksub(i, j, x1, x2, p):
+    """Sum over the mixture of MultiOutputHarmonizableSpectralKernel.Ksub (gpr/multioutput.py:353-387): the MOSM-like
+    stationary factor times a Gaussian window in the mid-point (x + x') / 2 (non-stationary)."""
+    tau = _tau(x1, x2)
+    avg = 0.5 * (x1.unsqueeze(1) + x2.unsqueeze(0))                                                        # kernel.py average()
+    D = x1.shape[1]
+    twopi = (2.0 * PI) ** float(D)                                                                         # :350
+    ones = torch.ones(D, dtype=torch.float64)
+    out = 0.0
+    for q in range(p["weight"].shape[0]):
+        if i == j:
+            variance = p["variance"][q, i]
+            ls = p["lengthscale"][q, i] ** 2
+            alpha = p["weight"][q, i] ** 2 * twopi * variance.prod().sqrt() * torch.pow(ls.sqrt(), float(D))   # :363
+            exp1 = torch.exp(-0.5 * torch.tensordot(tau ** 2, variance, dims=1))
+            exp2 = torch.exp(-0.5 * torch.tensordot((avg - p["center"][q]) ** 2, ls * ones, dims=1))
+            cos = torch.cos(2.0 * PI * torch.tensordot(tau, p["mean"][q, i], dims=1))
+            out = out + alpha * exp1 * cos * exp2
+        else:
+            li, lj = p["lengthscale"][q, i] ** 2, p["lengthscale"][q, j] ** 2
+            iv = 1.0 / (p["variance"][q, i] + p["variance"][q, j])
+            il = 1.0 / (li + lj)
+            dm = p["mean"][q, i] - p["mean"][q, j]
+            mag = p["weight"][q, i] * p["weight"][q, j] * torch.exp(-PI ** 2 * dm.dot(iv * dm))            # :375
+            mean = iv * (p["variance"][q, i] * p["mean"][q, j] + p["variance"][q, j] * p["mean"][q, i])
+            variance = 2.0 * p["variance"][q, i] * iv * p["variance"][q, j]
+            ls = 2.0 * li * il * lj
+            delay = p["delay"][q, i] - p["delay"][q, j]
+            phase = p["phase"][q, i] - p["phase"][q, j]
+            alpha = mag * twopi * variance.prod().sqrt() * torch.pow(ls.sqrt(), float(D))                  # :382
+            exp1 = torch.exp(-0.5 * torch.tensordot((tau + delay) ** 2, variance, dims=1))
+            exp2 = torch.exp(-0.5 * torch.tensordot((avg - p["center"][q]) ** 2, ls * ones, dims=1))
+            cos = torch.cos(2.0 * PI * torch.tensordot(tau + delay, mean, dims=1) + phase)
+            out = out + alpha * exp1 * cos * exp2
+    return out
+
+
 def derived_components(kind, p, i, j):
     """Per channel-pair component records (alpha, phi, v[D], m[D], theta[D]) of the derived form."""
     comps = []
@@ -77,6 +157,17 @@ def derived_components(kind, p, i, j):
                 e[d] = 1.0
                 comps.append((w[q] * p["magnitude"][q], torch.zeros((), dtype=torch.float64),
                               4.0 * PI ** 2 * p["variance"][q] * e, p["mean"][q] * e, torch.zeros(D, dtype=torch.float64)))
+    elif kind == "UMOSM":
+        Q, D = p["weight"].shape[0], p["mean"].shape[2]
+        for q in range(Q):
+            w = p["weight"][q].tril()
+            si, sj, mi, mj = p["variance"][q, i], p["variance"][q, j], p["mean"][q, i], p["mean"][q, j]
+            iv = 1.0 / (si + sj)
+            dm = mi - mj
+            v = 2.0 * si * iv * sj
+            alpha = w.mm(w.T)[i, j] * torch.exp(-PI ** 2 * dm.dot(iv * dm)) * (2.0 * PI) ** (D / 2.0) * v.prod().sqrt()
+            comps.append((alpha, (p["phase"][q, i] - p["phase"][q, j]) / (2.0 * PI), v, iv * (si * mj + sj * mi),
+                          p["delay"][q, i] - p["delay"][q, j]))
     else:
         raise ValueError(kind)
     return comps
@@ -103,9 +194,14 @@ def smlmc_ksub_diag(i, n, p):
     return (magnitude * p["magnitude"]).sum().repeat(n)
 
 
-KSUB = {"CSM": csm_ksub, "SMLMC": smlmc_ksub}
-KSUB_DIAG = {"CSM": csm_ksub_diag, "SMLMC": smlmc_ksub_diag}
-PARAM_NAMES = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance")}
+KSUB = {"CSM": csm_ksub, "SMLMC": smlmc_ksub, "UMOSM": umosm_ksub, "MOHSM": mohsm_ksub}
+KSUB_DIAG = {"CSM": csm_ksub_diag, "SMLMC": smlmc_ksub_diag, "UMOSM": umosm_ksub_diag}
+PARAM_NAMES = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance"),
+               "UMOSM": ("weight", "mean", "variance", "delay", "phase"),
+               "MOHSM": ("weight", "mean", "variance", "lengthscale", "center", "delay", "phase")}
+# families whose blocks fit the product's derived per-pair component form as it stands (MOHSM needs one more factor: a
+# Gaussian window in the mid-point, i.e. a kernel change, not only a table)
+DERIVED_FORM = ("CSM", "SMLMC", "UMOSM")
 
 
 def register():
@@ -113,4 +209,5 @@ def register():
     from oracle import mogp_oracle as orc
     orc.register_kind("CSM", PARAM_NAMES["CSM"], csm_ksub, csm_ksub_diag, lambda p: p["amplitude"].shape[1])
     orc.register_kind("SMLMC", PARAM_NAMES["SMLMC"], smlmc_ksub, smlmc_ksub_diag)
+    orc.register_kind("UMOSM", PARAM_NAMES["UMOSM"], umosm_ksub, umosm_ksub_diag, lambda p: p["weight"].shape[1])
     return orc

@@ -1,4 +1,5 @@
-"""CPU tests for the next kernel families on the hot path (CSM, SM-LMC): the oracle restatement
+"""CPU tests for the next kernel families on the hot path (CSM, SM-LMC, uMOSM; MOHSM K only --
+it is non-stationary and needs one more factor than the derived form has): the oracle restatement
 reproduces the reference's K (golden fixtures written by oracle/make_golden_next.py from the live reference), and the
 per channel-pair component table in the product's one derived form reproduces it too -- i.e. these families need a new
 table (csrc/covmath.cuh) but no new CUDA kernels."""
@@ -31,9 +32,10 @@ def test_restatement_matches_the_reference(name):
             assert float((blk - K[rows[i]][:, rows[j]]).abs().max()) <= 1e-13 * float(K.abs().max())
 
 
-@pytest.mark.parametrize("name", next_golden_names())
+@pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
 def test_derived_component_form_matches_the_reference(name):
     kind, C, p, X, rows, K = _load(name)
+    assert kind in nk.DERIVED_FORM
     for i in range(C):
         for j in range(C):
             comps = nk.derived_components(kind, p, i, j)
@@ -48,7 +50,7 @@ def test_derived_component_form_matches_the_reference(name):
 
 
 def test_fixtures_exist():
-    assert len(next_golden_names()) >= 4
+    assert len(next_golden_names()) >= 8
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -100,7 +102,7 @@ def _block_terms(comp, xa, xb, D):
     return alpha, E * np.cos(ang), E * np.sin(ang), u
 
 
-@pytest.mark.parametrize("name", next_golden_names())
+@pytest.mark.parametrize("name", [n for n in next_golden_names() if "csm" in n or "smlmc" in n])
 def test_component_table_and_chain_rule_of_the_next_families(explib, name):
     kind, Cn, p, X, rows, K = _load(name)
     Cn, Q, Rq, D = _dims(kind, p)
@@ -161,7 +163,7 @@ def test_component_table_and_chain_rule_of_the_next_families(explib, name):
         o += n
 
 
-@pytest.mark.parametrize("name", next_golden_names())
+@pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
 def test_oracle_step_of_the_next_families_matches_the_reference(name):
     """LML, gradients w.r.t. the constrained parameters and predictions of the reference's gpr.Exact on these kernels
     (fixtures from the live reference) against the oracle restatement -- the parity target of the round-2 GPU path."""
