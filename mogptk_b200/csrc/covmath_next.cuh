@@ -11,6 +11,8 @@
 
 #define MOGP_KIND_CSM 3
 #define MOGP_KIND_SMLMC 4
+#define MOGP_KIND_UMOSM 5    // MixtureKernel of Q UncoupledMultiOutputSpectralKernel (gpr/multioutput.py:261-293):
+                             // packed  weight (Q,C,C; lower triangle used) | mean (Q,C,D) | variance (Q,C,D) | delay (Q,C,D) | phase (Q,C)
 
 struct CsmOff { int amp, mu, var, sh; };
 __host__ __device__ inline CsmOff csm_off(int C, int Q, int Rq, int D) {
@@ -20,10 +22,24 @@ struct LmcOff { int w, mag, mu, var; };
 __host__ __device__ inline LmcOff lmc_off(int C, int Q, int Rq, int D) {
     LmcOff o; o.w = 0; o.mag = C * Q * Rq; o.mu = o.mag + Q; o.var = o.mu + Q * D; return o;
 }
+struct UmosmOff { int w, mu, var, th, ph; };
+__host__ __device__ inline UmosmOff umosm_off(int C, int Q, int D) {
+    UmosmOff o; o.w = 0; o.mu = Q * C * C; o.var = o.mu + Q * C * D; o.th = o.var + Q * C * D; o.ph = o.th + Q * C * D; return o;
+}
 __host__ __device__ inline int next_num_params(int kind, int C, int Q, int Rq, int D) {
+    if (kind == MOGP_KIND_UMOSM) return Q * C * C + 3 * Q * C * D + Q * C;
     return kind == MOGP_KIND_CSM ? 2 * Q * C * Rq + 2 * Q * D : C * Q * Rq + Q + 2 * Q * D;
 }
-__host__ __device__ inline int next_num_comps(int kind, int Q, int Rq, int D) { return kind == MOGP_KIND_CSM ? Q * Rq : Q * D; }
+__host__ __device__ inline int next_num_comps(int kind, int Q, int Rq, int D) {
+    return kind == MOGP_KIND_UMOSM ? Q : (kind == MOGP_KIND_CSM ? Q * Rq : Q * D);
+}
+// (L L^T)_ij of the lower triangle L of the q-th C x C weight matrix
+__host__ __device__ inline double umosm_mag(const double* w, int C, int i, int j) {
+    double m = 0.0;
+    const int kmax = i < j ? i : j;
+    for (int k = 0; k <= kmax; ++k) m += w[i * C + k] * w[j * C + k];
+    return m;
+}
 
 // comp record: [alpha, phi, v[D], m[D], theta[D]]
 __host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, int D, const double* __restrict__ p, int i,
@@ -32,7 +48,24 @@ __host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, i
     double* m = out + 2 + D;
     double* th = out + 2 + 2 * D;
     for (int d = 0; d < D; ++d) v[d] = m[d] = th[d] = 0.0;
-    if (kind == MOGP_KIND_CSM) {                         // multioutput.py:432-447; i == j is the same formula
+    if (kind == MOGP_KIND_UMOSM) {                       // multioutput.py:266-286; the i == j branch is the same formula
+        const UmosmOff o = umosm_off(C, Q, D);
+        const int q = r;
+        const double* mui = p + o.mu + (q * C + i) * D; const double* muj = p + o.mu + (q * C + j) * D;
+        const double* si = p + o.var + (q * C + i) * D; const double* sj = p + o.var + (q * C + j) * D;
+        double esum = 0.0, prod = 1.0;
+        for (int d = 0; d < D; ++d) {
+            const double iv = 1.0 / (si[d] + sj[d]);
+            const double dm = mui[d] - muj[d];
+            esum += dm * iv * dm;
+            m[d] = iv * (si[d] * muj[d] + sj[d] * mui[d]);
+            v[d] = 2.0 * si[d] * iv * sj[d];
+            th[d] = p[o.th + (q * C + i) * D + d] - p[o.th + (q * C + j) * D + d];
+            prod *= v[d];
+        }
+        out[0] = umosm_mag(p + o.w + q * C * C, C, i, j) * exp(-MOGP_PI * MOGP_PI * esum) * pow(2.0 * MOGP_PI, 0.5 * (double)D) * sqrt(prod);
+        out[1] = (p[o.ph + q * C + i] - p[o.ph + q * C + j]) / (2.0 * MOGP_PI);      // the phase sits outside the 2 pi factor (:285)
+    } else if (kind == MOGP_KIND_CSM) {                  // multioutput.py:432-447; i == j is the same formula
         const CsmOff o = csm_off(C, Q, Rq, D);
         const int q = r / Rq, s = r % Rq;
         out[0] = sqrt(p[o.amp + (q * C + i) * Rq + s] * p[o.amp + (q * C + j) * Rq + s]);
@@ -52,7 +85,9 @@ __host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, i
 
 // owners: CSM: [0, Q*C*Rq) one (q, c, s) each (amplitude, shift), then Q owners (mean, variance of q);
 //         SMLMC: [0, C*Q*Rq) one (c, q, s) each (weight), then Q owners (magnitude, mean, variance of q)
+//         UMOSM: Q*C owners (q, c): row c of the weight matrix, mean, variance, delay, phase of channel c
 __host__ __device__ inline int n_chain_owners_next(int kind, int C, int Q, int Rq) {
+    if (kind == MOGP_KIND_UMOSM) return Q * C;
     return (kind == MOGP_KIND_CSM ? Q * C * Rq : C * Q * Rq) + Q;
 }
 
@@ -61,7 +96,68 @@ __host__ __device__ inline void chain_owner_next(int kind, int C, int Q, int Rq,
                                                  const double* __restrict__ adj, int owner, double* __restrict__ g) {
     const int st = comp_stride(D);
     const int R = next_num_comps(kind, Q, Rq, D);
-    if (kind == MOGP_KIND_CSM) {
+    if (kind == MOGP_KIND_UMOSM) {
+        const UmosmOff o = umosm_off(C, Q, D);
+        const double PI2 = MOGP_PI * MOGP_PI;
+        const int q = owner / C, c = owner % C;
+        const double* wq = p + o.w + q * C * C;
+        double gph = 0.0, gL[64], gmu[MOGP_MAX_D], gs[MOGP_MAX_D], gth[MOGP_MAX_D];
+        for (int k = 0; k < C; ++k) gL[k] = 0.0;
+        for (int d = 0; d < D; ++d) gmu[d] = gs[d] = gth[d] = 0.0;
+        for (int other = 0; other < C; ++other) {
+            const int i = c > other ? c : other, j = c > other ? other : c;
+            const double* S = gs_rec(gsum, i, j, R, st, q);
+            const double* cp = comps + (size_t)((i * C + j) * R + q) * st;
+            const double alpha = cp[0];
+            const double* v = cp + 2; const double* m = cp + 2 + D;
+            double S0 = S[0];
+            const double S4 = S[1];
+            if (i == j) S0 += adj[c];
+            const double aGa = alpha * S0;
+            // alpha = M_ij * rest: d loss / d M_ij = S0 * rest, rest recomputed so that M_ij = 0 is harmless
+            double esum = 0.0, prod = 1.0;
+            for (int d = 0; d < D; ++d) {
+                const double si = p[o.var + (q * C + i) * D + d], sj = p[o.var + (q * C + j) * D + d];
+                const double dm = p[o.mu + (q * C + i) * D + d] - p[o.mu + (q * C + j) * D + d];
+                esum += dm * dm / (si + sj);
+                prod *= v[d];
+            }
+            const double GM = S0 * exp(-PI2 * esum) * pow(2.0 * MOGP_PI, 0.5 * (double)D) * sqrt(prod);
+            const int kmax = c < other ? c : other;
+            for (int k = 0; k <= kmax; ++k) gL[k] += GM * (other == c ? 2.0 * wq[c * C + k] : wq[other * C + k]);
+            const double Gph = -alpha * S4;                  // d loss / d (phase_i - phase_j): -2 pi alpha S4 / (2 pi)
+            for (int side = 0; side < 2; ++side) {
+                if (i != j && ((side == 0) != (c == i))) continue;
+                gph += side == 0 ? Gph : -Gph;
+                for (int d = 0; d < D; ++d) {
+                    const double si = p[o.var + (q * C + i) * D + d], sj = p[o.var + (q * C + j) * D + d];
+                    const double mui = p[o.mu + (q * C + i) * D + d], muj = p[o.mu + (q * C + j) * D + d];
+                    const double iv = 1.0 / (si + sj), dm = mui - muj;
+                    const double Gv = -0.5 * alpha * S[2 + d];
+                    const double Gm = -2.0 * MOGP_PI * alpha * S[2 + D + d];
+                    const double Gth = alpha * (-v[d] * S[2 + 2 * D + d] - 2.0 * MOGP_PI * m[d] * S4);
+                    if (side == 0) {
+                        gmu[d] += aGa * (-2.0 * PI2 * dm * iv) + Gm * sj * iv;
+                        gs[d] += aGa * (PI2 * dm * dm * iv * iv + 0.5 * sj * iv / si) + Gv * (2.0 * sj * sj * iv * iv)
+                                 + Gm * (-sj * dm * iv * iv);
+                        gth[d] += Gth;
+                    } else {
+                        gmu[d] += aGa * (2.0 * PI2 * dm * iv) + Gm * si * iv;
+                        gs[d] += aGa * (PI2 * dm * dm * iv * iv + 0.5 * si * iv / sj) + Gv * (2.0 * si * si * iv * iv)
+                                 + Gm * (si * dm * iv * iv);
+                        gth[d] -= Gth;
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < C; ++k) g[o.w + (q * C + c) * C + k] = k <= c ? gL[k] : 0.0;
+        g[o.ph + q * C + c] = gph;
+        for (int d = 0; d < D; ++d) {
+            g[o.mu + (q * C + c) * D + d] = gmu[d];
+            g[o.var + (q * C + c) * D + d] = gs[d];
+            g[o.th + (q * C + c) * D + d] = gth[d];
+        }
+    } else if (kind == MOGP_KIND_CSM) {
         const CsmOff o = csm_off(C, Q, Rq, D);
         if (owner < Q * C * Rq) {
             const int q = owner / (C * Rq), c = (owner / Rq) % C, s = owner % Rq, r = q * Rq + s;

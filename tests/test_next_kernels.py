@@ -61,8 +61,9 @@ import ctypes as C
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXP_LIB = os.path.join(ROOT, "mogptk_b200", "libmogp_b200_exp.so")
-KIND_ID = {"CSM": 3, "SMLMC": 4}
-ORDER = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance")}
+KIND_ID = {"CSM": 3, "SMLMC": 4, "UMOSM": 5}
+ORDER = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance"),
+         "UMOSM": ("weight", "mean", "variance", "delay", "phase")}
 
 
 @pytest.fixture(scope="module")
@@ -89,6 +90,9 @@ def _dims(kind, p):
     if kind == "CSM":
         Q, Cn, Rq = p["amplitude"].shape
         return Cn, Q, Rq, p["mean"].shape[1]
+    if kind == "UMOSM":
+        Q, Cn, _ = p["weight"].shape
+        return Cn, Q, 1, p["mean"].shape[2]
     Cn, Q, Rq = p["weight"].shape
     return Cn, Q, Rq, p["mean"].shape[1]
 
@@ -102,14 +106,14 @@ def _block_terms(comp, xa, xb, D):
     return alpha, E * np.cos(ang), E * np.sin(ang), u
 
 
-@pytest.mark.parametrize("name", [n for n in next_golden_names() if "csm" in n or "smlmc" in n])
+@pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
 def test_component_table_and_chain_rule_of_the_next_families(explib, name):
     kind, Cn, p, X, rows, K = _load(name)
     Cn, Q, Rq, D = _dims(kind, p)
     packed = _pack(kind, p)
     assert explib.mogp_exp_num_params(KIND_ID[kind], Cn, Q, Rq, D) == packed.size
     st = 2 + 3 * D
-    R = Q * Rq if kind == "CSM" else Q * D
+    R = {"CSM": Q * Rq, "SMLMC": Q * D, "UMOSM": Q}[kind]
     comps = np.zeros(Cn * Cn * R * st)
     assert explib.mogp_exp_host_pair_comps(KIND_ID[kind], Cn, Q, Rq, D, _ptr(packed), _ptr(comps)) == R
     comps = comps.reshape(Cn, Cn, R, st)
