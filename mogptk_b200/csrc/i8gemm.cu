@@ -210,9 +210,170 @@ __global__ void __launch_bounds__(128, 1) i8_gemm_kernel(const int8_t* __restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(I8_BN) : "memory");
 }
 
+// ------------------------------------------------------------------ second version: warp-specialised, pipelined
+// Same arithmetic and shared-memory layout; 128 x 128 tiles, a ring of WS_STAGES operand stages filled by two producer
+// warps (cp.async, completion signalled on an mbarrier with cp.async.mbarrier.arrive.noinc), one MMA-issuing thread,
+// two TMEM accumulator buffers so that the fp64 epilogue of anti-diagonal d (eight warps, 64 columns of one row per
+// thread) overlaps the int8 MMAs of d + 1.  Still no TMA / swizzle / cta_group::2: those come once this runs.
+#define WS_BN 128
+#define WS_STAGES 4
+#define WS_PRODUCERS 64                      // warps 0, 1
+#define WS_THREADS 384                       // + warp 2 (MMA, TMEM allocation), warp 3 idle, warps 4..11 epilogue
+struct __align__(128) I8WsSmem {
+    int8_t a[WS_STAGES][I8_BK / 16][I8_BM][16];      // 4 x 8 KB
+    int8_t b[WS_STAGES][I8_BK / 16][WS_BN][16];      // 4 x 8 KB
+    uint64_t full[WS_STAGES], empty[WS_STAGES];      // producers -> MMA, MMA (tcgen05.commit) -> producers
+    uint64_t acc_full[2], acc_empty[2];              // MMA -> epilogue, epilogue -> MMA
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) i8_gemm_ws_kernel(const int8_t* __restrict__ As, const int32_t* __restrict__ ea,
+                                                                    long long a_slice, const int8_t* __restrict__ Bs,
+                                                                    const int32_t* __restrict__ eb, long long b_slice, int M,
+                                                                    int N, int Kp, int S, int bbits, double alpha, double beta,
+                                                                    double* __restrict__ C, long long ldc) {
+    extern __shared__ __align__(128) unsigned char i8_smem_raw[];
+    I8WsSmem& sm = *reinterpret_cast<I8WsSmem*>(i8_smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * I8_BM, n0 = blockIdx.x * WS_BN;
+    const int nkb = Kp / I8_BK;
+
+    if (tid == 0) {
+        for (int i = 0; i < WS_STAGES; ++i) { mbar_init_(&sm.full[i], WS_PRODUCERS); mbar_init_(&sm.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init_(&sm.acc_full[i], 1); mbar_init_(&sm.acc_empty[i], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {      // 2 x 128 accumulator columns
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(2 * WS_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem0 = sm.tmem_base;
+
+    if (warp < 2) {
+        // ------------------------------------------------------------------ producers
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int d = 0; d < S; ++d)
+            for (int s = 0; s <= d; ++s) {
+                const int8_t* Ag = As + (long long)s * a_slice + (long long)m0 * Kp;
+                const int8_t* Bg = Bs + (long long)(d - s) * b_slice + (long long)n0 * Kp;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_(&sm.empty[stage], phase ^ 1);         // slot free (passes immediately on the first lap)
+                    // consecutive threads take consecutive rows of one 16-byte K chunk: conflict-free 128-byte core matrices
+                    for (int c = tid; c < I8_BM * (I8_BK / 16); c += WS_PRODUCERS) {
+                        const int kc = c / I8_BM, r = c % I8_BM;
+                        const bool ok = m0 + r < M;
+                        const int8_t* src = Ag + (long long)(ok ? r : 0) * Kp + kb * I8_BK + kc * 16;
+                        const int sz = ok ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&sm.a[stage][kc][r][0])), "l"(src), "r"(sz));
+                    }
+                    for (int c = tid; c < WS_BN * (I8_BK / 16); c += WS_PRODUCERS) {
+                        const int kc = c / WS_BN, r = c % WS_BN;
+                        const bool ok = n0 + r < N;
+                        const int8_t* src = Bg + (long long)(ok ? r : 0) * Kp + kb * I8_BK + kc * 16;
+                        const int sz = ok ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&sm.b[stage][kc][r][0])), "l"(src), "r"(sz));
+                    }
+                    // arrives on full[stage] when this thread's copies above have landed
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full[stage])) : "memory");
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase[2] = {0, 0};
+            for (int d = 0; d < S; ++d) {
+                const int buf = d & 1;
+                mbar_wait_(&sm.acc_empty[buf], acc_phase[buf] ^ 1);      // epilogue drained this buffer (immediate for d < 2)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem0 + (uint32_t)(buf * WS_BN);
+                bool first = true;
+                for (int s = 0; s <= d; ++s)
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait_(&sm.full[stage], phase);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) writes -> tensor core
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                        for (int ki = 0; ki < I8_BK / 32; ++ki) {
+                            const uint64_t da = umma_desc_kmajor(smem_u32(&sm.a[stage][2 * ki][0][0]), I8_BM * 16, 128);
+                            const uint64_t db = umma_desc_kmajor(smem_u32(&sm.b[stage][2 * ki][0][0]), WS_BN * 16, 128);
+                            umma_i8(tmem_d, da, db, idesc, (first && ki == 0) ? 0u : 1u);
+                        }
+                        first = false;
+                        umma_commit(&sm.empty[stage]);                    // frees the slot when these MMAs have read it
+                        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                umma_commit(&sm.acc_full[buf]);                           // anti-diagonal d is complete in TMEM
+                acc_phase[buf] ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue: row (lane quarter) x 64 columns per thread
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int row = m0 + q * 32 + lane;
+        double acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        uint32_t full_phase[2] = {0, 0};
+        for (int d = 0; d < S; ++d) {
+            const int buf = d & 1;
+            mbar_wait_(&sm.acc_full[buf], full_phase[buf]);
+            full_phase[buf] ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const double w = ldexp(1.0, -bbits * (d + 2));
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * WS_BN + half * 64 + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c0 + j] = fma((double)(int32_t)v[j], w, acc[c0 + j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_(&sm.acc_empty[buf]);                             // 256 epilogue threads release the buffer
+        }
+        if (row < M) {
+            const int er = ea[row];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int col = n0 + half * 64 + j;
+                if (col < N) {
+                    double v = alpha * ldexp(acc[j], er + eb[col]);
+                    double* p = C + (long long)row * ldc + col;
+                    if (beta != 0.0) v += beta * *p;
+                    *p = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(2 * WS_BN) : "memory");
+}
+
 // ------------------------------------------------------------------ host side
 // C (M x N, ldc) = alpha * A B^T + beta * C for fp64 A (M x K: element (i,k) at A[i*ars + k*acs]) and B (N x K likewise).
 // work: at least S * (M + N) * Kp bytes + 4 * (M + N) bytes, Kp = K rounded up to 64.
+static int g_i8_variant = 0;          // 0: simple single-buffered kernel, 1: warp-specialised pipelined kernel
+extern "C" void mogp_i8gemm_set_variant(int v) { g_i8_variant = v; }
+
 extern "C" int mogp_dgemm_i8(int M, int N, int K, double alpha, const double* A, long long ars, long long acs,
                              const double* B, long long brs, long long bcs, double beta, double* C, long long ldc, int S,
                              void* work, size_t work_bytes, void* stream) {
@@ -229,8 +390,19 @@ extern "C" int mogp_dgemm_i8(int M, int N, int K, double alpha, const double* A,
     int32_t* eb = ea + M;
     i8_slice_kernel<<<M, 256, 0, st>>>(A, ars, acs, K, Kp, S, b, As, (long long)M * Kp, ea);
     i8_slice_kernel<<<N, 256, 0, st>>>(B, brs, bcs, K, Kp, S, b, Bs, (long long)N * Kp, eb);
-    dim3 grid((N + I8_BN - 1) / I8_BN, (M + I8_BM - 1) / I8_BM);
-    i8_gemm_kernel<<<grid, 128, 0, st>>>(As, ea, (long long)M * Kp, Bs, eb, (long long)N * Kp, M, N, Kp, S, b, alpha, beta, C, ldc);
+    if (g_i8_variant == 1) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(i8_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8WsSmem)) != cudaSuccess) return -2;
+            attr_done = true;
+        }
+        dim3 grid((N + WS_BN - 1) / WS_BN, (M + I8_BM - 1) / I8_BM);
+        i8_gemm_ws_kernel<<<grid, WS_THREADS, sizeof(I8WsSmem), st>>>(As, ea, (long long)M * Kp, Bs, eb, (long long)N * Kp, M, N, Kp, S, b,
+                                                                     alpha, beta, C, ldc);
+    } else {
+        dim3 grid((N + I8_BN - 1) / I8_BN, (M + I8_BM - 1) / I8_BM);
+        i8_gemm_kernel<<<grid, 128, 0, st>>>(As, ea, (long long)M * Kp, Bs, eb, (long long)N * Kp, M, N, Kp, S, b, alpha, beta, C, ldc);
+    }
     MOGP_COUNT(3);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -424,7 +424,10 @@ def sec_i8(eng):
     explib.mogp_i8gemm_selftest.restype = C.c_int
     explib.mogp_i8gemm_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     out = (C.c_double * 3)()
-    for (M, N, K) in [(128, 64, 64), (256, 128, 256), (1024, 1024, 1024), (4096, 4096, 4096)]:
+    for variant in ([int(os.environ["I8_VARIANT"])] if "I8_VARIANT" in os.environ else [0, 1]):   # one per process if it faults
+      explib.mogp_i8gemm_set_variant(variant)
+      print("--- int8 GEMM kernel variant %d (0 simple, 1 warp-specialised pipeline)" % variant)
+      for (M, N, K) in [(128, 128, 64), (256, 128, 256), (1024, 1024, 1024), (4096, 4096, 4096)]:
         for S in (6, 7, 8):
             rc = explib.mogp_i8gemm_selftest(M, N, K, S, out)
             print("i8 gemm %5dx%5dx%5d S=%d rc=%d: rel. error %.2e | int8 path %.3f ms (%.1f TFLOP/s fp64-equivalent) | DMMA %.3f ms (%.1f TFLOP/s)" % (
