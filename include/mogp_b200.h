@@ -112,6 +112,11 @@ int mogp_lml_grad_host(mogp_handle_t h, int kind, int C, int Q, int D, const dou
 int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t* chan_off_s_host,
                  int full, double* mu_dev, double* var_dev, void* stream);
 
+/* alpha = K~^-1 (y - mean) of the last mogp_lml_grad call, N doubles in the caller's (channel-sorted) row order.
+ * d LML / d y = -alpha: lets the host chain the gradient into a trainable mean function, which the reference gets
+ * from autograd through y - mean(X) (gpr/model.py:445-452). */
+int mogp_alpha(mogp_handle_t h, double* alpha_dev, void* stream);
+
 /* ---- constrained parameters on the device ------------------------------------------------
  * Replaces Parameter.constrained / Softplus.forward / Sigmoid.forward (gpr/parameter.py:30-96,186-201) and
  * their autograd backward for the training loop (mogptk/model.py:563-565): forward maps the raw leaves to the

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "mogp_lml_grad_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp,
                                      C.c_double, C.c_int, c_dp]),
     "mogp_predict": (C.c_int, [C.c_void_p, c_dp, c_ip, C.c_int, c_dp, c_dp, C.c_void_p]),
+    "mogp_alpha": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "mogp_params_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, C.c_void_p]),
     "mogp_params_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "mogp_dgemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, C.c_int64,

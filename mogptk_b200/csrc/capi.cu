@@ -152,8 +152,15 @@ extern "C" const char* mogp_last_error(mogp_handle_t h) { return h ? h->err.c_st
 static TileList* get_tiles(mogp_handle_s* h, int C, const int32_t* off1, const int32_t* off2, int mode, cudaStream_t st) {
     std::vector<int32_t> o1(off1, off1 + C + 1), o2;
     if (off2) o2.assign(off2, off2 + C + 1);
-    for (TileList* t : h->tiles)
-        if (t->mode == mode && t->off1 == o1 && t->off2 == o2) return t;
+    for (size_t k = 0; k < h->tiles.size(); ++k) {
+        TileList* t = h->tiles[k];
+        if (t->mode == mode && t->off1 == o1 && t->off2 == o2) {
+            // least-recently-used order: a hit moves the list to the back
+            h->tiles.erase(h->tiles.begin() + k);
+            h->tiles.push_back(t);
+            return t;
+        }
+    }
     TileList* t = new TileList();
     t->mode = mode; t->off1 = o1; t->off2 = o2;
     const int T = MOGP_TILE;
@@ -185,13 +192,23 @@ static TileList* get_tiles(mogp_handle_s* h, int C, const int32_t* off1, const i
         if (cudaMalloc(&t->pair_first_dev, t->pair_first.size() * 4) != cudaSuccess) { delete t; return nullptr; }
         cudaMemcpyAsync(t->pair_first_dev, t->pair_first.data(), t->pair_first.size() * 4, cudaMemcpyHostToDevice, st);
     }
-    if (h->tiles.size() > 64) {   // bounded cache
-        TileList* old = h->tiles.front();
+    if (h->tiles.size() >= 64) {
+        // Bounded cache, least recently used first.  Captured step graphs (StepGraph) have the device arrays of the
+        // training lists (mode 0) baked in, so those are evicted last, and when one does go every captured graph is
+        // invalidated through realloc_epoch (re-captured on next use) -- replaying a graph over freed tiles would
+        // silently compute a wrong K.
+        size_t victim = h->tiles.size();
+        for (size_t k = 0; k + 1 < h->tiles.size(); ++k)     // (never the most recently used one: the caller may hold it)
+            if (h->tiles[k]->mode != 0) { victim = k; break; }
+        if (victim == h->tiles.size()) victim = 0;
+        TileList* old = h->tiles[victim];
         cudaStreamSynchronize(st);
+        cudaDeviceSynchronize();              // kernels on the handle's own streams may still read the list
+        if (old->mode == 0) h->realloc_epoch++;
         if (old->dev) cudaFree(old->dev);
         if (old->pair_first_dev) cudaFree(old->pair_first_dev);
         delete old;
-        h->tiles.erase(h->tiles.begin());
+        h->tiles.erase(h->tiles.begin() + victim);
     }
     h->tiles.push_back(t);
     return t;
@@ -635,6 +652,18 @@ extern "C" int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t
         MOGP_CHECK(h, launch_gemm(1, 0, c, 1, st));
         MOGP_CHECK(h, cudaMemcpy2DAsync(var_dev, M * 8, h->pred_S, Mp * 8, M * 8, M, cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+// alpha = K~^-1 y of the last evaluation (rows in the channel-sorted order the caller passed): d LML / d y = -alpha,
+// which is what the host layer needs to back-propagate into a trainable mean function (gpr/model.py:445-452).
+extern "C" int mogp_alpha(mogp_handle_t h, double* alpha_dev, void* stream) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    H_ARG(h, h->have_factor, "mogp_alpha needs a preceding mogp_lml_grad on this handle");
+    H_ARG(h, alpha_dev != nullptr, "NULL argument");
+    MOGP_CHECK(h, cudaMemcpyAsync(alpha_dev, h->vec + 2 * h->np_max, (size_t)h->N * 8, cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
     return 0;
 }
 

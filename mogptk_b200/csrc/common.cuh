@@ -146,6 +146,21 @@ struct mogp_handle_s {
         }                                                                            \
     } while (0)
 
+// Kernel attributes (dynamic shared-memory opt-in, carve-out) are per DEVICE: a process that drives several GPUs
+// (gpr.use_gpu(n), one Engine per device) has to set them once on each.  `static PerDeviceOnce once; if (once.first()) ...`
+struct PerDeviceOnce {
+    bool done[64] = {};
+    int sm_count[64] = {};
+    int device() const { int d = 0; cudaGetDevice(&d); return d & 63; }
+    bool first() { const int d = device(); if (done[d]) return false; done[d] = true; return true; }
+    int sms() {
+        const int d = device();
+        if (sm_count[d] <= 0 && (cudaDeviceGetAttribute(&sm_count[d], cudaDevAttrMultiProcessorCount, d) != cudaSuccess || sm_count[d] <= 0))
+            sm_count[d] = 148;
+        return sm_count[d];
+    }
+};
+
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern long long g_mogp_launches;
 extern long long g_mogp_cfg_epoch;

@@ -367,11 +367,10 @@ static cudaError_t launch_kbuild_t(const KernSpec& s, const TileList& tl, int nb
                                    int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem) + 64 * 65 * sizeof(double);
     auto kern = kbuild_kernel<DT, COS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     if (nblocks <= 0) return cudaSuccess;
     kern<<<nblocks, 256, smem, st>>>(s, tl.dev, tl.n, tl.mode, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk,
@@ -551,11 +550,10 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
 #define LAUNCH_GR(DT, COS)                                                                                         \
     do {                                                                                                           \
         auto kern = grad_reduce_kernel<DT, COS>;                                                                   \
-        static bool attr_done = false;                                                                             \
-        if (!attr_done) {                                                                                          \
+        static PerDeviceOnce once;                                                                                 \
+        if (once.first()) {                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
             if (e != cudaSuccess) return e;                                                                        \
-            attr_done = true;                                                                                      \
         }                                                                                                          \
         kern<<<tl.n, 256, smem, st>>>(s, tl.dev, comps, x, W, ldw, avec, tile_part);                                     \
         MOGP_COUNT(1);                                                                                             \

@@ -217,15 +217,14 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     constexpr int B_STAGE = TB ? BN * LDB_S : BK * LDB_S;
     constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
     auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, TA, TB>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
         // same (maximal) shared-memory carve-out as the Cholesky panel kernel, so that both can be
         // resident on one SM while the look-ahead overlaps them
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
     dim3 grid(g.N / BN, (g.M + BM - 1) / BM, batch);
@@ -1036,8 +1035,8 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
     const size_t smem_d = (size_t)(3 * 64 * LP) * sizeof(double);
     if ((ld | ldt) & 1) return cudaErrorInvalidValue;          // 16-byte row accesses
-    static bool attr_done = false;
-    static int n_sm = 148;
+    static PerDeviceOnce once;
+    const int n_sm = once.sms();
     // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
     // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
@@ -1048,10 +1047,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
-    if (!attr_done) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    if (once.first()) {
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1069,7 +1065,6 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(diag_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const int nb = (int)(Np / MOGP_NB);
     const bool two = ps != nullptr && ps->s2 != nullptr && ps->s1 != nullptr && nb > 2 && nb <= ps->nev;

@@ -277,6 +277,15 @@ class Engine:
         self._check(rc)
         return out_host
 
+    def alpha(self):
+        """alpha = K~^-1 y of the last evaluation, in the ORIGINAL row order of the training X (d LML / d y = -alpha)."""
+        if self._train is None:
+            raise RuntimeError("alpha() needs a preceding lml_grad() on this engine")
+        rows = self._train
+        a = torch.empty(rows.N, dtype=torch.float64, device=self.device)
+        self._check(self.lib.mogp_alpha(self.h, self._p(a), self._stream()))
+        return a if rows.sorted else a[rows.inv_t]
+
     def predict(self, Xs, full=False):
         """Posterior mean / variance of f at Xs from the factor of the last lml_grad call."""
         if self._train is None:

@@ -282,6 +282,19 @@ def default_engine(n_rows, device=None):
     return eng
 
 
+def _require_all_dims(kernel, D):
+    """The engine evaluates kernels on all D input columns.  In the reference a kernel with ``active_dims`` first
+    selects columns of the channel-stripped input (gpr/kernel.py:53-58 under gpr/multioutput.py:26-34,178-181), so
+    anything but None / the identity [0..D-1] would be silently ignored here: refuse it."""
+    ad = getattr(kernel, "active_dims", None)
+    if ad is None:
+        return
+    vals = ad.detach().cpu().reshape(-1).tolist() if torch.is_tensor(ad) else list(np.asarray(ad).reshape(-1))
+    if [int(v) for v in vals] != list(range(D)):
+        raise NotImplementedError("active_dims=%s on %s: only all input dimensions are supported by the B200 engine"
+                                  % (vals, kernel.__class__.__name__))
+
+
 def kernel_spec(kernel):
     """Recognise the kernels this engine implements and return (kind, params, (C,Q,D)), where
     params holds the *constrained* tensors (autograd-connected) in the packed order of
@@ -292,20 +305,19 @@ def kernel_spec(kernel):
         p = {"weight": kernel.weight(), "mean": kernel.mean(), "variance": kernel.variance(),
              "delay": kernel.delay(), "phase": kernel.phase()}
         C_, Q, D = p["mean"].shape
+        _require_all_dims(kernel, int(D))
         return "MOSM", p, (int(C_), int(Q), int(D))
     if cname == "IndependentMultiOutputKernel":
         subs = list(kernel.kernels)
         if all(k.__class__.__name__ == "SpectralMixtureKernel" for k in subs):
             if len({tuple(k.mean.shape) for k in subs}) != 1:
                 raise NotImplementedError("SM kernels of all channels must share Q and input_dims")
-            if any(getattr(k, "active_dims", None) is not None and
-                   list(np.asarray(k.active_dims.cpu() if torch.is_tensor(k.active_dims) else k.active_dims)) !=
-                   list(range(1, k.mean.shape[1] + 1)) for k in subs):
-                raise NotImplementedError("active_dims other than all inputs are not supported")
             p = {"magnitude": torch.stack([k.magnitude() for k in subs]),
                  "mean": torch.stack([k.mean() for k in subs]),
                  "variance": torch.stack([k.variance() for k in subs])}
             C_, Q, D = p["mean"].shape
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
             return "SM", p, (int(C_), int(Q), int(D))
     if cname in ("MixtureKernel", "AddKernel"):
         subs = list(kernel.kernels)
@@ -314,11 +326,14 @@ def kernel_spec(kernel):
                  "variance": torch.stack([k.variance() for k in subs]),
                  "base_variance": torch.stack([k.base_variance() for k in subs])}
             Q, C_, D = p["variance"].shape
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
             return "CONV", p, (int(C_), int(Q), int(D))
     if cname == "GaussianConvolutionProcessKernel":
         p = {"weight": kernel.weight()[None], "variance": kernel.variance()[None],
              "base_variance": kernel.base_variance()[None]}
         Q, C_, D = p["variance"].shape
+        _require_all_dims(kernel, int(D))
         return "CONV", p, (int(C_), int(Q), int(D))
     raise NotImplementedError(
         "mogptk_b200 implements the exact-GP path for MOSM, SM (IndependentMultiOutputKernel of "
@@ -579,19 +594,32 @@ class CholeskyException(Exception):
 
 class _ExactLML(torch.autograd.Function):
     """log p(y) with the analytic gradient from the CUDA engine: forward = one fused
-    mogp_lml_grad call (K build, Cholesky, inverse, LML, gradient), backward = a scale."""
+    mogp_lml_grad call (K build, Cholesky, inverse, LML, gradient), backward = a scale.
+
+    ``targets`` (y - mean(X), original row order) is an input only when a mean function is present: the reference
+    back-propagates through y - mean(X) into the mean's parameters (gpr/model.py:445-452), and
+    d LML / d targets = -K~^-1 targets = -alpha, which the engine already holds (mogp_alpha)."""
 
     @staticmethod
-    def forward(ctx, packed, sigma, model):
-        out = model._evaluate(packed.detach(), sigma.detach(), want_grad=True)
+    def forward(ctx, packed, sigma, targets, model):
+        out = model._evaluate(packed.detach(), sigma.detach(), want_grad=True,
+                              targets=None if targets is None else targets.detach())
         P = packed.numel()
-        ctx.save_for_backward(out[2:2 + P].to(packed.device), out[2 + P:2 + P + sigma.numel()].to(sigma.device))
+        alpha = None
+        if targets is not None and targets.requires_grad:
+            alpha = model._eng().alpha().to(targets.device).reshape(targets.shape)
+        ctx.has_targets = alpha is not None
+        saved = [out[2:2 + P].to(packed.device), out[2 + P:2 + P + sigma.numel()].to(sigma.device)]
+        if alpha is not None:
+            saved.append(alpha)
+        ctx.save_for_backward(*saved)
         return out[0].clone().to(packed.device)
 
     @staticmethod
     def backward(ctx, g):
-        gp, gs = ctx.saved_tensors          # d(-LML)/d constrained
-        return -g * gp, -g * gs, None
+        saved = ctx.saved_tensors           # d(-LML)/d constrained [, alpha]
+        gy = -g * saved[2] if ctx.has_targets else None
+        return -g * saved[0], -g * saved[1], gy, None
 
 
 class Exact(_Named):
@@ -802,6 +830,10 @@ class Exact(_Named):
         eng._train, eng._kind = rows, self._kind
         lml, info = out[:2].tolist()                           # the iteration's one synchronisation
         if info != 0:
+            # the reference raises in forward(), before backward() has produced anything (gpr/model.py:246-255,291):
+            # do not leave the non-finite chain-rule output in p.grad for callers that catch and continue
+            for q in plist:
+                q.grad = None
             self._raise_cholesky(int(info), packed[:P], packed[P:P + C_])
         self._factor_key = ("v", tuple((q.data_ptr(), q._version) for q in plist))
         return lossb.clone()[0]
@@ -837,16 +869,17 @@ class Exact(_Named):
             y = y - self.mean(self.X).reshape(-1, 1)
         return y.reshape(-1)
 
-    def _evaluate(self, packed, sigma, want_grad):
+    def _evaluate(self, packed, sigma, want_grad, targets=None):
         eng = self._eng()
         kind, p, dims = kernel_spec(self.kernel)
+        if targets is None:
+            targets = self._targets().detach()
         if self._rows is None or self._rows.owner is not eng:
-            rows = eng.prepare(kind, {k: v.detach() for k, v in p.items()}, self.X, self._targets().detach(),
-                               self.data_variance)
+            rows = eng.prepare(kind, {k: v.detach() for k, v in p.items()}, self.X, targets, self.data_variance)
             rows.owner = eng
             self._rows = rows
         elif self.mean is not None:
-            self._rows.y = self._rows.sort_vec(self._targets().detach(), eng.device)
+            self._rows.y = self._rows.sort_vec(targets, eng.device)
         out = eng.lml_grad_prepared(self._rows, packed.to(eng.device, torch.float64).contiguous(),
                                     sigma.to(eng.device, torch.float64).contiguous(), self.jitter, want_grad, check=False)
         info = int(out[1].item())            # the reference also synchronises here (float(loss))
@@ -865,9 +898,12 @@ class Exact(_Named):
     def log_marginal_likelihood(self):
         """log p(y) (gpr/model.py:438-453); differentiable w.r.t. the raw parameters."""
         packed, sigma = self._packed(), self._sigma()
-        if torch.is_grad_enabled() and (packed.requires_grad or sigma.requires_grad):
-            return _ExactLML.apply(packed, sigma, self)
-        return self._evaluate(packed.detach(), sigma.detach(), want_grad=False)[0].clone()
+        targets = self._targets() if self.mean is not None else None
+        if torch.is_grad_enabled() and (packed.requires_grad or sigma.requires_grad
+                                        or (targets is not None and targets.requires_grad)):
+            return _ExactLML.apply(packed, sigma, targets, self)
+        return self._evaluate(packed.detach(), sigma.detach(), want_grad=False,
+                              targets=None if targets is None else targets.detach())[0].clone()
 
     def _ensure_factor(self):
         """The reference re-factorises on every predict (gpr/model.py:463-469); here the factor of
@@ -880,6 +916,8 @@ class Exact(_Named):
                 return
             key = None
         packed, sigma = self._packed().detach(), self._sigma().detach()
+        if self.mean is not None:
+            key = None                       # alpha depends on the mean's parameters too: always re-evaluate
         if (key is None or eng._train is not self._rows or not torch.equal(key[0], packed)
                 or not torch.equal(key[1], sigma)):
             self._evaluate(packed, sigma, want_grad=False)

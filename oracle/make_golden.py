@@ -16,7 +16,6 @@ import argparse
 import os
 import sys
 import time
-from unittest.mock import MagicMock
 
 import numpy as np
 import torch
@@ -27,17 +26,9 @@ REF = "/root/reference"
 
 
 def import_reference():
-    """the reference imports matplotlib/IPython at module import."""
-    for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors",
-              "matplotlib.dates", "matplotlib.units", "mpl_toolkits", "mpl_toolkits.axes_grid1",
-              "IPython", "IPython.display"]:
-        sys.modules.setdefault(m, MagicMock())
-    import pandas.plotting
-    pandas.plotting.register_matplotlib_converters = lambda *a, **k: None
-    sys.path.insert(0, REF)
-    import mogptk
-    mogptk.gpr.use_cpu()
-    return mogptk
+    """the reference imports matplotlib/IPython at module import -- see oracle/ref_loader.py."""
+    from oracle import ref_loader
+    return ref_loader.import_reference("cpu")
 
 
 from oracle import mogp_oracle as orc            # noqa: E402
@@ -233,13 +224,53 @@ BIG = {
 }
 
 
+def add_prediction(mogptk, name, n_pred=48):
+    """Append predict_f outputs of the live reference to an existing fixture (forward only: used for cfg3, whose
+    gradients take minutes and tens of GB through autograd but whose posterior needs one K build + Cholesky)."""
+    t0 = time.time()
+    path = os.path.join(GOLDEN, name + ".npz")
+    z = np.load(path, allow_pickle=False)
+    out = {k: z[k] for k in z.files}
+    kind, C, Q, D = str(out["kind"]), int(out["C"]), int(out["Q"]), int(out["D"])
+    X, y, jitter = out["X"], out["y"], float(out["jitter"])
+    cons = {k[2:]: torch.tensor(v, dtype=torch.float64) for k, v in out.items() if k.startswith("p_")}
+    sig = torch.tensor(out["sigma"], dtype=torch.float64)
+    model = build_reference_model(mogptk, kind, C, Q, D, X, y, cons, sig, jitter, out.get("data_var"))
+    # the fixture was made from the raw values: restore them exactly (assign() is not an exact round trip)
+    _, _, objs, stack = read_back(kind, model, C, Q)
+    for n, lst in objs.items():
+        raw = torch.tensor(out["r_" + n], dtype=torch.float64)
+        for i, prm in enumerate(lst):
+            prm.data = (raw if len(lst) == 1 else raw[i]).clone().reshape(prm.shape)
+    with torch.no_grad():
+        lml = float(model.log_marginal_likelihood())
+    assert abs(lml - float(out["lml"])) <= 1e-12 * abs(lml), (lml, float(out["lml"]))
+    rng = np.random.default_rng(2)
+    cs = rng.integers(0, C, n_pred).astype(np.float64)
+    xs = rng.uniform(-0.5, 10.5, (n_pred, D))
+    Xs = np.concatenate([cs[:, None], xs], axis=1)
+    with torch.no_grad():
+        mu_ref, var_ref = model.predict_f(torch.tensor(Xs))
+    cons_rb, sig_rb, _, _ = read_back(kind, model, C, Q)
+    mu_or, var_or = orc.predict_f(kind, cons_rb, sig_rb, torch.tensor(X), y, Xs, jitter, data_var=out.get("data_var"))
+    assert relerr(mu_or, mu_ref) < 1e-9 and relerr(var_or, var_ref) < 1e-8, (relerr(mu_or, mu_ref), relerr(var_or, var_ref))
+    out.update(Xs=Xs, pred_mu=mu_ref.numpy().reshape(-1), pred_var=var_ref.numpy().reshape(-1))
+    np.savez_compressed(path, **out)
+    print("%-18s predictions added (%d points, %.1fs)" % (name, n_pred, time.time() - t0), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="")
+    ap.add_argument("--add-pred", default="", help="append reference predictions to these existing fixtures")
     ap.add_argument("--big", action="store_true", help="also cfg3 (N=8192; ~minutes and tens of GB of RAM)")
     args = ap.parse_args()
     mogptk = import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.add_pred:
+        for name in args.add_pred.split(","):
+            add_prediction(mogptk, name)
+        return
     cases = dict(CASES)
     if args.big:
         cases.update(BIG)

@@ -57,6 +57,12 @@ class FakeEngine:
         self._train, self._p, self._sigma, self._jitter = rows, p, sigma.detach().clone(), jitter
         return out
 
+    def alpha(self):
+        rows = self._train
+        Kn = orc._noisy_gram(rows.kind, self._p, self._sigma, rows.Xs, self._jitter, rows.dv)
+        a = torch.linalg.solve(Kn, rows.y.reshape(-1, 1)).reshape(-1)
+        return a if rows.sorted else a[rows.inv_t]
+
     def predict(self, Xs, full=False):
         rows = self._train
         mu, var = orc.predict_f(rows.kind, self._p, self._sigma, rows.Xs, rows.y, torch.as_tensor(np.asarray(Xs)),

@@ -221,3 +221,54 @@ def test_lbfgs_closure_and_resume_through_the_plugin():
     assert len(b.losses) == len(lb) + 2
     import pickle
     pickle.loads(pickle.dumps(b.gpr))                                       # what model.save() relies on
+
+
+def test_trainable_mean_function_receives_gradients():
+    """The reference back-propagates the LML through y - mean(X) (gpr/model.py:445-452); here d LML / d y = -alpha
+    from the engine is chained into the mean's parameters (they silently stayed untrained)."""
+    from oracle import mogp_oracle as orc
+    g = load_golden("mosm_shuffled")
+
+    class LinMean(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.bias = gpr.Parameter(0.3)
+            self.slope = gpr.Parameter(torch.tensor([-0.2, 0.05], dtype=torch.float64))
+
+        def forward(self, X):
+            return self.bias() + X.mm(self.slope().reshape(-1, 1))
+
+    eng = FakeEngine()
+    m, plist = build_mirror(g, eng)
+    mean = LinMean()
+    m.mean = mean
+    loss = m.loss()
+    # oracle: same LML on y - mean(X), autograd into (bias, slope)
+    b = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    s = torch.tensor([-0.2, 0.05], dtype=torch.float64, requires_grad=True)
+    X = torch.tensor(g["X"])
+    yt = torch.tensor(g["y"]).reshape(-1, 1) - (b + X.mm(s.reshape(-1, 1)))
+    p = {k: orc.softplus_forward(torch.tensor(g["r_" + k]), float(g["lower_" + k])) if bool(g["has_lower_" + k])
+         else torch.tensor(g["r_" + k]) for k in g["params"]}
+    sig = orc.softplus_forward(torch.tensor(g["r_sigma"]), float(g["lower_sigma"]))
+    ref = -orc.lml(g["kind"], p, sig, X, yt, g["jitter"])
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-10 * abs(float(ref))
+    assert mean.bias.grad is not None and mean.slope.grad is not None
+    assert abs(float(mean.bias.grad) - float(b.grad)) <= 1e-8 * abs(float(b.grad))
+    assert float((mean.slope.grad - s.grad).abs().max()) <= 1e-8 * float(s.grad.abs().max())
+    mu, _ = m.predict_f(g["Xs"])                                # mean is added back (gpr/model.py:473-474)
+    assert mu.shape == (g["Xs"].shape[0], 1)
+
+
+def test_active_dims_other_than_identity_are_refused():
+    k = gpr.MultiOutputSpectralMixtureKernel(Q=1, output_dims=2, input_dims=2)
+    k.active_dims = torch.tensor([0, 1])
+    gpr.kernel_spec(k)                                          # identity selection is fine
+    k.active_dims = torch.tensor([1, 0])
+    with pytest.raises(NotImplementedError):
+        gpr.kernel_spec(k)
+    sub = [gpr.SpectralMixtureKernel(Q=1, input_dims=1) for _ in range(2)]
+    sub[1].active_dims = [1]                                    # out of range after the channel column is stripped
+    with pytest.raises(NotImplementedError):
+        gpr.kernel_spec(gpr.IndependentMultiOutputKernel(sub, output_dims=2))
