@@ -143,6 +143,24 @@ int mogp_params_backward(mogp_handle_t h, const mogp_param_entry* entries_host, 
                          const double* gcons_dev, const double* dcons_dev, const double* lml_dev,
                          double* loss_out_dev, void* stream);
 
+/* Device-resident Adam training -- replaces `iters` passes of the body of mogptk.Model.train's loop
+ * (mogptk/model.py:563-565: loss = gpr.loss(); torch.optim.Adam.step()) without any host synchronisation.
+ *   entries_host: the raw leaves, as for mogp_params_forward (kernel parameters first, the C noise scales last); the
+ *                 raw values are updated IN PLACE, the raw-space gradient of the last iteration is left in .grad.
+ *   work_dev    : 3 * (2 + P + C) doubles of scratch.
+ *   exp_avg_dev, exp_avg_sq_dev: Adam moments, P + C doubles each in packed order (zero them for a fresh optimiser).
+ *   step0       : optimiser steps already taken (bias correction uses step0 + i + 1).
+ *   losses_dev  : iters doubles; losses_dev[i] = -LML at the parameters BEFORE update i (what the reference records).
+ *   fail_dev    : 2 int32, zeroed by the caller: [0] = LAPACK-style info of the first failed Cholesky (or -1 for a
+ *                 non-finite evaluation), [1] = its 1-based iteration.  From that iteration on the parameters are
+ *                 frozen, so the host can re-evaluate there and raise CholeskyException (gpr/model.py:246-255).
+ * torch.optim.Adam semantics with amsgrad = False, weight_decay = 0, maximize = False. */
+int mogp_train_adam(mogp_handle_t h, int kind, int C, int Q, int D, const mogp_param_entry* entries_host, int n_entries,
+                    const double* x_dev, const int32_t* chan_off_host, const double* y_dev, const double* data_var_dev,
+                    double jitter_rel, double* work_dev, double* exp_avg_dev, double* exp_avg_sq_dev, long long step0,
+                    int iters, double lr, double beta1, double beta2, double eps, double* losses_dev, int32_t* fail_dev,
+                    void* stream);
+
 /* ---- building blocks exposed for tests and micro-benchmarks --------------------------- */
 
 /* C = alpha * op(A) * op(B) + beta * C on the fp64 tensor pipe (DMMA).

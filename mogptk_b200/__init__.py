@@ -10,5 +10,6 @@ from .gpr import (CholeskyException, Exact, GaussianConvolutionProcessKernel, Ga
                   IndependentMultiOutputKernel, MixtureKernel, MultiOutputSpectralMixtureKernel, Parameter,
                   SpectralMixtureKernel)
 from .inference import B200Exact                 # noqa: F401
+from .train import fit_adam, install, uninstall  # noqa: F401
 
 __version__ = "0.1.0"

@@ -90,3 +90,85 @@ extern "C" int mogp_params_backward(mogp_handle_t h, const mogp_param_entry* ent
     MOGP_CHECK(h, cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------ device-resident Adam training
+// Replaces the body of the reference's training loop (mogptk/model.py:563-565: `progress(i, self.loss())`,
+// `optimizer.step()` with torch.optim.Adam) for `iters` iterations without a host synchronisation: per iteration
+//   raw leaves -> constrained (params_forward) -> fused exact-GP step (replayed CUDA graph) -> chain rule into the
+//   p.grad buffers and the Adam update of the raw leaves in one kernel.
+// The update restates torch.optim.Adam's single-tensor formula (amsgrad = False, weight_decay = 0, maximize = False):
+//   m <- m + (1 - b1) (g - m);  v <- b2 v + (1 - b2) g^2;  p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// A Cholesky failure (info != 0) freezes the parameters from that iteration on (sticky flag), so that the host can
+// re-evaluate at exactly the failing parameters and raise the reference's CholeskyException there.
+__global__ void params_backward_adam_kernel(const DevEntry* __restrict__ ent, const double* __restrict__ out /* lml, info, grads */,
+                                            const double* __restrict__ dcons, double* __restrict__ exp_avg,
+                                            double* __restrict__ exp_avg_sq, double one_minus_b1, double b2,
+                                            double step_size, double bc2_sqrt, double eps, double* __restrict__ loss_slot,
+                                            int32_t* __restrict__ fail /* [0] = info, [1] = iteration (1-based) */, int iter1) {
+    const DevEntry e = ent[blockIdx.x];
+    const double info = out[1];
+    const bool failed = (fail[0] != 0) || (info != 0.0) || !(info == info);
+    const double* gcons = out + 2;
+    for (long long i = threadIdx.x; i < e.n; i += blockDim.x) {
+        const double g = gcons[e.off + i] * dcons[e.off + i];
+        if (e.grad) e.grad[i] = g;
+        if (failed) continue;
+        double m = exp_avg[e.off + i], v = exp_avg_sq[e.off + i];
+        m = m + one_minus_b1 * (g - m);                       // torch lerp_(grad, 1 - beta1), weight < 0.5 branch
+        v = v * b2 + (1.0 - b2) * g * g;                      // mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+        exp_avg[e.off + i] = m;
+        exp_avg_sq[e.off + i] = v;
+        const double denom = sqrt(v) / bc2_sqrt + eps;
+        const_cast<double*>(e.raw)[i] = e.raw[i] - step_size * (m / denom);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        loss_slot[0] = -out[0];
+        // every block reads fail[] before this write can matter: the flag is only consulted by LATER launches
+        if (failed && fail[0] == 0) { fail[1] = iter1; }
+    }
+}
+// second tiny kernel so that the sticky flag is written after every block of the update kernel has read it
+__global__ void adam_flag_kernel(const double* __restrict__ out, int32_t* __restrict__ fail) {
+    const double info = out[1];
+    if (fail[0] == 0 && ((info != 0.0) || !(info == info))) fail[0] = (info == info && info > 0.0) ? (int32_t)info : -1;
+}
+
+extern "C" int mogp_train_adam(mogp_handle_t h, int kind, int C, int Q, int D, const mogp_param_entry* entries_host,
+                               int n_entries, const double* x_dev, const int32_t* chan_off_host, const double* y_dev,
+                               const double* data_var_dev, double jitter_rel, double* work_dev /* 3 * (2 + P + C) */,
+                               double* exp_avg_dev, double* exp_avg_sq_dev, long long step0, int iters, double lr,
+                               double beta1, double beta2, double eps, double* losses_dev, int32_t* fail_dev,
+                               void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    if (!entries_host || !work_dev || !exp_avg_dev || !exp_avg_sq_dev || !losses_dev || !fail_dev || iters < 0 ||
+        !(beta1 >= 0.0 && beta1 < 0.5 + 0.5) || !(beta2 >= 0.0 && beta2 < 1.0) || step0 < 0) {
+        h->err = "mogp_train_adam: bad argument";
+        return -1;
+    }
+    const int P = mogp_num_params(kind, C, Q, D);
+    if (P < 0) { h->err = "bad kernel spec (kind, C, Q, D)"; return -1; }
+    const size_t n = 2 + (size_t)P + C;
+    double* packed = work_dev;
+    double* dcons = work_dev + n;
+    double* out = work_dev + 2 * n;
+    int rc = upload_entries(h, entries_host, n_entries, st);
+    if (rc) return rc;
+    for (int i = 0; i < iters; ++i) {
+        params_forward_kernel<<<n_entries, 128, 0, st>>>((const DevEntry*)h->pent_dev, packed, dcons);
+        MOGP_COUNT(1);
+        rc = mogp_lml_grad(h, kind, C, Q, D, packed, x_dev, chan_off_host, y_dev, packed + P, data_var_dev, jitter_rel, 1, out,
+                           stream);
+        if (rc) return rc;
+        const double t = (double)(step0 + i + 1);
+        const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
+        params_backward_adam_kernel<<<n_entries, 128, 0, st>>>((const DevEntry*)h->pent_dev, out, dcons, exp_avg_dev,
+                                                              exp_avg_sq_dev, 1.0 - beta1, beta2, lr / bc1, sqrt(bc2), eps,
+                                                              losses_dev + i, fail_dev, i + 1);
+        adam_flag_kernel<<<1, 1, 0, st>>>(out, fail_dev);
+        MOGP_COUNT(2);
+    }
+    MOGP_CHECK(h, cudaGetLastError());
+    return 0;
+}

@@ -135,3 +135,25 @@ def test_sigmoid_bounded_parameter_on_the_device_path(gpr):
     lb = m.loss()
     assert abs(float(la) - float(lb)) <= 1e-13 * abs(float(lb))
     assert float((m.kernel.mean.grad - ga).abs().max()) <= 1e-12 * max(float(ga.abs().max()), 1e-12)
+
+
+def test_fused_adam_equals_loss_plus_torch_adam(gpr):
+    """mogp_train_adam (one C call for K iterations) against loss() + torch.optim.Adam.step() on a twin model."""
+    from mogptk_b200 import fit_adam
+    g = load_golden("mosm_mid")
+    a, _ = build(gpr, g)
+    b, _ = build(gpr, g)
+    opt = torch.optim.Adam(a.parameters(), lr=0.03, betas=(0.8, 0.95), eps=1e-7)
+    ref = []
+    for _ in range(40):
+        ref.append(float(a.loss()))
+        opt.step()
+    got, times = fit_adam(b, 40, lr=0.03, betas=(0.8, 0.95), eps=1e-7, sync_every=16)
+    assert got.shape == (40,) and np.all(np.diff(times) > 0)
+    assert np.abs(got - np.array(ref)).max() <= 1e-9 * np.abs(ref).max()
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert float((p.data - q.data).abs().max()) <= 1e-9 * max(float(p.data.abs().max()), 1.0)
+    assert abs(float(a.loss()) - float(b.loss())) <= 1e-9 * abs(float(a.loss()))
+    mu_a, _ = a.predict_f(g["Xs"])
+    mu_b, _ = b.predict_f(g["Xs"])                              # factor cache was invalidated by the in-place updates
+    assert float((mu_a - mu_b).abs().max()) <= 1e-8 * float(mu_a.abs().max())

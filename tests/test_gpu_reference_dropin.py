@@ -231,3 +231,52 @@ def test_trainable_mean_function_trains_like_the_reference(mogptk):
     _, Mb, _, _ = b.predict()
     for u, v in zip(Ma, Mb):
         assert close(u, v, 1e-6)
+
+
+def test_device_resident_adam_matches_the_reference_for_100_iterations(mogptk):
+    """mogptk_b200.install() routes mogptk.Model.train('Adam') to mogp_train_adam (K iterations per synchronisation):
+    the loss trajectory must equal the stock reference's (its own CPU path + torch.optim.Adam) to 1e-7 over 100
+    iterations, and losses / times / iters must keep the reference's bookkeeping, including resume."""
+    import mogptk_b200 as mb
+    a, b = make_pair(mogptk, "MOSM", 3, [64, 50, 70], 2, seed=11)
+    with on(mogptk, "cpu"):
+        la, _ = a.train(method="Adam", iters=100, lr=0.02, verbose=False, jit=False)
+        la2, _ = a.train(method="Adam", iters=5, lr=0.01, verbose=False, jit=False)
+        _, Ma, _, _ = a.predict()
+    mb.install(mogptk)
+    try:
+        calls = []
+        orig = b.gpr.loss
+        b.gpr.loss = lambda: (calls.append(1), orig())[1]
+        lb, eb = b.train(method="Adam", iters=100, lr=0.02, verbose=False, jit=False, sync_every=32)
+        assert len(calls) == 1                               # only the closing evaluation went through loss()
+        assert len(lb) == 101 and len(eb) == 101 and b.iters == 100 and b.times.shape == (101,)
+        assert np.all(np.diff(b.times) >= 0)
+        assert close(la, lb, 1e-7), np.abs(la - lb).max()
+        lb2, _ = b.train(method="Adam", iters=5, lr=0.01, verbose=False, jit=False)      # resume: fresh optimiser, appended history
+        assert len(lb2) == 106 and b.iters == 105 and close(la2, lb2, 1e-7)
+        _, Mb, _, _ = b.predict()
+        for u, v in zip(Ma, Mb):
+            assert close(u, v, 1e-6)
+        # requests the device loop does not cover fall through to the reference's own train()
+        b.train(method="LBFGS", iters=3, verbose=False, jit=False)
+        b.train(method="Adam", iters=2, lr=0.01, amsgrad=True, verbose=False, jit=False)
+        assert len(calls) > 3
+    finally:
+        mb.uninstall(mogptk)
+    assert mogptk.Model.train.__name__ == "train"
+
+
+def test_device_resident_adam_stops_at_a_cholesky_failure(mogptk):
+    import mogptk_b200 as mb
+    from mogptk_b200 import train as fused
+    g = load_golden("mosm_small")
+    k, _ = reference_kernel(mogptk, g)
+    m = mb.B200Exact(jitter=g["jitter"])._build(k, g["X"], g["y"].reshape(-1, 1))
+    losses, _ = fused.fit_adam(m, 6, lr=0.01, sync_every=4)
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    raw_before = k.variance.data.clone()
+    k.weight.data[0, 0] = float("nan")
+    with pytest.raises(mogptk.gpr.CholeskyException):
+        fused.fit_adam(m, 8, lr=0.01, sync_every=8)
+    assert torch.equal(k.variance.data, raw_before)          # frozen at the failing iteration

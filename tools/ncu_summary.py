@@ -19,7 +19,12 @@ WANT = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 pipe % (active)"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe cycles active %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe % of peak (elapsed)"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % of peak (active)"),
+    ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "  DMMA sub-pipe % (active)"),
+    ("sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active", "  IMMA sub-pipe % (active)"),
     ("sm__inst_executed_pipe_tensor.sum", "tensor-pipe instructions"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue active % (elapsed)"),
     ("smsp__inst_executed.sum", "instructions"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
