@@ -55,6 +55,8 @@ _SIGNATURES = {
 # not part of the public header: tuning / host self-check hooks
 _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
+    "mogp_set_i8": (C.c_int, [C.c_longlong, C.c_int]),
+    "mogp_i8_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mogp_set_graphs": (None, [C.c_int]),
     "mogp_set_graph_max_np": (None, [C.c_longlong]),
     "mogp_test_fail_capture": (None, [C.c_int]),

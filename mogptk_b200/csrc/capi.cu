@@ -106,6 +106,7 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         if (t->pair_first_dev) cudaFree(t->pair_first_dev);
         delete t;
     }
+    if (h->i8) i8_plan_destroy(h->i8);
     if (h->pent_dev) cudaFree(h->pent_dev);
     if (h->pent_host) cudaFreeHost(h->pent_host);
     for (StepGraph* g : h->graphs) {
@@ -290,6 +291,20 @@ extern "C" int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const 
     return 0;
 }
 
+// fp64-on-int8 tcgen05 path (i8mm.cu) for the K^-1 = L^-T L^-1 product: padded sizes >= g_i8_min_np use it (0 = never).
+long long g_i8_min_np = std::getenv("MOGP_I8_MIN_NP") ? std::atoll(std::getenv("MOGP_I8_MIN_NP")) : 4096;
+int g_i8_slices = std::getenv("MOGP_I8_SLICES") ? std::atoi(std::getenv("MOGP_I8_SLICES")) : 7;
+extern "C" int mogp_set_i8(long long min_np, int slices) {
+    if (slices != 7 && slices != 8) return -1;
+    g_i8_min_np = min_np; g_i8_slices = slices; ++g_mogp_cfg_epoch;
+    return 0;
+}
+static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }
+static cudaError_t kinv_dispatch(mogp_handle_s* h, int64_t Np, long long ld, cudaStream_t st) {
+    if (use_i8(Np) && h->i8) return i8_kinv(h->i8, h->Linv, h->W, Np, ld, g_i8_slices, st);
+    return kinv_padded(h->Linv, h->W, Np, ld, nullptr, st);
+}
+
 // ------------------------------------------------------------------ Cholesky
 extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda, int32_t* info_dev, void* stream) {
     if (!h) return -1;
@@ -321,7 +336,13 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     bool fused_inverse = false;
     MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
-    MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
+    if (use_i8(n)) {                     // same dispatch as the fused step (int8 tensor pipe for large n)
+        if (!h->i8) h->i8 = i8_plan_create();
+        MOGP_CHECK(h, i8_kinv_prepare(h->i8, n, g_i8_slices, st));
+        MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
+    } else {
+        MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
+    }
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
     h->have_factor = false;
     return 0;
@@ -383,7 +404,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     if (fork) {
         MOGP_CHECK(h, cudaEventRecord(h->ev_f1, st));
         MOGP_CHECK(h, cudaStreamWaitEvent(h->ps.s3, h->ev_f1, 0));
-        MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, nullptr, h->ps.s3));
+        MOGP_CHECK(h, kinv_dispatch(h, Np, ld, h->ps.s3));
         MOGP_CHECK(h, cudaEventRecord(h->ev_f2, h->ps.s3));
     }
     MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
@@ -392,7 +413,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     STAGE_MARK();
     if (want_grad) {
         if (fork) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ev_f2, 0));
-        else MOGP_CHECK(h, kinv_padded(h->Linv, h->W, Np, ld, nullptr, st));
+        else MOGP_CHECK(h, kinv_dispatch(h, Np, ld, st));
         STAGE_MARK();
         MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, alpha, h->tile_part, st));
     }
@@ -446,6 +467,10 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     if (want_grad) {
         const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * comp_stride(D);
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
+    }
+    if (want_grad && use_i8(Np)) {
+        if (!h->i8) h->i8 = i8_plan_create();
+        MOGP_CHECK(h, i8_kinv_prepare(h->i8, Np, g_i8_slices, st));
     }
     const size_t nout = 2 + (size_t)s.P + C;
     const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;

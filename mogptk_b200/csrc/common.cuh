@@ -75,6 +75,7 @@ struct GemmArgs {
 cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s);
 
 // ------------------------------------------------------------------ handle
+struct I8Plan;                 // int8 tensor-pipe GEMM state (i8mm.cu)
 struct StepGraph {             // one captured exact-GP step (see capi.cu)
     int kind = 0, C = 0, Q = 0, D = 0, want_grad = 0, has_dv = 0, uses = 0;
     int64_t N = 0;
@@ -131,6 +132,7 @@ struct mogp_handle_s {
     cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_f1 = nullptr, ev_f2 = nullptr;
     std::vector<int32_t> chan_uploaded;                       // content of chan_dev slot 0
     double *gbuf = nullptr; size_t gbuf_cap = 0;              // graph staging: params | sigma | y | data_var | out
+    I8Plan* i8 = nullptr;                                     // int8 tensor-pipe GEMM state (large problems)
     // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
     bool profile = false;
     cudaEvent_t ev[8] = {};
@@ -207,3 +209,15 @@ cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, 
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
                             double* var, cudaStream_t st);
 cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);
+
+// ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (i8mm.cu)
+struct I8Plan;
+I8Plan* i8_plan_create();
+void i8_plan_destroy(I8Plan* p);
+// host-side preparation (allocation, tile list) for a given padded size: call outside graph capture
+cudaError_t i8_kinv_prepare(I8Plan* p, int64_t Np, int S, cudaStream_t st);
+// W(lower tiles) = Linv^T Linv via tcgen05.mma kind::i8 (S digit planes of 7 bits); pure enqueue
+cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st);
+// Smallest padded size that takes the int8 path (0 = never) and the number of digit planes (7 or 8)
+extern long long g_i8_min_np;
+extern int g_i8_slices;

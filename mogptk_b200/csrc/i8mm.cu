@@ -1,0 +1,478 @@
+// fp64 GEMM on the int8 tensor pipe of sm_100a (tcgen05.mma kind::i8, int32 accumulators in TMEM) by Ozaki-style
+// slicing -- the tcgen05 path of the O(N^3) stages for large problems (there is no fp64 tcgen05.mma).
+//
+//   x[i, :] = 2^ex[i] * sum_s X_s[i, :] 2^(-7 (s+1)),   X_s signed 7-bit digits stored as int8, one exponent per row
+//   C[i, j] = alpha * 2^(ea[i] + eb[j]) * sum_{d < S} 2^(-7 (d+2)) * ( sum_{s+t=d} A_s B_t^T )[i, j]   (+ beta C)
+//
+// Every digit product is exact in int32 (|digit| <= 64, K * 2^12 * S < 2^31 up to K = 65536 at S = 8), so the only
+// rounding is the truncation of the operands to 7 S bits below their row maximum plus the fp64 sums over d: with
+// S = 7 a product carries ~1e-14 of the largest entry, with S = 8 it is as accurate as an fp64 GEMM
+// (profiles/r02_i8_bringup_v1.log, profiles/r01_ozaki_accuracy_study.txt).
+//
+// Kernel structure (one CTA per 128 x 64 output tile, 6 warps):
+//   * all S digit planes of the tile's A rows and B rows for one 32-deep K chunk form one pipeline stage (42 KB at
+//     S = 7), so a chunk is read from L2 ONCE for its S (S+1) / 2 MMAs (the bring-up kernel streamed the operands
+//     once per digit pair and was L2-bound at 0.5 POP/s);
+//   * the S anti-diagonal sums live in S x 64 TMEM columns at the same time (448 of 512 at S = 7);
+//   * warp 0 lane 0: producer -- 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of pre-tiled digits;
+//     warp 1 lane 0: issues the tcgen05.mma stream and releases stages with tcgen05.commit;
+//     warps 2-5: epilogue -- tcgen05.ld of the S accumulators, fp64 recombination, scaling, store.
+//   * the sliced operands are stored in global memory in exactly the shared-memory image the MMA wants (no-swizzle
+//     K-major core matrices: 8 rows x 16 bytes contiguous), tiled as [k chunk][row tile of 128][slice][k16][row][16 B],
+//     so a stage is one 4 S KB copy for A and 2 S copies of 1 KB for B.
+//   * per-tile K ranges (triangular operands) come from a host-built tile list.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdio>
+
+#define I8_TM 128          // tile rows (UMMA M)
+#define I8_TN 64           // tile columns (UMMA N)
+#define I8_KC 32           // K bytes per stage = one UMMA K step for 8-bit operands
+#define I8_STAGES 4
+#define I8_SMAX 8
+#define I8_BITS 7
+
+__device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------ slicing
+// Row maxima -> exponents.  Element (row r, k) of the operand is src[r * rs + k * cs]; `tri` = 1 restricts k to
+// k >= r - (r % 64) ... (lower-triangular L^-1 read column-wise: operand row r = column r of L^-1, nonzero for k >= r).
+__global__ void __launch_bounds__(256) i8_rowmax_kernel(const double* __restrict__ src, long long rs, long long cs, int R,
+                                                        int K, int tri, int* __restrict__ ex_bits) {
+    // block: 64 operand rows x 4 k-phases; grid.y splits K
+    const int r = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int ph = threadIdx.x >> 6;
+    const int kper = (K + gridDim.y - 1) / gridDim.y;
+    int k0 = blockIdx.y * kper, k1 = min(K, k0 + kper);
+    if (tri) k0 = max(k0, (int)(blockIdx.x * 64));
+    double m = 0.0;
+    if (r < R)
+        for (int k = k0 + ph; k < k1; k += 4) m = fmax(m, fabs(src[(long long)r * rs + (long long)k * cs]));
+    __shared__ double red[256];
+    red[threadIdx.x] = m;
+    __syncthreads();
+    if (ph == 0 && r < R) {
+        m = fmax(fmax(red[threadIdx.x], red[threadIdx.x + 64]), fmax(red[threadIdx.x + 128], red[threadIdx.x + 192]));
+        // non-negative doubles order like their bit patterns: keep the high word (sign + exponent + 20 mantissa bits)
+        if (m > 0.0) atomicMax(ex_bits + r, __double2hiint(m));
+    }
+}
+
+// digits[kc][rt][s][k16][row % 128][k % 16], kc = k / 32, rt = row / 128.  One block per (kc, rt): 128 rows x 32 k.
+// Thread (row, k16) slices 16 consecutive k of one row and writes one 16-byte vector per digit plane.
+// Blocks with tri != 0 that lie entirely in the zero part of a lower-triangular operand (all k < first row of the
+// tile) are never read by the tile lists and are skipped.
+__global__ void __launch_bounds__(256) i8_slice_tiled_kernel(const double* __restrict__ src, long long rs, long long cs,
+                                                             int R, int K, int S, int tri, const int* __restrict__ ex_bits,
+                                                             int8_t* __restrict__ digits, int nrt) {
+    const int kc = blockIdx.x, rt = blockIdx.y;
+    if (tri && kc * I8_KC + I8_KC <= rt * I8_TM) return;
+    const int row = rt * I8_TM + (threadIdx.x & 127), k16 = threadIdx.x >> 7;
+    int e = 0;
+    bool nz = false;
+    if (row < R) {
+        const int hi = ex_bits[row];
+        if (hi > 0) { nz = true; e = ((hi >> 20) & 0x7ff) - 1022 + 1; }     // |x| < 2^(e-1): x 2^-e in (-1/2, 1/2)
+    }
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = kc * I8_KC + k16 * 16 + i;
+        v[i] = (nz && k < K) ? src[(long long)row * rs + (long long)k * cs] : 0.0;
+    }
+    const double sc = nz ? __hiloint2double((1023 - e) << 20, 0) : 0.0;      // 2^-e
+    int8_t* base = digits + (((long long)kc * nrt + rt) * S) * (2 * I8_TM * 16) + (long long)(k16 * I8_TM + (threadIdx.x & 127)) * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= sc;
+    for (int s = 0; s < S; ++s) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double r = v[i] * 128.0;
+            const double d = rint(r);                                         // |r| <= 64 -> digit in [-64, 64]
+            v[i] = r - d;                                                     // exact
+            w[i >> 2] |= ((uint32_t)(int)d & 0xffu) << ((i & 3) * 8);
+        }
+        *reinterpret_cast<uint4*>(base + (long long)s * (2 * I8_TM * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ex[r] (int) from the bit pattern of the row maximum; rows of zeros get INT_MIN / 4 (their products scale to 0)
+__global__ void i8_exponent_kernel(const int* __restrict__ ex_bits, int* __restrict__ ex, int R) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int hi = ex_bits[r];
+    ex[r] = hi > 0 ? ((hi >> 20) & 0x7ff) - 1022 + 1 : -(1 << 20);
+}
+
+// ------------------------------------------------------------------ tcgen05 helpers
+__device__ __forceinline__ void i8_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(i8_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void i8_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(i8_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void i8_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(i8_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void i8_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(i8_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(i8_smem_u32(bar))
+                 : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes contiguous; SBO = stride between 8-row groups, LBO = stride
+// between the two 16-byte K chunks of one K = 32 instruction (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void i8_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(i8_smem_u32(bar)) : "memory");
+}
+
+struct I8Tile { int m0, n0, kc0, kc1; };       // output tile origin; K chunks [kc0, kc1)
+
+struct __align__(128) I8Smem {
+    int8_t a[I8_STAGES][I8_SMAX][2][I8_TM][16];      // [stage][slice][k16][row][16 B]   4 KB per slice
+    int8_t b[I8_STAGES][I8_SMAX][2][I8_TN][16];      //                                   2 KB per slice
+    uint64_t full[I8_STAGES], empty[I8_STAGES], acc_full;
+    uint32_t tmem_base;
+};
+
+struct I8Args {
+    const int8_t* A; const int* ea; int nrtA;       // tiled digits / exponents / row tiles of the A operand
+    const int8_t* B; const int* eb; int nrtB;
+    const I8Tile* tiles;
+    int S;
+    double alpha, beta;
+    double* C; long long ldc;
+};
+
+template <int S>
+__global__ void __launch_bounds__(192, 1) i8_gemm_tiles_kernel(I8Args g) {
+    extern __shared__ __align__(128) unsigned char i8_raw[];
+    I8Smem& sm = *reinterpret_cast<I8Smem*>(i8_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const I8Tile t = g.tiles[blockIdx.x];
+    const int nk = t.kc1 - t.kc0;
+    constexpr uint32_t TMEM_COLS = 512;             // S * 64 <= 512 rounded up to a power of two (S = 7, 8)
+
+    if (tid == 0) {
+        for (int i = 0; i < I8_STAGES; ++i) { i8_mbar_init(&sm.full[i], 1); i8_mbar_init(&sm.empty[i], 1); }
+        i8_mbar_init(&sm.acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(&sm.tmem_base)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem0 = sm.tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const int rtA = t.m0 / I8_TM, rtB = t.n0 / I8_TM, hb = (t.n0 % I8_TM) / I8_TN;
+            constexpr uint32_t A_BYTES = S * 2 * I8_TM * 16, B_BYTES = S * 2 * I8_TN * 16;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kc = t.kc0; kc < t.kc1; ++kc) {
+                i8_mbar_wait(&sm.empty[stage], phase ^ 1);                   // passes immediately on the first lap
+                i8_mbar_expect_tx(&sm.full[stage], A_BYTES + B_BYTES);
+                const int8_t* ga = g.A + ((long long)kc * g.nrtA + rtA) * (long long)A_BYTES;
+                i8_bulk_g2s(&sm.a[stage][0][0][0][0], ga, A_BYTES, &sm.full[stage]);
+                const int8_t* gb = g.B + ((long long)kc * g.nrtB + rtB) * (long long)A_BYTES + (long long)hb * I8_TN * 16;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                    for (int k16 = 0; k16 < 2; ++k16)
+                        i8_bulk_g2s(&sm.b[stage][s][k16][0][0], gb + (long long)(s * 2 + k16) * (I8_TM * 16), I8_TN * 16,
+                                    &sm.full[stage]);
+                if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nk; ++i) {
+                i8_mbar_wait(&sm.full[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = i8_smem_u32(&sm.a[stage][0][0][0][0]), b0 = i8_smem_u32(&sm.b[stage][0][0][0][0]);
+#pragma unroll
+                for (int d = 0; d < S; ++d)
+#pragma unroll
+                    for (int s = 0; s <= d; ++s) {
+                        const uint64_t da = i8_desc(a0 + s * (2 * I8_TM * 16), I8_TM * 16, 128);
+                        const uint64_t db = i8_desc(b0 + (d - s) * (2 * I8_TN * 16), I8_TN * 16, 128);
+                        i8_mma(tmem0 + (uint32_t)(d * I8_TN), da, db, idesc, (i > 0 || s > 0) ? 1u : 0u);
+                    }
+                i8_commit(&sm.empty[stage]);                                  // stage free once these MMAs have read it
+                if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+            }
+            i8_commit(&sm.acc_full);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = one output row
+        const int q = warp & 3;                                               // TMEM lane quarter this warp may read
+        const int row = t.m0 + q * 32 + lane;
+        i8_mbar_wait(&sm.acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int er = g.ea[row];
+        double* crow = g.C + (long long)row * g.ldc + t.n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < I8_TN; c0 += 16) {
+            double acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int d = S - 1; d >= 0; --d) {                                // smallest weights first
+                uint32_t v[16];
+                const uint32_t taddr = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * I8_TN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const double w = __hiloint2double((1023 - I8_BITS * (d + 2)) << 20, 0);     // 2^(-7 (d + 2))
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const int e0 = er + g.eb[t.n0 + c0 + j], e1 = er + g.eb[t.n0 + c0 + j + 1];
+                double x0 = g.alpha * ldexp(acc[j], e0), x1 = g.alpha * ldexp(acc[j + 1], e1);
+                double2* p = reinterpret_cast<double2*>(crow + c0 + j);
+                if (g.beta != 0.0) { const double2 o = *p; x0 = fma(g.beta, o.x, x0); x1 = fma(g.beta, o.y, x1); }
+                *p = make_double2(x0, x1);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(TMEM_COLS) : "memory");
+}
+
+// ------------------------------------------------------------------ host side
+struct I8Operand {                 // a sliced operand in device memory
+    int8_t* digits = nullptr; size_t digits_cap = 0;
+    int* ex_bits = nullptr; int* ex = nullptr; size_t rows_cap = 0;
+    int R = 0, K = 0, nrt = 0, nkc = 0;
+};
+struct I8Plan {
+    I8Operand opA, opB;
+    I8Tile* tiles = nullptr; size_t tiles_cap = 0;
+    std::vector<I8Tile> host_tiles;
+    long long tiles_key = -1;
+};
+
+static cudaError_t i8_reserve(I8Operand& op, int R, int K, int S) {
+    const int nrt = (R + I8_TM - 1) / I8_TM, nkc = (K + I8_KC - 1) / I8_KC;
+    const size_t need = (size_t)nkc * nrt * S * 2 * I8_TM * 16;
+    cudaError_t e;
+    if (need > op.digits_cap) {
+        if (op.digits) cudaFree(op.digits);
+        op.digits = nullptr; op.digits_cap = 0;
+        if ((e = cudaMalloc(&op.digits, need)) != cudaSuccess) return e;
+        op.digits_cap = need;
+    }
+    if ((size_t)nrt * I8_TM > op.rows_cap) {
+        if (op.ex_bits) cudaFree(op.ex_bits);
+        if (op.ex) cudaFree(op.ex);
+        op.ex_bits = op.ex = nullptr; op.rows_cap = 0;
+        if ((e = cudaMalloc(&op.ex_bits, (size_t)nrt * I8_TM * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&op.ex, (size_t)nrt * I8_TM * 4)) != cudaSuccess) return e;
+        op.rows_cap = (size_t)nrt * I8_TM;
+    }
+    op.R = R; op.K = K; op.nrt = nrt; op.nkc = nkc;
+    return cudaSuccess;
+}
+
+// Slice the operand whose element (row r, k) is src[r * rs + k * cs]  (R rows, K deep; tri: zero for k < r).
+static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long long cs, int R, int K, int S, int tri,
+                            cudaStream_t st) {
+    cudaError_t e = i8_reserve(op, R, K, S);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(op.ex_bits, 0, (size_t)op.nrt * I8_TM * 4, st)) != cudaSuccess) return e;
+    const int ksplit = std::max(1, std::min(32, K / 256));
+    i8_rowmax_kernel<<<dim3((R + 63) / 64, ksplit), 256, 0, st>>>(src, rs, cs, R, K, tri, op.ex_bits);
+    i8_exponent_kernel<<<(op.nrt * I8_TM + 255) / 256, 256, 0, st>>>(op.ex_bits, op.ex, op.nrt * I8_TM);
+    i8_slice_tiled_kernel<<<dim3(op.nkc, op.nrt), 256, 0, st>>>(src, rs, cs, R, K, S, tri, op.ex_bits, op.digits, op.nrt);
+    MOGP_COUNT(3);
+    return cudaGetLastError();
+}
+
+static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Tile* tiles_dev, int ntiles, int S, double alpha,
+                             double beta, double* C, long long ldc, cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.first()) {
+        cudaError_t e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
+        if (e != cudaSuccess) return e;
+    }
+    if (ntiles <= 0) return cudaSuccess;
+    I8Args g{};
+    g.A = A.digits; g.ea = A.ex; g.nrtA = A.nrt;
+    g.B = B.digits; g.eb = B.ex; g.nrtB = B.nrt;
+    g.tiles = tiles_dev; g.S = S; g.alpha = alpha; g.beta = beta; g.C = C; g.ldc = ldc;
+    if (S == 7) i8_gemm_tiles_kernel<7><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
+    else if (S == 8) i8_gemm_tiles_kernel<8><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
+    else return cudaErrorInvalidValue;
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
+static cudaError_t i8_upload_tiles(I8Plan& p, cudaStream_t st) {
+    const size_t n = p.host_tiles.size();
+    if (n > p.tiles_cap) {
+        if (p.tiles) cudaFree(p.tiles);
+        p.tiles = nullptr; p.tiles_cap = 0;
+        cudaError_t e = cudaMalloc(&p.tiles, n * sizeof(I8Tile));
+        if (e != cudaSuccess) return e;
+        p.tiles_cap = n;
+    }
+    return cudaMemcpyAsync(p.tiles, p.host_tiles.data(), n * sizeof(I8Tile), cudaMemcpyHostToDevice, st);
+}
+
+I8Plan* i8_plan_create() { return new I8Plan(); }
+void i8_plan_destroy(I8Plan* p) {
+    if (!p) return;
+    for (I8Operand* op : {&p->opA, &p->opB}) {
+        if (op->digits) cudaFree(op->digits);
+        if (op->ex_bits) cudaFree(op->ex_bits);
+        if (op->ex) cudaFree(op->ex);
+    }
+    if (p->tiles) cudaFree(p->tiles);
+    delete p;
+}
+
+// Host-side preparation (allocations, tile-list upload) of i8_kinv for a given size: never inside graph capture.
+cudaError_t i8_kinv_prepare(I8Plan* p, int64_t Np, int S, cudaStream_t st) {
+    cudaError_t e = i8_reserve(p->opA, (int)Np, (int)Np, S);
+    if (e != cudaSuccess) return e;
+    const long long key = Np * 16 + S;
+    if (p->tiles_key == key) return cudaSuccess;
+    p->host_tiles.clear();
+    const int nkc = (int)(Np / I8_KC);
+    for (int ti = 0; ti < (int)(Np / I8_TM); ++ti)                         // longest K ranges first
+        for (int tj = 0; tj * I8_TN < (ti + 1) * I8_TM; ++tj)
+            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, ti * I8_TM / I8_KC, nkc});
+    e = i8_upload_tiles(*p, st);
+    if (e != cudaSuccess) return e;
+    p->tiles_key = key;
+    return cudaStreamSynchronize(st);
+}
+
+// W(lower tiles) = Linv^T Linv with Linv lower triangular (zero above the diagonal): K^-1 of the factorised matrix.
+// Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
+// (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_kinv_prepare.
+cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
+    if (p->tiles_key != Np * 16 + S) return cudaErrorInvalidValue;
+    cudaError_t e = i8_slice(p->opA, Linv, 1, ld, (int)Np, (int)Np, S, 1, st);
+    if (e != cudaSuccess) return e;
+    return i8_launch(p->opA, p->opA, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, W, ld, st);
+}
+
+// ------------------------------------------------------------------ self-test hooks (tests, tools/gpu_diag.py)
+// General NT product against the DMMA GEMM on random data: out[0] = max |C_i8 - C_dmma| / max |C_dmma|, out[1] = ms of
+// the int8 path (slicing included), out[2] = ms of the MMA kernel alone, out[3] = ms of the DMMA GEMM.
+__global__ void i8t_fill_kernel(double* x, long long n, unsigned seed) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned h = (unsigned)i * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    const double u = (double)h / 4294967296.0 - 0.5;
+    x[i] = u * exp2((double)((int)(h % 13) - 6));
+}
+__global__ void i8t_maxdiff_kernel(const double* a, const double* b, long long n, double* out) {
+    __shared__ double sd[256], sm_[256];
+    double d = 0.0, m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = fabs(a[i] - b[i]);
+        d = (x == x) ? fmax(d, x) : 1e300;
+        m = fmax(m, fabs(b[i]));
+    }
+    sd[threadIdx.x] = d; sm_[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sd[threadIdx.x] = fmax(sd[threadIdx.x], sd[threadIdx.x + o]); sm_[threadIdx.x] = fmax(sm_[threadIdx.x], sm_[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(sd[0]));
+        atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(sm_[0]));
+    }
+}
+
+extern "C" int mogp_i8_selftest(int M, int N, int K, int S, double* out_host /*4*/) {
+    if (M % I8_TM || N % I8_TM || K % I8_KC || (S != 7 && S != 8)) return -1;
+    double *A = nullptr, *B = nullptr, *C1 = nullptr, *C2 = nullptr, *res = nullptr;
+    if (cudaMalloc(&A, (size_t)M * K * 8) || cudaMalloc(&B, (size_t)N * K * 8) || cudaMalloc(&C1, (size_t)M * N * 8) ||
+        cudaMalloc(&C2, (size_t)M * N * 8) || cudaMalloc(&res, 16))
+        return -2;
+    i8t_fill_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256>>>(A, (long long)M * K, 17u);
+    i8t_fill_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(B, (long long)N * K, 91u);
+    cudaMemset(res, 0, 16);
+    I8Plan* p = i8_plan_create();
+    int rc = 0;
+    for (int ti = 0; ti < M / I8_TM; ++ti)
+        for (int tj = 0; tj < N / I8_TN; ++tj) p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, 0, K / I8_KC});
+    if (i8_upload_tiles(*p, nullptr) != cudaSuccess) rc = -2;
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    for (int rep = 0; rep < 2 && rc == 0; ++rep) {
+        cudaEventRecord(e0);
+        if (i8_slice(p->opA, A, K, 1, M, K, S, 0, nullptr) != cudaSuccess) rc = -3;
+        if (rc == 0 && i8_slice(p->opB, B, K, 1, N, K, S, 0, nullptr) != cudaSuccess) rc = -3;
+        cudaEventRecord(e1);
+        if (rc == 0 && i8_launch(p->opA, p->opB, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, C1, N, nullptr) != cudaSuccess) rc = -4;
+        cudaEventRecord(e2);
+        GemmArgs g{};
+        g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = C2; g.ldc = N;
+        g.M = M; g.N = N; g.K = K; g.alpha = 1.0; g.beta = 0.0;
+        if (rc == 0 && launch_gemm(0, 1, g, 1, nullptr) != cudaSuccess) rc = -5;
+        cudaEventRecord(e3);
+    }
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = -6;
+    if (rc == 0) {
+        i8t_maxdiff_kernel<<<256, 256>>>(C1, C2, (long long)M * N, res);
+        double h[2];
+        if (cudaMemcpy(h, res, 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -7;
+        else {
+            float t01 = 0.f, t12 = 0.f, t23 = 0.f;
+            cudaEventElapsedTime(&t01, e0, e1); cudaEventElapsedTime(&t12, e1, e2); cudaEventElapsedTime(&t23, e2, e3);
+            out_host[0] = h[1] > 0.0 ? h[0] / h[1] : -1.0;
+            out_host[1] = t01 + t12; out_host[2] = t12; out_host[3] = t23;
+        }
+    }
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    i8_plan_destroy(p);
+    cudaFree(A); cudaFree(B); cudaFree(C1); cudaFree(C2); cudaFree(res);
+    return rc;
+}

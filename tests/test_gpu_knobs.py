@@ -81,3 +81,42 @@ def test_failed_graph_capture_falls_back_to_an_eager_run(engine, knobs):
         lib.mogp_test_fail_capture(0)
         knobs()                              # re-enables graphs and dependent launches
     _check(engine, g, reps=3)                # and the replayed graph still agrees afterwards
+
+
+# ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (tcgen05.mma kind::i8)
+@pytest.mark.parametrize("M,N,K,S,tol", [(128, 128, 32, 7, 1e-12), (256, 384, 4096, 7, 1e-12), (1024, 1024, 1024, 8, 1e-13),
+                                          (2048, 2048, 2048, 7, 1e-12)])
+def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol):
+    """A B^T from S signed 7-bit digit planes per operand (Ozaki slicing, exact int32 accumulation in TMEM) against the
+    fp64 DMMA GEMM: relative to the largest entry the difference is ~1e-14 at S = 7 and ~fp64 rounding at S = 8."""
+    import ctypes as C
+    out = (C.c_double * 4)()
+    rc = engine.lib.mogp_i8_selftest(M, N, K, S, out)
+    assert rc == 0
+    assert 0.0 <= out[0] < tol, out[0]
+
+
+def test_int8_kinv_equals_dmma_kinv(engine):
+    """K^-1 = L^-T L^-1 of an SPD matrix at n = 4096 through the int8 path (default for n >= 4096) and through DMMA."""
+    import torch
+    n = 4096
+    torch.manual_seed(3)
+    B = torch.randn(n, n, dtype=torch.float64, device=engine.device)
+    K = B @ B.T / n + torch.eye(n, dtype=torch.float64, device=engine.device)
+    try:
+        engine.lib.mogp_set_i8(0, 7)
+        _, Kd, info_d = engine.trtri_kinv_(K.clone())
+        engine.lib.mogp_set_i8(4096, 7)
+        _, K7, info_7 = engine.trtri_kinv_(K.clone())
+        engine.lib.mogp_set_i8(4096, 8)
+        _, K8, info_8 = engine.trtri_kinv_(K.clone())
+    finally:
+        engine.lib.mogp_set_i8(4096, 7)
+    assert info_d == 0 and info_7 == 0 and info_8 == 0
+    ref = torch.linalg.inv(K)
+    scale = float(ref.abs().max())
+    tril = torch.tril(torch.ones(n, n, dtype=torch.bool, device=engine.device))
+    for got, tol in ((Kd, 1e-11), (K7, 1e-11), (K8, 1e-11)):
+        assert float((got - ref)[tril].abs().max()) <= tol * scale
+    assert float((K7 - Kd)[tril].abs().max()) <= 1e-12 * scale
+    assert float((K8 - Kd)[tril].abs().max()) <= 1e-13 * scale

@@ -434,6 +434,19 @@ def sec_i8(eng):
                 M, N, K, S, rc, out[0], out[1], 2.0 * M * N * K / max(out[1], 1e-9) / 1e9, out[2], 2.0 * M * N * K / max(out[2], 1e-9) / 1e9))
 
 
+def sec_i8p(eng):
+    """Product int8 tensor-pipe GEMM (csrc/i8mm.cu): error, time of slicing + MMA kernel, against the DMMA GEMM."""
+    import ctypes as C
+    out = (C.c_double * 4)()
+    for (M, N, K) in [(128, 128, 32), (256, 256, 256), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (8192, 8192, 1024)]:
+        for S in (7, 8):
+            rc = eng.lib.mogp_i8_selftest(M, N, K, S, out)
+            ops = 2.0 * M * N * K
+            print("i8mm %5dx%5dx%5d S=%d rc=%d: rel. error %.2e | slicing+MMA %.3f ms, MMA kernel %.3f ms = %.1f TFLOP/s fp64-equivalent = %.0f TOP/s int8 | DMMA %.3f ms (%.1f TFLOP/s)" % (
+                M, N, K, S, rc, out[0], out[1], out[2], ops / max(out[2], 1e-9) / 1e9, ops * S * (S + 1) / 2 / max(out[2], 1e-9) / 1e9,
+                out[3], ops / max(out[3], 1e-9) / 1e9), flush=True)
+
+
 def sec_gemmk(eng):
     """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
     for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
@@ -504,7 +517,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"i8": sec_i8, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"i8p": sec_i8p, "i8": sec_i8, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
