@@ -30,6 +30,13 @@
  *   CONV : weight[Q][C] | variance[Q][C][D] | base_variance[Q][D]
  *          (MixtureKernel of GaussianConvolutionProcessKernel,
  *           gpr/kernel.py:264-276, gpr/multioutput.py:520-529)
+ *   CSM  : amplitude[Q][C][Rq] | mean[Q][D] | variance[Q][D] | shift[Q][C][Rq]
+ *          (MixtureKernel of CrossSpectralKernel, gpr/multioutput.py:397-454; what mogptk.CSM builds)
+ *   SMLMC: weight[C][Q][Rq] | magnitude[Q] | mean[Q][D] | variance[Q][D]
+ *          (LinearModelOfCoregionalizationKernel of SpectralKernel, gpr/multioutput.py:456-502,
+ *           gpr/singleoutput.py:520-561; what mogptk.SM_LMC builds)
+ *   UMOSM: weight[Q][C][C] (lower triangle used) | mean[Q][C][D] | variance[Q][C][D] | delay[Q][C][D] | phase[Q][C]
+ *          (MixtureKernel of UncoupledMultiOutputSpectralKernel, gpr/multioutput.py:212-293)
  */
 #ifndef MOGP_B200_H
 #define MOGP_B200_H
@@ -42,7 +49,10 @@ extern "C" {
 
 typedef struct mogp_handle_s* mogp_handle_t;
 
-enum { MOGP_KIND_MOSM = 0, MOGP_KIND_SM = 1, MOGP_KIND_CONV = 2 };
+enum { MOGP_KIND_MOSM = 0, MOGP_KIND_SM = 1, MOGP_KIND_CONV = 2, MOGP_KIND_CSM = 3, MOGP_KIND_SMLMC = 4, MOGP_KIND_UMOSM = 5 };
+/* CSM and SM-LMC have Rq sub-components per mixture term: pass kind = MOGP_KIND_WITH_RQ(MOGP_KIND_CSM, Rq)
+ * (family in the low 8 bits, Rq above; Rq = 0 means 1).  Every `kind` argument below accepts this form. */
+#define MOGP_KIND_WITH_RQ(kind, Rq) ((kind) | ((Rq) << 8))
 enum { MOGP_MAX_D = 8 };
 
 /* library / ABI version (major*1000 + minor) */

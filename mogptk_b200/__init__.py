@@ -6,9 +6,10 @@ libmogp_b200.so, called through the C ABI of include/mogp_b200.h.  No CPU fallba
 """
 from . import _cabi, engine, gpr, synth          # noqa: F401
 from .engine import Engine, NotPositiveDefiniteError  # noqa: F401
-from .gpr import (CholeskyException, Exact, GaussianConvolutionProcessKernel, GaussianLikelihood,  # noqa: F401
-                  IndependentMultiOutputKernel, MixtureKernel, MultiOutputSpectralMixtureKernel, Parameter,
-                  SpectralMixtureKernel)
+from .gpr import (CholeskyException, CrossSpectralKernel, Exact, GaussianConvolutionProcessKernel,  # noqa: F401
+                  GaussianLikelihood, IndependentMultiOutputKernel, LinearModelOfCoregionalizationKernel, MixtureKernel,
+                  MultiOutputSpectralMixtureKernel, Parameter, SpectralKernel, SpectralMixtureKernel,
+                  UncoupledMultiOutputSpectralKernel)
 from .inference import B200Exact                 # noqa: F401
 from .train import fit_adam, install, uninstall  # noqa: F401
 

@@ -11,7 +11,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mogp_b200.h")
 
-KIND = {"MOSM": 0, "SM": 1, "CONV": 2}
+FAMILY = {"MOSM": 0, "SM": 1, "CONV": 2, "CSM": 3, "SMLMC": 4, "UMOSM": 5}
+
+
+def kind_code(kind):
+    """`kind` argument of the C ABI: family in the low 8 bits, Rq (CSM / SM-LMC sub-components) above
+    (MOGP_KIND_WITH_RQ).  Host-side kinds are strings: "MOSM", "SM", "CONV", "CSM:<Rq>", "SMLMC:<Rq>", "UMOSM"."""
+    fam, _, rq = str(kind).partition(":")
+    return FAMILY[fam] | ((int(rq) << 8) if rq else 0)
+
+
+class _Kinds(dict):
+    def __missing__(self, kind):
+        return kind_code(kind)
+
+
+KIND = _Kinds(FAMILY)
 
 _lib = None
 
@@ -56,6 +71,7 @@ _SIGNATURES = {
 _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
     "mogp_set_i8": (C.c_int, [C.c_longlong, C.c_int]),
+    "mogp_set_i8_trtri_min": (C.c_int, [C.c_longlong]),
     "mogp_i8_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mogp_set_graphs": (None, [C.c_int]),
     "mogp_set_graph_max_np": (None, [C.c_longlong]),

@@ -299,6 +299,8 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
     g_i8_min_np = min_np; g_i8_slices = slices; ++g_mogp_cfg_epoch;
     return 0;
 }
+// smallest doubling-level block size of the triangular inverse that runs on the int8 pipe (0 = none)
+extern "C" int mogp_set_i8_trtri_min(long long rows) { g_i8_trtri_min = rows; ++g_mogp_cfg_epoch; return 0; }
 static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }
 static cudaError_t kinv_dispatch(mogp_handle_s* h, int64_t Np, long long ld, cudaStream_t st) {
     if (use_i8(Np) && h->i8) return i8_kinv(h->i8, h->Linv, h->W, Np, ld, g_i8_slices, st);
@@ -333,16 +335,16 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     MOGP_CHECK(h, cudaSetDevice(h->device));
     H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
+    const bool i8 = use_i8(n);           // same dispatch as the fused step (int8 tensor pipe for large n)
+    if (i8) {
+        if (!h->i8) h->i8 = i8_plan_create();
+        MOGP_CHECK(h, i8_prepare(h->i8, n, n, g_i8_slices, st));
+    }
     bool fused_inverse = false;
     MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
-    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st));
-    if (use_i8(n)) {                     // same dispatch as the fused step (int8 tensor pipe for large n)
-        if (!h->i8) h->i8 = i8_plan_create();
-        MOGP_CHECK(h, i8_kinv_prepare(h->i8, n, g_i8_slices, st));
-        MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
-    } else {
-        MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
-    }
+    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st, i8 ? h->i8 : nullptr, g_i8_slices));
+    if (i8) MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
+    else MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
     h->have_factor = false;
     return 0;
@@ -395,7 +397,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
     STAGE_MARK();
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
-    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st));
+    if (!fused_inverse) MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st, use_i8(Np) ? h->i8 : nullptr, g_i8_slices));
     STAGE_MARK();
     // K^-1 = Linv^T Linv does not need alpha: it runs on a second stream concurrently with the solves
     // (z = Linv y, alpha = Linv^T z, diag K^-1); the gradient kernel subtracts alpha alpha^T while loading.
@@ -470,7 +472,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     }
     if (want_grad && use_i8(Np)) {
         if (!h->i8) h->i8 = i8_plan_create();
-        MOGP_CHECK(h, i8_kinv_prepare(h->i8, Np, g_i8_slices, st));
+        MOGP_CHECK(h, i8_prepare(h->i8, Np, Np, g_i8_slices, st));
     }
     const size_t nout = 2 + (size_t)s.P + C;
     const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;

@@ -18,21 +18,30 @@
 __host__ __device__ inline int comp_stride(int D) { return 2 + 3 * D; }
 
 struct KernSpec {
-    int kind, C, Q, D;
-    int R;            // components per channel pair (MOSM: Q, SM: Q*D, CONV: Q)
+    int kind, C, Q, D;   // kind = family | Rq << 8 (MOGP_KIND_WITH_RQ)
+    int R;            // components per channel pair (MOSM: Q, SM: Q*D, CONV: Q, CSM: Q*Rq, SMLMC: Q*D, UMOSM: Q)
     int P;            // packed constrained kernel parameters
     bool has_cos;     // false for CONV (m = phi = 0)
+    int Rq;           // sub-components of CSM / SM-LMC (1 otherwise)
 };
+__host__ __device__ inline int kind_family(int kind) { return kind & 0xff; }
+__host__ __device__ inline int kind_rq(int kind) { return (kind >> 8) > 0 ? (kind >> 8) : 1; }
 
 inline int spec_init(KernSpec& s, int kind, int C, int Q, int D) {
-    if (C < 1 || Q < 1 || D < 1 || D > MOGP_MAX_D) return -1;
-    s.kind = kind; s.C = C; s.Q = Q; s.D = D;
-    switch (kind) {
-        case MOGP_KIND_MOSM: s.R = Q;     s.P = C * Q * (2 + 3 * D);       s.has_cos = true;  break;
-        case MOGP_KIND_SM:   s.R = Q * D; s.P = C * Q * (1 + 2 * D);       s.has_cos = true;  break;
-        case MOGP_KIND_CONV: s.R = Q;     s.P = Q * (C + C * D + D);       s.has_cos = false; break;
+    if (C < 1 || Q < 1 || D < 1 || D > MOGP_MAX_D || kind < 0) return -1;
+    const int Rq = kind_rq(kind);
+    if (Rq > 64) return -1;
+    s.kind = kind; s.C = C; s.Q = Q; s.D = D; s.Rq = Rq;
+    switch (kind_family(kind)) {
+        case MOGP_KIND_MOSM:  s.R = Q;      s.P = C * Q * (2 + 3 * D);                 s.has_cos = true;  break;
+        case MOGP_KIND_SM:    s.R = Q * D;  s.P = C * Q * (1 + 2 * D);                 s.has_cos = true;  break;
+        case MOGP_KIND_CONV:  s.R = Q;      s.P = Q * (C + C * D + D);                 s.has_cos = false; break;
+        case MOGP_KIND_CSM:   s.R = Q * Rq; s.P = 2 * Q * C * Rq + 2 * Q * D;          s.has_cos = true;  break;
+        case MOGP_KIND_SMLMC: s.R = Q * D;  s.P = C * Q * Rq + Q + 2 * Q * D;          s.has_cos = true;  break;
+        case MOGP_KIND_UMOSM: s.R = Q;      s.P = Q * C * C + 3 * Q * C * D + Q * C;   s.has_cos = true;  break;
         default: return -1;
     }
+    if (kind_family(kind) < MOGP_KIND_CSM && (kind >> 8) != 0) return -1;
     return 0;
 }
 
@@ -196,7 +205,8 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
                          bool* fused_inverse = nullptr);
-cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st);
+cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st,
+                         I8Plan* i8 = nullptr, int i8_slices = 7);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
 // z = Linv * y (lower-triangular mat-vec), rows [0,Np)
 cudaError_t launch_trmv_lower(const double* Linv, long long ld, const double* y, double* z, int64_t Np, cudaStream_t st);
@@ -214,8 +224,12 @@ cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);
 struct I8Plan;
 I8Plan* i8_plan_create();
 void i8_plan_destroy(I8Plan* p);
-// host-side preparation (allocation, tile list) for a given padded size: call outside graph capture
-cudaError_t i8_kinv_prepare(I8Plan* p, int64_t Np, int S, cudaStream_t st);
+// host-side preparation (allocation, tile lists) for a given padded size / leading dimension: call outside graph capture
+cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st);
+// one doubling level (block size S_ rows) of Linv = L^-1; cudaErrorNotSupported -> run the DMMA GEMMs instead
+cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scratch, int64_t Np, long long ld, int64_t S_,
+                           int S, cudaStream_t st);
+extern long long g_i8_trtri_min;
 // W(lower tiles) = Linv^T Linv via tcgen05.mma kind::i8 (S digit planes of 7 bits); pure enqueue
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st);
 // Smallest padded size that takes the int8 path (0 = never) and the number of digit planes (7 or 8)

@@ -24,9 +24,20 @@ __host__ __device__ inline ConvOff conv_off(int C, int Q, int D) {
     ConvOff o; o.w = 0; o.var = Q * C; o.base = o.var + Q * C * D; return o;
 }
 
-// comp record: [alpha, phi, v[D], m[D], theta[D]]
+// gsum record of lower pair (i, j), component r (see the chain rule below)
+__host__ __device__ inline const double* gs_rec(const double* gsum, int i, int j, int R, int st, int r) {
+    const int pl = i * (i + 1) / 2 + j;
+    return gsum + (size_t)(pl * R + r) * st;
+}
+#include "covmath_next.cuh"     // CSM / SM-LMC / uMOSM tables (families >= MOGP_KIND_CSM)
+
+// comp record: [alpha, phi, v[D], m[D], theta[D]].  kind = family | Rq << 8.
 __host__ __device__ inline void pair_comp(int kind, int C, int Q, int D, const double* __restrict__ p, int i, int j,
                                           int r, double* __restrict__ out) {
+    if (kind_family(kind) >= MOGP_KIND_CSM) {
+        pair_comp_next(kind_family(kind), C, Q, kind_rq(kind), D, p, i, j, r, out);
+        return;
+    }
     double alpha = 0.0, phi = 0.0;
     double* v = out + 2;
     double* m = out + 2 + D;
@@ -91,6 +102,16 @@ __host__ __device__ inline double kdiag_api_value(int kind, int C, int Q, int D,
     if (kind == MOGP_KIND_SM) {
         const SmOff o = sm_off(C, Q, D);
         for (int q = 0; q < Q; ++q) s += p[o.mag + c * Q + q];
+    } else if (kind_family(kind) == MOGP_KIND_SMLMC) {
+        // LMC.Ksub_diag over SpectralKernel.K_diag (multioutput.py:497-502, singleoutput.py:558-561): sum_q (sum_s w^2) magnitude_q,
+        // whatever D is (like SM, the reference's K_diag does not carry the factor D its K has for D > 1)
+        const int Rq = kind_rq(kind);
+        const LmcOff o = lmc_off(C, Q, Rq, D);
+        for (int q = 0; q < Q; ++q) {
+            double w = 0.0;
+            for (int t = 0; t < Rq; ++t) w += p[o.w + (c * Q + q) * Rq + t] * p[o.w + (c * Q + q) * Rq + t];
+            s += w * p[o.mag + q];
+        }
     } else {
         for (int r = 0; r < R; ++r) s += comps[(size_t)((c * C + c) * R + r) * st];
     }
@@ -103,17 +124,17 @@ __host__ __device__ inline double kdiag_api_value(int kind, int C, int Q, int D,
 // (W already carries the symmetric weight).  adj[c] is added to S0 of the diagonal pair (c,c)
 // (relative-jitter term).  `owner` enumerates disjoint output slices, see n_chain_owners().
 __host__ __device__ inline int n_chain_owners(int kind, int C, int Q) {
+    if (kind_family(kind) >= MOGP_KIND_CSM) return n_chain_owners_next(kind_family(kind), C, Q, kind_rq(kind));
     return kind == MOGP_KIND_CONV ? Q * C + Q : C * Q;
-}
-
-__host__ __device__ inline const double* gs_rec(const double* gsum, int i, int j, int R, int st, int r) {
-    const int pl = i * (i + 1) / 2 + j;
-    return gsum + (size_t)(pl * R + r) * st;
 }
 
 __host__ __device__ inline void chain_owner(int kind, int C, int Q, int D, const double* __restrict__ p,
                                             const double* __restrict__ comps, const double* __restrict__ gsum,
                                             const double* __restrict__ adj, int owner, double* __restrict__ g) {
+    if (kind_family(kind) >= MOGP_KIND_CSM) {
+        chain_owner_next(kind_family(kind), C, Q, kind_rq(kind), D, p, comps, gsum, adj, owner, g);
+        return;
+    }
     const int st = comp_stride(D);
     const double PI2 = MOGP_PI * MOGP_PI;
     if (kind == MOGP_KIND_MOSM) {

@@ -1,18 +1,13 @@
-// ROUND-2 GROUNDWORK (compiled only into libmogp_b200_exp.so; CPU-tested through tests/test_next_kernels.py):
-// per channel-pair component tables and chain rules of the next two kernel families on the hot path, in the same
-// derived form and with the same record / owner conventions as covmath.cuh, so that they can be merged into
-// pair_comp() / chain_owner() once they have been run on hardware.
+// Per channel-pair component tables and chain rules of the CSM, SM-LMC and uMOSM kernel families, in the same derived
+// form and with the same record / owner conventions as the MOSM / SM / CONV tables of covmath.cuh, which includes this
+// file and dispatches to it from pair_comp() / chain_owner() (families >= MOGP_KIND_CSM).
 //   CSM    MixtureKernel of Q CrossSpectralKernel (mogptk/gpr/multioutput.py:428-454):
 //          packed  amplitude (Q,C,Rq) | mean (Q,D) | variance (Q,D) | shift (Q,C,Rq);  R = Q*Rq components r = q*Rq + s
 //   SMLMC  LinearModelOfCoregionalizationKernel of Q SpectralKernel (gpr/multioutput.py:490-502, singleoutput.py:550-561):
 //          packed  weight (C,Q,Rq) | magnitude (Q) | mean (Q,D) | variance (Q,D);       R = Q*D  components r = q*D + d
+//   UMOSM  MixtureKernel of Q UncoupledMultiOutputSpectralKernel (gpr/multioutput.py:261-293):
+//          packed  weight (Q,C,C; lower triangle used) | mean (Q,C,D) | variance (Q,C,D) | delay (Q,C,D) | phase (Q,C)
 #pragma once
-#include "covmath.cuh"
-
-#define MOGP_KIND_CSM 3
-#define MOGP_KIND_SMLMC 4
-#define MOGP_KIND_UMOSM 5    // MixtureKernel of Q UncoupledMultiOutputSpectralKernel (gpr/multioutput.py:261-293):
-                             // packed  weight (Q,C,C; lower triangle used) | mean (Q,C,D) | variance (Q,C,D) | delay (Q,C,D) | phase (Q,C)
 
 struct CsmOff { int amp, mu, var, sh; };
 __host__ __device__ inline CsmOff csm_off(int C, int Q, int Rq, int D) {

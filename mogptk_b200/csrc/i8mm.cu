@@ -35,19 +35,25 @@
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------ slicing
-// Row maxima -> exponents.  Element (row r, k) of the operand is src[r * rs + k * cs]; `tri` = 1 restricts k to
-// k >= r - (r % 64) ... (lower-triangular L^-1 read column-wise: operand row r = column r of L^-1, nonzero for k >= r).
-__global__ void __launch_bounds__(256) i8_rowmax_kernel(const double* __restrict__ src, long long rs, long long cs, int R,
-                                                        int K, int tri, int* __restrict__ ex_bits) {
+// Row maxima -> exponents.  The operand has R rows in `batch` groups of Rb = R / batch rows: element (row r, k) is
+// src[(r / Rb) * bstride + (r % Rb) * rs + k * cs].  tri = 1: rows are zero for k < (r % Rb) rounded down to 64 (a
+// lower-triangular block read column-wise); tri = 2: zero for k > r % Rb (a lower-triangular block read row-wise).
+__global__ void __launch_bounds__(256) i8_rowmax_kernel(const double* __restrict__ src, long long rs, long long cs,
+                                                        long long bstride, int R, int Rb, int K, int tri,
+                                                        int* __restrict__ ex_bits) {
     // block: 64 operand rows x 4 k-phases; grid.y splits K
     const int r = blockIdx.x * 64 + (threadIdx.x & 63);
     const int ph = threadIdx.x >> 6;
     const int kper = (K + gridDim.y - 1) / gridDim.y;
     int k0 = blockIdx.y * kper, k1 = min(K, k0 + kper);
-    if (tri) k0 = max(k0, (int)(blockIdx.x * 64));
+    const int rl0 = (int)((blockIdx.x * 64) % Rb);
+    if (tri == 1) k0 = max(k0, rl0);
+    if (tri == 2) k1 = min(k1, rl0 + 64);
     double m = 0.0;
-    if (r < R)
-        for (int k = k0 + ph; k < k1; k += 4) m = fmax(m, fabs(src[(long long)r * rs + (long long)k * cs]));
+    if (r < R) {
+        const double* x = src + (long long)(r / Rb) * bstride + (long long)(r % Rb) * rs;
+        for (int k = k0 + ph; k < k1; k += 4) m = fmax(m, fabs(x[(long long)k * cs]));
+    }
     __shared__ double red[256];
     red[threadIdx.x] = m;
     __syncthreads();
@@ -60,13 +66,16 @@ __global__ void __launch_bounds__(256) i8_rowmax_kernel(const double* __restrict
 
 // digits[kc][rt][s][k16][row % 128][k % 16], kc = k / 32, rt = row / 128.  One block per (kc, rt): 128 rows x 32 k.
 // Thread (row, k16) slices 16 consecutive k of one row and writes one 16-byte vector per digit plane.
-// Blocks with tri != 0 that lie entirely in the zero part of a lower-triangular operand (all k < first row of the
-// tile) are never read by the tile lists and are skipped.
+// Blocks that lie entirely in the zero part of a triangular operand (see i8_rowmax_kernel) are never read by the
+// tile lists and are skipped.
 __global__ void __launch_bounds__(256) i8_slice_tiled_kernel(const double* __restrict__ src, long long rs, long long cs,
-                                                             int R, int K, int S, int tri, const int* __restrict__ ex_bits,
-                                                             int8_t* __restrict__ digits, int nrt) {
+                                                             long long bstride, int R, int Rb, int K, int S, int tri,
+                                                             const int* __restrict__ ex_bits, int8_t* __restrict__ digits,
+                                                             int nrt) {
     const int kc = blockIdx.x, rt = blockIdx.y;
-    if (tri && kc * I8_KC + I8_KC <= rt * I8_TM) return;
+    const int rl0 = (rt * I8_TM) % Rb;
+    if (tri == 1 && kc * I8_KC + I8_KC <= rl0) return;
+    if (tri == 2 && kc * I8_KC >= rl0 + I8_TM) return;
     const int row = rt * I8_TM + (threadIdx.x & 127), k16 = threadIdx.x >> 7;
     int e = 0;
     bool nz = false;
@@ -74,11 +83,12 @@ __global__ void __launch_bounds__(256) i8_slice_tiled_kernel(const double* __res
         const int hi = ex_bits[row];
         if (hi > 0) { nz = true; e = ((hi >> 20) & 0x7ff) - 1022 + 1; }     // |x| < 2^(e-1): x 2^-e in (-1/2, 1/2)
     }
+    const double* x = src + (long long)((row < R ? row : 0) / Rb) * bstride + (long long)((row < R ? row : 0) % Rb) * rs;
     double v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int k = kc * I8_KC + k16 * 16 + i;
-        v[i] = (nz && k < K) ? src[(long long)row * rs + (long long)k * cs] : 0.0;
+        v[i] = (nz && k < K) ? x[(long long)k * cs] : 0.0;
     }
     const double sc = nz ? __hiloint2double((1023 - e) << 20, 0) : 0.0;      // 2^-e
     int8_t* base = digits + (((long long)kc * nrt + rt) * S) * (2 * I8_TM * 16) + (long long)(k16 * I8_TM + (threadIdx.x & 127)) * 16;
@@ -143,7 +153,9 @@ __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(i8_smem_u32(bar)) : "memory");
 }
 
-struct I8Tile { int m0, n0, kc0, kc1; };       // output tile origin; K chunks [kc0, kc1)
+// One 128 x 64 output tile: first row of the A operand, first row of the B operand (a multiple of 64), K chunks
+// [kc0, kc1), and the element offset of C[0][0] of the tile.
+struct I8Tile { int m0, n0, kc0, kc1; long long c_off; };
 
 struct __align__(128) I8Smem {
     int8_t a[I8_STAGES][I8_SMAX][2][I8_TM][16];      // [stage][slice][k16][row][16 B]   4 KB per slice
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(192, 1) i8_gemm_tiles_kernel(I8Args g) {
         i8_mbar_wait(&sm.acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int er = g.ea[row];
-        double* crow = g.C + (long long)row * g.ldc + t.n0;
+        double* crow = g.C + t.c_off + (long long)(q * 32 + lane) * g.ldc;
 #pragma unroll 1
         for (int c0 = 0; c0 < I8_TN; c0 += 16) {
             double acc[16];
@@ -282,10 +294,13 @@ struct I8Operand {                 // a sliced operand in device memory
     int* ex_bits = nullptr; int* ex = nullptr; size_t rows_cap = 0;
     int R = 0, K = 0, nrt = 0, nkc = 0;
 };
+struct I8List { size_t first = 0, count = 0; };
 struct I8Plan {
     I8Operand opA, opB;
     I8Tile* tiles = nullptr; size_t tiles_cap = 0;
-    std::vector<I8Tile> host_tiles;
+    std::vector<I8Tile> host_tiles;          // all tile lists back to back
+    I8List kinv;                             // K^-1 = L^-T L^-1
+    std::vector<I8List> lvl_a, lvl_b;        // per doubling level (index = log2 of the block size in 64-blocks): the two GEMMs
     long long tiles_key = -1;
 };
 
@@ -311,16 +326,17 @@ static cudaError_t i8_reserve(I8Operand& op, int R, int K, int S) {
     return cudaSuccess;
 }
 
-// Slice the operand whose element (row r, k) is src[r * rs + k * cs]  (R rows, K deep; tri: zero for k < r).
-static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long long cs, int R, int K, int S, int tri,
-                            cudaStream_t st) {
+// Slice an operand of R rows (batch groups of R / batch rows, see i8_rowmax_kernel), K deep.
+static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long long cs, long long bstride, int batch,
+                            int R, int K, int S, int tri, cudaStream_t st) {
     cudaError_t e = i8_reserve(op, R, K, S);
     if (e != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(op.ex_bits, 0, (size_t)op.nrt * I8_TM * 4, st)) != cudaSuccess) return e;
     const int ksplit = std::max(1, std::min(32, K / 256));
-    i8_rowmax_kernel<<<dim3((R + 63) / 64, ksplit), 256, 0, st>>>(src, rs, cs, R, K, tri, op.ex_bits);
+    const int Rb = R / std::max(1, batch);
+    i8_rowmax_kernel<<<dim3((R + 63) / 64, ksplit), 256, 0, st>>>(src, rs, cs, bstride, R, Rb, K, tri, op.ex_bits);
     i8_exponent_kernel<<<(op.nrt * I8_TM + 255) / 256, 256, 0, st>>>(op.ex_bits, op.ex, op.nrt * I8_TM);
-    i8_slice_tiled_kernel<<<dim3(op.nkc, op.nrt), 256, 0, st>>>(src, rs, cs, R, K, S, tri, op.ex_bits, op.digits, op.nrt);
+    i8_slice_tiled_kernel<<<dim3(op.nkc, op.nrt), 256, 0, st>>>(src, rs, cs, bstride, R, Rb, K, S, tri, op.ex_bits, op.digits, op.nrt);
     MOGP_COUNT(3);
     return cudaGetLastError();
 }
@@ -370,17 +386,56 @@ void i8_plan_destroy(I8Plan* p) {
     delete p;
 }
 
-// Host-side preparation (allocations, tile-list upload) of i8_kinv for a given size: never inside graph capture.
-cudaError_t i8_kinv_prepare(I8Plan* p, int64_t Np, int S, cudaStream_t st) {
+// Smallest block size (rows) of a doubling level of the triangular inverse that runs on the int8 pipe
+long long g_i8_trtri_min = 1024;
+
+static bool i8_level_ok(int64_t Np, int64_t S) {
+    return g_i8_trtri_min > 0 && S >= g_i8_trtri_min && S % I8_TM == 0 && Np % (2 * S) == 0;     // no ragged last pair
+}
+
+// Host-side preparation (allocations, tile lists) for a given padded size: never inside graph capture.
+cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st) {
     cudaError_t e = i8_reserve(p->opA, (int)Np, (int)Np, S);
     if (e != cudaSuccess) return e;
-    const long long key = Np * 16 + S;
+    if ((e = i8_reserve(p->opB, (int)Np, (int)(Np / 2), S)) != cudaSuccess) return e;
+    const long long key = (Np * 16 + S) * 65536 + g_i8_trtri_min % 65536 + ld * 1000003ll;
     if (p->tiles_key == key) return cudaSuccess;
     p->host_tiles.clear();
+    p->lvl_a.assign(32, I8List());
+    p->lvl_b.assign(32, I8List());
     const int nkc = (int)(Np / I8_KC);
+    p->kinv.first = 0;
     for (int ti = 0; ti < (int)(Np / I8_TM); ++ti)                         // longest K ranges first
         for (int tj = 0; tj * I8_TN < (ti + 1) * I8_TM; ++tj)
-            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, ti * I8_TM / I8_KC, nkc});
+            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, ti * I8_TM / I8_KC, nkc, (long long)ti * I8_TM * ld + (long long)tj * I8_TN});
+    p->kinv.count = p->host_tiles.size();
+    // doubling levels of the triangular inverse: pairs of adjacent S x S diagonal blocks (A, B) at offset o = 2 S pair:
+    //   GEMM a: T = L_BA Linv_AA        operand A rows = rows of L_BA, operand B rows = columns of Linv_AA (nonzero k >= n)
+    //   GEMM b: Linv_BA = -Linv_BB T    operand A rows = rows of Linv_BB (nonzero k <= m), operand B rows = columns of T
+    // both operands of a level are the stacked blocks of all pairs (row index = pair * S + local row).
+    int lev = 0;
+    for (int64_t S_ = 64; S_ < Np; S_ *= 2, ++lev) {
+        if (!i8_level_ok(Np, S_)) continue;
+        const int npair = (int)(Np / (2 * S_)), Sn = (int)S_;
+        p->lvl_a[lev].first = p->host_tiles.size();
+        for (int tn = 0; tn < Sn / I8_TN; ++tn)                             // longest K ranges (small n) first
+            for (int pr = 0; pr < npair; ++pr)
+                for (int tm = 0; tm < Sn / I8_TM; ++tm) {
+                    const long long o = (long long)pr * 2 * S_;
+                    p->host_tiles.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * I8_TN, tn * I8_TN / I8_KC, Sn / I8_KC,
+                                             (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * I8_TN});
+                }
+        p->lvl_a[lev].count = p->host_tiles.size() - p->lvl_a[lev].first;
+        p->lvl_b[lev].first = p->host_tiles.size();
+        for (int tm = Sn / I8_TM - 1; tm >= 0; --tm)                        // longest K ranges (large m) first
+            for (int pr = 0; pr < npair; ++pr)
+                for (int tn = 0; tn < Sn / I8_TN; ++tn) {
+                    const long long o = (long long)pr * 2 * S_;
+                    p->host_tiles.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * I8_TN, 0, (tm + 1) * I8_TM / I8_KC,
+                                             (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * I8_TN});
+                }
+        p->lvl_b[lev].count = p->host_tiles.size() - p->lvl_b[lev].first;
+    }
     e = i8_upload_tiles(*p, st);
     if (e != cudaSuccess) return e;
     p->tiles_key = key;
@@ -389,12 +444,33 @@ cudaError_t i8_kinv_prepare(I8Plan* p, int64_t Np, int S, cudaStream_t st) {
 
 // W(lower tiles) = Linv^T Linv with Linv lower triangular (zero above the diagonal): K^-1 of the factorised matrix.
 // Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
-// (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_kinv_prepare.
+// (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_prepare.
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
-    if (p->tiles_key != Np * 16 + S) return cudaErrorInvalidValue;
-    cudaError_t e = i8_slice(p->opA, Linv, 1, ld, (int)Np, (int)Np, S, 1, st);
+    if (p->tiles_key < 0 || p->kinv.count == 0) return cudaErrorInvalidValue;
+    cudaError_t e = i8_slice(p->opA, Linv, 1, ld, 0, 1, (int)Np, (int)Np, S, 1, st);
     if (e != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opA, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, W, ld, st);
+    return i8_launch(p->opA, p->opA, p->tiles + p->kinv.first, (int)p->kinv.count, S, 1.0, 0.0, W, ld, st);
+}
+
+// One doubling level (block size S_ rows) of Linv = L^-1 on the int8 pipe; returns cudaErrorNotSupported when the level
+// is not eligible (the caller then runs the DMMA GEMMs).  scratch receives T = L_BA Linv_AA (as in trtri_padded).
+cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scratch, int64_t Np, long long ld, int64_t S_,
+                           int S, cudaStream_t st) {
+    if (!p || p->tiles_key < 0 || !i8_level_ok(Np, S_)) return cudaErrorNotSupported;
+    int lev = 0;
+    for (int64_t x = 64; x < S_; x *= 2) ++lev;
+    if (p->lvl_a[lev].count == 0) return cudaErrorNotSupported;
+    const int npair = (int)(Np / (2 * S_)), R = (int)(npair * S_), K = (int)S_;
+    const long long bs = 2 * S_ * (ld + 1);
+    cudaError_t e;
+    // GEMM a
+    if ((e = i8_slice(p->opA, L + S_ * ld, ld, 1, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
+    if ((e = i8_slice(p->opB, Linv, 1, ld, bs, npair, R, K, S, 1, st)) != cudaSuccess) return e;
+    if ((e = i8_launch(p->opA, p->opB, p->tiles + p->lvl_a[lev].first, (int)p->lvl_a[lev].count, S, 1.0, 0.0, scratch, ld, st)) != cudaSuccess) return e;
+    // GEMM b
+    if ((e = i8_slice(p->opA, Linv + S_ * ld + S_, ld, 1, bs, npair, R, K, S, 2, st)) != cudaSuccess) return e;
+    if ((e = i8_slice(p->opB, scratch + S_ * ld, 1, ld, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
+    return i8_launch(p->opA, p->opB, p->tiles + p->lvl_b[lev].first, (int)p->lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st);
 }
 
 // ------------------------------------------------------------------ self-test hooks (tests, tools/gpu_diag.py)
@@ -440,14 +516,15 @@ extern "C" int mogp_i8_selftest(int M, int N, int K, int S, double* out_host /*4
     I8Plan* p = i8_plan_create();
     int rc = 0;
     for (int ti = 0; ti < M / I8_TM; ++ti)
-        for (int tj = 0; tj < N / I8_TN; ++tj) p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, 0, K / I8_KC});
+        for (int tj = 0; tj < N / I8_TN; ++tj)
+            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, 0, K / I8_KC, (long long)ti * I8_TM * N + (long long)tj * I8_TN});
     if (i8_upload_tiles(*p, nullptr) != cudaSuccess) rc = -2;
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     for (int rep = 0; rep < 2 && rc == 0; ++rep) {
         cudaEventRecord(e0);
-        if (i8_slice(p->opA, A, K, 1, M, K, S, 0, nullptr) != cudaSuccess) rc = -3;
-        if (rc == 0 && i8_slice(p->opB, B, K, 1, N, K, S, 0, nullptr) != cudaSuccess) rc = -3;
+        if (i8_slice(p->opA, A, K, 1, 0, 1, M, K, S, 0, nullptr) != cudaSuccess) rc = -3;
+        if (rc == 0 && i8_slice(p->opB, B, K, 1, 0, 1, N, K, S, 0, nullptr) != cudaSuccess) rc = -3;
         cudaEventRecord(e1);
         if (rc == 0 && i8_launch(p->opA, p->opB, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, C1, N, nullptr) != cudaSuccess) rc = -4;
         cudaEventRecord(e2);

@@ -1265,10 +1265,16 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
 // Linv = L^-1 by level-batched block doubling: at level s (in 64-blocks) every pair of
 // adjacent diagonal super-blocks (A, B) gets Linv_BA = -Linv_BB * (L_BA * Linv_AA).
 // Two batched GEMMs per level (+2 for a ragged last pair); `scratch` holds L_BA*Linv_AA.
-cudaError_t trtri_padded(double* L, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st) {
+cudaError_t trtri_padded(double* L, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st, I8Plan* i8,
+                         int i8_slices) {
     const int64_t nblk = Np / 64;
     for (int64_t s = 1; s < nblk; s *= 2) {
         const int64_t S = s * 64;
+        if (i8) {          // the large levels (almost all of the flops) on the int8 tensor pipe (i8mm.cu)
+            cudaError_t e8 = i8_trtri_level(i8, L, Linv, scratch, Np, ld, S, i8_slices, st);
+            if (e8 == cudaSuccess) continue;
+            if (e8 != cudaErrorNotSupported) return e8;
+        }
         const int64_t nfull = nblk / (2 * s);
         const int64_t o_rem = nfull * 2 * S;
         const int64_t remB = (nblk - nfull * 2 * s > s) ? (nblk - nfull * 2 * s - s) * 64 : 0;

@@ -9,11 +9,28 @@ import torch
 
 from . import _cabi
 
-PARAM_ORDER = {
+class _ParamOrder(dict):
+    def __missing__(self, kind):                       # "CSM:2" -> the CSM layout
+        return self[family(kind)]
+
+
+PARAM_ORDER = _ParamOrder({
     "MOSM": ("weight", "mean", "variance", "delay", "phase"),
     "SM": ("magnitude", "mean", "variance"),
     "CONV": ("weight", "variance", "base_variance"),
-}
+    "CSM": ("amplitude", "mean", "variance", "shift"),
+    "SMLMC": ("weight", "magnitude", "mean", "variance"),
+    "UMOSM": ("weight", "mean", "variance", "delay", "phase"),
+})
+
+
+def family(kind):
+    return str(kind).partition(":")[0]
+
+
+def kind_rq(kind):
+    rq = str(kind).partition(":")[2]
+    return int(rq) if rq else 1
 
 
 class NotPositiveDefiniteError(RuntimeError):
@@ -34,6 +51,14 @@ def kernel_dims(kind, params):
         C_, Q, D = params["mean"].shape
     elif kind == "CONV":
         Q, C_, D = params["variance"].shape
+    elif family(kind) == "CSM":
+        Q, C_, _ = params["amplitude"].shape
+        D = params["mean"].shape[1]
+    elif family(kind) == "SMLMC":
+        C_, Q, _ = params["weight"].shape
+        D = params["mean"].shape[1]
+    elif kind == "UMOSM":
+        Q, C_, D = params["mean"].shape
     else:
         raise ValueError("unknown kernel kind %r" % (kind,))
     return int(C_), int(Q), int(D)
@@ -44,7 +69,16 @@ def param_shapes(kind, C_, Q, D):
         return {"weight": (C_, Q), "mean": (C_, Q, D), "variance": (C_, Q, D), "delay": (C_, Q, D), "phase": (C_, Q)}
     if kind == "SM":
         return {"magnitude": (C_, Q), "mean": (C_, Q, D), "variance": (C_, Q, D)}
-    return {"weight": (Q, C_), "variance": (Q, C_, D), "base_variance": (Q, D)}
+    if kind == "CONV":
+        return {"weight": (Q, C_), "variance": (Q, C_, D), "base_variance": (Q, D)}
+    Rq = kind_rq(kind)
+    if family(kind) == "CSM":
+        return {"amplitude": (Q, C_, Rq), "mean": (Q, D), "variance": (Q, D), "shift": (Q, C_, Rq)}
+    if family(kind) == "SMLMC":
+        return {"weight": (C_, Q, Rq), "magnitude": (Q,), "mean": (Q, D), "variance": (Q, D)}
+    if kind == "UMOSM":
+        return {"weight": (Q, C_, C_), "mean": (Q, C_, D), "variance": (Q, C_, D), "delay": (Q, C_, D), "phase": (Q, C_)}
+    raise ValueError("unknown kernel kind %r" % (kind,))
 
 
 def pack_params(kind, params, device=None):

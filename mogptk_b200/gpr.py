@@ -321,6 +321,22 @@ def kernel_spec(kernel):
             return "SM", p, (int(C_), int(Q), int(D))
     if cname in ("MixtureKernel", "AddKernel"):
         subs = list(kernel.kernels)
+        if all(k.__class__.__name__ == "CrossSpectralKernel" for k in subs):         # what mogptk.CSM builds
+            if len({tuple(k.amplitude.shape) for k in subs}) != 1:
+                raise NotImplementedError("CSM terms must share output_dims and Rq")
+            p = {"amplitude": torch.stack([k.amplitude() for k in subs]), "mean": torch.stack([k.mean() for k in subs]),
+                 "variance": torch.stack([k.variance() for k in subs]), "shift": torch.stack([k.shift() for k in subs])}
+            Q, C_, Rq = p["amplitude"].shape
+            D = p["mean"].shape[1]
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
+            return "CSM:%d" % Rq, p, (int(C_), int(Q), int(D))
+        if all(k.__class__.__name__ == "UncoupledMultiOutputSpectralKernel" for k in subs):
+            p = {n: torch.stack([getattr(k, n)() for k in subs]) for n in ("weight", "mean", "variance", "delay", "phase")}
+            Q, C_, D = p["mean"].shape
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
+            return "UMOSM", p, (int(C_), int(Q), int(D))
         if all(k.__class__.__name__ == "GaussianConvolutionProcessKernel" for k in subs):
             p = {"weight": torch.stack([k.weight() for k in subs]),
                  "variance": torch.stack([k.variance() for k in subs]),
@@ -329,6 +345,20 @@ def kernel_spec(kernel):
             for k in [kernel] + subs:
                 _require_all_dims(k, int(D))
             return "CONV", p, (int(C_), int(Q), int(D))
+    if cname == "LinearModelOfCoregionalizationKernel":                                # what mogptk.SM_LMC builds
+        subs = list(kernel.kernels)
+        if all(k.__class__.__name__ == "SpectralKernel" for k in subs):
+            w = kernel.weight()
+            C_, Q, Rq = w.shape
+            if Q != len(subs):
+                raise NotImplementedError("LMC weight and kernel list disagree on Q")
+            p = {"weight": w, "magnitude": torch.stack([k.magnitude().reshape(()) for k in subs]),
+                 "mean": torch.stack([k.mean().reshape(-1) for k in subs]),
+                 "variance": torch.stack([k.variance().reshape(-1) for k in subs])}
+            D = p["mean"].shape[1]
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
+            return "SMLMC:%d" % Rq, p, (int(C_), int(Q), int(D))
     if cname == "GaussianConvolutionProcessKernel":
         p = {"weight": kernel.weight()[None], "variance": kernel.variance()[None],
              "base_variance": kernel.base_variance()[None]}
@@ -336,18 +366,28 @@ def kernel_spec(kernel):
         _require_all_dims(kernel, int(D))
         return "CONV", p, (int(C_), int(Q), int(D))
     raise NotImplementedError(
-        "mogptk_b200 implements the exact-GP path for MOSM, SM (IndependentMultiOutputKernel of "
-        "SpectralMixtureKernel) and CONV (MixtureKernel of GaussianConvolutionProcessKernel) only; got %s" % cname)
+        "mogptk_b200 implements the exact-GP path for MOSM, SM (IndependentMultiOutputKernel of SpectralMixtureKernel), "
+        "CONV (MixtureKernel of GaussianConvolutionProcessKernel), CSM (MixtureKernel of CrossSpectralKernel), SM-LMC "
+        "(LinearModelOfCoregionalizationKernel of SpectralKernel) and uMOSM (MixtureKernel of "
+        "UncoupledMultiOutputSpectralKernel) only; got %s" % cname)
 
 
 def _param_tensors(kind, kernel):
     """The Parameter objects behind kernel_spec's tensors, in the same order (for gradient routing)."""
-    if kind == "MOSM":
+    fam = _engine.family(kind)
+    if fam == "MOSM":
         return [[kernel.weight], [kernel.mean], [kernel.variance], [kernel.delay], [kernel.phase]]
-    if kind == "SM":
+    if fam == "SM":
         subs = list(kernel.kernels)
         return [[k.magnitude for k in subs], [k.mean for k in subs], [k.variance for k in subs]]
+    if fam == "SMLMC":
+        subs = list(kernel.kernels)
+        return [[kernel.weight], [k.magnitude for k in subs], [k.mean for k in subs], [k.variance for k in subs]]
     subs = list(kernel.kernels) if hasattr(kernel, "kernels") else [kernel]
+    if fam == "CSM":
+        return [[k.amplitude for k in subs], [k.mean for k in subs], [k.variance for k in subs], [k.shift for k in subs]]
+    if fam == "UMOSM":
+        return [[getattr(k, n) for k in subs] for n in ("weight", "mean", "variance", "delay", "phase")]
     return [[k.weight for k in subs], [k.variance for k in subs], [k.base_variance for k in subs]]
 
 
@@ -499,8 +539,65 @@ class GaussianConvolutionProcessKernel(MultiOutputKernel):
         self.base_variance = Parameter(torch.ones(input_dims), lower=config.positive_minimum)
 
 
+class CrossSpectralKernel(MultiOutputKernel):
+    """CSM term (gpr/multioutput.py:397-426): amplitude / shift (C,Rq), mean / variance (D,)."""
+
+    def __init__(self, output_dims, input_dims=1, Rq=1, active_dims=None):
+        super().__init__(output_dims, input_dims, active_dims)
+        self.amplitude = Parameter(torch.ones(output_dims, Rq), lower=config.positive_minimum)
+        self.mean = Parameter(torch.zeros(input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(input_dims), lower=config.positive_minimum)
+        self.shift = Parameter(torch.zeros(output_dims, Rq))
+
+
+class UncoupledMultiOutputSpectralKernel(MultiOutputKernel):
+    """uMOSM term (gpr/multioutput.py:212-259): weight (C,C) lower triangle, mean / variance / delay (C,D), phase (C,)."""
+
+    def __init__(self, output_dims, input_dims=1, active_dims=None):
+        super().__init__(output_dims, input_dims, active_dims)
+        self.weight = Parameter(torch.ones(output_dims, output_dims).tril())
+        self.weight.num_parameters = (output_dims * output_dims + output_dims) // 2
+        self.mean = Parameter(torch.zeros(output_dims, input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(output_dims, input_dims), lower=config.positive_minimum)
+        self.delay = Parameter(torch.zeros(output_dims, input_dims))
+        self.phase = Parameter(torch.zeros(output_dims))
+        if output_dims == 1:
+            self.delay.train = False
+            self.phase.train = False
+
+
+class SpectralKernel(Kernel):
+    """Single spectral term (gpr/singleoutput.py:520-548): magnitude (), mean / variance (D,)."""
+
+    def __init__(self, input_dims=1, active_dims=None):
+        super().__init__(input_dims, active_dims)
+        self.magnitude = Parameter(1.0, lower=config.positive_minimum)
+        self.mean = Parameter(torch.zeros(input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(input_dims), lower=config.positive_minimum)
+
+    def K(self, X1, X2=None):
+        raise NotImplementedError("use LinearModelOfCoregionalizationKernel([SpectralKernel...]) (what mogptk.SM_LMC builds)")
+
+
+class LinearModelOfCoregionalizationKernel(MultiOutputKernel):
+    """LMC over Q single-output kernels (gpr/multioutput.py:456-488): weight (C,Q,Rq)."""
+
+    def __init__(self, *kernels, output_dims, input_dims=1, Q=None, Rq=1):
+        super().__init__(output_dims, input_dims)
+        if Q is None:
+            Q = len(kernels[0]) if len(kernels) == 1 and isinstance(kernels[0], list) else len(kernels)
+        self.kernels = torch.nn.ModuleList(_kernel_list(kernels, Q))
+        self.weight = Parameter(torch.ones(output_dims, Q, Rq), lower=config.positive_minimum)
+
+    def __getitem__(self, key):
+        return self.kernels[key]
+
+    def name(self):
+        return "%s[%s]" % (self.__class__.__name__, ",".join(k.name() for k in self.kernels))
+
+
 class AddKernel(Kernel):
-    """Sum of kernels (gpr/kernel.py:232-246); only sums of CONV kernels reach the engine."""
+    """Sum of kernels (gpr/kernel.py:232-246); sums of CONV / CSM / uMOSM terms reach the engine."""
 
     def __init__(self, *kernels):
         super().__init__()

@@ -8,6 +8,14 @@ import torch
 
 from mogptk_b200.engine import PARAM_ORDER, Rows, kernel_dims, param_shapes
 from oracle import mogp_oracle as orc
+from oracle import next_kernels as _nk
+
+_nk.register()                 # CSM / SM-LMC / uMOSM restatements into the oracle's block assembly
+
+
+def _ok(kind):
+    """Oracle kind name of a host kind ("CSM:2" -> "CSM")."""
+    return str(kind).partition(":")[0]
 
 
 def _unpack(kind, dims, flat):
@@ -46,12 +54,12 @@ class FakeEngine:
         try:
             if want_grad:
                 with torch.enable_grad():      # called from inside autograd.Function.forward (grad mode off)
-                    loss, g = orc.loss_and_grad(rows.kind, p, sigma, rows.Xs, rows.y, jitter, rows.dv)
+                    loss, g = orc.loss_and_grad(_ok(rows.kind), p, sigma, rows.Xs, rows.y, jitter, rows.dv)
                 out[0] = -loss
                 out[2:2 + packed.numel()] = torch.cat([g[n].reshape(-1) for n in PARAM_ORDER[rows.kind]])
                 out[2 + packed.numel():] = g["sigma"].reshape(-1)
             else:
-                out[0] = orc.lml(rows.kind, p, sigma, rows.Xs, rows.y, jitter, rows.dv)
+                out[0] = orc.lml(_ok(rows.kind), p, sigma, rows.Xs, rows.y, jitter, rows.dv)
         except torch.linalg.LinAlgError:
             out[1] = 1.0
         self._train, self._p, self._sigma, self._jitter = rows, p, sigma.detach().clone(), jitter
@@ -59,21 +67,21 @@ class FakeEngine:
 
     def alpha(self):
         rows = self._train
-        Kn = orc._noisy_gram(rows.kind, self._p, self._sigma, rows.Xs, self._jitter, rows.dv)
+        Kn = orc._noisy_gram(_ok(rows.kind), self._p, self._sigma, rows.Xs, self._jitter, rows.dv)
         a = torch.linalg.solve(Kn, rows.y.reshape(-1, 1)).reshape(-1)
         return a if rows.sorted else a[rows.inv_t]
 
     def predict(self, Xs, full=False):
         rows = self._train
-        mu, var = orc.predict_f(rows.kind, self._p, self._sigma, rows.Xs, rows.y, torch.as_tensor(np.asarray(Xs)),
+        mu, var = orc.predict_f(_ok(rows.kind), self._p, self._sigma, rows.Xs, rows.y, torch.as_tensor(np.asarray(Xs)),
                                 self._jitter, full=full, data_var=rows.dv)
         return mu.reshape(-1), (var if full else var.reshape(-1))
 
     def K(self, kind, params, X1, X2=None, sigma=None, data_var=None, jitter=0.0):
         p = {k: v.detach() for k, v in params.items()}
         if X2 is None and (sigma is not None or data_var is not None or jitter):
-            return orc._noisy_gram(kind, p, torch.as_tensor(sigma), orc.t64(X1), jitter, data_var)
-        return orc.K(kind, p, X1, X2)
+            return orc._noisy_gram(_ok(kind), p, torch.as_tensor(sigma), orc.t64(X1), jitter, data_var)
+        return orc.K(_ok(kind), p, X1, X2)
 
     def K_diag(self, kind, params, X):
-        return orc.K_diag(kind, {k: v.detach() for k, v in params.items()}, X)
+        return orc.K_diag(_ok(kind), {k: v.detach() for k, v in params.items()}, X)

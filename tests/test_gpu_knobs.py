@@ -120,3 +120,35 @@ def test_int8_kinv_equals_dmma_kinv(engine):
         assert float((got - ref)[tril].abs().max()) <= tol * scale
     assert float((K7 - Kd)[tril].abs().max()) <= 1e-12 * scale
     assert float((K8 - Kd)[tril].abs().max()) <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_int8_triangular_inverse_levels_equal_dmma(engine, n):
+    """L^-1 by block doubling with the large levels (block size >= 1024) on the int8 tensor pipe against the all-DMMA
+    recursion; n = 4096 with the pipelined inverse switched off so that the level-batched path runs."""
+    import torch
+    torch.manual_seed(5)
+    B = torch.randn(n, n // 2, dtype=torch.float64, device=engine.device)
+    K = B @ B.T / n + 0.5 * torch.eye(n, dtype=torch.float64, device=engine.device)
+    del B
+    lib = engine.lib
+    try:
+        lib.mogp_set_trtri_pipe(0)
+        lib.mogp_set_i8(0, 7)
+        Ld, Kd, info_d = engine.trtri_kinv_(K.clone())
+        lib.mogp_set_i8(4096, 7)
+        L7, K7, info_7 = engine.trtri_kinv_(K.clone())
+    finally:
+        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_trtri_pipe(1)
+    assert info_d == 0 and info_7 == 0
+    tril = torch.tril(torch.ones(n, n, dtype=torch.bool, device=engine.device))
+    sl, sk = float(Ld.abs().max()), float(Kd[tril].abs().max())
+    assert float((L7 - Ld)[tril].abs().max()) <= 1e-12 * sl
+    assert float((K7 - Kd)[tril].abs().max()) <= 1e-12 * sk
+    # and both invert K: K * Kinv = I on a column sample
+    Kfull = torch.tril(K7) + torch.tril(K7, -1).T
+    cols = torch.arange(0, n, n // 16, device=engine.device)
+    R = K @ Kfull[:, cols]
+    R[cols, torch.arange(cols.numel(), device=engine.device)] -= 1.0
+    assert float(R.abs().max()) <= 1e-9

@@ -5,11 +5,13 @@ size-independent properties at the BASELINE.json sizes.
 Tolerances (BASELINE.json north_star): log-marginal likelihood rtol 1e-8, posterior mean /
 variance rtol 1e-6; additionally K max-abs <= 1e-12 * max|K| and gradients <= 1e-6 of the
 largest entry of each parameter tensor."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, next_golden_names
 
 pytestmark = pytest.mark.gpu
 
@@ -318,3 +320,38 @@ def test_tile_cache_eviction_does_not_break_the_captured_training_graph():
         assert rel(mu, g["pred_mu"]) < 1e-6
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------ further kernel families
+def _next_case(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    fam = str(g["kind"])
+    kind = fam if fam == "UMOSM" else "%s:%d" % (fam, int(g["Rq"]))
+    p = {k[2:]: torch.tensor(v, dtype=torch.float64) for k, v in g.items() if k.startswith("p_")}
+    return g, kind, p
+
+
+@pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
+def test_further_kernel_families_match_the_reference(engine, name):
+    """CSM (gpr/multioutput.py:397-454), SM-LMC (:456-502) and uMOSM (:212-293) on the same tile kernels: K, K_diag,
+    LML (rtol 1e-8), constrained-space gradients (1e-6) and predictions (1e-6) against the live-reference fixtures."""
+    g, kind, p = _next_case(name)
+    X, y, sigma, jitter = g["X"], g["y"], torch.tensor(g["sigma"]), float(g["jitter"])
+    K = engine.K(kind, p, X)
+    assert rel(K, g["K"]) < 1e-12
+    assert torch.equal(K, K.T)
+    assert torch.equal(engine.K_diag(kind, p, X), K.diagonal())
+    assert rel(engine.K_diag(kind, p, X), g["K_diag"]) < 1e-12
+    Kx = engine.K(kind, p, X, g["Xs"])
+    from oracle import next_kernels as nk
+    orc = nk.register()
+    assert rel(Kx, orc.K(kind.partition(":")[0], p, X, g["Xs"])) < 1e-12
+    res = engine.lml_grad(kind, p, sigma, X, y, jitter, True)
+    assert abs(res["lml"] - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+    for k, got in res["grad"].items():
+        ref = g["gc_" + k]
+        assert np.abs(got.cpu().numpy().reshape(ref.shape) - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-12), k
+    mu, var = engine.predict(g["Xs"])
+    assert rel(mu, g["pred_mu"]) < 1e-6
+    assert np.abs(var.cpu().numpy() - g["pred_var"]).max() <= 1e-6 * np.abs(g["pred_var"]).max()

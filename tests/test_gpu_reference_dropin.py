@@ -280,3 +280,42 @@ def test_device_resident_adam_stops_at_a_cholesky_failure(mogptk):
     with pytest.raises(mogptk.gpr.CholeskyException):
         fused.fit_adam(m, 8, lr=0.01, sync_every=8)
     assert torch.equal(k.variance.data, raw_before)          # frozen at the failing iteration
+
+
+@pytest.mark.parametrize("family,kw", [("CSM", dict(Q=2, Rq=2)), ("SM_LMC", dict(Q=3, Rq=2))])
+def test_csm_and_sm_lmc_models_through_the_reference(mogptk, family, kw):
+    """mogptk.CSM / mogptk.SM_LMC (mogptk/models/csm.py, sm_lmc.py) with inference=B200Exact() against the stock
+    reference on the CPU: Adam training, predictions, and the device-resident loop after install()."""
+    import mogptk_b200 as mb
+    from mogptk_b200 import synth
+    X, y = synth.make_data(3, [60, 44, 72], seed=13)
+    cls = getattr(mogptk, family)
+    with on(mogptk, "cpu"):
+        torch.manual_seed(6)
+        a = cls(dataset(mogptk, X, y, 3), **kw)
+        g = torch.Generator().manual_seed(2)
+        for n, p in a.gpr.named_parameters():
+            if n.endswith(".mean"):
+                p.assign(0.2 + torch.rand(p.shape, generator=g, dtype=torch.float64))
+            elif n.endswith(".shift"):
+                p.assign(0.3 * torch.randn(p.shape, generator=g, dtype=torch.float64))
+    b = cls(dataset(mogptk, X, y, 3), inference=mb.B200Exact(), **kw)
+    c = cls(dataset(mogptk, X, y, 3), inference=mb.B200Exact(), **kw)
+    for (na, u), (nb, v), (nc, w) in zip(a.gpr.named_parameters(), b.gpr.named_parameters(), c.gpr.named_parameters()):
+        assert na == nb == nc
+        v.data = u.data.detach().clone().to(v.device)
+        w.data = u.data.detach().clone().to(w.device)
+    with on(mogptk, "cpu"):
+        la, _ = a.train(method="Adam", iters=30, lr=0.03, verbose=False, jit=False)
+        _, Ma, _, _ = a.predict()
+    lb, _ = b.train(method="Adam", iters=30, lr=0.03, verbose=False, jit=False)
+    assert close(la, lb, 1e-8), np.abs(la - lb).max()
+    _, Mb, _, _ = b.predict()
+    for u, v in zip(Ma, Mb):
+        assert close(u, v, 1e-6)
+    mb.install(mogptk)
+    try:
+        lc, _ = c.train(method="Adam", iters=30, lr=0.03, verbose=False, jit=False)
+    finally:
+        mb.uninstall(mogptk)
+    assert close(la, lc, 1e-7), np.abs(la - lc).max()

@@ -272,3 +272,46 @@ def test_active_dims_other_than_identity_are_refused():
     sub[1].active_dims = [1]                                    # out of range after the channel column is stripped
     with pytest.raises(NotImplementedError):
         gpr.kernel_spec(gpr.IndependentMultiOutputKernel(sub, output_dims=2))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout only exists in the build container")
+@pytest.mark.parametrize("family,kw", [("CSM", dict(Q=2, Rq=2)), ("SM_LMC", dict(Q=2, Rq=2)), ("CSM", dict(Q=3, Rq=1))])
+def test_drop_in_for_csm_and_sm_lmc(family, kw):
+    """mogptk.CSM (mixture of CrossSpectralKernel) and mogptk.SM_LMC (LMC of SpectralKernel) through the plug-in:
+    kernel_spec's packing of the reference's parameter objects and the gradient routing back into them."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from make_golden import import_reference
+    mogptk = import_reference()
+    from mogptk_b200 import synth
+    Xd, yd = synth.make_data(3, [22, 30, 18], seed=8)
+
+    def dataset():
+        ds = mogptk.DataSet()
+        for c in range(3):
+            msk = Xd[:, 0] == c
+            ds.append(mogptk.Data(Xd[msk, 1], yd[msk], name=str(c)))
+        return ds
+
+    cls = getattr(mogptk, family)
+    torch.manual_seed(4)
+    a = cls(dataset(), **kw)
+    torch.manual_seed(4)
+    b = cls(dataset(), inference=mb.B200Exact(engine=FakeEngine()), **kw)
+    g = torch.Generator().manual_seed(1)
+    for (na, pa), (nb, pb) in zip(a.gpr.named_parameters(), b.gpr.named_parameters()):
+        assert na == nb
+        if na.endswith(".mean"):                     # off the constructor's dead-mean start
+            pa.assign(0.2 + torch.rand(pa.shape, generator=g, dtype=torch.float64))
+        elif na.endswith(".shift"):
+            pa.assign(0.3 * torch.randn(pa.shape, generator=g, dtype=torch.float64))
+        pb.data = pa.data.detach().clone()
+    assert b.gpr._kind.startswith("CSM" if family == "CSM" else "SMLMC")
+    la, _ = a.train(method="Adam", iters=4, lr=0.05, verbose=False, jit=False)
+    lb, _ = b.train(method="Adam", iters=4, lr=0.05, verbose=False, jit=False)
+    assert np.abs(la - lb).max() <= 1e-8 * np.abs(la).max()
+    for (na, pa), (nb, pb) in zip(a.gpr.named_parameters(), b.gpr.named_parameters()):
+        assert float((pa.grad - pb.grad).abs().max()) <= 1e-7 * max(float(pa.grad.abs().max()), 1e-10), na
+    _, Ma, _, _ = a.predict()
+    _, Mb, _, _ = b.predict()
+    for u, v in zip(Ma, Mb):
+        assert np.abs(u - v).max() <= 1e-7 * max(np.abs(u).max(), 1e-12)

@@ -1,8 +1,8 @@
-"""CPU tests for the next kernel families on the hot path (CSM, SM-LMC, uMOSM; MOHSM K only --
-it is non-stationary and needs one more factor than the derived form has): the oracle restatement
-reproduces the reference's K (golden fixtures written by oracle/make_golden_next.py from the live reference), and the
-per channel-pair component table in the product's one derived form reproduces it too -- i.e. these families need a new
-table (csrc/covmath.cuh) but no new CUDA kernels."""
+"""CPU tests for the further kernel families on the hot path (CSM, SM-LMC, uMOSM -- in the product
+since round 2; MOHSM K only -- it is non-stationary and needs one more factor than the derived form has): the oracle
+restatement reproduces the reference's K (golden fixtures written by oracle/make_golden_next.py from the live reference),
+and the per channel-pair component table of the product (csrc/covmath_next.cuh through the host hooks of
+libmogp_b200.so) reproduces it too, with an analytic chain rule that matches autograd."""
 import os
 
 import numpy as np
@@ -54,28 +54,23 @@ def test_fixtures_exist():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# csrc/covmath_next.cuh through the host hooks of the experimental library: the component table reproduces the
+# csrc/covmath_next.cuh through the host hooks of the product library: the component table reproduces the
 # reference's K, and the analytic chain rule reproduces autograd through the restatement (a synthetic symmetric
 # weight matrix W plays the role of (K^-1 - a a^T) / 2, adj the relative-jitter term on the diagonal pairs).
 import ctypes as C
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXP_LIB = os.path.join(ROOT, "mogptk_b200", "libmogp_b200_exp.so")
 KIND_ID = {"CSM": 3, "SMLMC": 4, "UMOSM": 5}
 ORDER = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance"),
          "UMOSM": ("weight", "mean", "variance", "delay", "phase")}
 
 
 @pytest.fixture(scope="module")
-def explib():
-    if not os.path.exists(EXP_LIB):
-        import __graft_entry__
-        __graft_entry__.build()
-    lib = C.CDLL(EXP_LIB)
-    lib.mogp_exp_host_pair_comps.restype = C.c_int
-    lib.mogp_exp_host_chain.restype = C.c_int
-    lib.mogp_exp_num_params.restype = C.c_int
+def explib(lib):
     return lib
+
+
+def _code(kind, Rq):
+    return KIND_ID[kind] | ((Rq << 8) if kind != "UMOSM" else 0)      # MOGP_KIND_WITH_RQ
 
 
 def _ptr(a):
@@ -111,11 +106,11 @@ def test_component_table_and_chain_rule_of_the_next_families(explib, name):
     kind, Cn, p, X, rows, K = _load(name)
     Cn, Q, Rq, D = _dims(kind, p)
     packed = _pack(kind, p)
-    assert explib.mogp_exp_num_params(KIND_ID[kind], Cn, Q, Rq, D) == packed.size
+    assert explib.mogp_num_params(_code(kind, Rq), Cn, Q, D) == packed.size
     st = 2 + 3 * D
     R = {"CSM": Q * Rq, "SMLMC": Q * D, "UMOSM": Q}[kind]
     comps = np.zeros(Cn * Cn * R * st)
-    assert explib.mogp_exp_host_pair_comps(KIND_ID[kind], Cn, Q, Rq, D, _ptr(packed), _ptr(comps)) == R
+    assert explib.mogp_host_pair_comps(_code(kind, Rq), Cn, Q, D, _ptr(packed), _ptr(comps)) == R
     comps = comps.reshape(Cn, Cn, R, st)
     xs = [X[rows[c], 1:].numpy() for c in range(Cn)]
     Kn = K.numpy()
@@ -147,7 +142,7 @@ def test_component_table_and_chain_rule_of_the_next_families(explib, name):
                     rec[2 + D + d] = (Wb * ES * u[..., d]).sum()
                     rec[2 + 2 * D + d] = (Wb * EC * u[..., d]).sum()
     grad = np.zeros(packed.size)
-    assert explib.mogp_exp_host_chain(KIND_ID[kind], Cn, Q, Rq, D, _ptr(packed), _ptr(gsum), _ptr(adj), _ptr(grad)) == packed.size
+    assert explib.mogp_host_chain(_code(kind, Rq), Cn, Q, D, _ptr(packed), _ptr(gsum), _ptr(adj), _ptr(grad)) == packed.size
     pt = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     loss = 0.0
     xt = [torch.tensor(x) for x in xs]
@@ -170,7 +165,7 @@ def test_component_table_and_chain_rule_of_the_next_families(explib, name):
 @pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
 def test_oracle_step_of_the_next_families_matches_the_reference(name):
     """LML, gradients w.r.t. the constrained parameters and predictions of the reference's gpr.Exact on these kernels
-    (fixtures from the live reference) against the oracle restatement -- the parity target of the round-2 GPU path."""
+    (fixtures from the live reference) against the oracle restatement -- the parity target of the GPU path (tests/test_gpu_parity.py::test_further_kernel_families_match_the_reference)."""
     orc = nk.register()
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     kind, C_, p, X, rows, K = _load(name)
