@@ -49,113 +49,111 @@ def use_gpu(n=None):
 
 
 # --------------------------------------------------------------------------------------
-# transforms + Parameter  (gpr/parameter.py:30-346)
+# constrained parameters
 # --------------------------------------------------------------------------------------
-class Softplus:
-    """y = lower + log(1 + exp(beta x)) / beta  (gpr/parameter.py:30-59)."""
-
-    def __init__(self, lower=0.0, beta=0.1, threshold=20.0):
-        self.lower, self.beta, self.threshold = lower, beta, threshold
-
-    def forward(self, x):
-        return self.lower + torch.nn.functional.softplus(x, beta=self.beta, threshold=self.threshold)
-
-    def inverse(self, y):
-        if self.beta < 0.0:
-            if torch.any(self.lower < y):
-                raise ValueError("values must be smaller than %s" % self.lower)
-        elif torch.any(y < self.lower):
-            raise ValueError("values must be greater than %s" % self.lower)
-        # the reference's expression (parameter.py:59): note -beta*y - lower, kept for parity
-        return (y - self.lower) + torch.log(-torch.expm1(-self.beta * y - self.lower)) / self.beta
+# What the engine needs from a hyper-parameter is small: the unconstrained leaf tensor the optimiser updates, the box
+# (lower, upper) that defines its constraint, and which of the three maps of mogp_param_entry (identity / softplus /
+# sigmoid, include/mogp_b200.h) turns one into the other.  `Constraint` is that description plus its torch form for
+# the autograd path; `Parameter` is a leaf tensor carrying one, with the reference's user-facing behaviour
+# (gpr/parameter.py:99-346: p() is the constrained value, assign() stores the unconstrained one, names, pegging,
+# priors, pickling) because mogptk.Model and the tests drive it exactly like the reference's class.
+_META = ("_name", "lower", "upper", "prior", "train", "pegged_parameter", "pegged_transform", "num_parameters")
 
 
-class Sigmoid:
-    """y = lower + (upper - lower) sigmoid(x)  (gpr/parameter.py:61-96)."""
+def _fit_shape(t, shape, what):
+    """Add / drop trailing singleton axes until `t` has `shape` (scalars broadcast)."""
+    if t.ndim == 0:
+        return t
+    orig = tuple(t.shape)
+    while t.ndim < len(shape) and shape[t.ndim] == 1:
+        t = t.unsqueeze(-1)
+    while t.ndim > len(shape) and t.shape[-1] == 1:
+        t = t.squeeze(-1)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: %s != %s" % (what, orig, tuple(shape)))
+    return t
 
-    def __init__(self, lower=0.0, upper=1.0):
+
+class Constraint:
+    """Box constraint of a parameter and the smooth map onto it.
+
+    kind       map (unconstrained x -> constrained y)                         C-ABI entry type
+    identity   y = x                                                          0
+    softplus   y = b + log(1 + exp(beta x)) / beta, beta = +0.1 (lower bound  1
+               b) or -0.1 (upper bound b), linear beyond beta x > 20
+    sigmoid    y = lower + (upper - lower) / (1 + exp(-x))                    2
+    """
+
+    def __init__(self, lower=None, upper=None):
         self.lower, self.upper = lower, upper
+        self.threshold = 20.0
+        if lower is not None and upper is not None:
+            if torch.any(upper < lower):
+                raise ValueError("lower limit %s must be lower than upper limit %s" % (lower, upper))
+            self.kind, self.beta, self.offset = "sigmoid", None, lower
+        elif lower is not None or upper is not None:
+            self.kind = "softplus"
+            self.beta, self.offset = (0.1, lower) if lower is not None else (-0.1, upper)
+        else:
+            self.kind, self.beta, self.offset = "identity", None, None
+
+    def engine_entry(self):
+        """(type, beta, lower, upper) of mogp_param_entry."""
+        if self.kind == "identity":
+            return 0, 0.0, None, None
+        if self.kind == "softplus":
+            return 1, self.beta, self.offset, None
+        return 2, 0.0, self.lower, self.upper
 
     def forward(self, x):
+        if self.kind == "identity":
+            return x
+        if self.kind == "softplus":
+            return self.offset + torch.nn.functional.softplus(x, beta=self.beta, threshold=self.threshold)
         return self.lower + (self.upper - self.lower) * torch.sigmoid(x)
 
     def inverse(self, y):
+        """Unconstrained value stored for a requested constrained value.  For the softplus map this follows the
+        reference's expression (gpr/parameter.py:59, `-beta*y - lower` inside the expm1), which is not an exact
+        inverse: assign(1.0) reads back 1.0000000995 there and must do so here."""
+        if self.kind == "identity":
+            return y
+        if self.kind == "softplus":
+            outside = (self.offset < y) if self.beta < 0.0 else (y < self.offset)
+            if torch.any(outside):
+                raise ValueError("values must be %s than %s" % ("smaller" if self.beta < 0.0 else "greater", self.offset))
+            return (y - self.offset) + torch.log(-torch.expm1(-self.beta * y - self.offset)) / self.beta
         if torch.any(y < self.lower) or torch.any(self.upper < y):
             raise ValueError("values must be between %s and %s" % (self.lower, self.upper))
-        s = (y - self.lower) / (self.upper - self.lower)
-        lo = torch.as_tensor(self.lower, dtype=s.dtype, device=s.device).expand_as(s)
-        up = torch.as_tensor(self.upper, dtype=s.dtype, device=s.device).expand_as(s)
-        s = torch.where(torch.isclose(lo, up), torch.full_like(s, sys.float_info.epsilon), s)
-        return torch.log(s) - torch.log(1 - s)
+        frac = (y - self.lower) / (self.upper - self.lower)
+        degenerate = torch.isclose(torch.as_tensor(self.lower, dtype=frac.dtype, device=frac.device).expand_as(frac),
+                                   torch.as_tensor(self.upper, dtype=frac.dtype, device=frac.device).expand_as(frac))
+        frac = torch.where(degenerate, torch.full_like(frac, sys.float_info.epsilon), frac)
+        return torch.log(frac) - torch.log1p(-frac)
 
-
-def _bound(b, like):
-    if b is None:
-        return None
-    if not isinstance(b, torch.Tensor):
-        b = torch.tensor(b, device=config.device, dtype=config.dtype)
-    else:
-        b = b.detach().to(config.device, config.dtype)
-    if b.ndim != 0:
-        while b.ndim < like.ndim and like.shape[b.ndim] == 1:
-            b = b.unsqueeze(-1)
-        while like.ndim < b.ndim and b.shape[-1] == 1:
-            b = b.squeeze(-1)
-        if b.shape != like.shape:
-            raise ValueError("bound and value must match shapes: %s != %s" % (b.shape, like.shape))
-    return b
+    def clip(self, y):
+        if self.lower is not None:
+            y = torch.maximum(y, self.lower.to(y.dtype) * torch.ones_like(y))
+        if self.upper is not None:
+            y = torch.minimum(y, self.upper.to(y.dtype) * torch.ones_like(y))
+        return y
 
 
 class Parameter(torch.nn.Parameter):
-    """Trainable parameter stored unconstrained; ``p()`` is the constrained value
-    (gpr/parameter.py:99-346).  The optimiser updates the raw leaf tensor, gradients
-    arrive in ``p.grad`` through torch autograd of the transform."""
+    """Leaf tensor in unconstrained space with its Constraint; ``p()`` / ``p.constrained`` is the constrained value."""
 
     def __new__(cls, value, name=None, lower=None, upper=None, prior=None, train=True):
-        value = Parameter.to_tensor(value)
-        self = super().__new__(cls, value)
-        self._name = name
-        self.lower = self.upper = None
-        self.prior = prior
-        self.train = train
-        self.pegged_parameter = self.pegged_transform = None
-        self.transform = None
-        self.num_parameters = int(np.prod(self.shape))
-        self.assign(value, lower=lower, upper=upper)
+        self = super().__new__(cls, Parameter.to_tensor(value))
+        self.__dict__.update(_name=name, lower=None, upper=None, prior=prior, train=train, pegged_parameter=None,
+                             pegged_transform=None, constraint=Constraint(), num_parameters=int(self.numel()))
+        self.assign(self.data, lower=lower, upper=upper)
         return self
 
-    def __repr__(self):
-        vals = self.constrained.tolist()
-        return "{}".format(vals) if self._name is None else "{}={}".format(self._name, vals)
-
-    def __call__(self):
-        return self.constrained
-
-    def _copy_meta(self, other):
-        for k in ("_name", "lower", "upper", "prior", "train", "pegged_parameter", "pegged_transform", "num_parameters"):
-            setattr(other, k, getattr(self, k))
-        other.transform = Parameter.to_transform(self.lower, self.upper)
-
-    def __deepcopy__(self, memo):
-        out = torch.nn.Parameter(self.data.clone(memory_format=torch.preserve_format), self.requires_grad)
-        out.__class__ = self.__class__
-        self._copy_meta(out)
-        memo[id(self)] = out
-        return out
-
-    def __reduce_ex__(self, proto):
-        parent = super().__reduce_ex__(proto)
-        return (Parameter._rebuild, (parent[0], parent[1], self._name, self.lower, self.upper, self.prior, self.train,
-                                     self.pegged_parameter, self.pegged_transform, self.num_parameters))
-
-    @staticmethod
-    def _rebuild(call, args, name, lower, upper, prior, train, pegged_parameter, pegged_transform, num_parameters):
-        out = call(*args)
-        out.__class__ = Parameter
-        out._name, out.lower, out.upper, out.prior, out.train = name, lower, upper, prior, train
-        out.pegged_parameter, out.pegged_transform, out.num_parameters = pegged_parameter, pegged_transform, num_parameters
-        out.transform = Parameter.to_transform(lower, upper)
-        return out
+    # -- value ---------------------------------------------------------------------------
+    @property
+    def transform(self):
+        """The reference exposes ``transform`` (None when unconstrained); kept for code written against it."""
+        return None if self.constraint.kind == "identity" else self.constraint
 
     @property
     def pegged(self):
@@ -163,13 +161,22 @@ class Parameter(torch.nn.Parameter):
 
     @property
     def constrained(self):
-        if self.pegged:
-            other = self.pegged_parameter.constrained
-            return self.pegged_transform(other) if self.pegged_transform is not None else other
-        return self.transform.forward(self) if self.transform is not None else self
+        if self.pegged_parameter is not None:
+            src = self.pegged_parameter.constrained
+            return src if self.pegged_transform is None else self.pegged_transform(src)
+        return self.constraint.forward(self)
+
+    __call__ = lambda self: self.constrained
 
     def numpy(self):
         return self.constrained.detach().cpu().numpy()
+
+    def __repr__(self):
+        vals = self.constrained.tolist()
+        return "%s" % (vals,) if self._name is None else "%s=%s" % (self._name, vals)
+
+    def log_prior(self):
+        return 0.0 if self.prior is None else self.prior.log_prob(self()).sum()
 
     @staticmethod
     def to_tensor(value):
@@ -179,52 +186,38 @@ class Parameter(torch.nn.Parameter):
             return value.detach().to(config.device, config.dtype)
         return torch.tensor(np.array(value), device=config.device, dtype=config.dtype)
 
-    @staticmethod
-    def to_transform(lower, upper):
-        if lower is not None and upper is not None:
-            if torch.any(upper < lower):
-                raise ValueError("lower limit %s must be lower than upper limit %s" % (lower, upper))
-            return Sigmoid(lower=lower, upper=upper)
-        if lower is not None:
-            return Softplus(lower=lower)
-        if upper is not None:
-            return Softplus(lower=upper, beta=-0.1)
-        return None
+    # -- assignment ----------------------------------------------------------------------
+    def _bound(self, b, current, like):
+        if b is None:
+            return current
+        b = b.detach().to(config.device, config.dtype) if torch.is_tensor(b) else \
+            torch.tensor(b, device=config.device, dtype=config.dtype)
+        return _fit_shape(b, like.shape, "bound and value must match shapes")
 
     def assign(self, value=None, name=None, lower=None, upper=None, prior=None, train=None):
-        """Assign a constrained value and/or new bounds (gpr/parameter.py:232-319).  As in the
-        reference, passing bounds without a value re-interprets the stored raw tensor as the
-        constrained value."""
-        if value is not None:
-            value = Parameter.to_tensor(value)
-            orig = value.shape
-            while value.ndim < self.ndim and self.shape[value.ndim] == 1:
-                value = value.unsqueeze(-1)
-            while self.ndim < value.ndim and value.shape[-1] == 1:
-                value = value.squeeze(-1)
-            if value.shape != self.shape:
-                raise ValueError("parameter shape must match: %s != %s" % (orig, self.shape))
-        else:
+        """Store the unconstrained image of a constrained `value` and / or change the box, name, prior, train flag.
+        Two behaviours of the reference are load-bearing and kept: values outside the box are clipped onto it, and
+        changing the bounds WITHOUT a value re-reads the stored unconstrained tensor as if it were the constrained
+        value (gpr/parameter.py:232-319; this is what narrows `mean` in mogptk.MOSM's constructor)."""
+        if value is None:
             value = self.data
-        lower = _bound(lower, value) if lower is not None else self.lower
-        upper = _bound(upper, value) if upper is not None else self.upper
-        if name is not None and self._name is not None and "." in self._name:
-            name = self._name[:self._name.rfind(".") + 1] + name
-        transform = Parameter.to_transform(lower, upper)
-        if transform is not None:
-            if lower is not None:
-                value = torch.where(value < lower, lower * torch.ones_like(value), value)
-            if upper is not None:
-                value = torch.where(upper < value, upper * torch.ones_like(value), value)
-            value = transform.inverse(value)
-        value.requires_grad = True
-        self._name = name if name is not None else self._name
-        self.data = value
-        self.lower, self.upper, self.transform = lower, upper, transform
-        self.prior = prior if prior is not None else self.prior
-        if train is None:
-            train = True if self.pegged else self.train
-        self.train = train
+        else:
+            value = Parameter.to_tensor(value)
+            if value.ndim != 0 or self.ndim == 0:
+                value = _fit_shape(value, self.shape, "parameter shape must match") if value.ndim else value
+            if value.shape != self.shape:
+                raise ValueError("parameter shape must match: %s != %s" % (tuple(value.shape), tuple(self.shape)))
+        box = Constraint(self._bound(lower, self.lower, value), self._bound(upper, self.upper, value))
+        raw = box.inverse(box.clip(value)) if box.kind != "identity" else value
+        raw.requires_grad = True
+        self.data = raw
+        self.lower, self.upper, self.constraint = box.lower, box.upper, box
+        if name is not None:
+            head = self._name[:self._name.rfind(".") + 1] if self._name is not None and "." in self._name else ""
+            self._name = head + name
+        if prior is not None:
+            self.prior = prior
+        self.train = (True if self.pegged else self.train) if train is None else train
         self.pegged_parameter = self.pegged_transform = None
 
     def peg(self, other, transform=None):
@@ -234,8 +227,25 @@ class Parameter(torch.nn.Parameter):
             raise ValueError("cannot peg parameter to another pegged parameter")
         self.pegged_parameter, self.pegged_transform, self.train = other, transform, False
 
-    def log_prior(self):
-        return 0.0 if self.prior is None else self.prior.log_prob(self()).sum()
+    # -- copies / pickles ------------------------------------------------------------------
+    def _meta(self):
+        return {k: getattr(self, k) for k in _META}
+
+    @staticmethod
+    def _restore(data, requires_grad, meta):
+        out = torch.nn.Parameter(data, requires_grad)
+        out.__class__ = Parameter
+        out.__dict__.update(meta)
+        out.constraint = Constraint(meta["lower"], meta["upper"])
+        return out
+
+    def __deepcopy__(self, memo):
+        out = Parameter._restore(self.data.clone(memory_format=torch.preserve_format), self.requires_grad, self._meta())
+        memo[id(self)] = out
+        return out
+
+    def __reduce_ex__(self, proto):
+        return Parameter._restore, (self.data, self.requires_grad, self._meta())
 
 
 class _Named(torch.nn.Module):
@@ -882,17 +892,25 @@ class Exact(_Named):
             e.lower_n = e.upper_n = 0
             e.type, e.beta = 0, 0.0
             if t is not None:
-                name = t.__class__.__name__
-                if name == "Softplus" and getattr(t, "threshold", 20.0) == 20.0:
-                    lo = dev(t.lower, q.data)
+                if hasattr(t, "engine_entry"):                   # mogptk_b200.gpr.Constraint
+                    typ, beta, lo_b, up_b = t.engine_entry()
+                else:                                            # the reference's transform objects (gpr/parameter.py:30-96)
+                    name = t.__class__.__name__
+                    if name == "Softplus" and getattr(t, "threshold", 20.0) == 20.0:
+                        typ, beta, lo_b, up_b = 1, float(t.beta), t.lower, None
+                    elif name == "Sigmoid":
+                        typ, beta, lo_b, up_b = 2, 0.0, t.lower, t.upper
+                    else:
+                        return None
+                e.type, e.beta = typ, float(beta)
+                if lo_b is not None:
+                    lo = dev(lo_b, q.data)
                     keep.append(lo)
-                    e.type, e.beta, e.lower, e.lower_n = 1, float(t.beta), lo.data_ptr(), lo.numel()
-                elif name == "Sigmoid":
-                    lo, up = dev(t.lower, q.data), dev(t.upper, q.data)
-                    keep += [lo, up]
-                    e.type, e.lower, e.lower_n, e.upper, e.upper_n = 2, lo.data_ptr(), lo.numel(), up.data_ptr(), up.numel()
-                else:
-                    return None
+                    e.lower, e.lower_n = lo.data_ptr(), lo.numel()
+                if up_b is not None:
+                    up = dev(up_b, q.data)
+                    keep.append(up)
+                    e.upper, e.upper_n = up.data_ptr(), up.numel()
             off += q.numel()
         P = off - C_
         n = 2 + P + C_

@@ -128,7 +128,7 @@ def test_sigmoid_bounded_parameter_on_the_device_path(gpr):
     g = load_golden("mosm_small")
     m, plist = build(gpr, g)
     m.kernel.mean.assign(m.kernel.mean().detach(), upper=torch.full_like(m.kernel.mean().detach(), 5.0))
-    assert m.kernel.mean.transform.__class__.__name__ == "Sigmoid"
+    assert m.kernel.mean.transform.kind == "sigmoid"
     la = m.loss()
     ga = m.kernel.mean.grad.clone()
     m._fast_table = lambda: None

@@ -63,7 +63,7 @@ def test_parameter_semantics():
     with pytest.raises(ValueError):
         p.assign(torch.ones(3))
     p.assign(upper=5.0)                                         # bounds-only assign re-reads the raw tensor
-    assert p.transform.__class__.__name__ == "Sigmoid"
+    assert p.transform.kind == "sigmoid"
     q = pickle.loads(pickle.dumps(p))
     assert torch.equal(q.data, p.data) and q._name == p._name and float(q.upper) == 5.0
     k = gpr.MultiOutputSpectralMixtureKernel(Q=2, output_dims=1)
