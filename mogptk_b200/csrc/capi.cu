@@ -299,9 +299,20 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
     g_i8_min_np = min_np; g_i8_slices = slices; ++g_mogp_cfg_epoch;
     return 0;
 }
+long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 8192;
+extern "C" int mogp_set_i8_potrf_min(long long np) { g_i8_potrf_min = np; ++g_mogp_cfg_epoch; return 0; }
 // smallest doubling-level block size of the triangular inverse that runs on the int8 pipe (0 = none)
 extern "C" int mogp_set_i8_trtri_min(long long rows) { g_i8_trtri_min = rows; ++g_mogp_cfg_epoch; return 0; }
 static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }
+// host-side preparation of the int8 path for a padded size (never inside capture); invalidates captured graphs when the
+// tile lists had to be rebuilt (another size / leading dimension / slice count used this handle in between)
+static int i8_ready(mogp_handle_s* h, int64_t Np, long long ld, cudaStream_t st) {
+    if (!h->i8) h->i8 = i8_plan_create();
+    bool changed = false;
+    MOGP_CHECK(h, i8_prepare(h->i8, Np, ld, g_i8_slices, st, &changed));
+    if (changed) h->realloc_epoch++;
+    return 0;
+}
 static cudaError_t kinv_dispatch(mogp_handle_s* h, int64_t Np, long long ld, cudaStream_t st) {
     if (use_i8(Np) && h->i8) return i8_kinv(h->i8, h->Linv, h->W, Np, ld, g_i8_slices, st);
     return kinv_padded(h->Linv, h->W, Np, ld, nullptr, st);
@@ -317,11 +328,17 @@ extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda
     const int64_t Np = round_up(n, MOGP_PAD);
     if (zero_linv_for(h, Np, st)) return -2;
     h->have_factor = false;
-    if (n == Np && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(A_dev) % 16) == 0) {
-        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps));
+    const bool direct = n == Np && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(A_dev) % 16) == 0;
+    // int8 trailing updates (large n) only for the handle's standard leading dimension: one set of tile lists per handle
+    const bool i8 = use_i8(Np) && (!direct || lda == Np);
+    if (i8 && i8_ready(h, Np, Np, st)) return -2;
+    if (direct) {
+        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps, nullptr,
+                                   i8 ? h->i8 : nullptr, g_i8_slices));
     } else {
         MOGP_CHECK(h, launch_copy_tri(0, A_dev, lda, h->A, Np, n, Np, st));
-        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps));
+        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps, nullptr,
+                                   i8 ? h->i8 : nullptr, g_i8_slices));
         MOGP_CHECK(h, launch_copy_tri(1, A_dev, lda, h->A, Np, n, Np, st));
     }
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -336,12 +353,10 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     H_ARG(h, n % MOGP_PAD == 0 && n <= h->np_max, "n must be a multiple of 128 within max_n");
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
     const bool i8 = use_i8(n);           // same dispatch as the fused step (int8 tensor pipe for large n)
-    if (i8) {
-        if (!h->i8) h->i8 = i8_plan_create();
-        MOGP_CHECK(h, i8_prepare(h->i8, n, n, g_i8_slices, st));
-    }
+    if (i8 && i8_ready(h, n, n, st)) return -2;
     bool fused_inverse = false;
-    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse,
+                               i8 ? h->i8 : nullptr, g_i8_slices));
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st, i8 ? h->i8 : nullptr, g_i8_slices));
     if (i8) MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
     else MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
@@ -394,7 +409,8 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     STAGE_MARK();
     // (with the pipelined inverse the GEMMs of Linv = L^-1 are issued behind the panel chain, inside potrf_padded)
     bool fused_inverse = false;
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps, &fused_inverse));
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps, &fused_inverse,
+                               use_i8(Np) ? h->i8 : nullptr, g_i8_slices));
     STAGE_MARK();
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st, use_i8(Np) ? h->i8 : nullptr, g_i8_slices));
@@ -470,10 +486,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
         const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * comp_stride(D);
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
     }
-    if (want_grad && use_i8(Np)) {
-        if (!h->i8) h->i8 = i8_plan_create();
-        MOGP_CHECK(h, i8_prepare(h->i8, Np, Np, g_i8_slices, st));
-    }
+    if (use_i8(Np) && i8_ready(h, Np, Np, st)) return -2;
     const size_t nout = 2 + (size_t)s.P + C;
     const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;
     if (ensure(h, h->gbuf, h->gbuf_cap, stage_need)) return -2;

@@ -204,7 +204,7 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 // *fused_inverse tells whether Linv is complete (true) or trtri_padded still has to run (false).
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
-                         bool* fused_inverse = nullptr);
+                         bool* fused_inverse = nullptr, I8Plan* i8 = nullptr, int i8_slices = 7);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st,
                          I8Plan* i8 = nullptr, int i8_slices = 7);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
@@ -225,11 +225,16 @@ struct I8Plan;
 I8Plan* i8_plan_create();
 void i8_plan_destroy(I8Plan* p);
 // host-side preparation (allocation, tile lists) for a given padded size / leading dimension: call outside graph capture
-cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st);
+// (*changed = true when the device-side tile lists were rebuilt: graphs that replay the old ones are stale)
+cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st, bool* changed = nullptr);
 // one doubling level (block size S_ rows) of Linv = L^-1; cudaErrorNotSupported -> run the DMMA GEMMs instead
 cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scratch, int64_t Np, long long ld, int64_t S_,
                            int S, cudaStream_t st);
 extern long long g_i8_trtri_min;
+// rank-256 trailing update of the blocked Cholesky (see i8mm.cu); smallest padded size that uses it (0 = never)
+cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
+                           cudaStream_t st);
+extern long long g_i8_potrf_min;
 // W(lower tiles) = Linv^T Linv via tcgen05.mma kind::i8 (S digit planes of 7 bits); pure enqueue
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st);
 // Smallest padded size that takes the int8 path (0 = never) and the number of digit planes (7 or 8)

@@ -31,6 +31,7 @@
 #define I8_STAGES 4
 #define I8_SMAX 8
 #define I8_BITS 7
+#define I8_PANEL 256       // width of the Cholesky outer panel whose trailing update runs here (MOGP_NB_OUT)
 
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -296,12 +297,18 @@ struct I8Operand {                 // a sliced operand in device memory
 };
 struct I8List { size_t first = 0, count = 0; };
 struct I8Plan {
-    I8Operand opA, opB;
+    I8Operand opA, opB, opP;                 // opP: the 256-column panel of the blocked Cholesky
     I8Tile* tiles = nullptr; size_t tiles_cap = 0;
     std::vector<I8Tile> host_tiles;          // all tile lists back to back
     I8List kinv;                             // K^-1 = L^-T L^-1
     std::vector<I8List> lvl_a, lvl_b;        // per doubling level (index = log2 of the block size in 64-blocks): the two GEMMs
+    // trailing update of the blocked Cholesky, coordinates relative to the first row below the outer panel: master lists
+    // ordered by row tile, so that the list for a smaller trailing matrix is a prefix (prefix counts per row-tile count)
+    I8List syrk_a, syrk_b;
+    std::vector<size_t> syrk_a_count, syrk_b_count;
     long long tiles_key = -1;
+    int64_t Np = 0; long long ld = 0; int S = 0;     // what the lists were built for
+    bool ready(int64_t Np_, long long ld_, int S_) const { return tiles_key >= 0 && Np == Np_ && ld == ld_ && S == S_; }
 };
 
 static cudaError_t i8_reserve(I8Operand& op, int R, int K, int S) {
@@ -377,7 +384,7 @@ static cudaError_t i8_upload_tiles(I8Plan& p, cudaStream_t st) {
 I8Plan* i8_plan_create() { return new I8Plan(); }
 void i8_plan_destroy(I8Plan* p) {
     if (!p) return;
-    for (I8Operand* op : {&p->opA, &p->opB}) {
+    for (I8Operand* op : {&p->opA, &p->opB, &p->opP}) {
         if (op->digits) cudaFree(op->digits);
         if (op->ex_bits) cudaFree(op->ex_bits);
         if (op->ex) cudaFree(op->ex);
@@ -394,12 +401,15 @@ static bool i8_level_ok(int64_t Np, int64_t S) {
 }
 
 // Host-side preparation (allocations, tile lists) for a given padded size: never inside graph capture.
-cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st) {
+cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t st, bool* changed) {
+    if (changed) *changed = false;
     cudaError_t e = i8_reserve(p->opA, (int)Np, (int)Np, S);
     if (e != cudaSuccess) return e;
     if ((e = i8_reserve(p->opB, (int)Np, (int)(Np / 2), S)) != cudaSuccess) return e;
     const long long key = (Np * 16 + S) * 65536 + g_i8_trtri_min % 65536 + ld * 1000003ll;
     if (p->tiles_key == key) return cudaSuccess;
+    if (changed) *changed = true;            // captured graphs that replay the old lists must be re-captured
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;      // nothing may still read the lists being replaced
     p->host_tiles.clear();
     p->lvl_a.assign(32, I8List());
     p->lvl_b.assign(32, I8List());
@@ -436,17 +446,55 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
                 }
         p->lvl_b[lev].count = p->host_tiles.size() - p->lvl_b[lev].first;
     }
+    // trailing updates C -= P P^T (K = 256): (a) the 256 columns of the next outer panel, (b) the rest (both lower tiles)
+    if ((e = i8_reserve(p->opP, (int)Np, I8_PANEL, S)) != cudaSuccess) return e;
+    const int ntm = (int)(Np / I8_TM);
+    p->syrk_a.first = p->host_tiles.size();
+    p->syrk_a_count.assign(ntm + 1, 0);
+    for (int tm = 0; tm < ntm; ++tm) {
+        for (int tn = 0; tn < I8_PANEL / I8_TN && tn * I8_TN < (tm + 1) * I8_TM; ++tn)
+            p->host_tiles.push_back({tm * I8_TM, tn * I8_TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * I8_TN});
+        p->syrk_a_count[tm + 1] = p->host_tiles.size() - p->syrk_a.first;
+    }
+    p->syrk_a.count = p->host_tiles.size() - p->syrk_a.first;
+    p->syrk_b.first = p->host_tiles.size();
+    p->syrk_b_count.assign(ntm + 1, 0);
+    for (int tm = 0; tm < ntm; ++tm) {
+        for (int tn = I8_PANEL / I8_TN; tn * I8_TN < (tm + 1) * I8_TM; ++tn)
+            p->host_tiles.push_back({tm * I8_TM, tn * I8_TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * I8_TN});
+        p->syrk_b_count[tm + 1] = p->host_tiles.size() - p->syrk_b.first;
+    }
+    p->syrk_b.count = p->host_tiles.size() - p->syrk_b.first;
     e = i8_upload_tiles(*p, st);
     if (e != cudaSuccess) return e;
     p->tiles_key = key;
+    p->Np = Np; p->ld = ld; p->S = S;
     return cudaStreamSynchronize(st);
+}
+
+// Rank-256 trailing update of the blocked Cholesky on the int8 pipe: with P = A[r0 .. Np) x [k0, k0 + 256) (the finished
+// outer panel below its diagonal block), part 0 slices P and updates the next outer panel's 256 columns
+// A[r0.., r0 .. r0+256) -= P P^T (lower tiles), part 1 updates the rest A[r0+256.., r0+256..) -= P P^T (lower tiles).
+// r0 a multiple of 256.  Pure enqueue; cudaErrorNotSupported when this size is not prepared.
+cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
+                           cudaStream_t st) {
+    if (!p || (r0 % I8_PANEL) != 0) return cudaErrorNotSupported;
+    if (!p->ready(Np, ld, S) || p->syrk_a.count == 0) return cudaErrorInvalidValue;
+    const int M = (int)(Np - r0), ntm = M / I8_TM;
+    cudaError_t e;
+    if (part == 0) {
+        if ((e = i8_slice(p->opP, A + r0 * ld + k0, ld, 1, 0, 1, M, I8_PANEL, S, 0, st)) != cudaSuccess) return e;
+        return i8_launch(p->opP, p->opP, p->tiles + p->syrk_a.first, (int)p->syrk_a_count[ntm], S, -1.0, 1.0,
+                         A + r0 * (ld + 1), ld, st);
+    }
+    return i8_launch(p->opP, p->opP, p->tiles + p->syrk_b.first, (int)p->syrk_b_count[ntm], S, -1.0, 1.0, A + r0 * (ld + 1), ld, st);
 }
 
 // W(lower tiles) = Linv^T Linv with Linv lower triangular (zero above the diagonal): K^-1 of the factorised matrix.
 // Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
 // (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_prepare.
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
-    if (p->tiles_key < 0 || p->kinv.count == 0) return cudaErrorInvalidValue;
+    if (!p->ready(Np, ld, S) || p->kinv.count == 0) return cudaErrorInvalidValue;      // i8_prepare was not run for this size
     cudaError_t e = i8_slice(p->opA, Linv, 1, ld, 0, 1, (int)Np, (int)Np, S, 1, st);
     if (e != cudaSuccess) return e;
     return i8_launch(p->opA, p->opA, p->tiles + p->kinv.first, (int)p->kinv.count, S, 1.0, 0.0, W, ld, st);
@@ -456,7 +504,8 @@ cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long l
 // is not eligible (the caller then runs the DMMA GEMMs).  scratch receives T = L_BA Linv_AA (as in trtri_padded).
 cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scratch, int64_t Np, long long ld, int64_t S_,
                            int S, cudaStream_t st) {
-    if (!p || p->tiles_key < 0 || !i8_level_ok(Np, S_)) return cudaErrorNotSupported;
+    if (!p || !i8_level_ok(Np, S_)) return cudaErrorNotSupported;
+    if (!p->ready(Np, ld, S)) return cudaErrorInvalidValue;
     int lev = 0;
     for (int64_t x = 64; x < S_; x *= 2) ++lev;
     if (p->lvl_a[lev].count == 0) return cudaErrorNotSupported;

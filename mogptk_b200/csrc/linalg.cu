@@ -1028,7 +1028,7 @@ extern "C" int mogp_set_trtri_pipe(int v) { g_trtri_pipe = v; ++g_mogp_cfg_epoch
 
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
-                         bool* fused_inverse) {
+                         bool* fused_inverse, I8Plan* i8, int i8_slices) {
     if (fused_inverse) *fused_inverse = false;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
@@ -1203,6 +1203,22 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 if ((e = cudaStreamWaitEvent(s2, ps->ev1[J + 1], 0)) != cudaSuccess) return e;
             }
             const int64_t W2 = std::min<int64_t>(MOGP_NB_OUT, Np - Kend);
+            if (i8 && g_i8_potrf_min > 0 && Np >= g_i8_potrf_min && Wd == MOGP_NB_OUT && W2 == MOGP_NB_OUT &&
+                (Np - Kend) % 128 == 0) {
+                // the rank-256 update on the int8 tensor pipe (i8mm.cu): same split, same events
+                cudaError_t e8 = i8_syrk_update(i8, A, ld, Kend, K0, Np, 0, i8_slices, s2);
+                if (e8 == cudaSuccess) {
+                    if (two && (e = cudaEventRecord(ps->ev2[2 * J], s2)) != cudaSuccess) return e;
+                    last = two ? ps->ev2[2 * J] : nullptr;
+                    if (Np - Kend - W2 > 0) {
+                        if ((e = i8_syrk_update(i8, A, ld, Kend, K0, Np, 1, i8_slices, s2)) != cudaSuccess) return e;
+                        if (two && (e = cudaEventRecord(ps->ev2[2 * J + 1], s2)) != cudaSuccess) return e;
+                        last = two ? ps->ev2[2 * J + 1] : nullptr;
+                    }
+                    continue;
+                }
+                if (e8 != cudaErrorNotSupported) return e8;
+            }
             {                                               // priority: columns of the next outer panel
                 GemmArgs u{};
                 u.A = A + Kend * ld + K0; u.lda = ld;

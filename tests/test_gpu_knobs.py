@@ -154,3 +154,41 @@ def test_int8_triangular_inverse_levels_equal_dmma(engine, n):
     R = K @ Kfull[:, cols]
     R[cols, torch.arange(cols.numel(), device=engine.device)] -= 1.0
     assert float(R.abs().max()) <= 1e-9
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_int8_trailing_updates_of_the_cholesky(engine, n):
+    """Blocked Cholesky with the rank-256 trailing updates on the int8 tensor pipe against the all-DMMA factorisation and
+    LAPACK (default on for n >= 8192; forced on at 4096 here)."""
+    import torch
+    torch.manual_seed(7)
+    B = torch.randn(n, n // 2, dtype=torch.float64, device=engine.device)
+    K = B @ B.T / n + 0.5 * torch.eye(n, dtype=torch.float64, device=engine.device)
+    del B
+    lib = engine.lib
+    try:
+        lib.mogp_set_i8(0, 7)
+        Ad = K.clone()
+        assert engine.potrf_(Ad) == 0
+        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8_potrf_min(4096)
+        A7 = K.clone()
+        assert engine.potrf_(A7) == 0
+    finally:
+        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8_potrf_min(8192)
+    ref = torch.linalg.cholesky(K)
+    scale = float(ref.abs().max())
+    assert float((torch.tril(Ad) - ref).abs().max()) <= 1e-11 * scale
+    assert float((torch.tril(A7) - ref).abs().max()) <= 1e-11 * scale
+    assert float((torch.tril(A7) - torch.tril(Ad)).abs().max()) <= 1e-11 * scale
+
+
+def test_int8_path_survives_alternating_problem_sizes(engine):
+    """One handle alternating between two sizes that both use the int8 path: the tile lists are rebuilt per size and the
+    captured step graphs of the other size are invalidated (they would replay stale lists otherwise)."""
+    ga, gb = load_golden("cfg4"), load_golden("cfg3")
+    for g in (ga, gb, ga, gb, ga):
+        for _ in range(3):                               # plain run, capture, replay
+            res = engine.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], True)
+            assert abs(res["lml"] - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
