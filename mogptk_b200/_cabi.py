@@ -75,6 +75,7 @@ _EXTRA = {
     "mogp_set_i8_potrf_min": (C.c_int, [C.c_longlong]),
     "mogp_i8_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mogp_set_graphs": (None, [C.c_int]),
+    "mogp_set_cov_minb": (C.c_int, [C.c_int]),
     "mogp_set_graph_max_np": (None, [C.c_longlong]),
     "mogp_test_fail_capture": (None, [C.c_int]),
     "mogp_set_small_tile_threshold": (None, [C.c_longlong]),

@@ -8,6 +8,7 @@
 // (cp.async.bulk + mbarrier); outputs are written with 16-byte vector stores.
 #include "covmath.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 #define RC 8   // components processed per shared-memory trig table
 
@@ -161,7 +162,9 @@ cudaError_t launch_prep(const KernSpec& s, const double* params, const double* s
 }
 
 // ------------------------------------------------------------------ shared tile machinery
-// Thread (ty, tx) of 256 owns rows ty + 16*i (i<4) and columns tx*4 + j (j<4) of the 64x64 tile.
+// Thread (ty, tx) of 256 owns rows ty + 16*i (i<4) and columns tx + 16*j (j<4) of the 64x64 tile: for a fixed j the 16
+// lanes of a half-warp read consecutive doubles of the per-column tables (conflict-free; the round-1 mapping tx*4 + j
+// put them 32 bytes apart: 4-way bank conflicts, 35 M per N = 8192 build) and write 128 contiguous bytes of an output row.
 struct TileSmem {
     double xa[MOGP_TILE * MOGP_MAX_D];
     double xb[MOGP_TILE * MOGP_MAX_D];
@@ -230,8 +233,8 @@ __device__ __forceinline__ void fill_tables(TileSmem& sm, const double* __restri
 // ------------------------------------------------------------------ kbuild
 // mode 0: Gram lower tiles into the padded factor buffer (+ padding rows);  mode 1: Gram, every
 // lower tile is also written transposed (full symmetric output);  mode 2: cross-covariance.
-template <int DT, bool COS>
-__global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* __restrict__ tiles, int ntiles, int mode,
+template <int DT, bool COS, int MINB>
+__global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const CovTile* __restrict__ tiles, int ntiles, int mode,
                                                      const double* __restrict__ comps, const double* __restrict__ chanbuf,
                                                      const double* __restrict__ x1, const double* __restrict__ x2,
                                                      const double* __restrict__ data_var, int add_diag,
@@ -274,14 +277,14 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* 
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                    if (d < D) xb[j][d] = sm.xb[(tx * 4 + j) * D + d];
+                    if (d < D) xb[j][d] = sm.xb[(tx + 16 * j) * D + d];
             for (int r = 0; r < nrc; ++r) {
                 const double* cp = sm.comp[r];
                 const double alpha = cp[0];
                 double cB[4], sB[4];
                 if (COS) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx * 4 + j]; sB[j] = sm.cs[r][tx * 4 + j]; }
+                    for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx + 16 * j]; sB[j] = sm.cs[r][tx + 16 * j]; }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* 
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int row = ty + 16 * i, col = tx * 4 + j;
+                const int row = ty + 16 * i, col = tx + 16 * j;
                 if (row == col && row < t.nr) {
                     double v = chanbuf[pi];
                     if (add_diag) {
@@ -326,47 +329,45 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernSpec s, const CovTile* 
             }
     }
 
-    const bool vec_ok = ((ldk & 1) == 0) && ((t.c0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = ty + 16 * i;
         if (row >= t.nr) continue;
-        double* dst = K + (long long)(t.r0 + row) * ldk + t.c0 + tx * 4;
-        const int colb = tx * 4;
-        if (vec_ok && colb + 3 < t.nc) {
-            reinterpret_cast<double2*>(dst)[0] = make_double2(acc[i][0], acc[i][1]);
-            reinterpret_cast<double2*>(dst)[1] = make_double2(acc[i][2], acc[i][3]);
-        } else {
+        double* dst = K + (long long)(t.r0 + row) * ldk + t.c0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (colb + j < t.nc) dst[j] = acc[i][j];
-        }
+        for (int j = 0; j < 4; ++j)
+            if (tx + 16 * j < t.nc) dst[tx + 16 * j] = acc[i][j];
     }
     if (mode == 1 && !(t.flags & 1)) {                // mirrored copy, transposed through shared memory
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tbuf[(ty + 16 * i) * 65 + tx * 4 + j] = acc[i][j];
+            for (int j = 0; j < 4; ++j) tbuf[(ty + 16 * i) * 65 + tx + 16 * j] = acc[i][j];
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int orow = ty + 16 * i;            // output row = original column
             if (orow >= t.nc) continue;
-            double* dst = K + (long long)(t.c0 + orow) * ldk + t.r0 + tx * 4;
+            double* dst = K + (long long)(t.c0 + orow) * ldk + t.r0;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (tx * 4 + j < t.nr) dst[j] = tbuf[(tx * 4 + j) * 65 + orow];
+                if (tx + 16 * j < t.nr) dst[tx + 16 * j] = tbuf[(tx + 16 * j) * 65 + orow];
         }
     }
 }
 
-template <int DT, bool COS>
+// resident CTAs per SM the covariance kernels are compiled for: 2 (125 registers, no spills) or 3 (80 registers, a few
+// spilled words); selectable at run time so that both can be measured (MOGP_COV_MINB / mogp_set_cov_minb)
+static int g_cov_minb = std::getenv("MOGP_COV_MINB") ? std::atoi(std::getenv("MOGP_COV_MINB")) : 2;
+extern "C" int mogp_set_cov_minb(int v) { g_cov_minb = v == 3 ? 3 : 2; ++g_mogp_cfg_epoch; return 0; }
+
+template <int DT, bool COS, int MINB>
 static cudaError_t launch_kbuild_t(const KernSpec& s, const TileList& tl, int nblocks, const double* comps,
                                    const double* chanbuf, const double* x1, const double* x2, const double* data_var,
                                    int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem) + 64 * 65 * sizeof(double);
-    auto kern = kbuild_kernel<DT, COS>;
+    auto kern = kbuild_kernel<DT, COS, MINB>;
     static PerDeviceOnce once;
     if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -384,12 +385,14 @@ cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* c
                           int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
     (void)chan1_dev;
     const int nblocks = tl.n + (tl.mode == 0 ? (int)(Np - N) : 0);
-    if (s.D == 1) {
-        if (s.has_cos) return launch_kbuild_t<1, true>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
-        return launch_kbuild_t<1, false>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+#define KB_ARGS s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st
+    if (g_cov_minb == 3) {
+        if (s.D == 1) return s.has_cos ? launch_kbuild_t<1, true, 3>(KB_ARGS) : launch_kbuild_t<1, false, 3>(KB_ARGS);
+        return s.has_cos ? launch_kbuild_t<0, true, 3>(KB_ARGS) : launch_kbuild_t<0, false, 3>(KB_ARGS);
     }
-    if (s.has_cos) return launch_kbuild_t<0, true>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
-    return launch_kbuild_t<0, false>(s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st);
+    if (s.D == 1) return s.has_cos ? launch_kbuild_t<1, true, 2>(KB_ARGS) : launch_kbuild_t<1, false, 2>(KB_ARGS);
+    return s.has_cos ? launch_kbuild_t<0, true, 2>(KB_ARGS) : launch_kbuild_t<0, false, 2>(KB_ARGS);
+#undef KB_ARGS
 }
 
 __global__ void kdiag_kernel(int C, const double* __restrict__ chanbuf, const int32_t* __restrict__ chan, long long N,
@@ -409,8 +412,8 @@ cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t
 
 // ------------------------------------------------------------------ grad_reduce
 // Per tile and component: [S0, S4, S1[D], S2[D], S3[D]] with the symmetric weight folded into W.
-template <int DT, bool COS>
-__global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovTile* __restrict__ tiles,
+template <int DT, bool COS, int MINB>
+__global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, const CovTile* __restrict__ tiles,
                                                           const double* __restrict__ comps, const double* __restrict__ x,
                                                           const double* __restrict__ W, long long ldw,
                                                           const double* __restrict__ avec,
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int row = ty + 16 * i, col = tx * 4 + j;
+            const int row = ty + 16 * i, col = tx + 16 * j;
             double v = 0.0;
             if (row < t.nr && col < t.nc) {
                 double wgt = 2.0;
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                if (d < D) xb[j][d] = sm.xb[(tx * 4 + j) * D + d];
+                if (d < D) xb[j][d] = sm.xb[(tx + 16 * j) * D + d];
         for (int r = 0; r < nrc; ++r) {
             const double* cp = sm.comp[r];
             double s0 = 0.0, s4 = 0.0;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(KernSpec s, const CovT
             double cB[4], sB[4];
             if (COS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx * 4 + j]; sB[j] = sm.cs[r][tx * 4 + j]; }
+                for (int j = 0; j < 4; ++j) { cB[j] = sm.cc[r][tx + 16 * j]; sB[j] = sm.cs[r][tx + 16 * j]; }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -549,7 +552,11 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
     if (tl.n <= 0) return cudaSuccess;
 #define LAUNCH_GR(DT, COS)                                                                                         \
     do {                                                                                                           \
-        auto kern = grad_reduce_kernel<DT, COS>;                                                                   \
+        if (g_cov_minb == 3) { LAUNCH_GR_M(DT, COS, 3); } else { LAUNCH_GR_M(DT, COS, 2); }                       \
+    } while (0)
+#define LAUNCH_GR_M(DT, COS, MB)                                                                                   \
+    do {                                                                                                           \
+        auto kern = grad_reduce_kernel<DT, COS, MB>;                                                               \
         static PerDeviceOnce once;                                                                                 \
         if (once.first()) {                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
@@ -561,6 +568,7 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
     if (s.D == 1) { if (s.has_cos) LAUNCH_GR(1, true); else LAUNCH_GR(1, false); }
     else { if (s.has_cos) LAUNCH_GR(0, true); else LAUNCH_GR(0, false); }
 #undef LAUNCH_GR
+#undef LAUNCH_GR_M
     return cudaGetLastError();
 }
 

