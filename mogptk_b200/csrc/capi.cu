@@ -305,6 +305,9 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
 // (profiles/r02_i8_potrf_updates.txt).  Kept selectable (tests cover it) for a later persistent-tile version.
 long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 0;
 extern "C" int mogp_set_i8_potrf_min(long long np) { g_i8_potrf_min = np; ++g_mogp_cfg_epoch; return 0; }
+extern int g_i8_ts;
+extern "C" int mogp_set_i8_ts(int on) { g_i8_ts = on ? 1 : 0; ++g_mogp_cfg_epoch; return 0; }
+extern "C" int mogp_get_i8_ts(void) { return g_i8_ts; }
 // smallest doubling-level block size of the triangular inverse that runs on the int8 pipe (0 = none)
 extern "C" int mogp_set_i8_trtri_min(long long rows) { g_i8_trtri_min = rows; ++g_mogp_cfg_epoch; return 0; }
 static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }

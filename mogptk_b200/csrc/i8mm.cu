@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #define I8_TM 128          // tile rows (UMMA M)
 #define I8_TN 64           // tile columns (UMMA N)
@@ -150,6 +151,17 @@ __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (lane = row, 8 columns = the 32 K bytes of one UMMA K step), B from shared memory
+__device__ __forceinline__ void i8_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bits described by a matrix descriptor
+__device__ __forceinline__ void i8_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(i8_smem_u32(bar)) : "memory");
 }
@@ -174,7 +186,13 @@ struct I8Args {
     double* C; long long ldc;
 };
 
-template <int S>
+// TS = true: the S digit planes of the A tile are first copied from shared into tensor memory (tcgen05.cp, 8 columns per
+// plane next to the accumulators: 7 * 64 + 7 * 8 = 504 of 512 columns at S = 7) and every MMA takes A from there.  With
+// both operands in shared memory (TS = false) an M = 128, N = 64, K = 32 MMA reads 6 KB of shared memory for 32 cycles of
+// math, i.e. 192 B/cycle against the ~128 B/cycle an SM's shared memory delivers -- together with the TMA writes that is
+// what held the first version at ~51 % of the int8 peak; from tensor memory the A plane is read from shared memory once
+// per K chunk instead of once per MMA.
+template <int S, bool TS>
 __global__ void __launch_bounds__(192, 1) i8_gemm_tiles_kernel(I8Args g) {
     extern __shared__ __align__(128) unsigned char i8_raw[];
     I8Smem& sm = *reinterpret_cast<I8Smem*>(i8_raw);
@@ -232,14 +250,30 @@ __global__ void __launch_bounds__(192, 1) i8_gemm_tiles_kernel(I8Args g) {
                 i8_mbar_wait(&sm.full[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = i8_smem_u32(&sm.a[stage][0][0][0][0]), b0 = i8_smem_u32(&sm.b[stage][0][0][0][0]);
+                if (TS) {
+                    // the tensor pipe executes tcgen05.cp and tcgen05.mma in issue order: these copies wait for the
+                    // previous chunk's MMAs (which read the same columns) and the MMAs below wait for the copies
+                    const uint32_t ta = tmem0 + (uint32_t)(S * I8_TN);
 #pragma unroll
-                for (int d = 0; d < S; ++d)
+                    for (int s = 0; s < S; ++s)
+                        i8_cp_128x256b(ta + (uint32_t)(s * 8), i8_desc(a0 + s * (2 * I8_TM * 16), I8_TM * 16, 128));
 #pragma unroll
-                    for (int s = 0; s <= d; ++s) {
-                        const uint64_t da = i8_desc(a0 + s * (2 * I8_TM * 16), I8_TM * 16, 128);
-                        const uint64_t db = i8_desc(b0 + (d - s) * (2 * I8_TN * 16), I8_TN * 16, 128);
-                        i8_mma(tmem0 + (uint32_t)(d * I8_TN), da, db, idesc, (i > 0 || s > 0) ? 1u : 0u);
-                    }
+                    for (int s = 0; s < S; ++s)
+#pragma unroll
+                        for (int t2 = 0; t2 < S - s; ++t2) {
+                            const uint64_t db = i8_desc(b0 + t2 * (2 * I8_TN * 16), I8_TN * 16, 128);
+                            i8_mma_ts(tmem0 + (uint32_t)((s + t2) * I8_TN), ta + (uint32_t)(s * 8), db, idesc, (i > 0 || s > 0) ? 1u : 0u);
+                        }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < S; ++d)
+#pragma unroll
+                        for (int s = 0; s <= d; ++s) {
+                            const uint64_t da = i8_desc(a0 + s * (2 * I8_TM * 16), I8_TM * 16, 128);
+                            const uint64_t db = i8_desc(b0 + (d - s) * (2 * I8_TN * 16), I8_TN * 16, 128);
+                            i8_mma(tmem0 + (uint32_t)(d * I8_TN), da, db, idesc, (i > 0 || s > 0) ? 1u : 0u);
+                        }
+                }
                 i8_commit(&sm.empty[stage]);                                  // stage free once these MMAs have read it
                 if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -348,13 +382,18 @@ static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long
     return cudaGetLastError();
 }
 
+// 1: A planes through tensor memory (S = 7 only: 8 planes do not fit beside 8 accumulators), 0: both operands from shared memory
+int g_i8_ts = std::getenv("MOGP_I8_TS") ? std::atoi(std::getenv("MOGP_I8_TS")) : 0;
+
 static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Tile* tiles_dev, int ntiles, int S, double alpha,
                              double beta, double* C, long long ldc, cudaStream_t st) {
     static PerDeviceOnce once;
     if (once.first()) {
-        cudaError_t e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
+        cudaError_t e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
+        e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
         if (e != cudaSuccess) return e;
     }
     if (ntiles <= 0) return cudaSuccess;
@@ -362,8 +401,9 @@ static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Til
     g.A = A.digits; g.ea = A.ex; g.nrtA = A.nrt;
     g.B = B.digits; g.eb = B.ex; g.nrtB = B.nrt;
     g.tiles = tiles_dev; g.S = S; g.alpha = alpha; g.beta = beta; g.C = C; g.ldc = ldc;
-    if (S == 7) i8_gemm_tiles_kernel<7><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
-    else if (S == 8) i8_gemm_tiles_kernel<8><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
+    if (S == 7 && g_i8_ts) i8_gemm_tiles_kernel<7, true><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
+    else if (S == 7) i8_gemm_tiles_kernel<7, false><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
+    else if (S == 8) i8_gemm_tiles_kernel<8, false><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
     else return cudaErrorInvalidValue;
     MOGP_COUNT(1);
     return cudaGetLastError();

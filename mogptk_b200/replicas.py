@@ -84,3 +84,36 @@ def barrier():
 def finish():
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ several replicas on ONE GPU
+# At BASELINE configs[1] (N = 2048) one evaluation is a latency chain: the Cholesky panel kernel occupies 46 of the 148
+# SMs and the GPU draws ~270 W of 1000 W.  Independent replicas (restarts, sweeps) therefore also stack on one GPU: each
+# gets its own workspace handle and CUDA stream, and their kernels interleave on the idle SMs.
+def train_restarts(models, iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, sync_every=64):
+    """Train independent mogptk_b200.gpr.Exact models concurrently on the current GPU with the device-resident Adam loop
+    (one host thread and one CUDA stream per model).  Returns the list of per-model loss histories."""
+    import threading
+
+    from .train import fit_adam
+    out = [None] * len(models)
+    errs = []
+
+    def work(i, m):
+        try:
+            stream = torch.cuda.Stream(device=m.X.device)
+            with torch.cuda.stream(stream):
+                out[i] = fit_adam(m, iters, lr=lr, betas=betas, eps=eps, sync_every=sync_every)[0]
+                stream.synchronize()
+        except BaseException as e:          # surfaced to the caller below
+            errs.append(e)
+
+    torch.cuda.synchronize()
+    threads = [threading.Thread(target=work, args=(i, m)) for i, m in enumerate(models)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out

@@ -84,14 +84,20 @@ def test_failed_graph_capture_falls_back_to_an_eager_run(engine, knobs):
 
 
 # ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (tcgen05.mma kind::i8)
+@pytest.mark.parametrize("ts", [0, 1])
 @pytest.mark.parametrize("M,N,K,S,tol", [(128, 128, 32, 7, 1e-12), (256, 384, 4096, 7, 1e-12), (1024, 1024, 1024, 8, 1e-13),
                                           (2048, 2048, 2048, 7, 1e-12)])
-def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol):
+def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol, ts):
     """A B^T from S signed 7-bit digit planes per operand (Ozaki slicing, exact int32 accumulation in TMEM) against the
     fp64 DMMA GEMM: relative to the largest entry the difference is ~1e-14 at S = 7 and ~fp64 rounding at S = 8."""
     import ctypes as C
     out = (C.c_double * 4)()
-    rc = engine.lib.mogp_i8_selftest(M, N, K, S, out)
+    default_ts = engine.lib.mogp_get_i8_ts()
+    try:
+        engine.lib.mogp_set_i8_ts(ts)          # A planes through tensor memory (S = 7) or both operands from shared memory
+        rc = engine.lib.mogp_i8_selftest(M, N, K, S, out)
+    finally:
+        engine.lib.mogp_set_i8_ts(default_ts)
     assert rc == 0
     assert 0.0 <= out[0] < tol, out[0]
 

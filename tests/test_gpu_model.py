@@ -157,3 +157,36 @@ def test_fused_adam_equals_loss_plus_torch_adam(gpr):
     mu_a, _ = a.predict_f(g["Xs"])
     mu_b, _ = b.predict_f(g["Xs"])                              # factor cache was invalidated by the in-place updates
     assert float((mu_a - mu_b).abs().max()) <= 1e-8 * float(mu_a.abs().max())
+
+
+def test_concurrent_restarts_on_one_gpu_equal_sequential_training(gpr):
+    """replicas.train_restarts: several models, each with its own handle / stream / host thread, train concurrently and end
+    exactly where they end when trained one after the other (bit-for-bit: the per-model arithmetic does not change)."""
+    from mogptk_b200 import fit_adam, replicas
+    from mogptk_b200.engine import Engine
+    g = load_golden("mosm_mid")
+    engines = [Engine(device=0, max_n=512) for _ in range(3)]
+    try:
+        seq, con = [], []
+        for i in range(3):
+            a, _ = build_with_engine(gpr, g, engines[i])
+            a.kernel.weight.data += 0.01 * i
+            seq.append(a)
+            b, _ = build_with_engine(gpr, g, engines[i])
+            b.kernel.weight.data += 0.01 * i
+            con.append(b)
+        ref = [fit_adam(m, 24, lr=0.02, sync_every=8)[0] for m in seq]
+        got = replicas.train_restarts(con, 24, lr=0.02, sync_every=8)
+        for r, h in zip(ref, got):
+            assert np.array_equal(r, h)
+        for a, b in zip(seq, con):
+            for p, q in zip(a.parameters(), b.parameters()):
+                assert torch.equal(p.data, q.data)
+    finally:
+        for e in engines:
+            e.close()
+
+
+def build_with_engine(gpr, g, engine):
+    from test_host_layer import build_mirror
+    return build_mirror(g, engine)
