@@ -458,6 +458,24 @@ def run_b200(args):
     h2d = 8 * (N * dims[2] + N)
     d2h = 16 + 8                                                      # [lml, info] read inside loss() + float(loss)
 
+    # the same loop with torch's fused Adam (model.train(method='Adam', fused=True) passes it through, mogptk/model.py:556)
+    opt_f = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+
+    def api_step_fused():
+        model._rows.x.copy_(xh, non_blocking=True)
+        model._rows.y.copy_(yh, non_blocking=True)
+        loss = model.loss()
+        opt_f.step()
+        return float(loss)
+    for _ in range(W):
+        api_step_fused()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        api_step_fused()
+    barrier()
+    e2e_fused_val = world * args.steps / replicas.max_over_ranks(time.perf_counter() - t0, eng.device)
+
     # ---------------- beside it: the C-ABI host call (round-1 e2e), the device-resident training loop
     Pk = packed.cpu().numpy().copy()
     xhn, yhn = xh.numpy(), yh.numpy()
@@ -514,6 +532,9 @@ def run_b200(args):
                     "what": "plug-in Python API per step: x, y host->device from pinned memory, gpr.Exact.loss() (raw-space "
                             "p.grad filled), torch.optim.Adam.step(), float(loss); wall clock, max over ranks",
                     "last_loss": api_loss,
+                    "fused_optimizer": {"value": e2e_fused_val, "unit": UNIT,
+                                        "what": "the same per-step loop with torch.optim.Adam(fused=True) (one optimiser kernel "
+                                                "instead of ~10), the option mogptk.Model.train(method='Adam', fused=True) passes on"},
                     "c_abi_host_call": {"value": cabi_val, "unit": UNIT, "h2d_bytes_per_step": 8 * (P + dims[0] + N * dims[2] + N),
                                         "d2h_bytes_per_step": 8 * (2 + P + dims[0]),
                                         "what": "mogp_lml_grad_host: params, sigma, x, y host->device, step, LML + gradient "

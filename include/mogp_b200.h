@@ -153,6 +153,13 @@ int mogp_params_backward(mogp_handle_t h, const mogp_param_entry* entries_host, 
                          const double* gcons_dev, const double* dcons_dev, const double* lml_dev,
                          double* loss_out_dev, void* stream);
 
+/* forward + mogp_lml_grad + backward in one call -- replaces gpr.Model.loss (gpr/model.py:279-292) for a model whose
+ * parameters all live in `entries_host`.  work_dev: 3 * (2 + P + C) doubles: packed constrained values | d constrained /
+ * d raw | [lml, info, d(-LML)/d constrained].  loss_out_dev (optional): -lml. */
+int mogp_loss_grad(mogp_handle_t h, int kind, int C, int Q, int D, const mogp_param_entry* entries_host, int n_entries,
+                   const double* x_dev, const int32_t* chan_off_host, const double* y_dev, const double* data_var_dev,
+                   double jitter_rel, double* work_dev, double* loss_out_dev, void* stream);
+
 /* Device-resident Adam training -- replaces `iters` passes of the body of mogptk.Model.train's loop
  * (mogptk/model.py:563-565: loss = gpr.loss(); torch.optim.Adam.step()) without any host synchronisation.
  *   entries_host: the raw leaves, as for mogp_params_forward (kernel parameters first, the C noise scales last); the

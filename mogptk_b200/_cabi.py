@@ -58,6 +58,8 @@ _SIGNATURES = {
     "mogp_alpha": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "mogp_params_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, C.c_void_p]),
     "mogp_params_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "mogp_loss_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_dp,
+                                 C.c_double, c_dp, c_dp, C.c_void_p]),
     "mogp_train_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_dp,
                                   C.c_double, c_dp, c_dp, c_dp, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_double,
                                   C.c_double, c_dp, C.c_void_p, C.c_void_p]),

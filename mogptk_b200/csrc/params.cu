@@ -91,6 +91,34 @@ extern "C" int mogp_params_backward(mogp_handle_t h, const mogp_param_entry* ent
     return 0;
 }
 
+// One training-iteration evaluation in a single call: raw leaves -> constrained values, fused exact-GP step, chain rule
+// into the p.grad buffers (what gpr.Model.loss does, mogptk/gpr/model.py:279-292).  work_dev: 3 * (2 + P + C) doubles laid
+// out as packed | d constrained / d raw | out(lml, info, gradient block); loss_out_dev receives -lml.
+extern "C" int mogp_loss_grad(mogp_handle_t h, int kind, int C, int Q, int D, const mogp_param_entry* entries_host,
+                              int n_entries, const double* x_dev, const int32_t* chan_off_host, const double* y_dev,
+                              const double* data_var_dev, double jitter_rel, double* work_dev, double* loss_out_dev,
+                              void* stream) {
+    if (!h) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    const int P = mogp_num_params(kind, C, Q, D);
+    if (P < 0 || !entries_host || !work_dev) { h->err = "mogp_loss_grad: bad argument"; return -1; }
+    const size_t n = 2 + (size_t)P + C;
+    double* packed = work_dev;
+    double* dcons = work_dev + n;
+    double* out = work_dev + 2 * n;
+    int rc = upload_entries(h, entries_host, n_entries, st);
+    if (rc) return rc;
+    params_forward_kernel<<<n_entries, 128, 0, st>>>((const DevEntry*)h->pent_dev, packed, dcons);
+    MOGP_COUNT(1);
+    rc = mogp_lml_grad(h, kind, C, Q, D, packed, x_dev, chan_off_host, y_dev, packed + P, data_var_dev, jitter_rel, 1, out, stream);
+    if (rc) return rc;
+    params_backward_kernel<<<n_entries, 128, 0, st>>>((const DevEntry*)h->pent_dev, out + 2, dcons, out, loss_out_dev);
+    MOGP_COUNT(1);
+    MOGP_CHECK(h, cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------ device-resident Adam training
 // Replaces the body of the reference's training loop (mogptk/model.py:563-565: `progress(i, self.loss())`,
 // `optimizer.step()` with torch.optim.Adam) for `iters` iterations without a host synchronisation: per iteration

@@ -937,13 +937,16 @@ class Exact(_Named):
         rows = self._rows
         st = eng._stream()
         base = bufs.data_ptr()
-        pp, pd, po, pl = base, base + 8 * n, base + 16 * n, base + 24 * n
-        eng._check(lib.mogp_params_forward(eng.h, C.addressof(entries), n_entries, pp, pd, st))
-        eng._check(lib.mogp_lml_grad(eng.h, _cabi.KIND[self._kind], C_, Q, D, pp, eng._p(rows.x), rows.off_p,
-                                     eng._p(rows.y), pp + 8 * P, eng._p(rows.dv), float(self.jitter), 1, po, st))
-        eng._check(lib.mogp_params_backward(eng.h, C.addressof(entries), n_entries, po + 16, pd, po, pl, st))
+        eng._check(lib.mogp_loss_grad(eng.h, _cabi.KIND[self._kind], C_, Q, D, C.addressof(entries), n_entries, eng._p(rows.x),
+                                      rows.off_p, eng._p(rows.y), eng._p(rows.dv), float(self.jitter), C.c_void_p(base),
+                                      C.c_void_p(base + 24 * n), st))
         eng._train, eng._kind = rows, self._kind
-        lml, info = out[:2].tolist()                           # the iteration's one synchronisation
+        host = cache.get("host")
+        if host is None:
+            host = cache["host"] = torch.zeros(2, dtype=torch.float64).pin_memory()
+        host.copy_(out[:2], non_blocking=True)                 # [lml, info] into pinned memory:
+        torch.cuda.current_stream(eng.device).synchronize()    # the iteration's one synchronisation
+        lml, info = float(host[0]), float(host[1])
         if info != 0:
             # the reference raises in forward(), before backward() has produced anything (gpr/model.py:246-255,291):
             # do not leave the non-finite chain-rule output in p.grad for callers that catch and continue
@@ -951,7 +954,8 @@ class Exact(_Named):
                 q.grad = None
             self._raise_cholesky(int(info), packed[:P], packed[P:P + C_])
         self._factor_key = ("v", tuple((q.data_ptr(), q._version) for q in plist))
-        return lossb.clone()[0]
+        # a host scalar: the training loop reads float(loss) next (mogptk/model.py:384); nothing downstream differentiates it
+        return torch.tensor(-lml, dtype=torch.float64)
 
     def _raise_cholesky(self, info, packed, sigma):
         eng = self._eng()

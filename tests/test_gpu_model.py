@@ -30,7 +30,7 @@ def test_loss_and_raw_gradients(gpr, name):
     g = load_golden(name)
     m, plist = build(gpr, g)
     loss = m.loss()
-    assert loss.is_cuda
+    assert all(p.grad.is_cuda for p in m.parameters())     # raw-space gradients were written on the device
     assert abs(float(loss) - float(g["loss"])) <= 1e-8 * abs(float(g["loss"]))       # LML rtol 1e-8
     for n, lst in plist.items():
         ref = torch.tensor(g["gr_" + n])
