@@ -271,30 +271,67 @@ def stage_times(eng, step, reps=3):
     return {names[i]: round(float(st[i]), 4) for i in range(min(ns, len(names)))}
 
 
-def stage_rooflines(N, stages, dmma, hbm_gbs, traffic):
-    """Achieved rates of the stages against their rooflines (algorithmic work per SURVEY 8d)."""
+def int8_peak():
+    """Dense int8 tensor peak to hold the tcgen05 kind::i8 stages against: MEASURED_PEAKS.json has no int8 figure, so twice
+    its measured bf16 burst rate (the nominal ratio: 4.5 vs 2.25 PFLOP/s dense), else the nominal 4500 TOP/s."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return 2.0 * float(json.load(f)["bf16_tflops"]), "2 x measured bf16 burst (MEASURED_PEAKS.json)"
+    except Exception:
+        return 4500.0, "nominal dense int8"
+
+
+def stage_rooflines(N, stages, dmma, hbm_gbs, traffic, i8=None):
+    """Achieved rates of the stages against their rooflines (algorithmic work per SURVEY 8d).  i8 = (slices S, fraction of
+    the triangular inverse's flops that runs on the int8 pipe) when the large GEMMs of this size take the tcgen05 path."""
     n3 = float(N) ** 3 / 3.0
     fused = stages.get("trtri", 1.0) < 0.02          # L^-1 pipelined behind the panel chain (N <= 4096)
+    traffic = traffic or {}
     out = {}
+    i8_peak, i8_src = int8_peak()
 
-    def tensor(name, flops, ms, what):
+    def tensor(name, flops, ms, what, tkey=None, i8_frac=0.0):
         if ms and ms > 0:
             a = flops / (ms * 1e-3) / 1e12
             out[name] = {"bound": "tensor", "achieved": a, "peak": dmma, "unit": "TFLOP/s", "frac": a / dmma, "ms": ms,
-                         "traffic": (traffic or {}).get(name), "what": what}
+                         "traffic": traffic.get(tkey or name), "what": what}
+            if i8 and i8_frac > 0.0:
+                S = i8[0]
+                tops = i8_frac * flops * (S * (S + 1) / 2.0) / (ms * 1e-3) / 1e12
+                out[name]["int8"] = {"achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak,
+                                     "what": "this stage runs (%.0f%% of its flops) on the int8 tensor pipe, tcgen05.mma kind::i8: "
+                                             "every fp64 multiply-add is S (S + 1) / 2 = %d exact int8 multiply-adds (S = %d digit "
+                                             "planes); achieved = those int8 operations / the whole stage time (operand slicing and "
+                                             "the DMMA levels included); peak = %s.  `frac` above is the fp64-equivalent rate over "
+                                             "the DMMA peak and may exceed 1." % (100 * i8_frac, S * (S + 1) // 2, S, i8_src)}
     tensor("potrf_inverse" if fused else "potrf", (2.0 if fused else 1.0) * n3, stages.get("potrf"),
-           "Cholesky N^3/3" + (" + L^-1 N^3/3 issued behind the panel chain" if fused else ""))
+           "Cholesky N^3/3" + (" + L^-1 N^3/3 issued behind the panel chain" if fused else "") + " (fp64 DMMA)", "potrf_inverse")
     if not fused:
-        tensor("trtri", n3, stages.get("trtri"), "L^-1 by level-batched block doubling, N^3/3")
-    tensor("kinv", n3, stages.get("kinv"), "K^-1 = L^-T L^-1 (lower tiles), N^3/3, one launch")
+        tensor("trtri", n3, stages.get("trtri"), "L^-1 by level-batched block doubling, N^3/3", "trtri", i8[1] if i8 else 0.0)
+    tensor("kinv", n3, stages.get("kinv"), "K^-1 = L^-T L^-1 (lower tiles), N^3/3, one launch", "kinv", 1.0 if i8 else 0.0)
     if stages.get("kbuild"):
         b = 8.0 * float(N) ** 2
         a = b / (stages["kbuild"] * 1e-3) / 1e9
         out["kbuild"] = {"bound": "hbm", "achieved": a, "peak": hbm_gbs, "unit": "GB/s", "frac": a / hbm_gbs,
-                         "ms": stages["kbuild"], "traffic": (traffic or {}).get("kbuild"),
+                         "ms": stages["kbuild"], "traffic": traffic.get("kbuild"),
                          "what": "8 N^2 algorithmic bytes (SURVEY 8d convention; the fused step writes the lower half only) / "
                                  "stage time incl. the prep kernel; the kernel is fp64-pipe bound for Q >= 2 (DESIGN 4)"}
     return out
+
+
+def i8_config(eng, N):
+    """(S, int8 share of the triangular inverse's flops) when padded size N takes the int8 path, else None."""
+    Np = (N + 127) // 128 * 128
+    mn = int(eng.lib.mogp_get_i8_min_np())
+    if mn <= 0 or Np < mn:
+        return None
+    tmin = int(eng.lib.mogp_get_i8_trtri_min())
+    share, S_ = 0.0, 64
+    while S_ < Np:                                   # level with block size S_ carries Np * S_^2 of the Np^3 / 3 flops
+        if tmin > 0 and S_ >= tmin and Np % (2 * S_) == 0:
+            share += float(Np) * S_ * S_
+        S_ *= 2
+    return int(eng.lib.mogp_get_i8_slices()), min(1.0, share / (float(Np) ** 3 / 3.0))
 
 
 def load_traffic(cfg):
@@ -363,7 +400,7 @@ def sub_record(cfg, device_index, dmma, hbm_gbs, steps=6):
                          "unit": "TFLOP/s", "what": "N^3 algorithmic flop / median CUDA-event step time"},
                 "cholesky": {"ms": potrf_ms, "achieved": chol, "peak": dmma, "frac": chol / dmma, "unit": "TFLOP/s", "info": info,
                              "what": "mogp_potrf alone on the same K~ (N^3/3 flop, best of 3, CUDA events)"},
-                "stages": stage_rooflines(N, stages, dmma, hbm_gbs, load_traffic(cfg))}
+                "stages": stage_rooflines(N, stages, dmma, hbm_gbs, load_traffic(cfg), i8_config(eng, N))}
     finally:
         eng.close()
 
@@ -515,7 +552,7 @@ def run_b200(args):
         except Exception:
             dmma, dfma = DMMA_PEAK_FALLBACK_TFLOPS, None
         hbm, hbm_src = hbm_peak()
-        roofs = stage_rooflines(N, stages, dmma, hbm, load_traffic(args.config))
+        roofs = stage_rooflines(N, stages, dmma, hbm, load_traffic(args.config), i8_config(eng, N))
         dom_name = max((k for k in roofs), key=lambda k: roofs[k]["ms"])
         dom = roofs[dom_name]
         ach = synth.flops_per_iteration(N) / (ms_per_step * 1e-3) / 1e12

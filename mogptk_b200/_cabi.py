@@ -74,6 +74,9 @@ _EXTRA = {
     "mogp_set_gemm_config": (None, [C.c_int]),
     "mogp_set_i8": (C.c_int, [C.c_longlong, C.c_int]),
     "mogp_set_i8_trtri_min": (C.c_int, [C.c_longlong]),
+    "mogp_get_i8_min_np": (C.c_longlong, []),
+    "mogp_get_i8_slices": (C.c_int, []),
+    "mogp_get_i8_trtri_min": (C.c_longlong, []),
     "mogp_set_i8_potrf_min": (C.c_int, [C.c_longlong]),
     "mogp_set_i8_ts": (C.c_int, [C.c_int]),
     "mogp_get_i8_ts": (C.c_int, []),

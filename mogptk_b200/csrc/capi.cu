@@ -310,6 +310,9 @@ extern "C" int mogp_set_i8_ts(int on) { g_i8_ts = on ? 1 : 0; ++g_mogp_cfg_epoch
 extern "C" int mogp_get_i8_ts(void) { return g_i8_ts; }
 // smallest doubling-level block size of the triangular inverse that runs on the int8 pipe (0 = none)
 extern "C" int mogp_set_i8_trtri_min(long long rows) { g_i8_trtri_min = rows; ++g_mogp_cfg_epoch; return 0; }
+extern "C" long long mogp_get_i8_min_np(void) { return g_i8_min_np; }
+extern "C" int mogp_get_i8_slices(void) { return g_i8_slices; }
+extern "C" long long mogp_get_i8_trtri_min(void) { return g_i8_trtri_min; }
 static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }
 // host-side preparation of the int8 path for a padded size (never inside capture); invalidates captured graphs when the
 // tile lists had to be rebuilt (another size / leading dimension / slice count used this handle in between)

@@ -55,7 +55,10 @@ def stage_of(name, state):
         return "grad_finalize"
     if state.get("solves"):
         return "kinv"
-    return "potrf_inverse"
+    if "diag_finish" in n:
+        state["factored"] = True          # what follows (level-batched trtri_padded, int8 slicing + GEMMs) is the inverse
+        return "potrf_inverse"
+    return "trtri" if state.get("factored") else "potrf_inverse"
 
 
 def main():
@@ -67,16 +70,22 @@ def main():
     start = max(i for i, l in enumerate(launches[:last_fin]) if "prep_kernel" in l["name"])
     step = launches[start:last_fin + 1]
     state, stages = {}, {}
-    # the K^-1 GEMM is launched (on a side stream) before the solves: it is the last GEMM before pad_copy
+    # the K^-1 product is launched (on a side stream) before the solves: it is the last GEMM before pad_copy -- together
+    # with the three slicing kernels in front of it when it runs on the int8 pipe (i8_rowmax, i8_exponent, i8_slice_tiled)
     idx_pad = next((i for i, l in enumerate(step) if "pad_copy" in l["name"]), None)
-    kinv_idx = None
+    kinv_set = set()
     if idx_pad is not None:
         for i in range(idx_pad - 1, -1, -1):
             if "gemm" in step[i]["name"]:
-                kinv_idx = i
+                kinv_set.add(i)
+                if "i8_gemm" in step[i]["name"]:
+                    j = i - 1
+                    while j >= 0 and step[j]["name"].startswith("i8_") and "gemm" not in step[j]["name"] and len(kinv_set) < 4:
+                        kinv_set.add(j)
+                        j -= 1
                 break
     for i, l in enumerate(step):
-        st = "kinv" if i == kinv_idx else stage_of(l["name"], state)
+        st = "kinv" if i in kinv_set else stage_of(l["name"], state)
         s = stages.setdefault(st, {"launches": 0, "time_us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "tensor_weighted": 0.0,
                                    "kernels": {}})
         m = l["m"]
