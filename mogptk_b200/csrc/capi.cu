@@ -299,10 +299,10 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
     g_i8_min_np = min_np; g_i8_slices = slices; ++g_mogp_cfg_epoch;
     return 0;
 }
-// Measured and switched OFF by default (0): at K = 256 a 128 x 64 tile has only 8 K chunks, so the per-tile fixed costs of
-// the int8 kernel (TMEM allocation, pipeline fill, the 7-accumulator epilogue with a read-modify-write of C) outweigh
-// the MMA time, and its one-CTA-per-SM footprint starves the panel chain: cfg3 potrf 7.6 -> 11.5 ms, cfg4 2.44 -> 3.29 ms
-// (profiles/r02_i8_potrf_updates.txt).  Kept selectable (tests cover it) for a later persistent-tile version.
+// Three-level Cholesky for the largest matrices: super-panels of 1024 columns whose rank-1024 trailing update runs on the
+// int8 tensor pipe (padded sizes >= this, multiples of 1024; 0 = never).  (A first version with rank-256 int8 updates was
+// slower than DMMA: at K = 256 a tile has 8 K chunks and the kernel's fixed costs dominate -- cfg3 potrf 7.6 -> 11.5 ms,
+// profiles/r02_i8_potrf_updates.txt.)
 long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 0;
 extern "C" int mogp_set_i8_potrf_min(long long np) { g_i8_potrf_min = np; ++g_mogp_cfg_epoch; return 0; }
 extern int g_i8_ts;

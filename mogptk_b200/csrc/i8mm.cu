@@ -32,7 +32,7 @@
 #define I8_STAGES 4
 #define I8_SMAX 8
 #define I8_BITS 7
-#define I8_PANEL 256       // width of the Cholesky outer panel whose trailing update runs here (MOGP_NB_OUT)
+#define I8_PANEL 1024      // width of the Cholesky super-panel whose rank-1024 trailing update runs here
 
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -486,7 +486,7 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
                 }
         p->lvl_b[lev].count = p->host_tiles.size() - p->lvl_b[lev].first;
     }
-    // trailing updates C -= P P^T (K = 256): (a) the 256 columns of the next outer panel, (b) the rest (both lower tiles)
+    // trailing updates C -= P P^T (K = I8_PANEL): (a) the I8_PANEL columns of the next super-panel, (b) the rest (lower tiles)
     if ((e = i8_reserve(p->opP, (int)Np, I8_PANEL, S)) != cudaSuccess) return e;
     const int ntm = (int)(Np / I8_TM);
     p->syrk_a.first = p->host_tiles.size();
@@ -512,10 +512,10 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
     return cudaStreamSynchronize(st);
 }
 
-// Rank-256 trailing update of the blocked Cholesky on the int8 pipe: with P = A[r0 .. Np) x [k0, k0 + 256) (the finished
-// outer panel below its diagonal block), part 0 slices P and updates the next outer panel's 256 columns
-// A[r0.., r0 .. r0+256) -= P P^T (lower tiles), part 1 updates the rest A[r0+256.., r0+256..) -= P P^T (lower tiles).
-// r0 a multiple of 256.  Pure enqueue; cudaErrorNotSupported when this size is not prepared.
+// Rank-1024 trailing update of the blocked Cholesky on the int8 pipe: with P = A[r0 .. Np) x [k0, k0 + 1024) (a finished
+// super-panel below its diagonal block), part 0 slices P and updates the next super-panel's 1024 columns
+// A[r0.., r0 .. r0+1024) -= P P^T (lower tiles), part 1 updates the rest A[r0.., r0+1024..) -= P P^T (lower tiles).
+// r0 a multiple of 1024.  Pure enqueue; cudaErrorNotSupported when this size is not prepared.
 cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
                            cudaStream_t st) {
     if (!p || (r0 % I8_PANEL) != 0) return cudaErrorNotSupported;

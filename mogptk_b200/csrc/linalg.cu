@@ -1162,9 +1162,14 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         // panel's columns (priority) and the rest; both run on S2 while S1 factors the next outer panel.
         cudaEvent_t last = nullptr;
         const bool two3 = two && ps->s3 != nullptr;
+        // three levels for the largest matrices: inside a super-panel of SW = 1024 columns the rank-256 DMMA updates only
+        // reach the super-panel's own columns; what lies beyond is updated once per super-panel with K = 1024 on the int8 pipe
+        const int64_t SW = 1024;
+        const bool super = i8 != nullptr && g_i8_potrf_min > 0 && Np >= g_i8_potrf_min && Np % SW == 0;
         int J = 0;
         for (int64_t K0 = 0; K0 < Np; K0 += MOGP_NB_OUT, ++J) {
             const int64_t Wd = std::min<int64_t>(MOGP_NB_OUT, Np - K0), Kend = K0 + Wd;
+            const int64_t Kse = super ? (K0 / SW + 1) * SW : Np;          // first column beyond this super-panel
             if (two && J >= 1 && (e = cudaStreamWaitEvent(st, ps->ev2[2 * (J - 1)], 0)) != cudaSuccess) return e;
             cudaEvent_t last_inner = nullptr;
             for (int64_t k = K0; k < Kend; k += MOGP_NB) {
@@ -1203,21 +1208,19 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 if ((e = cudaStreamWaitEvent(s2, ps->ev1[J + 1], 0)) != cudaSuccess) return e;
             }
             const int64_t W2 = std::min<int64_t>(MOGP_NB_OUT, Np - Kend);
-            if (i8 && g_i8_potrf_min > 0 && Np >= g_i8_potrf_min && Wd == MOGP_NB_OUT && W2 == MOGP_NB_OUT &&
-                (Np - Kend) % 128 == 0) {
-                // the rank-256 update on the int8 tensor pipe (i8mm.cu): same split, same events
-                cudaError_t e8 = i8_syrk_update(i8, A, ld, Kend, K0, Np, 0, i8_slices, s2);
-                if (e8 == cudaSuccess) {
-                    if (two && (e = cudaEventRecord(ps->ev2[2 * J], s2)) != cudaSuccess) return e;
-                    last = two ? ps->ev2[2 * J] : nullptr;
-                    if (Np - Kend - W2 > 0) {
-                        if ((e = i8_syrk_update(i8, A, ld, Kend, K0, Np, 1, i8_slices, s2)) != cudaSuccess) return e;
-                        if (two && (e = cudaEventRecord(ps->ev2[2 * J + 1], s2)) != cudaSuccess) return e;
-                        last = two ? ps->ev2[2 * J + 1] : nullptr;
-                    }
-                    continue;
+            if (super && Kend == Kse) {
+                // end of a super-panel: ONE rank-1024 update of everything below / right of it on the int8 tensor pipe
+                // (i8mm.cu) replaces the four rank-256 DMMA updates beyond the super-panel; same split (next super-panel's
+                // columns first, then the rest) and the same events as the DMMA updates below
+                if ((e = i8_syrk_update(i8, A, ld, Kse, Kse - SW, Np, 0, i8_slices, s2)) != cudaSuccess) return e;
+                if (two && (e = cudaEventRecord(ps->ev2[2 * J], s2)) != cudaSuccess) return e;
+                last = two ? ps->ev2[2 * J] : nullptr;
+                if (Np - Kse - SW > 0) {
+                    if ((e = i8_syrk_update(i8, A, ld, Kse, Kse - SW, Np, 1, i8_slices, s2)) != cudaSuccess) return e;
+                    if (two && (e = cudaEventRecord(ps->ev2[2 * J + 1], s2)) != cudaSuccess) return e;
+                    last = two ? ps->ev2[2 * J + 1] : nullptr;
                 }
-                if (e8 != cudaErrorNotSupported) return e8;
+                continue;
             }
             {                                               // priority: columns of the next outer panel
                 GemmArgs u{};
@@ -1230,13 +1233,13 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 if (two && (e = cudaEventRecord(ps->ev2[2 * J], s2)) != cudaSuccess) return e;
                 last = two ? ps->ev2[2 * J] : nullptr;
             }
-            const int64_t R0 = Kend + W2, MR = Np - R0;
-            if (MR > 0) {                                   // the rest of the trailing matrix
+            const int64_t R0 = Kend + W2, MR = Np - R0, NR = std::min<int64_t>(Np, Kse) - R0;
+            if (MR > 0 && NR > 0) {                         // the rest of the trailing matrix (of this super-panel)
                 GemmArgs u{};
                 u.A = A + R0 * ld + K0; u.lda = ld;
                 u.B = A + R0 * ld + K0; u.ldb = ld;
                 u.C = A + R0 * ld + R0; u.ldc = ld;
-                u.M = (int)MR; u.N = (int)MR; u.K = (int)Wd;
+                u.M = (int)MR; u.N = (int)NR; u.K = (int)Wd;
                 u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
                 if ((e = launch_gemm(0, 1, u, 1, s2)) != cudaSuccess) return e;
                 if (two && (e = cudaEventRecord(ps->ev2[2 * J + 1], s2)) != cudaSuccess) return e;

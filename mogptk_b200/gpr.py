@@ -957,6 +957,12 @@ class Exact(_Named):
         # a host scalar: the training loop reads float(loss) next (mogptk/model.py:384); nothing downstream differentiates it
         return torch.tensor(-lml, dtype=torch.float64)
 
+    def fit_adam(self, iters, **kwargs):
+        """`iters` Adam iterations on the device, one host synchronisation per chunk (mogptk_b200.train.fit_adam);
+        returns (losses, times)."""
+        from .train import fit_adam
+        return fit_adam(self, iters, **kwargs)
+
     def _raise_cholesky(self, info, packed, sigma):
         eng = self._eng()
         kind, p, _ = kernel_spec(self.kernel)

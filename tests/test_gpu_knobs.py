@@ -164,8 +164,8 @@ def test_int8_triangular_inverse_levels_equal_dmma(engine, n):
 
 @pytest.mark.parametrize("n", [4096, 8192])
 def test_int8_trailing_updates_of_the_cholesky(engine, n):
-    """Blocked Cholesky with the rank-256 trailing updates on the int8 tensor pipe against the all-DMMA factorisation and
-    LAPACK (an option that is off by default -- slower than DMMA at K = 256, see capi.cu -- and forced on here)."""
+    """Three-level blocked Cholesky (super-panels of 1024 columns whose rank-1024 trailing update runs on the int8 tensor
+    pipe) against the all-DMMA factorisation and LAPACK; forced on here whatever the default is."""
     import torch
     torch.manual_seed(7)
     B = torch.randn(n, n // 2, dtype=torch.float64, device=engine.device)
