@@ -80,6 +80,8 @@ _EXTRA = {
     "mogp_set_i8_potrf_min": (C.c_int, [C.c_longlong]),
     "mogp_set_i8_ts": (C.c_int, [C.c_int]),
     "mogp_get_i8_ts": (C.c_int, []),
+    "mogp_set_i8_wide": (C.c_int, [C.c_int]),
+    "mogp_get_i8_wide": (C.c_int, []),
     "mogp_i8_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "mogp_set_graphs": (None, [C.c_int]),
     "mogp_set_cov_minb": (C.c_int, [C.c_int]),

@@ -303,9 +303,12 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
 // int8 tensor pipe (padded sizes >= this, multiples of 1024; 0 = never).  (A first version with rank-256 int8 updates was
 // slower than DMMA: at K = 256 a tile has 8 K chunks and the kernel's fixed costs dominate -- cfg3 potrf 7.6 -> 11.5 ms,
 // profiles/r02_i8_potrf_updates.txt.)
-long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 0;
+// Measured (profiles/r02_i8_potrf_three_level.txt): cfg3 (N = 8192) potrf 7.60 -> 6.71 ms, cfg4 (N = 4096) 2.42 -> 2.61 ms: on from 8192.
+long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 8192;
 extern "C" int mogp_set_i8_potrf_min(long long np) { g_i8_potrf_min = np; ++g_mogp_cfg_epoch; return 0; }
-extern int g_i8_ts;
+extern int g_i8_ts, g_i8_wide;
+extern "C" int mogp_set_i8_wide(int on) { g_i8_wide = on ? 1 : 0; ++g_mogp_cfg_epoch; return 0; }
+extern "C" int mogp_get_i8_wide(void) { return g_i8_wide; }
 extern "C" int mogp_set_i8_ts(int on) { g_i8_ts = on ? 1 : 0; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_get_i8_ts(void) { return g_i8_ts; }
 // smallest doubling-level block size of the triangular inverse that runs on the int8 pipe (0 = none)

@@ -323,6 +323,136 @@ __global__ void __launch_bounds__(192, 1) i8_gemm_tiles_kernel(I8Args g) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------ wide variant: 128 x 128 tiles, two passes
+// The 128 x 64 kernel above keeps all S anti-diagonal accumulators in tensor memory at once, which limits N to 64 and makes
+// every MMA read 6 KB of shared memory for 32 cycles of math.  Here a launch only computes the anti-diagonals
+// d in [DLO, DHI] (at most 4: 4 x 128 = 512 TMEM columns), so N = 128 fits: an MMA reads 8 KB for 64 cycles (128 B/cycle
+// instead of 192).  A product takes two launches -- d = 0..3 (10 digit pairs, planes 0..3) and d = 4..S-1 (18 pairs at
+// S = 7, all planes), the second accumulating onto the first's output -- and streams the operands twice from L2, which
+// has the headroom (the narrow kernel ran it at ~18 %).
+template <int DLO, int DHI>
+struct I8Wide {
+    static constexpr int NACC = DHI - DLO + 1;
+    static constexpr int PLANES = DHI + 1;                        // digit planes 0 .. DHI of both operands are needed
+    static constexpr uint32_t STAGE_BYTES = PLANES * 2 * (2 * I8_TM * 16);     // A planes + B planes (128 rows each)
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+    static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 256;
+    static constexpr uint32_t TMEM_COLS = NACC * 128 > 256 ? 512 : 256;
+};
+
+template <int DLO, int DHI>
+__global__ void __launch_bounds__(192, 1) i8_gemm_wide_kernel(I8Args g, int splanes) {
+    using W = I8Wide<DLO, DHI>;
+    constexpr int TN = 128;
+    extern __shared__ __align__(128) unsigned char i8_raw[];
+    unsigned char* stages = i8_raw;
+    uint64_t* full = reinterpret_cast<uint64_t*>(i8_raw + W::STAGES * W::STAGE_BYTES);
+    uint64_t* empty = full + W::STAGES;
+    uint64_t* acc_full = empty + W::STAGES;
+    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const I8Tile t = g.tiles[blockIdx.x];
+    const int nk = t.kc1 - t.kc0;
+    constexpr uint32_t PLANE_BYTES = 2 * I8_TM * 16;              // 4 KB: one digit plane of 128 rows x 32 K bytes
+    constexpr uint32_t OP_BYTES = W::PLANES * PLANE_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < W::STAGES; ++i) { i8_mbar_init(&full[i], 1); i8_mbar_init(&empty[i], 1); }
+        i8_mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_base)), "n"(W::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem0 = *tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // a (K chunk, row tile) block of an operand holds all `splanes` planes; planes 0 .. DHI are its first OP_BYTES
+            const long long blockA = (long long)splanes * PLANE_BYTES;
+            const int rtA = t.m0 / I8_TM, rtB = t.n0 / I8_TM;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kc = t.kc0; kc < t.kc1; ++kc) {
+                i8_mbar_wait(&empty[stage], phase ^ 1);
+                i8_mbar_expect_tx(&full[stage], 2 * OP_BYTES);
+                unsigned char* sp = stages + (size_t)stage * W::STAGE_BYTES;
+                i8_bulk_g2s(sp, g.A + ((long long)kc * g.nrtA + rtA) * blockA, OP_BYTES, &full[stage]);
+                i8_bulk_g2s(sp + OP_BYTES, g.B + ((long long)kc * g.nrtB + rtB) * blockA, OP_BYTES, &full[stage]);
+                if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nk; ++i) {
+                i8_mbar_wait(&full[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = i8_smem_u32(stages + (size_t)stage * W::STAGE_BYTES), b0 = a0 + OP_BYTES;
+#pragma unroll
+                for (int d = DLO; d <= DHI; ++d)
+#pragma unroll
+                    for (int s = 0; s <= d; ++s) {
+                        const uint64_t da = i8_desc(a0 + s * PLANE_BYTES, I8_TM * 16, 128);
+                        const uint64_t db = i8_desc(b0 + (d - s) * PLANE_BYTES, I8_TM * 16, 128);
+                        i8_mma(tmem0 + (uint32_t)((d - DLO) * TN), da, db, idesc, (i > 0 || s > 0) ? 1u : 0u);
+                    }
+                i8_commit(&empty[stage]);
+                if (++stage == W::STAGES) { stage = 0; phase ^= 1; }
+            }
+            i8_commit(acc_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = t.m0 + q * 32 + lane;
+        i8_mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int er = g.ea[row];
+        double* crow = g.C + t.c_off + (long long)(q * 32 + lane) * g.ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 16) {
+            double acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int d = DHI; d >= DLO; --d) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - DLO) * TN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const double w = __hiloint2double((1023 - I8_BITS * (d + 2)) << 20, 0);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const int e0 = er + g.eb[t.n0 + c0 + j], e1 = er + g.eb[t.n0 + c0 + j + 1];
+                double x0 = g.alpha * ldexp(acc[j], e0), x1 = g.alpha * ldexp(acc[j + 1], e1);
+                double2* p = reinterpret_cast<double2*>(crow + c0 + j);
+                if (g.beta != 0.0) { const double2 o = *p; x0 = fma(g.beta, o.x, x0); x1 = fma(g.beta, o.y, x1); }
+                *p = make_double2(x0, x1);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(W::TMEM_COLS) : "memory");
+}
+
 // ------------------------------------------------------------------ host side
 struct I8Operand {                 // a sliced operand in device memory
     int8_t* digits = nullptr; size_t digits_cap = 0;
@@ -330,16 +460,19 @@ struct I8Operand {                 // a sliced operand in device memory
     int R = 0, K = 0, nrt = 0, nkc = 0;
 };
 struct I8List { size_t first = 0, count = 0; };
-struct I8Plan {
-    I8Operand opA, opB, opP;                 // opP: the 256-column panel of the blocked Cholesky
-    I8Tile* tiles = nullptr; size_t tiles_cap = 0;
-    std::vector<I8Tile> host_tiles;          // all tile lists back to back
-    I8List kinv;                             // K^-1 = L^-T L^-1
-    std::vector<I8List> lvl_a, lvl_b;        // per doubling level (index = log2 of the block size in 64-blocks): the two GEMMs
-    // trailing update of the blocked Cholesky, coordinates relative to the first row below the outer panel: master lists
+struct I8Lists {                                 // the tile lists of one tile width (64 or 128 columns)
+    I8List kinv;                                 // K^-1 = L^-T L^-1
+    std::vector<I8List> lvl_a, lvl_b;            // per doubling level (index = log2 of the block size in 64-blocks): the two GEMMs
+    // trailing update of the blocked Cholesky, coordinates relative to the first row below the super-panel: master lists
     // ordered by row tile, so that the list for a smaller trailing matrix is a prefix (prefix counts per row-tile count)
     I8List syrk_a, syrk_b;
     std::vector<size_t> syrk_a_count, syrk_b_count;
+};
+struct I8Plan {
+    I8Operand opA, opB, opP;                 // opP: the 1024-column super-panel of the blocked Cholesky
+    I8Tile* tiles = nullptr; size_t tiles_cap = 0;
+    std::vector<I8Tile> host_tiles;          // all tile lists back to back
+    I8Lists L[2];                            // [0]: 128 x 64 tiles (one-pass kernel), [1]: 128 x 128 tiles (two-pass kernel)
     long long tiles_key = -1;
     int64_t Np = 0; long long ld = 0; int S = 0;     // what the lists were built for
     bool ready(int64_t Np_, long long ld_, int S_) const { return tiles_key >= 0 && Np == Np_ && ld == ld_ && S == S_; }
@@ -384,7 +517,11 @@ static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long
 
 // 1: A planes through tensor memory (S = 7 only: 8 planes do not fit beside 8 accumulators), 0: both operands from shared memory
 int g_i8_ts = std::getenv("MOGP_I8_TS") ? std::atoi(std::getenv("MOGP_I8_TS")) : 0;
+// 1: 128 x 128 tiles in two passes over the anti-diagonals (S = 7), 0: 128 x 64 tiles in one pass
+int g_i8_wide = std::getenv("MOGP_I8_WIDE") ? std::atoi(std::getenv("MOGP_I8_WIDE")) : 0;
+static int i8_width(int S) { return (g_i8_wide && S == 7) ? 1 : 0; }
 
+// `lists` = the I8Lists of i8_width(S); `l` one of its lists, `count` tiles of it
 static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Tile* tiles_dev, int ntiles, int S, double alpha,
                              double beta, double* C, long long ldc, cudaStream_t st) {
     static PerDeviceOnce once;
@@ -395,12 +532,23 @@ static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Til
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(i8_gemm_wide_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Wide<0, 3>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(i8_gemm_wide_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Wide<4, 6>::SMEM);
+        if (e != cudaSuccess) return e;
     }
     if (ntiles <= 0) return cudaSuccess;
     I8Args g{};
     g.A = A.digits; g.ea = A.ex; g.nrtA = A.nrt;
     g.B = B.digits; g.eb = B.ex; g.nrtB = B.nrt;
     g.tiles = tiles_dev; g.S = S; g.alpha = alpha; g.beta = beta; g.C = C; g.ldc = ldc;
+    if (i8_width(S) == 1) {
+        i8_gemm_wide_kernel<0, 3><<<ntiles, 192, I8Wide<0, 3>::SMEM, st>>>(g, S);
+        g.beta = 1.0;                                   // the second pass accumulates onto the first
+        i8_gemm_wide_kernel<4, 6><<<ntiles, 192, I8Wide<4, 6>::SMEM, st>>>(g, S);
+        MOGP_COUNT(2);
+        return cudaGetLastError();
+    }
     if (S == 7 && g_i8_ts) i8_gemm_tiles_kernel<7, true><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
     else if (S == 7) i8_gemm_tiles_kernel<7, false><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
     else if (S == 8) i8_gemm_tiles_kernel<8, false><<<ntiles, 192, sizeof(I8Smem), st>>>(g);
@@ -450,61 +598,66 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
     if (p->tiles_key == key) return cudaSuccess;
     if (changed) *changed = true;            // captured graphs that replay the old lists must be re-captured
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;      // nothing may still read the lists being replaced
-    p->host_tiles.clear();
-    p->lvl_a.assign(32, I8List());
-    p->lvl_b.assign(32, I8List());
-    const int nkc = (int)(Np / I8_KC);
-    p->kinv.first = 0;
-    for (int ti = 0; ti < (int)(Np / I8_TM); ++ti)                         // longest K ranges first
-        for (int tj = 0; tj * I8_TN < (ti + 1) * I8_TM; ++tj)
-            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, ti * I8_TM / I8_KC, nkc, (long long)ti * I8_TM * ld + (long long)tj * I8_TN});
-    p->kinv.count = p->host_tiles.size();
-    // doubling levels of the triangular inverse: pairs of adjacent S x S diagonal blocks (A, B) at offset o = 2 S pair:
-    //   GEMM a: T = L_BA Linv_AA        operand A rows = rows of L_BA, operand B rows = columns of Linv_AA (nonzero k >= n)
-    //   GEMM b: Linv_BA = -Linv_BB T    operand A rows = rows of Linv_BB (nonzero k <= m), operand B rows = columns of T
-    // both operands of a level are the stacked blocks of all pairs (row index = pair * S + local row).
-    int lev = 0;
-    for (int64_t S_ = 64; S_ < Np; S_ *= 2, ++lev) {
-        if (!i8_level_ok(Np, S_)) continue;
-        const int npair = (int)(Np / (2 * S_)), Sn = (int)S_;
-        p->lvl_a[lev].first = p->host_tiles.size();
-        for (int tn = 0; tn < Sn / I8_TN; ++tn)                             // longest K ranges (small n) first
-            for (int pr = 0; pr < npair; ++pr)
-                for (int tm = 0; tm < Sn / I8_TM; ++tm) {
-                    const long long o = (long long)pr * 2 * S_;
-                    p->host_tiles.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * I8_TN, tn * I8_TN / I8_KC, Sn / I8_KC,
-                                             (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * I8_TN});
-                }
-        p->lvl_a[lev].count = p->host_tiles.size() - p->lvl_a[lev].first;
-        p->lvl_b[lev].first = p->host_tiles.size();
-        for (int tm = Sn / I8_TM - 1; tm >= 0; --tm)                        // longest K ranges (large m) first
-            for (int pr = 0; pr < npair; ++pr)
-                for (int tn = 0; tn < Sn / I8_TN; ++tn) {
-                    const long long o = (long long)pr * 2 * S_;
-                    p->host_tiles.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * I8_TN, 0, (tm + 1) * I8_TM / I8_KC,
-                                             (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * I8_TN});
-                }
-        p->lvl_b[lev].count = p->host_tiles.size() - p->lvl_b[lev].first;
-    }
-    // trailing updates C -= P P^T (K = I8_PANEL): (a) the I8_PANEL columns of the next super-panel, (b) the rest (lower tiles)
     if ((e = i8_reserve(p->opP, (int)Np, I8_PANEL, S)) != cudaSuccess) return e;
-    const int ntm = (int)(Np / I8_TM);
-    p->syrk_a.first = p->host_tiles.size();
-    p->syrk_a_count.assign(ntm + 1, 0);
-    for (int tm = 0; tm < ntm; ++tm) {
-        for (int tn = 0; tn < I8_PANEL / I8_TN && tn * I8_TN < (tm + 1) * I8_TM; ++tn)
-            p->host_tiles.push_back({tm * I8_TM, tn * I8_TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * I8_TN});
-        p->syrk_a_count[tm + 1] = p->host_tiles.size() - p->syrk_a.first;
+    p->host_tiles.clear();
+    const int nkc = (int)(Np / I8_KC);
+    for (int w = 0; w < 2; ++w) {
+        I8Lists& L = p->L[w];
+        const int TN = w == 0 ? I8_TN : 128;
+        std::vector<I8Tile>& T = p->host_tiles;
+        L.lvl_a.assign(32, I8List());
+        L.lvl_b.assign(32, I8List());
+        L.kinv.first = T.size();
+        for (int ti = 0; ti < (int)(Np / I8_TM); ++ti)                         // longest K ranges first
+            for (int tj = 0; tj * TN < (ti + 1) * I8_TM; ++tj)
+                T.push_back({ti * I8_TM, tj * TN, ti * I8_TM / I8_KC, nkc, (long long)ti * I8_TM * ld + (long long)tj * TN});
+        L.kinv.count = T.size() - L.kinv.first;
+        // doubling levels of the triangular inverse: pairs of adjacent S x S diagonal blocks (A, B) at offset o = 2 S pair:
+        //   GEMM a: T = L_BA Linv_AA        operand A rows = rows of L_BA, operand B rows = columns of Linv_AA (nonzero k >= n)
+        //   GEMM b: Linv_BA = -Linv_BB T    operand A rows = rows of Linv_BB (nonzero k <= m), operand B rows = columns of T
+        // both operands of a level are the stacked blocks of all pairs (row index = pair * S + local row).
+        int lev = 0;
+        for (int64_t S_ = 64; S_ < Np; S_ *= 2, ++lev) {
+            if (!i8_level_ok(Np, S_)) continue;
+            const int npair = (int)(Np / (2 * S_)), Sn = (int)S_;
+            L.lvl_a[lev].first = T.size();
+            for (int tn = 0; tn < Sn / TN; ++tn)                                // longest K ranges (small n) first
+                for (int pr = 0; pr < npair; ++pr)
+                    for (int tm = 0; tm < Sn / I8_TM; ++tm) {
+                        const long long o = (long long)pr * 2 * S_;
+                        T.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * TN, tn * TN / I8_KC, Sn / I8_KC,
+                                     (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * TN});
+                    }
+            L.lvl_a[lev].count = T.size() - L.lvl_a[lev].first;
+            L.lvl_b[lev].first = T.size();
+            for (int tm = Sn / I8_TM - 1; tm >= 0; --tm)                        // longest K ranges (large m) first
+                for (int pr = 0; pr < npair; ++pr)
+                    for (int tn = 0; tn < Sn / TN; ++tn) {
+                        const long long o = (long long)pr * 2 * S_;
+                        T.push_back({pr * Sn + tm * I8_TM, pr * Sn + tn * TN, 0, (tm + 1) * I8_TM / I8_KC,
+                                     (o + S_ + (long long)tm * I8_TM) * ld + o + (long long)tn * TN});
+                    }
+            L.lvl_b[lev].count = T.size() - L.lvl_b[lev].first;
+        }
+        // trailing updates C -= P P^T (K = I8_PANEL): (a) the I8_PANEL columns of the next super-panel, (b) the rest (lower tiles)
+        const int ntm = (int)(Np / I8_TM);
+        L.syrk_a.first = T.size();
+        L.syrk_a_count.assign(ntm + 1, 0);
+        for (int tm = 0; tm < ntm; ++tm) {
+            for (int tn = 0; tn < I8_PANEL / TN && tn * TN < (tm + 1) * I8_TM; ++tn)
+                T.push_back({tm * I8_TM, tn * TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.syrk_a_count[tm + 1] = T.size() - L.syrk_a.first;
+        }
+        L.syrk_a.count = T.size() - L.syrk_a.first;
+        L.syrk_b.first = T.size();
+        L.syrk_b_count.assign(ntm + 1, 0);
+        for (int tm = 0; tm < ntm; ++tm) {
+            for (int tn = I8_PANEL / TN; tn * TN < (tm + 1) * I8_TM; ++tn)
+                T.push_back({tm * I8_TM, tn * TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.syrk_b_count[tm + 1] = T.size() - L.syrk_b.first;
+        }
+        L.syrk_b.count = T.size() - L.syrk_b.first;
     }
-    p->syrk_a.count = p->host_tiles.size() - p->syrk_a.first;
-    p->syrk_b.first = p->host_tiles.size();
-    p->syrk_b_count.assign(ntm + 1, 0);
-    for (int tm = 0; tm < ntm; ++tm) {
-        for (int tn = I8_PANEL / I8_TN; tn * I8_TN < (tm + 1) * I8_TM; ++tn)
-            p->host_tiles.push_back({tm * I8_TM, tn * I8_TN, 0, I8_PANEL / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * I8_TN});
-        p->syrk_b_count[tm + 1] = p->host_tiles.size() - p->syrk_b.first;
-    }
-    p->syrk_b.count = p->host_tiles.size() - p->syrk_b.first;
     e = i8_upload_tiles(*p, st);
     if (e != cudaSuccess) return e;
     p->tiles_key = key;
@@ -519,25 +672,27 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
 cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
                            cudaStream_t st) {
     if (!p || (r0 % I8_PANEL) != 0) return cudaErrorNotSupported;
-    if (!p->ready(Np, ld, S) || p->syrk_a.count == 0) return cudaErrorInvalidValue;
+    const I8Lists& L = p->L[i8_width(S)];
+    if (!p->ready(Np, ld, S) || L.syrk_a.count == 0) return cudaErrorInvalidValue;
     const int M = (int)(Np - r0), ntm = M / I8_TM;
     cudaError_t e;
     if (part == 0) {
         if ((e = i8_slice(p->opP, A + r0 * ld + k0, ld, 1, 0, 1, M, I8_PANEL, S, 0, st)) != cudaSuccess) return e;
-        return i8_launch(p->opP, p->opP, p->tiles + p->syrk_a.first, (int)p->syrk_a_count[ntm], S, -1.0, 1.0,
+        return i8_launch(p->opP, p->opP, p->tiles + L.syrk_a.first, (int)L.syrk_a_count[ntm], S, -1.0, 1.0,
                          A + r0 * (ld + 1), ld, st);
     }
-    return i8_launch(p->opP, p->opP, p->tiles + p->syrk_b.first, (int)p->syrk_b_count[ntm], S, -1.0, 1.0, A + r0 * (ld + 1), ld, st);
+    return i8_launch(p->opP, p->opP, p->tiles + L.syrk_b.first, (int)L.syrk_b_count[ntm], S, -1.0, 1.0, A + r0 * (ld + 1), ld, st);
 }
 
 // W(lower tiles) = Linv^T Linv with Linv lower triangular (zero above the diagonal): K^-1 of the factorised matrix.
 // Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
 // (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_prepare.
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
-    if (!p->ready(Np, ld, S) || p->kinv.count == 0) return cudaErrorInvalidValue;      // i8_prepare was not run for this size
+    const I8Lists& L = p->L[i8_width(S)];
+    if (!p->ready(Np, ld, S) || L.kinv.count == 0) return cudaErrorInvalidValue;      // i8_prepare was not run for this size
     cudaError_t e = i8_slice(p->opA, Linv, 1, ld, 0, 1, (int)Np, (int)Np, S, 1, st);
     if (e != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opA, p->tiles + p->kinv.first, (int)p->kinv.count, S, 1.0, 0.0, W, ld, st);
+    return i8_launch(p->opA, p->opA, p->tiles + L.kinv.first, (int)L.kinv.count, S, 1.0, 0.0, W, ld, st);
 }
 
 // One doubling level (block size S_ rows) of Linv = L^-1 on the int8 pipe; returns cudaErrorNotSupported when the level
@@ -548,18 +703,19 @@ cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scr
     if (!p->ready(Np, ld, S)) return cudaErrorInvalidValue;
     int lev = 0;
     for (int64_t x = 64; x < S_; x *= 2) ++lev;
-    if (p->lvl_a[lev].count == 0) return cudaErrorNotSupported;
+    const I8Lists& TL = p->L[i8_width(S)];
+    if (TL.lvl_a[lev].count == 0) return cudaErrorNotSupported;
     const int npair = (int)(Np / (2 * S_)), R = (int)(npair * S_), K = (int)S_;
     const long long bs = 2 * S_ * (ld + 1);
     cudaError_t e;
     // GEMM a
     if ((e = i8_slice(p->opA, L + S_ * ld, ld, 1, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, Linv, 1, ld, bs, npair, R, K, S, 1, st)) != cudaSuccess) return e;
-    if ((e = i8_launch(p->opA, p->opB, p->tiles + p->lvl_a[lev].first, (int)p->lvl_a[lev].count, S, 1.0, 0.0, scratch, ld, st)) != cudaSuccess) return e;
+    if ((e = i8_launch(p->opA, p->opB, p->tiles + TL.lvl_a[lev].first, (int)TL.lvl_a[lev].count, S, 1.0, 0.0, scratch, ld, st)) != cudaSuccess) return e;
     // GEMM b
     if ((e = i8_slice(p->opA, Linv + S_ * ld + S_, ld, 1, bs, npair, R, K, S, 2, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, scratch + S_ * ld, 1, ld, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opB, p->tiles + p->lvl_b[lev].first, (int)p->lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st);
+    return i8_launch(p->opA, p->opB, p->tiles + TL.lvl_b[lev].first, (int)TL.lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st);
 }
 
 // ------------------------------------------------------------------ self-test hooks (tests, tools/gpu_diag.py)
@@ -604,9 +760,10 @@ extern "C" int mogp_i8_selftest(int M, int N, int K, int S, double* out_host /*4
     cudaMemset(res, 0, 16);
     I8Plan* p = i8_plan_create();
     int rc = 0;
+    const int TNs = i8_width(S) == 1 ? 128 : I8_TN;
     for (int ti = 0; ti < M / I8_TM; ++ti)
-        for (int tj = 0; tj < N / I8_TN; ++tj)
-            p->host_tiles.push_back({ti * I8_TM, tj * I8_TN, 0, K / I8_KC, (long long)ti * I8_TM * N + (long long)tj * I8_TN});
+        for (int tj = 0; tj < N / TNs; ++tj)
+            p->host_tiles.push_back({ti * I8_TM, tj * TNs, 0, K / I8_KC, (long long)ti * I8_TM * N + (long long)tj * TNs});
     if (i8_upload_tiles(*p, nullptr) != cudaSuccess) rc = -2;
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);

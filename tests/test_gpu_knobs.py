@@ -84,7 +84,7 @@ def test_failed_graph_capture_falls_back_to_an_eager_run(engine, knobs):
 
 
 # ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (tcgen05.mma kind::i8)
-@pytest.mark.parametrize("ts", [0, 1])
+@pytest.mark.parametrize("ts", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K,S,tol", [(128, 128, 32, 7, 1e-12), (256, 384, 4096, 7, 1e-12), (1024, 1024, 1024, 8, 1e-13),
                                           (2048, 2048, 2048, 7, 1e-12)])
 def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol, ts):
@@ -92,12 +92,15 @@ def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol, ts):
     fp64 DMMA GEMM: relative to the largest entry the difference is ~1e-14 at S = 7 and ~fp64 rounding at S = 8."""
     import ctypes as C
     out = (C.c_double * 4)()
-    default_ts = engine.lib.mogp_get_i8_ts()
+    default_ts, default_wide = engine.lib.mogp_get_i8_ts(), engine.lib.mogp_get_i8_wide()
     try:
-        engine.lib.mogp_set_i8_ts(ts)          # A planes through tensor memory (S = 7) or both operands from shared memory
+        # 0: 128 x 64 tiles, both operands from shared memory; 1: A planes through tensor memory; 2: 128 x 128 tiles, two passes
+        engine.lib.mogp_set_i8_ts(1 if ts == 1 else 0)
+        engine.lib.mogp_set_i8_wide(1 if ts == 2 else 0)
         rc = engine.lib.mogp_i8_selftest(M, N, K, S, out)
     finally:
         engine.lib.mogp_set_i8_ts(default_ts)
+        engine.lib.mogp_set_i8_wide(default_wide)
     assert rc == 0
     assert 0.0 <= out[0] < tol, out[0]
 
@@ -182,7 +185,7 @@ def test_int8_trailing_updates_of_the_cholesky(engine, n):
         assert engine.potrf_(A7) == 0
     finally:
         lib.mogp_set_i8(4096, 7)
-        lib.mogp_set_i8_potrf_min(0)
+        lib.mogp_set_i8_potrf_min(8192)
     ref = torch.linalg.cholesky(K)
     scale = float(ref.abs().max())
     assert float((torch.tril(Ad) - ref).abs().max()) <= 1e-11 * scale

@@ -438,9 +438,12 @@ def sec_i8p(eng):
     """Product int8 tensor-pipe GEMM (csrc/i8mm.cu): error, time of slicing + MMA kernel, against the DMMA GEMM."""
     import ctypes as C
     out = (C.c_double * 4)()
-    for ts in ([int(os.environ["I8_TS"])] if "I8_TS" in os.environ else [0, 1]):
-      eng.lib.mogp_set_i8_ts(ts)
-      print("--- A operand from %s" % ("tensor memory (tcgen05.cp + TS-form MMA)" if ts else "shared memory (SS-form MMA)"))
+    for ts in ([int(os.environ["I8_TS"])] if "I8_TS" in os.environ else [0, 1, 2]):
+      eng.lib.mogp_set_i8_ts(1 if ts == 1 else 0)
+      eng.lib.mogp_set_i8_wide(1 if ts == 2 else 0)
+      print("--- %s" % ["128 x 64 tiles, one pass, both operands from shared memory (SS-form MMA)",
+                        "128 x 64 tiles, A planes through tensor memory (tcgen05.cp + TS-form MMA)",
+                        "128 x 128 tiles, two passes over the anti-diagonals (SS-form MMA)"][ts])
       for (M, N, K) in [(128, 128, 32), (256, 256, 256), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (8192, 8192, 1024)]:
         for S in ((7,) if ts else (7, 8)):
             rc = eng.lib.mogp_i8_selftest(M, N, K, S, out)
@@ -449,6 +452,7 @@ def sec_i8p(eng):
                 M, N, K, S, rc, out[0], out[1], out[2], ops / max(out[2], 1e-9) / 1e9, ops * S * (S + 1) / 2 / max(out[2], 1e-9) / 1e9,
                 out[3], ops / max(out[3], 1e-9) / 1e9), flush=True)
     eng.lib.mogp_set_i8_ts(0)
+    eng.lib.mogp_set_i8_wide(0)
 
 
 def sec_gemmk(eng):
