@@ -307,7 +307,7 @@ extern "C" int mogp_set_i8(long long min_np, int slices) {
 long long g_i8_potrf_min = std::getenv("MOGP_I8_POTRF_MIN") ? std::atoll(std::getenv("MOGP_I8_POTRF_MIN")) : 8192;
 extern "C" int mogp_set_i8_potrf_min(long long np) { g_i8_potrf_min = np; ++g_mogp_cfg_epoch; return 0; }
 extern int g_i8_ts, g_i8_wide;
-extern "C" int mogp_set_i8_wide(int on) { g_i8_wide = on ? 1 : 0; ++g_mogp_cfg_epoch; return 0; }
+extern "C" int mogp_set_i8_wide(int level) { g_i8_wide = level < 0 ? 0 : (level > 3 ? 3 : level); ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_get_i8_wide(void) { return g_i8_wide; }
 extern "C" int mogp_set_i8_ts(int on) { g_i8_ts = on ? 1 : 0; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_get_i8_ts(void) { return g_i8_ts; }

@@ -517,13 +517,17 @@ static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long
 
 // 1: A planes through tensor memory (S = 7 only: 8 planes do not fit beside 8 accumulators), 0: both operands from shared memory
 int g_i8_ts = std::getenv("MOGP_I8_TS") ? std::atoi(std::getenv("MOGP_I8_TS")) : 0;
-// 1: 128 x 128 tiles in two passes over the anti-diagonals (S = 7), 0: 128 x 64 tiles in one pass
-int g_i8_wide = std::getenv("MOGP_I8_WIDE") ? std::atoi(std::getenv("MOGP_I8_WIDE")) : 0;
-static int i8_width(int S) { return (g_i8_wide && S == 7) ? 1 : 0; }
+// 128 x 128 tiles in two passes over the anti-diagonals (S = 7) instead of 128 x 64 tiles in one pass.  Measured
+// (profiles/r02_i8mm_variants.log): 8192^3 99.5 vs 82.9 TFLOP/s fp64-equivalent, but slower when K is short (K = 1024:
+// 52.4 vs 59.7) because a product is two launches.  0: never; 1: the K^-1 product (K up to N); 2: also the levels of the
+// triangular inverse with block size >= 4096; 3: everything (self-test).
+int g_i8_wide = std::getenv("MOGP_I8_WIDE") ? std::atoi(std::getenv("MOGP_I8_WIDE")) : 1;
+enum { I8_USE_KINV = 1, I8_USE_TRTRI_TOP = 2, I8_USE_OTHER = 3 };
+static int i8_width(int S, int use) { return (S == 7 && g_i8_wide >= use) ? 1 : 0; }
 
-// `lists` = the I8Lists of i8_width(S); `l` one of its lists, `count` tiles of it
+// tiles_dev: a list built for the tile width `width` (0: 128 x 64, 1: 128 x 128)
 static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Tile* tiles_dev, int ntiles, int S, double alpha,
-                             double beta, double* C, long long ldc, cudaStream_t st) {
+                             double beta, double* C, long long ldc, cudaStream_t st, int width) {
     static PerDeviceOnce once;
     if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
@@ -542,7 +546,7 @@ static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Til
     g.A = A.digits; g.ea = A.ex; g.nrtA = A.nrt;
     g.B = B.digits; g.eb = B.ex; g.nrtB = B.nrt;
     g.tiles = tiles_dev; g.S = S; g.alpha = alpha; g.beta = beta; g.C = C; g.ldc = ldc;
-    if (i8_width(S) == 1) {
+    if (width == 1) {
         i8_gemm_wide_kernel<0, 3><<<ntiles, 192, I8Wide<0, 3>::SMEM, st>>>(g, S);
         g.beta = 1.0;                                   // the second pass accumulates onto the first
         i8_gemm_wide_kernel<4, 6><<<ntiles, 192, I8Wide<4, 6>::SMEM, st>>>(g, S);
@@ -672,27 +676,29 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
 cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
                            cudaStream_t st) {
     if (!p || (r0 % I8_PANEL) != 0) return cudaErrorNotSupported;
-    const I8Lists& L = p->L[i8_width(S)];
+    const int width = i8_width(S, I8_USE_OTHER);
+    const I8Lists& L = p->L[width];
     if (!p->ready(Np, ld, S) || L.syrk_a.count == 0) return cudaErrorInvalidValue;
     const int M = (int)(Np - r0), ntm = M / I8_TM;
     cudaError_t e;
     if (part == 0) {
         if ((e = i8_slice(p->opP, A + r0 * ld + k0, ld, 1, 0, 1, M, I8_PANEL, S, 0, st)) != cudaSuccess) return e;
         return i8_launch(p->opP, p->opP, p->tiles + L.syrk_a.first, (int)L.syrk_a_count[ntm], S, -1.0, 1.0,
-                         A + r0 * (ld + 1), ld, st);
+                         A + r0 * (ld + 1), ld, st, width);
     }
-    return i8_launch(p->opP, p->opP, p->tiles + L.syrk_b.first, (int)L.syrk_b_count[ntm], S, -1.0, 1.0, A + r0 * (ld + 1), ld, st);
+    return i8_launch(p->opP, p->opP, p->tiles + L.syrk_b.first, (int)L.syrk_b_count[ntm], S, -1.0, 1.0, A + r0 * (ld + 1), ld, st, width);
 }
 
 // W(lower tiles) = Linv^T Linv with Linv lower triangular (zero above the diagonal): K^-1 of the factorised matrix.
 // Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
 // (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_prepare.
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
-    const I8Lists& L = p->L[i8_width(S)];
+    const int width = i8_width(S, I8_USE_KINV);
+    const I8Lists& L = p->L[width];
     if (!p->ready(Np, ld, S) || L.kinv.count == 0) return cudaErrorInvalidValue;      // i8_prepare was not run for this size
     cudaError_t e = i8_slice(p->opA, Linv, 1, ld, 0, 1, (int)Np, (int)Np, S, 1, st);
     if (e != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opA, p->tiles + L.kinv.first, (int)L.kinv.count, S, 1.0, 0.0, W, ld, st);
+    return i8_launch(p->opA, p->opA, p->tiles + L.kinv.first, (int)L.kinv.count, S, 1.0, 0.0, W, ld, st, width);
 }
 
 // One doubling level (block size S_ rows) of Linv = L^-1 on the int8 pipe; returns cudaErrorNotSupported when the level
@@ -703,7 +709,8 @@ cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scr
     if (!p->ready(Np, ld, S)) return cudaErrorInvalidValue;
     int lev = 0;
     for (int64_t x = 64; x < S_; x *= 2) ++lev;
-    const I8Lists& TL = p->L[i8_width(S)];
+    const int width = i8_width(S, S_ >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
+    const I8Lists& TL = p->L[width];
     if (TL.lvl_a[lev].count == 0) return cudaErrorNotSupported;
     const int npair = (int)(Np / (2 * S_)), R = (int)(npair * S_), K = (int)S_;
     const long long bs = 2 * S_ * (ld + 1);
@@ -711,11 +718,11 @@ cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scr
     // GEMM a
     if ((e = i8_slice(p->opA, L + S_ * ld, ld, 1, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, Linv, 1, ld, bs, npair, R, K, S, 1, st)) != cudaSuccess) return e;
-    if ((e = i8_launch(p->opA, p->opB, p->tiles + TL.lvl_a[lev].first, (int)TL.lvl_a[lev].count, S, 1.0, 0.0, scratch, ld, st)) != cudaSuccess) return e;
+    if ((e = i8_launch(p->opA, p->opB, p->tiles + TL.lvl_a[lev].first, (int)TL.lvl_a[lev].count, S, 1.0, 0.0, scratch, ld, st, width)) != cudaSuccess) return e;
     // GEMM b
     if ((e = i8_slice(p->opA, Linv + S_ * ld + S_, ld, 1, bs, npair, R, K, S, 2, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, scratch + S_ * ld, 1, ld, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opB, p->tiles + TL.lvl_b[lev].first, (int)TL.lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st);
+    return i8_launch(p->opA, p->opB, p->tiles + TL.lvl_b[lev].first, (int)TL.lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st, width);
 }
 
 // ------------------------------------------------------------------ self-test hooks (tests, tools/gpu_diag.py)
@@ -760,7 +767,8 @@ extern "C" int mogp_i8_selftest(int M, int N, int K, int S, double* out_host /*4
     cudaMemset(res, 0, 16);
     I8Plan* p = i8_plan_create();
     int rc = 0;
-    const int TNs = i8_width(S) == 1 ? 128 : I8_TN;
+    const int wsel = i8_width(S, I8_USE_OTHER);          // the self-test follows the "everything" setting (g_i8_wide = 3)
+    const int TNs = wsel == 1 ? 128 : I8_TN;
     for (int ti = 0; ti < M / I8_TM; ++ti)
         for (int tj = 0; tj < N / TNs; ++tj)
             p->host_tiles.push_back({ti * I8_TM, tj * TNs, 0, K / I8_KC, (long long)ti * I8_TM * N + (long long)tj * TNs});
@@ -772,7 +780,7 @@ extern "C" int mogp_i8_selftest(int M, int N, int K, int S, double* out_host /*4
         if (i8_slice(p->opA, A, K, 1, 0, 1, M, K, S, 0, nullptr) != cudaSuccess) rc = -3;
         if (rc == 0 && i8_slice(p->opB, B, K, 1, 0, 1, N, K, S, 0, nullptr) != cudaSuccess) rc = -3;
         cudaEventRecord(e1);
-        if (rc == 0 && i8_launch(p->opA, p->opB, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, C1, N, nullptr) != cudaSuccess) rc = -4;
+        if (rc == 0 && i8_launch(p->opA, p->opB, p->tiles, (int)p->host_tiles.size(), S, 1.0, 0.0, C1, N, nullptr, wsel) != cudaSuccess) rc = -4;
         cudaEventRecord(e2);
         GemmArgs g{};
         g.A = A; g.lda = K; g.B = B; g.ldb = K; g.C = C2; g.ldc = N;

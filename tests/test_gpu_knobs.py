@@ -96,7 +96,7 @@ def test_int8_tensor_pipe_gemm_against_dmma(engine, M, N, K, S, tol, ts):
     try:
         # 0: 128 x 64 tiles, both operands from shared memory; 1: A planes through tensor memory; 2: 128 x 128 tiles, two passes
         engine.lib.mogp_set_i8_ts(1 if ts == 1 else 0)
-        engine.lib.mogp_set_i8_wide(1 if ts == 2 else 0)
+        engine.lib.mogp_set_i8_wide(3 if ts == 2 else 0)
         rc = engine.lib.mogp_i8_selftest(M, N, K, S, out)
     finally:
         engine.lib.mogp_set_i8_ts(default_ts)

@@ -440,7 +440,7 @@ def sec_i8p(eng):
     out = (C.c_double * 4)()
     for ts in ([int(os.environ["I8_TS"])] if "I8_TS" in os.environ else [0, 1, 2]):
       eng.lib.mogp_set_i8_ts(1 if ts == 1 else 0)
-      eng.lib.mogp_set_i8_wide(1 if ts == 2 else 0)
+      eng.lib.mogp_set_i8_wide(3 if ts == 2 else 0)
       print("--- %s" % ["128 x 64 tiles, one pass, both operands from shared memory (SS-form MMA)",
                         "128 x 64 tiles, A planes through tensor memory (tcgen05.cp + TS-form MMA)",
                         "128 x 128 tiles, two passes over the anti-diagonals (SS-form MMA)"][ts])
@@ -452,7 +452,7 @@ def sec_i8p(eng):
                 M, N, K, S, rc, out[0], out[1], out[2], ops / max(out[2], 1e-9) / 1e9, ops * S * (S + 1) / 2 / max(out[2], 1e-9) / 1e9,
                 out[3], ops / max(out[3], 1e-9) / 1e9), flush=True)
     eng.lib.mogp_set_i8_ts(0)
-    eng.lib.mogp_set_i8_wide(0)
+    eng.lib.mogp_set_i8_wide(1)
 
 
 def sec_gemmk(eng):
