@@ -519,9 +519,10 @@ static cudaError_t i8_slice(I8Operand& op, const double* src, long long rs, long
 int g_i8_ts = std::getenv("MOGP_I8_TS") ? std::atoi(std::getenv("MOGP_I8_TS")) : 0;
 // 128 x 128 tiles in two passes over the anti-diagonals (S = 7) instead of 128 x 64 tiles in one pass.  Measured
 // (profiles/r02_i8mm_variants.log): 8192^3 99.5 vs 82.9 TFLOP/s fp64-equivalent, but slower when K is short (K = 1024:
-// 52.4 vs 59.7) because a product is two launches.  0: never; 1: the K^-1 product (K up to N); 2: also the levels of the
-// triangular inverse with block size >= 4096; 3: everything (self-test).
-int g_i8_wide = std::getenv("MOGP_I8_WIDE") ? std::atoi(std::getenv("MOGP_I8_WIDE")) : 1;
+// 52.4 vs 59.7) because a product is two launches.  0: never; 1: the K^-1 product for N >= 8192 (K up to N; at N = 4096 the
+// one-pass kernel is faster: 0.466 vs 0.491 ms); 2: also the levels of the triangular inverse with block size >= 4096
+// (cfg3 step 14.19 -> 14.06 ms); 3: everything (self-test).
+int g_i8_wide = std::getenv("MOGP_I8_WIDE") ? std::atoi(std::getenv("MOGP_I8_WIDE")) : 2;
 enum { I8_USE_KINV = 1, I8_USE_TRTRI_TOP = 2, I8_USE_OTHER = 3 };
 static int i8_width(int S, int use) { return (S == 7 && g_i8_wide >= use) ? 1 : 0; }
 
@@ -693,7 +694,7 @@ cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64
 // Operand row i = column i of Linv (element (i, k) = Linv[k * ld + i]), nonzero for k >= i: K range of output tile
 // (ti, tj), tj <= ti, starts at the tile's first row.  Pure enqueue (capturable) after i8_prepare.
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st) {
-    const int width = i8_width(S, I8_USE_KINV);
+    const int width = (Np >= 8192 || g_i8_wide >= I8_USE_OTHER) ? i8_width(S, I8_USE_KINV) : 0;
     const I8Lists& L = p->L[width];
     if (!p->ready(Np, ld, S) || L.kinv.count == 0) return cudaErrorInvalidValue;      // i8_prepare was not run for this size
     cudaError_t e = i8_slice(p->opA, Linv, 1, ld, 0, 1, (int)Np, (int)Np, S, 1, st);

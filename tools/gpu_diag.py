@@ -452,7 +452,7 @@ def sec_i8p(eng):
                 M, N, K, S, rc, out[0], out[1], out[2], ops / max(out[2], 1e-9) / 1e9, ops * S * (S + 1) / 2 / max(out[2], 1e-9) / 1e9,
                 out[3], ops / max(out[3], 1e-9) / 1e9), flush=True)
     eng.lib.mogp_set_i8_ts(0)
-    eng.lib.mogp_set_i8_wide(1)
+    eng.lib.mogp_set_i8_wide(2)
 
 
 def sec_gemmk(eng):
