@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/mogp_b200.h"
@@ -160,20 +162,29 @@ struct mogp_handle_s {
 // Kernel attributes (dynamic shared-memory opt-in, carve-out) are per DEVICE: a process that drives several GPUs
 // (gpr.use_gpu(n), one Engine per device) has to set them once on each.  `static PerDeviceOnce once; if (once.first()) ...`
 struct PerDeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
     int sm_count[64] = {};
     int device() const { int d = 0; cudaGetDevice(&d); return d & 63; }
-    bool first() { const int d = device(); if (done[d]) return false; done[d] = true; return true; }
     int sms() {
         const int d = device();
+        std::lock_guard<std::mutex> lk(mu);
         if (sm_count[d] <= 0 && (cudaDeviceGetAttribute(&sm_count[d], cudaDevAttrMultiProcessorCount, d) != cudaSuccess || sm_count[d] <= 0))
             sm_count[d] = 148;
         return sm_count[d];
     }
 };
+// `if (OnceGuard og{once}; og.needed()) { set the attributes }`: the lock is held while they are being set, so that a second
+// host thread (replicas.train_restarts runs one per model) cannot launch the kernel before its attributes exist.
+struct OnceGuard {
+    PerDeviceOnce& o; int d; bool need;
+    explicit OnceGuard(PerDeviceOnce& o_) : o(o_), d(o_.device()) { o.mu.lock(); need = !o.done[d]; }
+    bool needed() const { return need; }
+    ~OnceGuard() { if (need) o.done[d] = true; o.mu.unlock(); }
+};
 
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
-extern long long g_mogp_launches;
+extern std::atomic<long long> g_mogp_launches;
 extern long long g_mogp_cfg_epoch;
 #define MOGP_COUNT(n) (g_mogp_launches += (n))
 

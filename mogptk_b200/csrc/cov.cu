@@ -369,7 +369,7 @@ static cudaError_t launch_kbuild_t(const KernSpec& s, const TileList& tl, int nb
     const size_t smem = sizeof(TileSmem) + 64 * 65 * sizeof(double);
     auto kern = kbuild_kernel<DT, COS, MINB>;
     static PerDeviceOnce once;
-    if (once.first()) {
+    if (OnceGuard og{once}; og.needed()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -558,7 +558,7 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
     do {                                                                                                           \
         auto kern = grad_reduce_kernel<DT, COS, MB>;                                                               \
         static PerDeviceOnce once;                                                                                 \
-        if (once.first()) {                                                                                        \
+        if (OnceGuard og{once}; og.needed()) {                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
             if (e != cudaSuccess) return e;                                                                        \
         }                                                                                                          \

@@ -530,7 +530,7 @@ static int i8_width(int S, int use) { return (S == 7 && g_i8_wide >= use) ? 1 : 
 static cudaError_t i8_launch(const I8Operand& A, const I8Operand& B, const I8Tile* tiles_dev, int ntiles, int S, double alpha,
                              double beta, double* C, long long ldc, cudaStream_t st, int width) {
     static PerDeviceOnce once;
-    if (once.first()) {
+    if (OnceGuard og{once}; og.needed()) {
         cudaError_t e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(i8_gemm_tiles_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(I8Smem));

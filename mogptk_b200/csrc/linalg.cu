@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     }   // pair loop
 }
 
-long long g_mogp_launches = 0;
+std::atomic<long long> g_mogp_launches{0};
 long long g_mogp_cfg_epoch = 0;      // bumped by the tuning setters: captured step graphs are re-captured
 // 0 (default): 64x64 tiles   1: force 128x128 tiles (256 threads)   3: force 128x64 tiles
 static int g_gemm_cfg = -1;
@@ -218,7 +218,7 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
     auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, TA, TB>;
     static PerDeviceOnce once;
-    if (once.first()) {
+    if (OnceGuard og{once}; og.needed()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
         // same (maximal) shared-memory carve-out as the Cholesky panel kernel, so that both can be
@@ -1047,7 +1047,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
-    if (once.first()) {
+    if (OnceGuard og{once}; og.needed()) {
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
