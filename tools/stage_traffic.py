@@ -75,15 +75,20 @@ def main():
     idx_pad = next((i for i, l in enumerate(step) if "pad_copy" in l["name"]), None)
     kinv_set = set()
     if idx_pad is not None:
-        for i in range(idx_pad - 1, -1, -1):
-            if "gemm" in step[i]["name"]:
+        i = idx_pad - 1
+        while i >= 0 and "gemm" not in step[i]["name"]:
+            i -= 1
+        if i >= 0 and "i8_gemm" in step[i]["name"]:
+            while i >= 0 and "i8_gemm" in step[i]["name"]:          # one launch (128 x 64 tiles) or two passes (128 x 128)
                 kinv_set.add(i)
-                if "i8_gemm" in step[i]["name"]:
-                    j = i - 1
-                    while j >= 0 and step[j]["name"].startswith("i8_") and "gemm" not in step[j]["name"] and len(kinv_set) < 4:
-                        kinv_set.add(j)
-                        j -= 1
-                break
+                i -= 1
+            n = 0
+            while i >= 0 and n < 3 and step[i]["name"].startswith("i8_") and "gemm" not in step[i]["name"]:
+                kinv_set.add(i)                                       # i8_slice_tiled, i8_exponent, i8_rowmax of its operand
+                i -= 1
+                n += 1
+        elif i >= 0:
+            kinv_set.add(i)
     for i, l in enumerate(step):
         st = "kinv" if i in kinv_set else stage_of(l["name"], state)
         s = stages.setdefault(st, {"launches": 0, "time_us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "tensor_weighted": 0.0,
