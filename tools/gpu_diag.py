@@ -417,23 +417,6 @@ def sec_spans(eng):
     eng.lib.mogp_set_panel_variant(2)
 
 
-def sec_i8(eng):
-    """Experimental fp64-on-int8 tcgen05 GEMM (csrc/i8gemm.cu) against the DMMA GEMM: error and time per slice count."""
-    import ctypes as C
-    explib = C.CDLL(os.path.join(ROOT, "mogptk_b200", "libmogp_b200_exp.so"))     # product objects + csrc/i8gemm.cu
-    explib.mogp_i8gemm_selftest.restype = C.c_int
-    explib.mogp_i8gemm_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-    out = (C.c_double * 3)()
-    for variant in ([int(os.environ["I8_VARIANT"])] if "I8_VARIANT" in os.environ else [0, 1]):   # one per process if it faults
-      explib.mogp_i8gemm_set_variant(variant)
-      print("--- int8 GEMM kernel variant %d (0 simple, 1 warp-specialised pipeline)" % variant)
-      for (M, N, K) in [(128, 128, 64), (256, 128, 256), (1024, 1024, 1024), (4096, 4096, 4096)]:
-        for S in (6, 7, 8):
-            rc = explib.mogp_i8gemm_selftest(M, N, K, S, out)
-            print("i8 gemm %5dx%5dx%5d S=%d rc=%d: rel. error %.2e | int8 path %.3f ms (%.1f TFLOP/s fp64-equivalent) | DMMA %.3f ms (%.1f TFLOP/s)" % (
-                M, N, K, S, rc, out[0], out[1], 2.0 * M * N * K / max(out[1], 1e-9) / 1e9, out[2], 2.0 * M * N * K / max(out[2], 1e-9) / 1e9))
-
-
 def sec_i8p(eng):
     """Product int8 tensor-pipe GEMM (csrc/i8mm.cu): error, time of slicing + MMA kernel, against the DMMA GEMM."""
     import ctypes as C
@@ -525,7 +508,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"i8p": sec_i8p, "i8": sec_i8, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"i8p": sec_i8p, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
