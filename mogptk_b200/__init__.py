@@ -4,7 +4,7 @@ Hot path: MOSM / SM / CONV Gram build, blocked Cholesky, l
 likelihood with analytic gradient, posterior mean/variance -- hand-written sm_100a CUDA in
 libmogp_b200.so, called through the C ABI of include/mogp_b200.h.  No CPU fallback.
 """
-from . import _cabi, engine, gpr, synth          # noqa: F401
+from . import _cabi, engine, gpr, init, synth    # noqa: F401
 from .engine import Engine, NotPositiveDefiniteError  # noqa: F401
 from .gpr import (CholeskyException, CrossSpectralKernel, Exact, GaussianConvolutionProcessKernel,  # noqa: F401
                   GaussianLikelihood, IndependentMultiOutputKernel, LinearModelOfCoregionalizationKernel, MixtureKernel,

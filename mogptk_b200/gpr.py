@@ -60,9 +60,9 @@ def use_gpu(n=None):
 _META = ("_name", "lower", "upper", "prior", "train", "pegged_parameter", "pegged_transform", "num_parameters")
 
 
-def _fit_shape(t, shape, what):
-    """Add / drop trailing singleton axes until `t` has `shape` (scalars broadcast)."""
-    if t.ndim == 0:
+def _fit_shape(t, shape, what, scalar_ok=True):
+    """Add / drop trailing singleton axes until `t` has `shape` (bounds given as scalars broadcast: scalar_ok)."""
+    if t.ndim == 0 and scalar_ok:
         return t
     orig = tuple(t.shape)
     while t.ndim < len(shape) and shape[t.ndim] == 1:
@@ -202,11 +202,7 @@ class Parameter(torch.nn.Parameter):
         if value is None:
             value = self.data
         else:
-            value = Parameter.to_tensor(value)
-            if value.ndim != 0 or self.ndim == 0:
-                value = _fit_shape(value, self.shape, "parameter shape must match") if value.ndim else value
-            if value.shape != self.shape:
-                raise ValueError("parameter shape must match: %s != %s" % (tuple(value.shape), tuple(self.shape)))
+            value = _fit_shape(Parameter.to_tensor(value), self.shape, "parameter shape must match", scalar_ok=False)
         box = Constraint(self._bound(lower, self.lower, value), self._bound(upper, self.upper, value))
         raw = box.inverse(box.clip(value)) if box.kind != "identity" else value
         raw.requires_grad = True

@@ -133,10 +133,18 @@ def train(model, method="Adam", iters=500, verbose=False, error=None, plot=False
 
 
 def install(mogptk=None):
-    """Route ``mogptk.Model.train`` through :func:`train` (idempotent).  The reference's method stays reachable as
-    ``mogptk.Model._train_reference`` and is what runs for every request the device path does not cover."""
+    """Route the reference's exact-GP entry points that sit OUTSIDE the `inference=` seam to the engine (idempotent):
+
+    * ``mogptk.Model.train`` -> :func:`train` (device-resident Adam loop when the request allows it);
+    * ``mogptk.init.BNSE`` / the name ``BNSE`` imported into ``mogptk.data`` -> ``mogptk_b200.init.BNSE``;
+    * ``Data.get_sm_estimation`` -> per-channel ``mogptk.SM`` built through ``B200Exact``;
+    * ``DataSet.get_bnse_estimation`` -> the channels fitted concurrently.
+
+    The reference's own functions stay reachable (``mogptk.Model._train_reference`` etc.) and are what runs for every
+    request the engine does not cover; :func:`uninstall` restores them."""
     if mogptk is None:
         import mogptk
+    from . import init as _init
     cls = mogptk.Model
     if getattr(cls, "_train_reference", None) is None:
         cls._train_reference = cls.train
@@ -146,6 +154,24 @@ def install(mogptk=None):
 
         _train.__doc__ = cls._train_reference.__doc__
         cls.train = _train
+    if getattr(mogptk, "_b200_saved", None) is None:
+        import mogptk.data as mdata
+        import mogptk.dataset as mdataset
+        import mogptk.init as minit
+        mogptk._b200_saved = {"init.BNSE": minit.BNSE, "data.BNSE": mdata.BNSE,
+                              "Data.get_sm_estimation": mdata.Data.get_sm_estimation,
+                              "DataSet.get_bnse_estimation": mdataset.DataSet.get_bnse_estimation}
+        minit.BNSE = _init.BNSE
+        mdata.BNSE = _init.BNSE
+
+        def _get_sm_estimation(self, Q=1, method="LS", optimizer="Adam", iters=200, params={}):
+            return _init.sm_estimation(self, Q, method, optimizer, iters, params)
+
+        def _get_bnse_estimation(self, Q=1, n=1000, iters=200):
+            return _init.bnse_estimation_concurrent(self, Q, n, iters)
+
+        mdata.Data.get_sm_estimation = _get_sm_estimation
+        mdataset.DataSet.get_bnse_estimation = _get_bnse_estimation
     return cls
 
 
@@ -156,3 +182,13 @@ def uninstall(mogptk=None):
     if getattr(cls, "_train_reference", None) is not None:
         cls.train = cls._train_reference
         cls._train_reference = None
+    saved = getattr(mogptk, "_b200_saved", None)
+    if saved is not None:
+        import mogptk.data as mdata
+        import mogptk.dataset as mdataset
+        import mogptk.init as minit
+        minit.BNSE = saved["init.BNSE"]
+        mdata.BNSE = saved["data.BNSE"]
+        mdata.Data.get_sm_estimation = saved["Data.get_sm_estimation"]
+        mdataset.DataSet.get_bnse_estimation = saved["DataSet.get_bnse_estimation"]
+        mogptk._b200_saved = None

@@ -319,3 +319,57 @@ def test_csm_and_sm_lmc_models_through_the_reference(mogptk, family, kw):
     finally:
         mb.uninstall(mogptk)
     assert close(la, lc, 1e-7), np.abs(la - lc).max()
+
+
+# ------------------------------------------------------------------ initialisers that run exact GPs
+def _signal(n, seed):
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.uniform(0.0, 12.0, n))
+    y = np.sin(2 * np.pi * 0.45 * x) + 0.6 * np.sin(2 * np.pi * 1.2 * x + 0.4) + 0.1 * rng.standard_normal(n)
+    return x, y
+
+
+def test_bnse_on_the_engine_matches_the_reference(mogptk):
+    """mogptk_b200.init.BNSE (training, Gram, factor and the N^2 n products through the C ABI) against the reference's
+    mogptk.init.BNSE (mogptk/init.py:5-126) on the CPU: same grid, PSD mean / variance to 1e-5 / 1e-4 of their maxima."""
+    import mogptk_b200 as mb
+    x, y = _signal(150, 21)
+    with on(mogptk, "cpu"):
+        w0, m0, v0 = mogptk.init.BNSE(x.copy(), y.copy(), n=400, iters=30, jit=False)
+    w1, m1, v1 = mb.init.BNSE(x.copy(), y.copy(), n=400, iters=30)
+    assert np.array_equal(w0, w1) or np.abs(w0 - w1).max() <= 1e-14 * np.abs(w0).max()
+    assert np.abs(m0 - m1).max() <= 1e-5 * np.abs(m0).max(), np.abs(m0 - m1).max() / np.abs(m0).max()
+    assert np.abs(v0 - v1).max() <= 1e-4 * np.abs(v0).max()
+    # with measurement errors (data variance in the training model only, init.py:40)
+    ye = 0.05 + 0.05 * np.cos(x) ** 2
+    with on(mogptk, "cpu"):
+        _, m2, _ = mogptk.init.BNSE(x.copy(), y.copy(), y_err=ye, n=200, iters=15, jit=False)
+    _, m3, _ = mb.init.BNSE(x.copy(), y.copy(), y_err=ye, n=200, iters=15)
+    assert np.abs(m2 - m3).max() <= 1e-5 * np.abs(m2).max()
+
+
+@pytest.mark.parametrize("method", ["BNSE", "SM"])
+def test_init_parameters_through_the_engine(mogptk, method):
+    """mogptk.MOSM(...).init_parameters(method) (mogptk/models/mosm.py:62-113) after mogptk_b200.install(): the per-channel
+    exact GPs of BNSE / Data.get_sm_estimation run on the engine (channels concurrently for BNSE) and give the reference's
+    starting values."""
+    import mogptk_b200 as mb
+    from mogptk_b200 import synth
+    X, y = synth.make_data(3, [90, 70, 110], seed=17)
+    with on(mogptk, "cpu"):
+        torch.manual_seed(3)
+        a = mogptk.MOSM(dataset(mogptk, X, y, 3), Q=2)
+        a.init_parameters(method, iters=25)
+    torch.manual_seed(3)
+    b = mogptk.MOSM(dataset(mogptk, X, y, 3), Q=2, inference=mb.B200Exact())
+    mb.install(mogptk)
+    try:
+        b.init_parameters(method, iters=25)
+    finally:
+        mb.uninstall(mogptk)
+    for name in ("weight", "mean", "variance"):
+        u = getattr(a.gpr.kernel, name).numpy()
+        v = getattr(b.gpr.kernel, name).numpy()
+        assert np.abs(u - v).max() <= 1e-4 * max(np.abs(u).max(), 1e-12), (name, u, v)
+    assert close(a.gpr.likelihood.scale.numpy(), b.gpr.likelihood.scale.numpy(), 1e-10)
+    assert mogptk.init.BNSE.__module__ == "mogptk.init"          # uninstall() restored the reference's functions
