@@ -513,6 +513,23 @@ def run_b200(args):
     barrier()
     e2e_fused_val = world * args.steps / replicas.max_over_ranks(time.perf_counter() - t0, eng.device)
 
+    # the same per-step protocol (copies in, loss out, every step) with the optimiser update inside the C call:
+    # Exact.fit_adam(1) = transforms + step + chain rule + Adam in one mogp_train_adam call, one synchronisation
+    state = {}
+
+    def api_step_device_adam():
+        model._rows.x.copy_(xh, non_blocking=True)
+        model._rows.y.copy_(yh, non_blocking=True)
+        return float(model.fit_adam(1, lr=1e-3, sync_every=1, state=state)[0][0])
+    for _ in range(W):
+        api_step_device_adam()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        api_step_device_adam()
+    barrier()
+    e2e_dev_adam_val = world * args.steps / replicas.max_over_ranks(time.perf_counter() - t0, eng.device)
+
     # ---------------- beside it: the C-ABI host call (round-1 e2e), the device-resident training loop
     Pk = packed.cpu().numpy().copy()
     xhn, yhn = xh.numpy(), yh.numpy()
@@ -572,6 +589,9 @@ def run_b200(args):
                     "fused_optimizer": {"value": e2e_fused_val, "unit": UNIT,
                                         "what": "the same per-step loop with torch.optim.Adam(fused=True) (one optimiser kernel "
                                                 "instead of ~10), the option mogptk.Model.train(method='Adam', fused=True) passes on"},
+                    "per_step_device_adam": {"value": e2e_dev_adam_val, "unit": UNIT,
+                                             "what": "same per-step copies and loss read-back, but loss + Adam update in one call: "
+                                                     "gpr.Exact.fit_adam(1) (mogp_train_adam, one synchronisation per step)"},
                     "c_abi_host_call": {"value": cabi_val, "unit": UNIT, "h2d_bytes_per_step": 8 * (P + dims[0] + N * dims[2] + N),
                                         "d2h_bytes_per_step": 8 * (2 + P + dims[0]),
                                         "what": "mogp_lml_grad_host: params, sigma, x, y host->device, step, LML + gradient "

@@ -66,25 +66,38 @@ def fit_adam(gpr_model, iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, sync_every
     if "exp_avg" not in state:
         state.update(exp_avg=torch.zeros(T, dtype=torch.float64, device=dev),
                      exp_avg_sq=torch.zeros(T, dtype=torch.float64, device=dev), step=0)
-    work = torch.empty(3 * (2 + T), dtype=torch.float64, device=dev)
-    losses = torch.empty(max(iters, 1), dtype=torch.float64, device=dev)
-    fail = torch.zeros(2, dtype=torch.int32, device=dev)
-    fail_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+    # scratch lives in `state` so that a caller stepping one iteration at a time does not re-allocate (pinned memory is slow to get)
+    sync_every = max(1, int(sync_every))
+    chunk = min(sync_every, max(iters, 1))
+    bufs = state.get("_bufs")
+    if bufs is None or bufs["T"] != T or bufs["chunk"] < chunk or bufs["dev"] != dev:
+        bufs = state["_bufs"] = {
+            "T": T, "chunk": chunk, "dev": dev,
+            "work": torch.empty(3 * (2 + T), dtype=torch.float64, device=dev),
+            "losses": torch.empty(chunk, dtype=torch.float64, device=dev),
+            "fail": torch.zeros(2, dtype=torch.int32, device=dev),
+            "host_losses": torch.zeros(chunk, dtype=torch.float64).pin_memory(),
+            "host_fail": torch.zeros(2, dtype=torch.int32).pin_memory()}
+    work, losses_dev, fail = bufs["work"], bufs["losses"], bufs["fail"]
+    host_losses, fail_host = bufs["host_losses"], bufs["host_fail"]
+    fail.zero_()
     st = eng._stream()
+    out_losses = np.empty(iters)
     times = np.zeros(iters)
     t0 = time.perf_counter()
     done, t_prev = 0, 0.0
-    sync_every = max(1, int(sync_every))
     while done < iters:
         k = min(sync_every, iters - done)
         eng._check(lib.mogp_train_adam(
             eng.h, _cabi.KIND[m._kind], C_, Q, D, C.addressof(entries), n_entries, eng._p(rows.x), rows.off_p,
             eng._p(rows.y), eng._p(rows.dv), float(m.jitter), eng._p(work), eng._p(state["exp_avg"]),
             eng._p(state["exp_avg_sq"]), int(state["step"]), int(k), float(lr), float(betas[0]), float(betas[1]),
-            float(eps), C.c_void_p(losses.data_ptr() + 8 * done), C.c_void_p(fail.data_ptr()), st))
+            float(eps), eng._p(losses_dev), eng._p(fail), st))
+        host_losses[:k].copy_(losses_dev[:k], non_blocking=True)
         fail_host.copy_(fail, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()     # the chunk's one synchronisation
         t_now = time.perf_counter() - t0
+        out_losses[done:done + k] = host_losses[:k].numpy()
         times[done:done + k] = t_prev + (t_now - t_prev) * (np.arange(1, k + 1) / k)
         t_prev = t_now
         eng._train, eng._kind = rows, m._kind
@@ -97,8 +110,8 @@ def fit_adam(gpr_model, iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, sync_every
         state["step"] += k
         done += k
         if on_sync is not None:
-            on_sync(done, losses[:done])
-    return losses[:iters].cpu().numpy(), times
+            on_sync(done, out_losses[:done])
+    return out_losses, times
 
 
 def train(model, method="Adam", iters=500, verbose=False, error=None, plot=False, jit=None, sync_every=64, **kwargs):

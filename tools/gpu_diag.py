@@ -438,6 +438,30 @@ def sec_i8p(eng):
     eng.lib.mogp_set_i8_wide(2)
 
 
+def sec_gemm3(eng):
+    """fp64 A B^T three ways per size: the DMMA kernel, the int8 tensor-pipe kernels (slicing included), cuBLAS dgemm."""
+    import ctypes as C
+    out = (C.c_double * 4)()
+    print("%-22s %12s %12s %12s %12s   (TFLOP/s, fp64 or fp64-equivalent; int8 incl. operand slicing)" % (
+        "M x N x K", "DMMA", "int8 128x64", "int8 128x128", "cuBLAS"))
+    for (M, N, K) in [(1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (8192, 8192, 8192), (8192, 8192, 1024),
+                      (8192, 8192, 256), (4096, 4096, 256), (2048, 2048, 256)]:
+        ops = 2.0 * M * N * K
+        res = {}
+        for name, wide in (("narrow", 0), ("wide", 3)):
+            eng.lib.mogp_set_i8_wide(wide)
+            eng.lib.mogp_i8_selftest(M, N, K, 7, out)
+            res[name] = ops / max(out[1], 1e-9) / 1e9
+            res["dmma"] = ops / max(out[3], 1e-9) / 1e9
+        A = torch.randn((M, K), dtype=torch.float64, device="cuda")
+        B = torch.randn((N, K), dtype=torch.float64, device="cuda")
+        med, mn = ev_time(lambda: torch.matmul(A, B.T), reps=5, warm=2)
+        print("%-22s %12.1f %12.1f %12.1f %12.1f" % ("%d x %d x %d" % (M, N, K), res["dmma"], res["narrow"], res["wide"], ops / mn / 1e9),
+              flush=True)
+        del A, B
+    eng.lib.mogp_set_i8_wide(2)
+
+
 def sec_gemmk(eng):
     """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
     for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
@@ -508,7 +532,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"i8p": sec_i8p, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"i8p": sec_i8p, "gemm3": sec_gemm3, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
