@@ -292,7 +292,8 @@ extern "C" int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const 
 }
 
 // fp64-on-int8 tcgen05 path (i8mm.cu) for the K^-1 = L^-T L^-1 product: padded sizes >= g_i8_min_np use it (0 = never).
-long long g_i8_min_np = std::getenv("MOGP_I8_MIN_NP") ? std::atoll(std::getenv("MOGP_I8_MIN_NP")) : 4096;
+// (measured at N = 2048, cfg2: K^-1 stage 0.126 -> 0.114 ms, step 0.847 -> 0.822 ms; below that the DMMA GEMM wins)
+long long g_i8_min_np = std::getenv("MOGP_I8_MIN_NP") ? std::atoll(std::getenv("MOGP_I8_MIN_NP")) : 2048;
 int g_i8_slices = std::getenv("MOGP_I8_SLICES") ? std::atoi(std::getenv("MOGP_I8_SLICES")) : 7;
 extern "C" int mogp_set_i8(long long min_np, int slices) {
     if (slices != 7 && slices != 8) return -1;

@@ -142,7 +142,8 @@ __global__ void params_backward_adam_kernel(const DevEntry* __restrict__ ent, co
         if (e.grad) e.grad[i] = g;
         if (failed) continue;
         double m = exp_avg[e.off + i], v = exp_avg_sq[e.off + i];
-        m = m + one_minus_b1 * (g - m);                       // torch lerp_(grad, 1 - beta1), weight < 0.5 branch
+        // torch's lerp_(grad, w = 1 - beta1): m + w (g - m) for w < 0.5, g - (g - m) (1 - w) otherwise
+        m = one_minus_b1 < 0.5 ? m + one_minus_b1 * (g - m) : g - (g - m) * (1.0 - one_minus_b1);
         v = v * b2 + (1.0 - b2) * g * g;                      // mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
         exp_avg[e.off + i] = m;
         exp_avg_sq[e.off + i] = v;

@@ -115,12 +115,12 @@ def test_int8_kinv_equals_dmma_kinv(engine):
     try:
         engine.lib.mogp_set_i8(0, 7)
         _, Kd, info_d = engine.trtri_kinv_(K.clone())
-        engine.lib.mogp_set_i8(4096, 7)
+        engine.lib.mogp_set_i8(2048, 7)
         _, K7, info_7 = engine.trtri_kinv_(K.clone())
         engine.lib.mogp_set_i8(4096, 8)
         _, K8, info_8 = engine.trtri_kinv_(K.clone())
     finally:
-        engine.lib.mogp_set_i8(4096, 7)
+        engine.lib.mogp_set_i8(2048, 7)
     assert info_d == 0 and info_7 == 0 and info_8 == 0
     ref = torch.linalg.inv(K)
     scale = float(ref.abs().max())
@@ -145,10 +145,10 @@ def test_int8_triangular_inverse_levels_equal_dmma(engine, n):
         lib.mogp_set_trtri_pipe(0)
         lib.mogp_set_i8(0, 7)
         Ld, Kd, info_d = engine.trtri_kinv_(K.clone())
-        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8(2048, 7)
         L7, K7, info_7 = engine.trtri_kinv_(K.clone())
     finally:
-        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8(2048, 7)
         lib.mogp_set_trtri_pipe(1)
     assert info_d == 0 and info_7 == 0
     tril = torch.tril(torch.ones(n, n, dtype=torch.bool, device=engine.device))
@@ -179,12 +179,12 @@ def test_int8_trailing_updates_of_the_cholesky(engine, n):
         lib.mogp_set_i8(0, 7)
         Ad = K.clone()
         assert engine.potrf_(Ad) == 0
-        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8(2048, 7)
         lib.mogp_set_i8_potrf_min(4096)
         A7 = K.clone()
         assert engine.potrf_(A7) == 0
     finally:
-        lib.mogp_set_i8(4096, 7)
+        lib.mogp_set_i8(2048, 7)
         lib.mogp_set_i8_potrf_min(8192)
     ref = torch.linalg.cholesky(K)
     scale = float(ref.abs().max())
