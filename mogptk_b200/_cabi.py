@@ -95,6 +95,15 @@ _EXTRA = {
     "mogp_probe_issue": (C.c_int, [C.POINTER(C.c_double)]),
     "mogp_set_panel_variant": (C.c_int, [C.c_int]),
     "mogp_set_trtri_pipe": (C.c_int, [C.c_int]),
+    "mogp_set_rowpipe": (C.c_int, [C.c_int, C.c_longlong, C.c_int]),
+    "mogp_get_rowpipe": (C.c_int, []),
+    "mogp_set_launch_prio": (C.c_int, [C.c_int]),
+    "mogp_set_rowpipe_kinv": (C.c_int, [C.c_int]),
+    "mogp_set_rowpipe_wmin": (C.c_int, [C.c_int]),
+    "mogp_host_kinv_chunk_start": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mogp_set_rowpipe_super": (C.c_int, [C.c_int, C.c_int]),
+    "mogp_host_rowpipe_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]),
+    "mogp_set_stamps": (C.c_int, [C.c_int]),
     "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
     "mogp_set_two_level_above": (C.c_int, [C.c_longlong]),
     "mogp_set_panel_pdl": (C.c_int, [C.c_int]),

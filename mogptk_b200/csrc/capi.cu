@@ -79,7 +79,8 @@ extern "C" int mogp_create(int device, int64_t max_n, mogp_handle_t* out) {
         if ((e = cudaStreamCreateWithPriority(&h->ps.s4, cudaStreamNonBlocking, plo + (phi - plo) / 2)) != cudaSuccess) return fail(e);
         for (int i = 0; i < 8; ++i)
             if ((e = cudaStreamCreateWithPriority(&h->ps.sl[i], cudaStreamNonBlocking, plo + (phi - plo) / 2)) != cudaSuccess) return fail(e);
-        h->ps.nevq = 3 * nev + 16;
+        h->ps.nevq = 4 * nev + 16;
+        if ((e = cudaEventCreateWithFlags(&h->ps.ev_kinv, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
         h->ps.evq = new cudaEvent_t[h->ps.nevq]();
         for (int i = 0; i < h->ps.nevq; ++i)
             if ((e = cudaEventCreateWithFlags(&h->ps.evq[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -125,6 +126,7 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
         for (int i = 0; i < h->ps.nevq; ++i)
             if (h->ps.evq[i]) cudaEventDestroy(h->ps.evq[i]);
     delete[] h->ps.evq;
+    if (h->ps.ev_kinv) cudaEventDestroy(h->ps.ev_kinv);
     for (int i = 0; i < 8; ++i)
         if (h->ps.sl[i]) cudaStreamDestroy(h->ps.sl[i]);
     delete[] h->ps.ev1;
@@ -139,7 +141,7 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
     if (h->ps.s1) cudaStreamDestroy(h->ps.s1);
     if (h->ps.s3) cudaStreamDestroy(h->ps.s3);
     if (h->ps.s4) cudaStreamDestroy(h->ps.s4);
-    void* ptrs[] = {h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
+    void* ptrs[] = {h->T, h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
                     h->comps, h->comps2, h->chanbuf2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -317,6 +319,7 @@ extern "C" int mogp_set_i8_trtri_min(long long rows) { g_i8_trtri_min = rows; ++
 extern "C" long long mogp_get_i8_min_np(void) { return g_i8_min_np; }
 extern "C" int mogp_get_i8_slices(void) { return g_i8_slices; }
 extern "C" long long mogp_get_i8_trtri_min(void) { return g_i8_trtri_min; }
+extern int g_rowpipe_kinv;      // linalg.cu
 static bool use_i8(int64_t Np) { return g_i8_min_np > 0 && Np >= g_i8_min_np; }
 // host-side preparation of the int8 path for a padded size (never inside capture); invalidates captured graphs when the
 // tile lists had to be rebuilt (another size / leading dimension / slice count used this handle in between)
@@ -368,11 +371,15 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     MOGP_CHECK(h, cudaMemsetAsync(Linv_dev, 0, (size_t)n * n * 8, st));
     const bool i8 = use_i8(n);           // same dispatch as the fused step (int8 tensor pipe for large n)
     if (i8 && i8_ready(h, n, n, st)) return -2;
-    bool fused_inverse = false;
-    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps, &fused_inverse,
-                               i8 ? h->i8 : nullptr, g_i8_slices));
+    bool fused_inverse = false, fused_kinv = false;
+    const bool rowp = rowpipe_applies(n);          // same dispatch as the fused step (row-wise pipeline for small n)
+    if (rowp && ensure(h, h->T, h->T_cap, (size_t)n * n)) return -2;
+    MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, rowp ? h->T : Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps,
+                               &fused_inverse, i8 ? h->i8 : nullptr, g_i8_slices, rowp && g_rowpipe_kinv ? Kinv_dev : nullptr,
+                               &fused_kinv));
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st, i8 ? h->i8 : nullptr, g_i8_slices));
-    if (i8) MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
+    if (fused_kinv) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ps.ev_kinv, 0));
+    else if (i8) MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
     else MOGP_CHECK(h, kinv_padded(Linv_dev, Kinv_dev, n, n, nullptr, st));
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
     h->have_factor = false;
@@ -417,22 +424,28 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     } while (0)
     h->n_ev = 0;
     STAGE_MARK();
+    MOGP_CHECK(h, launch_stamp(0, st));
     MOGP_CHECK(h, launch_prep(s, params, sigma, dv, h->chan_dev, N, jitter_rel, h->comps, h->chanbuf, st));
     // K~ (lower) -> L, diag blocks of Linv
     MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, dv, 1, h->A, ld, N, Np, st));
     STAGE_MARK();
+    MOGP_CHECK(h, launch_stamp(1, st));
     // (with the pipelined inverse the GEMMs of Linv = L^-1 are issued behind the panel chain, inside potrf_padded)
-    bool fused_inverse = false;
-    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, h->W, ld, Np, h->logdet_part, h->info, st, &h->ps, &fused_inverse,
-                               use_i8(Np) ? h->i8 : nullptr, g_i8_slices));
+    // Small sizes (row-wise pipeline, linalg.cu): Linv AND K^-1 (into W) are built behind the panel chain; the scratch is T then.
+    bool fused_inverse = false, fused_kinv = false;
+    const bool rowp = want_grad && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
+    MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, rowp ? h->T : h->W, ld, Np, h->logdet_part, h->info, st, &h->ps,
+                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp && g_rowpipe_kinv ? h->W : nullptr,
+                               &fused_kinv));
     STAGE_MARK();
+    MOGP_CHECK(h, launch_stamp(2, st));
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(h->A, h->Linv, h->W, Np, ld, st, use_i8(Np) ? h->i8 : nullptr, g_i8_slices));
     STAGE_MARK();
     // K^-1 = Linv^T Linv does not need alpha: it runs on a second stream concurrently with the solves
     // (z = Linv y, alpha = Linv^T z, diag K^-1); the gradient kernel subtracts alpha alpha^T while loading.
     // (Profiling keeps the stages sequential so that the stage timers stay meaningful.)
-    const bool fork = want_grad && !h->profile && h->ps.s3 != nullptr;
+    const bool fork = want_grad && !fused_kinv && !h->profile && h->ps.s3 != nullptr;
     if (fork) {
         MOGP_CHECK(h, cudaEventRecord(h->ev_f1, st));
         MOGP_CHECK(h, cudaStreamWaitEvent(h->ps.s3, h->ev_f1, 0));
@@ -443,15 +456,19 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
     MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
     STAGE_MARK();
+    MOGP_CHECK(h, launch_stamp(3, st));
     if (want_grad) {
-        if (fork) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ev_f2, 0));
+        if (fused_kinv) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ps.ev_kinv, 0));
+        else if (fork) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ev_f2, 0));
         else MOGP_CHECK(h, kinv_dispatch(h, Np, ld, st));
         STAGE_MARK();
+        MOGP_CHECK(h, launch_stamp(4, st));
         MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, alpha, h->tile_part, st));
     }
     MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params, sigma, h->comps, h->chanbuf, h->tile_part, z, alpha, kdiag,
                                   h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out, st));
     STAGE_MARK();
+    MOGP_CHECK(h, launch_stamp(5, st));
 #undef STAGE_MARK
     return 0;
 }
@@ -501,6 +518,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
     }
     if (use_i8(Np) && i8_ready(h, Np, Np, st)) return -2;
+    if (want_grad && rowpipe_applies(Np) && ensure(h, h->T, h->T_cap, (size_t)Np * Np)) return -2;
     const size_t nout = 2 + (size_t)s.P + C;
     const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;
     if (ensure(h, h->gbuf, h->gbuf_cap, stage_need)) return -2;

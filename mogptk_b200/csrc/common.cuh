@@ -77,6 +77,9 @@ struct GemmArgs {
     int epi;        // 0: C = alpha*acc + beta*C      1: C = 0.5*((alpha*acc + beta*C) - avec[row]*avec[col])
     int pair;       // 0: one tile per CTA   1: also tile (ntn-1-tn) (with klo_mode 1)   2: also tile (ntm-1-tm) (khi_mode 1)
     int first_touch_row1; // 0: off; else tiles whose first row is >= (value - 1) use beta = 0 (first touch)
+    int first_touch_col1; // same for tiles whose first column is >= (value - 1)
+    int prio;       // 0: the stream's priority; p > 0: launch attribute priority -(p - 1) (1 = lowest ... 6 = highest), which
+                    // -- unlike a stream priority -- is also recorded in a captured graph's kernel node
     double alpha, beta;
     const double* avec;
 };
@@ -106,6 +109,7 @@ struct PotrfStreams {          // look-ahead resources owned by the handle
     cudaEvent_t* evp = nullptr;   // [nev + 2] recorded on s1 after every panel step (pipelined inverse)
     cudaStream_t sl[8] = {};      // medium priority: one stream per doubling level of the pipelined inverse
     cudaEvent_t* evq = nullptr;   // [nevq] completion events of the pipelined inverse's operations (+ 8 join events)
+    cudaEvent_t ev_kinv = nullptr; // row-wise pipeline: K^-1 (accumulated behind the panel chain) is complete
     int nevq = 0;
     int nev = 0;
 };
@@ -113,6 +117,7 @@ struct mogp_handle_s {
     int device = 0;
     int64_t max_n = 0, np_max = 0;
     double *A = nullptr, *Linv = nullptr, *W = nullptr;      // np_max^2 each
+    double *T = nullptr; size_t T_cap = 0;                    // scratch of the row-wise pipelined inverse (Np^2, small sizes only)
     double *comps = nullptr; size_t comps_cap = 0;            // C*C*R*stride (state of the last lml_grad)
     double *chanbuf = nullptr;                                // per-channel scalars of the last lml_grad
     double *comps2 = nullptr; size_t comps2_cap = 0;          // same, scratch of mogp_kbuild / mogp_kdiag
@@ -213,9 +218,15 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 // fused_inverse: NULL -> factor only (diagonal blocks of Linv get inv(L_kk)); else the triangular inverse may be
 // pipelined behind the panel chain (needs Ltmp == the scratch trtri_padded would use, ldt == ldi == lda); on return
 // *fused_inverse tells whether Linv is complete (true) or trtri_padded still has to run (false).
+// Kacc != NULL (a further Np x Np buffer, ld = lda, distinct from Ltmp) allows the row-wise pipeline (small sizes): Linv
+// is built row group by row group behind the panel chain and K^-1 = Linv^T Linv (lower) is accumulated into Kacc by
+// rank updates as the rows complete; *fused_kinv then says that Kacc is (will be) complete once ps->ev_kinv -- recorded
+// before the call returns -- has been reached, and the caller must make its stream wait for that event.
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
-                         bool* fused_inverse = nullptr, I8Plan* i8 = nullptr, int i8_slices = 7);
+                         bool* fused_inverse = nullptr, I8Plan* i8 = nullptr, int i8_slices = 7, double* Kacc = nullptr,
+                         bool* fused_kinv = nullptr);
+bool rowpipe_applies(int64_t Np);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st,
                          I8Plan* i8 = nullptr, int i8_slices = 7);
 cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld, const double* avec, cudaStream_t st);
@@ -230,6 +241,7 @@ cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, 
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
                             double* var, cudaStream_t st);
 cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);
+cudaError_t launch_stamp(int slot, cudaStream_t st);      // diagnostics: global-timer stamp of a point of the step (mogp_set_stamps)
 
 // ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (i8mm.cu)
 struct I8Plan;

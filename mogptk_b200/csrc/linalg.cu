@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     cp_async_wait<0>();
 
     const long long ldc = g.ldc;
-    const double beta = (g.first_touch_row1 > 0 && m0 >= g.first_touch_row1 - 1) ? 0.0 : g.beta;   // first touch of this tile
+    const double beta = ((g.first_touch_row1 > 0 && m0 >= g.first_touch_row1 - 1) ||
+                         (g.first_touch_col1 > 0 && n0 >= g.first_touch_col1 - 1)) ? 0.0 : g.beta;   // first touch of this tile
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int row = am0 + i * 8 + gq;
@@ -199,6 +200,9 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     }   // pair loop
 }
 
+// explicit per-launch priorities (GemmArgs::prio, panel steps): 1 = on
+static int g_launch_prio = std::getenv("MOGP_LAUNCH_PRIO") ? std::atoi(std::getenv("MOGP_LAUNCH_PRIO")) : 1;
+extern "C" int mogp_set_launch_prio(int on) { g_launch_prio = on; ++g_mogp_cfg_epoch; return 0; }
 std::atomic<long long> g_mogp_launches{0};
 long long g_mogp_cfg_epoch = 0;      // bumped by the tuning setters: captured step graphs are re-captured
 // 0 (default): 64x64 tiles   1: force 128x128 tiles (256 threads)   3: force 128x64 tiles
@@ -230,6 +234,17 @@ static cudaError_t launch_gemm_cfg(const GemmArgs& g, int batch, cudaStream_t s)
     dim3 grid(g.N / BN, (g.M + BM - 1) / BM, batch);
     if (g.pair == 1) grid.x = (grid.x + 1) / 2;
     if (g.pair == 2) grid.y = (grid.y + 1) / 2;
+    if (g.prio > 0 && g_launch_prio) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(WM * WN * 32);
+        cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = -(g.prio - 1);
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MOGP_COUNT(1);
+        return cudaLaunchKernelEx(&cfg, kern, g);
+    }
     kern<<<grid, WM * WN * 32, SMEM, s>>>(g);
     MOGP_COUNT(1);
     return cudaGetLastError();
@@ -921,6 +936,16 @@ extern "C" int mogp_panel_spans(int on, unsigned long long* out_host, int n) {
     if (n > 136) n = 136;
     return cudaMemcpyFromSymbol(out_host, g_span, (size_t)2 * n * 8) == cudaSuccess ? 0 : -2;
 }
+// Timeline stamps of one step (diagnostics): slot i of 16 lives in g_span[256 + i]; launched by enqueue_step when armed
+// through mogp_set_stamps (which also re-captures the step graphs).
+__global__ void stamp_kernel(int slot) { g_span[256 + slot] = global_ns(); }
+int g_mogp_stamps = 0;
+extern "C" int mogp_set_stamps(int on) { g_mogp_stamps = on; ++g_mogp_cfg_epoch; return 0; }
+cudaError_t launch_stamp(int slot, cudaStream_t st) {
+    if (!g_mogp_stamps || slot < 0 || slot >= 16) return cudaSuccess;
+    stamp_kernel<<<1, 1, 0, st>>>(slot);
+    return cudaGetLastError();
+}
 static long long* g_panel_dbg = nullptr;   // optional phase timestamps of the first panel kernel
 // 0: phase-alternating panel step; 1: warp-specialised, 64 own rows per CTA; 2 (default): warp-specialised with 32 own
 // rows per CTA while twice the CTAs fit one wave.  (Two further schedules -- tensor warps a full sub-panel ahead of the
@@ -967,14 +992,28 @@ static void launch_panel_ws(double* A, long long ld, double* Ltmp, long long ldt
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256);
         cfg.dynamicSmemBytes = WsCfg<OT>::SMEM; cfg.stream = s_;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributePriority;
+        at[1].val.priority = -5;
+        cfg.attrs = at; cfg.numAttrs = g_launch_prio ? 2 : 1;
         if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
             return;
         cudaGetLastError();               // not supported in this context: plain launches from now on
         g_panel_pdl = 0;
+    }
+    if (g_launch_prio) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = WsCfg<OT>::SMEM; cfg.stream = s_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = -5;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
+            return;
+        cudaGetLastError();
     }
     potrf_panel_ws_kernel<OT><<<grid, 256, WsCfg<OT>::SMEM, s_>>>(A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp);
 }
@@ -1026,10 +1065,83 @@ extern "C" int mogp_host_inverse_plan(int nb, int32_t* out, int cap) {
 static int g_trtri_pipe = std::getenv("MOGP_TRTRI_PIPE") ? std::atoi(std::getenv("MOGP_TRTRI_PIPE")) : 1;
 extern "C" int mogp_set_trtri_pipe(int v) { g_trtri_pipe = v; ++g_mogp_cfg_epoch; return 0; }
 
+// Row-wise pipeline for the small sizes, whose step time is the panel chain: the block-doubling plan above leaves the last pair
+// of EVERY level (and then the whole K^-1 = Linv^T Linv product) for after the last panel step.  Here Linv is built by row
+// groups of G 64-blocks instead: X_II (the group's diagonal block, by doubling inside the group) as soon as the group's panels
+// are done, X[I, 0:r0) = -X_II T[I, 0:r0) with T[I, :] = sum_{J<I} L[I,J] X[J, :] kept up to date by one rank-(64 G) update per
+// finished group (right-looking, into Ltmp below the group diagonal), and K^-1 += X[I, :]^T X[I, :] (lower tiles, rank 64 G)
+// accumulated into Kacc as the rows complete.  What is left after the last panel step is the last group's diagonal inverse, one
+// thin GEMM and one rank-(64 G) update.
+static int g_rowpipe = std::getenv("MOGP_ROWPIPE") ? std::atoi(std::getenv("MOGP_ROWPIPE")) : 1;
+static long long g_rowpipe_max_np = std::getenv("MOGP_ROWPIPE_MAX_NP") ? std::atoll(std::getenv("MOGP_ROWPIPE_MAX_NP")) : 4096;
+static int g_rowpipe_group = std::getenv("MOGP_ROWPIPE_GROUP") ? std::atoi(std::getenv("MOGP_ROWPIPE_GROUP")) : 1;
+extern "C" int mogp_set_rowpipe(int on, long long max_np, int group) {
+    if (group != 1 && group != 2 && group != 4 && group != 8) return -1;
+    g_rowpipe = on; g_rowpipe_max_np = max_np; g_rowpipe_group = group; ++g_mogp_cfg_epoch;
+    return 0;
+}
+extern "C" int mogp_get_rowpipe(void) { return g_rowpipe; }
+// 0: only Linv row-wise, K^-1 = Linv^T Linv afterwards as one product; 1: K^-1 accumulated behind the chain per super-group;
+// 2: accumulated in halving chunks (see issue_group_ops)
+int g_rowpipe_kinv = std::getenv("MOGP_ROWPIPE_KINV") ? std::atoi(std::getenv("MOGP_ROWPIPE_KINV")) : 0;
+static int g_rowpipe_wmin = std::getenv("MOGP_ROWPIPE_WMIN") ? std::atoi(std::getenv("MOGP_ROWPIPE_WMIN")) : 4;
+extern "C" int mogp_set_rowpipe_kinv(int mode) { g_rowpipe_kinv = mode; ++g_mogp_cfg_epoch; return 0; }
+extern "C" int mogp_set_rowpipe_wmin(int blocks) { if (blocks < 1) return -1; g_rowpipe_wmin = blocks; ++g_mogp_cfg_epoch; return 0; }
+// Two levels: the rank-(64 G) updates of a finished group only reach the rows of its own super-group (S blocks); rows beyond
+// it and K^-1 get ONE rank-(64 S) update per super-group (a rank-64 update of a 2048^2 matrix runs at ~14 TFLOP/s, a rank-256
+// one at ~25: profiles/r01_gemm_sweep.txt).  With `taper` the last super-groups shrink (S/2, S/4, ...) so that the update
+// left for after the last panel step is a thin one.
+static int g_rowpipe_super = std::getenv("MOGP_ROWPIPE_SUPER") ? std::atoi(std::getenv("MOGP_ROWPIPE_SUPER")) : 1;
+static int g_rowpipe_taper = std::getenv("MOGP_ROWPIPE_TAPER") ? std::atoi(std::getenv("MOGP_ROWPIPE_TAPER")) : 0;
+extern "C" int mogp_set_rowpipe_super(int super_blocks, int taper) {
+    if (super_blocks < 1 || super_blocks > 32) return -1;
+    g_rowpipe_super = super_blocks; g_rowpipe_taper = taper; ++g_mogp_cfg_epoch;
+    return 0;
+}
+bool rowpipe_applies(int64_t Np) { return g_rowpipe != 0 && g_trtri_pipe != 0 && Np >= 256 && Np <= g_rowpipe_max_np; }
+struct RowGroup { int lo, hi, ev_inv, slo, shi; };      // 64-blocks [lo, hi) of super-group [slo, shi)
+// Host self-check hook: the group / super-group partition for nb blocks, 4 int32 per group [lo, hi, slo, shi]
+static void rowpipe_partition(int nb, int G, int S, int taper, std::vector<RowGroup>& groups) {
+    S = std::max(G, S / G * G);
+    for (int pos = 0; pos < nb;) {
+        const int rem = nb - pos;
+        int size = S;
+        if (rem <= S) size = taper ? std::max(G, (rem / 2 + G - 1) / G * G) : rem;
+        size = std::min(size, rem);
+        for (int lo = pos; lo < pos + size; lo += G) groups.push_back({lo, std::min(pos + size, lo + G), -1, pos, pos + size});
+        pos += size;
+    }
+}
+// Chunks of the K^-1 accumulation (mode 2): halves of what is left (nb/2, nb/4, ...) down to wmin blocks, multiples of G.
+// Returns the first block of the chunk that ends at block `hi`, or -1 if no chunk ends there.
+static int kinv_chunk_start(int nb, int G, int wmin, int hi) {
+    wmin = std::max(wmin, G);
+    for (int lo = 0; lo < nb;) {
+        const int rem = nb - lo;
+        int size = rem / 2;
+        if (size < wmin) size = std::min(rem, wmin);
+        size = std::min(rem, (size + G - 1) / G * G);
+        if (lo + size == hi) return lo;
+        if (lo + size > hi) return -1;
+        lo += size;
+    }
+    return -1;
+}
+extern "C" int mogp_host_kinv_chunk_start(int nb, int G, int wmin, int hi) { return kinv_chunk_start(nb, G, wmin, hi); }
+extern "C" int mogp_host_rowpipe_partition(int nb, int G, int S, int taper, int32_t* out, int cap) {
+    std::vector<RowGroup> g;
+    if (nb < 1 || G < 1 || S < 1) return -1;
+    rowpipe_partition(nb, G, S, taper, g);
+    if ((int)g.size() > cap) return -1;
+    for (size_t i = 0; i < g.size(); ++i) { out[4 * i] = g[i].lo; out[4 * i + 1] = g[i].hi; out[4 * i + 2] = g[i].slo; out[4 * i + 3] = g[i].shi; }
+    return (int)g.size();
+}
+
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
-                         bool* fused_inverse, I8Plan* i8, int i8_slices) {
+                         bool* fused_inverse, I8Plan* i8, int i8_slices, double* Kacc, bool* fused_kinv) {
     if (fused_inverse) *fused_inverse = false;
+    if (fused_kinv) *fused_kinv = false;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
@@ -1097,12 +1209,84 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                       (Np <= 4096 || g_trtri_pipe >= 2);      // measured at N = 8192: no gain over the level-batched trtri_padded
                                                               // (13.33 ms against 7.71 + 5.80 ms): the machine is already full
     std::vector<InvOp> plan;
-    size_t next_op = 0;
+    size_t next_op = 0, next_group = 0;
     bool level_used[8] = {};
-    if (pipe) {
+    // (Kacc == NULL: Linv row-wise only, K^-1 is left to the caller)
+    const bool rowp = pipe && (Kacc == nullptr || (fused_kinv != nullptr && Kacc != Ltmp && ps->ev_kinv != nullptr)) &&
+                      rowpipe_applies(Np) && 4 * nb + 16 <= ps->nevq;
+    std::vector<RowGroup> groups;
+    if (rowp) {
+        int ne = 0;
+        rowpipe_partition(nb, g_rowpipe_group, g_rowpipe_super, g_rowpipe_taper, groups);
+        for (RowGroup& gr : groups) gr.ev_inv = build_inverse_plan(gr.lo, gr.hi, plan, ne);
+    } else if (pipe) {
         int ne = 0;
         build_inverse_plan(0, nb, plan, ne);
     }
+    // group-level operations of the row-wise pipeline, issued once the group's last panel step is in the chain
+    auto issue_group_ops = [&](const RowGroup& gr, int gi) -> cudaError_t {
+        cudaError_t ee;
+        cudaStream_t sX = ps->sl[6], sW = ps->sl[7];
+        level_used[6] = true;
+        level_used[7] = Kacc != nullptr;
+        const long long r0 = (long long)gr.lo * 64, R = (long long)(gr.hi - gr.lo) * 64, c1 = (long long)gr.hi * 64;
+        cudaEvent_t ex = ps->evq[3 * nb + gi];
+        if ((ee = cudaStreamWaitEvent(sX, ps->evq[gr.ev_inv], 0)) != cudaSuccess) return ee;
+        if (r0 > 0) {                // X[I, 0:r0) = -X_II T[I, 0:r0)   (X_II lower triangular: k ends at the row tile)
+            GemmArgs g{};
+            g.A = Linv + r0 * ld + r0; g.lda = ld;
+            g.B = Ltmp + r0 * ld; g.ldb = ld;
+            g.C = Linv + r0 * ld; g.ldc = ld;
+            g.M = (int)R; g.N = (int)r0; g.K = (int)R;
+            g.khi_mode = 1; g.alpha = -1.0; g.beta = 0.0; g.prio = 5;
+            if ((ee = launch_gemm(0, 0, g, 1, sX)) != cudaSuccess) return ee;
+        }
+        if ((ee = cudaEventRecord(ex, sX)) != cudaSuccess) return ee;
+        const long long s0 = (long long)gr.slo * 64, s1 = (long long)gr.shi * 64;       // the super-group's rows / columns
+        if (c1 < s1) {               // fine: T[rest of the super-group, 0:c1) += L[those rows, group columns] X[I, 0:c1)
+            GemmArgs g{};            // (first touch of the group's own columns)
+            g.A = A + c1 * ld + r0; g.lda = ld;
+            g.B = Linv + r0 * ld; g.ldb = ld;
+            g.C = Ltmp + c1 * ld; g.ldc = ld;
+            g.M = (int)(s1 - c1); g.N = (int)c1; g.K = (int)R;
+            g.alpha = 1.0; g.beta = 1.0; g.first_touch_col1 = (int)r0 + 1; g.prio = 4;
+            if ((ee = launch_gemm(0, 0, g, 1, sX)) != cudaSuccess) return ee;
+        }
+        if (gr.hi == gr.shi) {       // the super-group is complete: one rank-(s1 - s0) update of everything beyond it
+            if (s1 < Np) {           // coarse: T[rows beyond, 0:s1) += L[rows beyond, super-group columns] X[super-group rows, 0:s1)
+                GemmArgs g{};
+                g.A = A + s1 * ld + s0; g.lda = ld;
+                g.B = Linv + s0 * ld; g.ldb = ld;
+                g.C = Ltmp + s1 * ld; g.ldc = ld;
+                g.M = (int)(Np - s1); g.N = (int)s1; g.K = (int)(s1 - s0);
+                g.alpha = 1.0; g.beta = 1.0; g.first_touch_col1 = (int)s0 + 1; g.prio = 2;
+                if ((ee = launch_gemm(0, 0, g, 1, sX)) != cudaSuccess) return ee;
+            }
+        }
+        if (!Kacc) return cudaSuccess;
+        // K^-1[0:w1, 0:w1) (lower) += X[chunk rows, 0:w1)^T X[chunk rows, 0:w1) once the rows [w0, w1) of a chunk are complete
+        // (first touch of rows >= w0).  Chunks: the super-groups (mode 1) or halves of what is left (mode 2: nb/2, nb/4, ...
+        // down to g_rowpipe_wmin blocks), which keeps these products deep while leaving a thin one for after the chain.
+        long long w0 = -1, w1 = (long long)gr.hi * 64;
+        if (g_rowpipe_kinv == 2) {
+            const int lo = kinv_chunk_start(nb, g_rowpipe_group, g_rowpipe_wmin, gr.hi);
+            if (lo >= 0) w0 = (long long)lo * 64;
+        } else if (gr.hi == gr.shi) {
+            w0 = s0;
+        }
+        if (w0 >= 0) {
+            if ((ee = cudaStreamWaitEvent(sW, ex, 0)) != cudaSuccess) return ee;
+            GemmArgs g{};
+            g.A = Linv + w0 * ld; g.lda = ld;
+            g.B = Linv + w0 * ld; g.ldb = ld;
+            g.C = Kacc; g.ldc = ld;
+            g.M = (int)w1; g.N = (int)w1; g.K = (int)(w1 - w0);
+            if (w0 == 0) g.klo_mode = 2;     // X[0:w1, 0:w1) is lower triangular: k starts at the row tile
+            g.lower = 1; g.alpha = 1.0; g.beta = 1.0; g.first_touch_row1 = (int)w0 + 1; g.prio = 1;
+            if ((ee = launch_gemm(1, 0, g, 1, sW)) != cudaSuccess) return ee;
+        }
+        return cudaSuccess;
+    };
     auto issue_inverse_ops = [&](int s) -> cudaError_t {
         cudaError_t ee;
         if ((ee = cudaEventRecord(ps->evp[s], st)) != cudaSuccess) return ee;
@@ -1127,16 +1311,20 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
                 g.C = Ltmp + (o + S) * ld + o; g.ldc = ld;
                 g.M = (int)MB; g.N = (int)S; g.K = (int)S;
                 g.klo_mode = 1; g.pair = 1; g.alpha = 1.0; g.beta = 0.0;
+                if (rowp) g.prio = 5;
             } else {                     // Linv_BA = -Linv_BB * T   (Linv_BB lower triangular: k ends at the row tile)
                 g.A = Linv + (o + S) * ld + (o + S); g.lda = ld;
                 g.B = Ltmp + (o + S) * ld + o; g.ldb = ld;
                 g.C = Linv + (o + S) * ld + o; g.ldc = ld;
                 g.M = (int)MB; g.N = (int)S; g.K = (int)MB;
                 g.khi_mode = 1; g.pair = 2; g.alpha = -1.0; g.beta = 0.0;
+                if (rowp) g.prio = 5;
             }
             if ((ee = launch_gemm(0, 0, g, 1, sv)) != cudaSuccess) return ee;
             if ((ee = cudaEventRecord(ps->evq[op.done], sv)) != cudaSuccess) return ee;
         }
+        for (; next_group < groups.size() && groups[next_group].hi - 1 <= s; ++next_group)
+            if ((ee = issue_group_ops(groups[next_group], (int)next_group)) != cudaSuccess) return ee;
         return cudaSuccess;
     };
     // join of the pipelined inverse: bulk stream, panel chain and every inverse stream back into the caller's stream
@@ -1149,6 +1337,11 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         if ((ee = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return ee;
         for (int l = 0; l < 8; ++l) {
             if (!level_used[l]) continue;
+            if (rowp && Kacc && l == 7) {        // the K^-1 accumulation is joined by the caller (the solves do not need it)
+                if ((ee = cudaEventRecord(ps->ev_kinv, ps->sl[l])) != cudaSuccess) return ee;
+                *fused_kinv = true;
+                continue;
+            }
             cudaEvent_t ej = ps->evq[ps->nevq - 8 + l];
             if ((ee = cudaEventRecord(ej, ps->sl[l])) != cudaSuccess) return ee;
             if ((ee = cudaStreamWaitEvent(user, ej, 0)) != cudaSuccess) return ee;
@@ -1268,6 +1461,7 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
             u.C = A + c0 * ld + c0; u.ldc = ld;
             u.M = (int)M; u.N = (int)M; u.K = MOGP_NB;
             u.lower = 1; u.alpha = -1.0; u.beta = 1.0;
+            if (rowp) u.prio = 4;
             e = g_skip_bulk ? cudaSuccess : launch_gemm(0, 1, u, 1, s2);
             if (e != cudaSuccess) return e;
             if (two) {

@@ -16,11 +16,13 @@ pytestmark = pytest.mark.gpu
 def knobs(engine):
     lib = engine.lib
 
-    def set_(variant=2, pipe=1, pdl=1, graphs=1):
+    def set_(variant=2, pipe=1, pdl=1, graphs=1, rowpipe=(1, 4096, 1, 1, 0), kinv=(0, 4)):
         lib.mogp_set_panel_variant(variant)
         lib.mogp_set_trtri_pipe(pipe)
         lib.mogp_set_panel_pdl(pdl)
         lib.mogp_set_graphs(graphs)
+        assert lib.mogp_set_rowpipe(*rowpipe[:3]) == 0 and lib.mogp_set_rowpipe_super(*rowpipe[3:]) == 0
+        assert lib.mogp_set_rowpipe_kinv(kinv[0]) == 0 and lib.mogp_set_rowpipe_wmin(kinv[1]) == 0
     yield set_
     set_()          # back to the defaults for the rest of the session
 
@@ -44,6 +46,36 @@ def _check(engine, g, reps=3):
 def test_panel_variants_and_inverse_schedules(engine, knobs, name, variant, pipe):
     knobs(variant=variant, pipe=pipe)
     _check(engine, load_golden(name))
+
+
+@pytest.mark.parametrize("rowpipe", [(0, 2048, 2, 4, 1), (1, 2048, 1, 1, 0), (1, 2048, 1, 4, 1), (1, 2048, 2, 8, 0), (1, 2048, 4, 4, 1),
+                                     (1, 4096, 8, 16, 1), (1, 4096, 2, 6, 1)])
+@pytest.mark.parametrize("kinv", [(0, 4), (1, 4), (2, 4), (2, 1)])
+@pytest.mark.parametrize("name", ["mosm_small", "mosm_mid", "cfg1", "cfg2", "cfg4"])
+def test_rowwise_pipelined_inverse(engine, knobs, name, rowpipe, kinv):
+    """The row-wise pipeline (Linv by row groups and K^-1 by rank updates behind the panel chain; on, max_np, group, super-group,
+    taper) against the block-doubling pipeline (rowpipe off): group / super-group sizes, ragged last groups (mosm_*) and the
+    two-level Cholesky sweep (cfg4 with max_np 4096); K^-1 afterwards (kinv mode 0), accumulated per super-group (1) or in
+    halving chunks (2, smallest chunk 4 / 1 blocks)."""
+    knobs(rowpipe=rowpipe, kinv=kinv)
+    _check(engine, load_golden(name))
+
+
+@pytest.mark.parametrize("group,sup,taper", [(1, 1, 0), (1, 4, 1), (2, 4, 0), (2, 8, 1), (4, 8, 1), (8, 8, 0)])
+@pytest.mark.parametrize("kinv", [(1, 4), (2, 4), (2, 2)])
+@pytest.mark.parametrize("n", [256, 640, 1152, 2048])
+def test_rowwise_trtri_kinv(engine, knobs, n, group, sup, taper, kinv):
+    knobs(rowpipe=(1, 2048, group, sup, taper), kinv=kinv)
+    gen = torch.Generator().manual_seed(n + group + sup)
+    B = torch.randn((n, n + 8), generator=gen, dtype=torch.float64)
+    A = B @ B.T / n + 0.3 * torch.eye(n, dtype=torch.float64)
+    for _ in range(2):            # the second run finds stale values in the scratch / accumulation buffers
+        Linv, Kinv, info = engine.trtri_kinv_(A.cuda().clone())
+        assert info == 0
+        Linv_ref = torch.linalg.inv(torch.linalg.cholesky(A))
+        assert float((torch.tril(Linv).cpu() - Linv_ref).abs().max() / Linv_ref.abs().max()) < 1e-10
+        Kinv_ref = torch.tril(torch.linalg.inv(A))
+        assert float((torch.tril(Kinv).cpu() - Kinv_ref).abs().max() / Kinv_ref.abs().max()) < 1e-10
 
 
 @pytest.mark.parametrize("pdl,graphs", [(0, 1), (2, 1), (2, 0), (1, 0)])

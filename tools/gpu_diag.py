@@ -356,6 +356,94 @@ def sec_exp(eng):
     eng.lib.mogp_set_two_level_above(2048)
 
 
+def sec_rowp(eng):
+    """A/B of the row-wise pipelined inverse (ROWP_COMBOS="on:max_np:group,...") : numerics verdict + step time per config."""
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params, unpack_grads
+    combos = [tuple(int(v) for v in c.split(":")) for c in
+              os.environ.get("ROWP_COMBOS", "0:2048:1:4:1,1:2048:1:1:0,1:2048:1:4:1,1:2048:1:4:0,1:2048:1:8:1,1:2048:2:4:1,"
+                                            "1:2048:2:8:1,1:4096:2:8:1,1:4096:4:16:1").split(",")]
+    names = os.environ.get("DIAG_CFGS", "cfg1,mosm_mid,cfg2,cfg4").split(",")
+    prepared = {}
+    for name in names:
+        g = load_golden(name)
+        prepared[name] = (g, eng.prepare(g["kind"], g["params"], g["X"], g["y"]), pack_params(g["kind"], g["params"], eng.device),
+                          torch.tensor(g["sigma"], device=eng.device))
+    for combo in combos:
+        assert eng.lib.mogp_set_rowpipe(*combo[:3]) == 0 and eng.lib.mogp_set_rowpipe_super(*combo[3:]) == 0
+        tag = "rowp %d:%d:%d:%d:%d" % combo
+        for n in (256, 640, 2048):
+            A = spd(n, n)
+            Ad = A.cuda().clone()
+            Linv, Kinv, info = eng.trtri_kinv_(Ad)
+            Li = torch.linalg.inv(torch.linalg.cholesky(A))
+            print("[%s] trtri n=%4d info=%d relerr(Linv) %.2e relerr(Kinv) %.2e" % (
+                tag, n, info, rel(torch.tril(Linv).cpu(), Li), rel(torch.tril(Kinv).cpu(), torch.tril(Li.T @ Li))))
+        for name in names:
+            g, rows, p, sig = prepared[name]
+            N = g["X"].shape[0]
+            t1, m1 = ev_time(lambda: eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False), reps=31, warm=5)
+            r = eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            lml_got, lml_ref = float(r[0].item()), float(g["lml"])
+            P = p.numel()
+            C_, Q, D = rows.dims
+            gd = unpack_grads(g["kind"], C_, Q, D, r[2:2 + P].cpu())
+            gerr = 0.0
+            for k, got in gd.items():
+                ref = g["gc_" + k]
+                gerr = max(gerr, float(np.abs(got.numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-12)))
+            ok = abs(lml_got - lml_ref) <= 1e-8 * abs(lml_ref) and gerr <= 1e-6 and int(r[1].item()) == 0
+            print("[%s] step %-8s N=%d: %.3f ms (min %.3f) -> %.1f it/s | lml rel %.1e grad %.1e %s" % (
+                tag, name, N, t1, m1, 1e3 / t1, abs(lml_got - lml_ref) / abs(lml_ref), gerr, "STEP_OK" if ok else "STEP_FAIL"))
+        sys.stdout.flush()
+    eng.lib.mogp_set_rowpipe(1, 2048, 1)
+    eng.lib.mogp_set_rowpipe_super(1, 0)
+
+
+def sec_timeline(eng):
+    """Global-timer timeline of one replayed step: stage stamps (mogp_set_stamps) + the span of every panel step, per
+    row-pipeline setting (ROWP_COMBOS) and config (DIAG_CFGS)."""
+    import ctypes as C
+    from conftest import load_golden
+    from mogptk_b200.engine import pack_params
+    combos = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("ROWP_COMBOS", "0:2048:1:4:1,1:2048:1:1:0,1:2048:1:4:1,1:2048:2:8:1").split(",")]
+    names = os.environ.get("DIAG_CFGS", "cfg2").split(",")
+    eng.lib.mogp_set_stamps(1)
+    out = (C.c_ulonglong * 272)()
+    for name in names:
+        g = load_golden(name)
+        rows = eng.prepare(g["kind"], g["params"], g["X"], g["y"])
+        p = pack_params(g["kind"], g["params"], eng.device)
+        sig = torch.tensor(g["sigma"], device=eng.device)
+        nb = (g["X"].shape[0] + 127) // 128 * 2
+        for combo in combos:
+            eng.lib.mogp_set_rowpipe(*combo[:3])
+            eng.lib.mogp_set_rowpipe_super(*combo[3:])
+            for _ in range(6):
+                eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            torch.cuda.synchronize()
+            eng.lib.mogp_panel_spans(1, out, 136)
+            eng.lml_grad_prepared(rows, p, sig, g["jitter"], True, check=False)
+            torch.cuda.synchronize()
+            eng.lib.mogp_panel_spans(0, out, 136)
+            t = [int(x) for x in out]
+            t0 = t[256]
+            st = [(t[256 + i] - t0) / 1e3 for i in range(6)]
+            ent = [(t[2 * s] - t0) / 1e3 for s in range(nb)]
+            ext = [(t[2 * s + 1] - t0) / 1e3 for s in range(nb)]
+            spans = [ext[s] - ent[s] for s in range(nb)]
+            gaps = [ent[s + 1] - ext[s] for s in range(nb - 1)]
+            print("[timeline %s rowp %d:%d:%d:%d:%d] stamps us: kbuild done %.1f | chain %.1f -> %.1f (span mean %.2f, gap mean %.2f) | "
+                  "potrf joined %.1f | solves done %.1f | kinv joined %.1f | end %.1f" % (
+                      (name,) + combo + (st[1], ent[0], ext[nb - 1], float(np.mean(spans)), float(np.mean(gaps)), st[2], st[3], st[4], st[5])))
+            print("    panel exit times: " + " ".join("%.0f" % x for x in ext))
+            print("    spans: " + " ".join("%.1f" % x for x in spans))
+            sys.stdout.flush()
+    eng.lib.mogp_set_stamps(0)
+    eng.lib.mogp_set_rowpipe(1, 2048, 1)
+    eng.lib.mogp_set_rowpipe_super(1, 0)
+
+
 def sec_gaps(eng):
     """Panel chain versus interference from the concurrent trailing updates (timing only: skip_bulk gives a wrong factor)."""
     for n in (2048, 4096):
@@ -532,7 +620,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"i8p": sec_i8p, "gemm3": sec_gemm3, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"timeline": sec_timeline, "rowp": sec_rowp, "i8p": sec_i8p, "gemm3": sec_gemm3, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
