@@ -37,6 +37,10 @@
  *           gpr/singleoutput.py:520-561; what mogptk.SM_LMC builds)
  *   UMOSM: weight[Q][C][C] (lower triangle used) | mean[Q][C][D] | variance[Q][C][D] | delay[Q][C][D] | phase[Q][C]
  *          (MixtureKernel of UncoupledMultiOutputSpectralKernel, gpr/multioutput.py:212-293)
+ *   MOHSM: weight[Q][C] | mean[Q][C][D] | variance[Q][C][D] | lengthscale[Q][C] | center[Q][D] | delay[Q][C][D] | phase[Q][C]
+ *          (MixtureKernel of MultiOutputHarmonizableSpectralKernel, gpr/multioutput.py:295-395; what mogptk.MOHSM builds with
+ *           Q = P*Q of that model).  Non-stationary: every term carries a Gaussian window in the mid-point (x + x')/2, so the
+ *           Gram diagonal depends on the row and K_diag needs the inputs: use mogp_kdiag_x.
  */
 #ifndef MOGP_B200_H
 #define MOGP_B200_H
@@ -49,7 +53,8 @@ extern "C" {
 
 typedef struct mogp_handle_s* mogp_handle_t;
 
-enum { MOGP_KIND_MOSM = 0, MOGP_KIND_SM = 1, MOGP_KIND_CONV = 2, MOGP_KIND_CSM = 3, MOGP_KIND_SMLMC = 4, MOGP_KIND_UMOSM = 5 };
+enum { MOGP_KIND_MOSM = 0, MOGP_KIND_SM = 1, MOGP_KIND_CONV = 2, MOGP_KIND_CSM = 3, MOGP_KIND_SMLMC = 4, MOGP_KIND_UMOSM = 5,
+       MOGP_KIND_MOHSM = 6 };
 /* CSM and SM-LMC have Rq sub-components per mixture term: pass kind = MOGP_KIND_WITH_RQ(MOGP_KIND_CSM, Rq)
  * (family in the low 8 bits, Rq above; Rq = 0 means 1).  Every `kind` argument below accepts this form. */
 #define MOGP_KIND_WITH_RQ(kind, Rq) ((kind) | ((Rq) << 8))
@@ -85,6 +90,10 @@ int mogp_kbuild(mogp_handle_t h, int kind, int C, int Q, int D, const double* pa
  * gpr/multioutput.py:36-39,206-210,549-553).  out_dev has n entries. */
 int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
                const int32_t* chan_off_host, double* out_dev, void* stream);
+/* The same with the n x D inputs (sorted by channel): required for MOHSM (gpr/multioutput.py:389-395: the prior variance
+ * depends on x), accepted for every kind. */
+int mogp_kdiag_x(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev, const double* x_dev,
+                 const int32_t* chan_off_host, double* out_dev, void* stream);
 
 /* In-place lower Cholesky A = L L^T of an n x n row-major matrix (only the lower triangle
  * is read; on return the lower triangle holds L, the strict upper triangle is unspecified).

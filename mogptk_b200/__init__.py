@@ -8,8 +8,8 @@ from . import _cabi, engine, gpr, init, synth    # noqa: F401
 from .engine import Engine, NotPositiveDefiniteError  # noqa: F401
 from .gpr import (CholeskyException, CrossSpectralKernel, Exact, GaussianConvolutionProcessKernel,  # noqa: F401
                   GaussianLikelihood, IndependentMultiOutputKernel, LinearModelOfCoregionalizationKernel, MixtureKernel,
-                  MultiOutputSpectralMixtureKernel, Parameter, SpectralKernel, SpectralMixtureKernel,
-                  UncoupledMultiOutputSpectralKernel)
+                  MultiOutputHarmonizableSpectralKernel, MultiOutputSpectralMixtureKernel, Parameter, SpectralKernel,
+                  SpectralMixtureKernel, UncoupledMultiOutputSpectralKernel)
 from .inference import B200Exact                 # noqa: F401
 from .train import fit_adam, install, uninstall  # noqa: F401
 

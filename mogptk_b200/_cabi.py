@@ -11,12 +11,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mogp_b200.h")
 
-FAMILY = {"MOSM": 0, "SM": 1, "CONV": 2, "CSM": 3, "SMLMC": 4, "UMOSM": 5}
+FAMILY = {"MOSM": 0, "SM": 1, "CONV": 2, "CSM": 3, "SMLMC": 4, "UMOSM": 5, "MOHSM": 6}
 
 
 def kind_code(kind):
     """`kind` argument of the C ABI: family in the low 8 bits, Rq (CSM / SM-LMC sub-components) above
-    (MOGP_KIND_WITH_RQ).  Host-side kinds are strings: "MOSM", "SM", "CONV", "CSM:<Rq>", "SMLMC:<Rq>", "UMOSM"."""
+    (MOGP_KIND_WITH_RQ).  Host-side kinds are strings: "MOSM", "SM", "CONV", "CSM:<Rq>", "SMLMC:<Rq>", "UMOSM", "MOHSM"."""
     fam, _, rq = str(kind).partition(":")
     return FAMILY[fam] | ((int(rq) << 8) if rq else 0)
 
@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mogp_kbuild": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_ip,
                               c_dp, c_dp, C.c_double, c_dp, C.c_int64, C.c_void_p]),
     "mogp_kdiag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_void_p]),
+    "mogp_kdiag_x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, C.c_void_p]),
     "mogp_potrf": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mogp_lml_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp,
                                 C.c_double, C.c_int, c_dp, C.c_void_p]),

@@ -142,7 +142,7 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
     if (h->ps.s3) cudaStreamDestroy(h->ps.s3);
     if (h->ps.s4) cudaStreamDestroy(h->ps.s4);
     void* ptrs[] = {h->T, h->A, h->Linv, h->W, h->vec, h->chanbuf, h->logdet_part, h->info, h->chan_dev, h->colpart,
-                    h->comps, h->comps2, h->chanbuf2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
+                    h->comps, h->comps2, h->chanbuf2, h->winsum, h->winsum2, h->gbuf, h->tile_part, h->xbuf, h->pbuf, h->out_dev, h->pred_K, h->pred_V, h->pred_S};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -231,7 +231,7 @@ static int upload_chan(mogp_handle_s* h, int C, const int32_t* off, int slot, cu
 
 static int prep_common(mogp_handle_s* h, KernSpec& s, int kind, int C, int Q, int D, const double* params_dev,
                        const double* sigma_dev, const double* data_var_dev, const int32_t* off, int64_t N,
-                       double jitter_rel, bool scratch, cudaStream_t st) {
+                       double jitter_rel, bool scratch, cudaStream_t st, const double* x_dev = nullptr) {
     H_ARG(h, spec_init(s, kind, C, Q, D) == 0, "bad kernel spec (kind, C, Q, D)");
     H_ARG(h, C <= 64, "at most 64 channels");
     H_ARG(h, (size_t)(3 * C + 2) <= 1024, "too many channels");
@@ -240,9 +240,15 @@ static int prep_common(mogp_handle_s* h, KernSpec& s, int kind, int C, int Q, in
     h->chan_uploaded.assign(off, off + C + 1);
     double*& comps = scratch ? h->comps2 : h->comps;
     size_t& cap = scratch ? h->comps2_cap : h->comps_cap;
-    if (ensure(h, comps, cap, (size_t)C * C * s.R * comp_stride(D))) return -2;
+    if (ensure(h, comps, cap, (size_t)C * C * s.R * s.st)) return -2;
+    double*& ws = scratch ? h->winsum2 : h->winsum;
+    size_t& wcap = scratch ? h->winsum2_cap : h->winsum_cap;
+    if (s.window) {
+        H_ARG(h, x_dev != nullptr || N == 0, "this kernel is non-stationary (MOHSM): the inputs are required");
+        if (ensure(h, ws, wcap, (size_t)C * s.R * (2 + D))) return -2;
+    }
     MOGP_CHECK(h, launch_prep(s, params_dev, sigma_dev, data_var_dev, h->chan_dev, N, jitter_rel, comps,
-                              scratch ? h->chanbuf2 : h->chanbuf, st));
+                              scratch ? h->chanbuf2 : h->chanbuf, st, x_dev, s.window ? ws : nullptr));
     return 0;
 }
 
@@ -270,7 +276,7 @@ extern "C" int mogp_kbuild(mogp_handle_t h, int kind, int C, int Q, int D, const
     if (!gram && check_offsets(h, C, chan_off2_host)) return -1;
     const int add_diag = gram && (noise_sigma_dev || data_var_dev || jitter_rel != 0.0);
     int rc = prep_common(h, s, kind, C, Q, D, params_dev, noise_sigma_dev, gram ? data_var_dev : nullptr, chan_off1_host,
-                         N1, gram ? jitter_rel : 0.0, true, st);
+                         N1, gram ? jitter_rel : 0.0, true, st, x1_dev);
     if (rc) return rc;
     TileList* tl = get_tiles(h, C, chan_off1_host, gram ? nullptr : chan_off2_host, gram ? 1 : 2, st);
     H_ARG(h, tl != nullptr, "tile list allocation failed");
@@ -279,18 +285,23 @@ extern "C" int mogp_kbuild(mogp_handle_t h, int kind, int C, int Q, int D, const
     return 0;
 }
 
-extern "C" int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
-                          const int32_t* chan_off_host, double* out_dev, void* stream) {
+extern "C" int mogp_kdiag_x(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev, const double* x_dev,
+                            const int32_t* chan_off_host, double* out_dev, void* stream) {
     if (!h) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     MOGP_CHECK(h, cudaSetDevice(h->device));
     KernSpec s;
     if (check_offsets(h, C, chan_off_host)) return -1;
     const int64_t N = chan_off_host[C];
-    int rc = prep_common(h, s, kind, C, Q, D, params_dev, nullptr, nullptr, chan_off_host, std::max<int64_t>(N, 1), 0.0, true, st);
+    int rc = prep_common(h, s, kind, C, Q, D, params_dev, nullptr, nullptr, chan_off_host, std::max<int64_t>(N, 1), 0.0, true, st,
+                         x_dev);
     if (rc) return rc;
-    if (N > 0) MOGP_CHECK(h, launch_kdiag(s, h->chanbuf2, h->chan_dev, N, out_dev, st));
+    if (N > 0) MOGP_CHECK(h, launch_kdiag(s, h->chanbuf2, h->chan_dev, N, out_dev, st, h->comps2, x_dev));
     return 0;
+}
+extern "C" int mogp_kdiag(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_dev,
+                          const int32_t* chan_off_host, double* out_dev, void* stream) {
+    return mogp_kdiag_x(h, kind, C, Q, D, params_dev, nullptr, chan_off_host, out_dev, stream);
 }
 
 // fp64-on-int8 tcgen05 path (i8mm.cu) for the K^-1 = L^-T L^-1 product: padded sizes >= g_i8_min_np use it (0 = never).
@@ -425,7 +436,8 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     h->n_ev = 0;
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(0, st));
-    MOGP_CHECK(h, launch_prep(s, params, sigma, dv, h->chan_dev, N, jitter_rel, h->comps, h->chanbuf, st));
+    MOGP_CHECK(h, launch_prep(s, params, sigma, dv, h->chan_dev, N, jitter_rel, h->comps, h->chanbuf, st, h->xbuf,
+                              s.window ? h->winsum : nullptr));
     // K~ (lower) -> L, diag blocks of Linv
     MOGP_CHECK(h, launch_kbuild(s, *tl, h->comps, h->chanbuf, h->xbuf, nullptr, h->chan_dev, dv, 1, h->A, ld, N, Np, st));
     STAGE_MARK();
@@ -466,7 +478,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
         MOGP_CHECK(h, launch_grad_reduce(s, *tl, h->comps, h->xbuf, h->W, ld, alpha, h->tile_part, st));
     }
     MOGP_CHECK(h, launch_finalize(s, tl, want_grad, params, sigma, h->comps, h->chanbuf, h->tile_part, z, alpha, kdiag,
-                                  h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out, st));
+                                  h->logdet_part, h->info, h->chan_dev, N, Np, jitter_rel, out, st, s.window ? h->winsum : nullptr));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(5, st));
 #undef STAGE_MARK
@@ -508,13 +520,14 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
         if (upload_chan(h, C, chan_off_host, 0, st)) return -2;
         h->chan_uploaded = off;
     }
-    if (ensure(h, h->comps, h->comps_cap, (size_t)C * C * s.R * comp_stride(D))) return -2;
+    if (ensure(h, h->comps, h->comps_cap, (size_t)C * C * s.R * s.st)) return -2;
+    if (s.window && ensure(h, h->winsum, h->winsum_cap, (size_t)C * s.R * (2 + D))) return -2;
     if (zero_linv_for(h, Np, st)) return -2;
     TileList* tl = get_tiles(h, C, chan_off_host, nullptr, 0, st);
     H_ARG(h, tl != nullptr, "tile list allocation failed");
     if (ensure(h, h->xbuf, h->xbuf_cap, (size_t)N * D)) return -2;
     if (want_grad) {
-        const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * comp_stride(D);
+        const size_t need = ((size_t)tl->n + (size_t)C * (C + 1) / 2) * s.R * s.st;
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
     }
     if (use_i8(Np) && i8_ready(h, Np, Np, st)) return -2;
@@ -701,7 +714,12 @@ extern "C" int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t
     MOGP_CHECK(h, launch_gemm(0, 0, g, 1, st));
     if (!full) {
         MOGP_CHECK(h, launch_colpass(h->pred_V, Mp, alpha, Np, Mp, h->colpart, h->colpart_cap, nullptr, colsq, st));
-        MOGP_CHECK(h, launch_pred_var(h->chanbuf, s.C, chan_s_dev, colsq, M, var_dev, st));
+        const double* kss = nullptr;
+        if (s.window) {          // the prior variance at the test points depends on the input
+            MOGP_CHECK(h, launch_kdiag(s, h->chanbuf, chan_s_dev, M, mu_tmp, st, h->comps, xs_dev));
+            kss = mu_tmp;        // (mu has been copied out above)
+        }
+        MOGP_CHECK(h, launch_pred_var(h->chanbuf, s.C, chan_s_dev, colsq, M, var_dev, st, kss));
     } else {
         const size_t sneed = (size_t)Mp * Mp;
         if (sneed > h->pred_s_cap) {

@@ -16,8 +16,13 @@
 // ------------------------------------------------------------------ block-component table
 // Every supported kernel is K_ij[a,b] = sum_r alpha_r exp(-1/2 sum_d v_rd u_d^2) cos(2 pi (sum_d m_rd u_d + phi_r)),
 // u_d = x_a,d - x_b,d + theta_rd, with per channel-pair (i,j) derived constants.
-// comp record layout (doubles): [alpha, phi, v[D], m[D], theta[D]]
-__host__ __device__ inline int comp_stride(int D) { return 2 + 3 * D; }
+// comp record layout (doubles): [alpha, phi, v[D], m[D], theta[D]]; the harmonizable family (MOHSM) multiplies every
+// component by a Gaussian window in the mid-point, exp(-1/2 l sum_d ((x_a,d + x_b,d)/2 - c_d)^2), and appends [l, c[D]].
+__host__ __device__ inline int kind_family(int kind) { return kind & 0xff; }
+__host__ __device__ inline int kind_rq(int kind) { return (kind >> 8) > 0 ? (kind >> 8) : 1; }
+__host__ __device__ inline bool kind_window(int kind) { return kind_family(kind) == MOGP_KIND_MOHSM; }
+__host__ __device__ inline int comp_stride(int kind, int D) { return kind_window(kind) ? 3 + 4 * D : 2 + 3 * D; }
+#define MOGP_MAX_STRIDE (3 + 4 * MOGP_MAX_D)
 
 struct KernSpec {
     int kind, C, Q, D;   // kind = family | Rq << 8 (MOGP_KIND_WITH_RQ)
@@ -25,9 +30,9 @@ struct KernSpec {
     int P;            // packed constrained kernel parameters
     bool has_cos;     // false for CONV (m = phi = 0)
     int Rq;           // sub-components of CSM / SM-LMC (1 otherwise)
+    bool window;      // MOHSM: non-stationary mid-point window (row-dependent Gram diagonal)
+    int st;           // comp / gradient-sum record length
 };
-__host__ __device__ inline int kind_family(int kind) { return kind & 0xff; }
-__host__ __device__ inline int kind_rq(int kind) { return (kind >> 8) > 0 ? (kind >> 8) : 1; }
 
 inline int spec_init(KernSpec& s, int kind, int C, int Q, int D) {
     if (C < 1 || Q < 1 || D < 1 || D > MOGP_MAX_D || kind < 0) return -1;
@@ -41,8 +46,11 @@ inline int spec_init(KernSpec& s, int kind, int C, int Q, int D) {
         case MOGP_KIND_CSM:   s.R = Q * Rq; s.P = 2 * Q * C * Rq + 2 * Q * D;          s.has_cos = true;  break;
         case MOGP_KIND_SMLMC: s.R = Q * D;  s.P = C * Q * Rq + Q + 2 * Q * D;          s.has_cos = true;  break;
         case MOGP_KIND_UMOSM: s.R = Q;      s.P = Q * C * C + 3 * Q * C * D + Q * C;   s.has_cos = true;  break;
+        case MOGP_KIND_MOHSM: s.R = Q;      s.P = Q * (3 * C + 3 * C * D + D);         s.has_cos = true;  break;
         default: return -1;
     }
+    s.window = kind_window(kind);
+    s.st = comp_stride(kind, D);
     if (kind_family(kind) < MOGP_KIND_CSM && (kind >> 8) != 0) return -1;
     return 0;
 }
@@ -121,6 +129,8 @@ struct mogp_handle_s {
     double *comps = nullptr; size_t comps_cap = 0;            // C*C*R*stride (state of the last lml_grad)
     double *chanbuf = nullptr;                                // per-channel scalars of the last lml_grad
     double *comps2 = nullptr; size_t comps2_cap = 0;          // same, scratch of mogp_kbuild / mogp_kdiag
+    double *winsum = nullptr; size_t winsum_cap = 0;          // window kinds: row sums of the Gram diagonal (prep -> finalize)
+    double *winsum2 = nullptr; size_t winsum2_cap = 0;        // same, scratch of mogp_kbuild
     double *chanbuf2 = nullptr;
     int64_t linv_np = 0;                                      // layout (ld) Linv was last zero-initialised for
     double *vec = nullptr;                                    // 8 * np_max doubles of vector scratch
@@ -195,15 +205,16 @@ extern long long g_mogp_cfg_epoch;
 
 // ------------------------------------------------------------------ covariance kernels (cov.cu)
 // chanbuf layout (doubles): [0..C) kdiag_gram | [C..2C) kdiag_api | [2C..3C) noise variance | [3C] jitter add | [3C+1] trW scratch
+// window kinds (MOHSM) also need the N x D inputs and a C * R * (2 + D) buffer for the row sums of the Gram diagonal
 cudaError_t launch_prep(const KernSpec& s, const double* params, const double* sigma, const double* data_var,
                         const int32_t* chan_dev, int64_t N, double jitter_rel, double* comps, double* chanbuf,
-                        cudaStream_t st);
+                        cudaStream_t st, const double* x = nullptr, double* winsum = nullptr);
 // mode 0: Gram lower into padded A (ld = Np), also initialises the padding; mode 1: Gram full; mode 2: cross
 cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* comps, const double* chanbuf,
                           const double* x1, const double* x2, const int32_t* chan1_dev, const double* data_var,
                           int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st);
 cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t* chan_dev, int64_t N, double* out,
-                         cudaStream_t st);
+                         cudaStream_t st, const double* comps = nullptr, const double* x = nullptr);
 // avec != NULL: W holds K^-1 and the kernel forms (K^-1 - avec avec^T)/2 while loading
 cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
                                const double* W, long long ldw, const double* avec, double* tile_part, cudaStream_t st);
@@ -212,7 +223,8 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
                             const double* sigma, const double* comps, const double* chanbuf,
                             const double* tile_part, const double* z, const double* alpha, const double* kinv_diag,
                             const double* logdet_part, const int32_t* info, const int32_t* chan_dev,
-                            int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st);
+                            int64_t N, int64_t Np, double jitter_rel, double* out, cudaStream_t st,
+                            const double* winsum = nullptr);
 
 // ------------------------------------------------------------------ dense linear algebra (linalg.cu)
 // fused_inverse: NULL -> factor only (diagonal blocks of Linv get inv(L_kk)); else the triangular inverse may be
@@ -238,8 +250,9 @@ cudaError_t launch_colpass(const double* M, long long ld, const double* v, int64
 cudaError_t launch_pad_copy(const double* src, int64_t n, double* dst, int64_t np, cudaStream_t st);
 cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, long long ldw, int64_t n, int64_t np,
                             cudaStream_t st);
+// var = prior variance - colsq; the prior variance is the per-channel constant chanbuf[C + c] or, if kss != NULL, kss[m]
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
-                            double* var, cudaStream_t st);
+                            double* var, cudaStream_t st, const double* kss = nullptr);
 cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);
 cudaError_t launch_stamp(int slot, cudaStream_t st);      // diagnostics: global-timer stamp of a point of the step (mogp_set_stamps)
 

@@ -116,13 +116,17 @@ __device__ __forceinline__ void stage_xy(double* dsta, const double* srca, int n
 
 // ------------------------------------------------------------------ prep
 // chanbuf: [0..C) kdiag_gram | [C..2C) kdiag_api | [2C..3C) sigma^2 | [3C] jitter_add
+// Window kinds (MOHSM): the Gram diagonal depends on the row, K_rr = sum_q alpha_q E_q(x_r), E_q(x) = exp(-1/2 l_q sum_d (x_d - c_qd)^2);
+// winsum[(c R + q)(2 + D)] = [sum_r E_q, sum_r E_q sum_d s_d^2, sum_r E_q s_d] over the rows of channel c (the relative jitter
+// and its gradient need them), chanbuf[c] = sum over the channel's rows of K_rr.
 __global__ void __launch_bounds__(256) prep_kernel(KernSpec s, const double* __restrict__ params,
                                                    const double* __restrict__ sigma, const double* __restrict__ data_var,
                                                    const int32_t* __restrict__ chan, long long N, double jitter_rel,
-                                                   double* __restrict__ comps, double* __restrict__ chanbuf) {
+                                                   double* __restrict__ comps, double* __restrict__ chanbuf,
+                                                   const double* __restrict__ x, double* __restrict__ winsum) {
     __shared__ double red[256];
     const int tid = threadIdx.x;
-    const int st = comp_stride(s.D);
+    const int st = s.st;
     const int total = s.C * s.C * s.R;
     for (int e = tid; e < total; e += 256) {
         const int r = e % s.R, pj = e / s.R, j = pj % s.C, i = pj / s.C;
@@ -137,10 +141,38 @@ __global__ void __launch_bounds__(256) prep_kernel(KernSpec s, const double* __r
         if (tid < o) red[tid] += red[tid + o];
         __syncthreads();
     }
+    if (s.window) {
+        const int warp = tid >> 5, lane = tid & 31, D = s.D, wst = 2 + D;
+        for (int e = warp; e < s.C * s.R; e += 8) {
+            const int c = e / s.R, r = e % s.R;
+            const double* cp = comps + (size_t)((c * s.C + c) * s.R + r) * st;
+            const double ell = cp[2 + 3 * D];
+            double b0 = 0.0, b5 = 0.0, b6[MOGP_MAX_D];
+            for (int d = 0; d < D; ++d) b6[d] = 0.0;
+            for (long long row = chan[c] + lane; row < chan[c + 1]; row += 32) {
+                double ss = 0.0, sd[MOGP_MAX_D];
+                for (int d = 0; d < D; ++d) { sd[d] = x[row * D + d] - cp[3 + 3 * D + d]; ss = fma(sd[d], sd[d], ss); }
+                const double E = exp(-0.5 * ell * ss);
+                b0 += E; b5 += E * ss;
+                for (int d = 0; d < D; ++d) b6[d] += E * sd[d];
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+                b5 += __shfl_xor_sync(0xffffffffu, b5, o);
+                for (int d = 0; d < D; ++d) b6[d] += __shfl_xor_sync(0xffffffffu, b6[d], o);
+            }
+            if (lane == 0) {
+                winsum[(size_t)e * wst] = b0; winsum[(size_t)e * wst + 1] = b5;
+                for (int d = 0; d < D; ++d) winsum[(size_t)e * wst + 2 + d] = b6[d];
+            }
+        }
+        __syncthreads();
+    }
     if (tid < s.C) {
         const int c = tid;
         double kd = 0.0;
-        for (int r = 0; r < s.R; ++r) kd += comps[(size_t)((c * s.C + c) * s.R + r) * st];
+        for (int r = 0; r < s.R; ++r)
+            kd += comps[(size_t)((c * s.C + c) * s.R + r) * st] * (s.window ? winsum[(size_t)(c * s.R + r) * (2 + s.D)] : 1.0);
         chanbuf[c] = kd;
         chanbuf[s.C + c] = kdiag_api_value(s.kind, s.C, s.Q, s.D, params, comps, s.R, c);
         chanbuf[2 * s.C + c] = sigma ? sigma[c] * sigma[c] : 0.0;
@@ -148,15 +180,19 @@ __global__ void __launch_bounds__(256) prep_kernel(KernSpec s, const double* __r
     __syncthreads();
     if (tid == 0) {
         double tot = red[0];
-        for (int c = 0; c < s.C; ++c) tot += (double)(chan[c + 1] - chan[c]) * (chanbuf[c] + chanbuf[2 * s.C + c]);
+        for (int c = 0; c < s.C; ++c) {
+            const double n_c = (double)(chan[c + 1] - chan[c]);
+            tot += (s.window ? chanbuf[c] : n_c * chanbuf[c]) + n_c * chanbuf[2 * s.C + c];
+        }
         chanbuf[3 * s.C] = jitter_rel * tot / (double)N;
     }
 }
 
 cudaError_t launch_prep(const KernSpec& s, const double* params, const double* sigma, const double* data_var,
                         const int32_t* chan_dev, int64_t N, double jitter_rel, double* comps, double* chanbuf,
-                        cudaStream_t st) {
-    prep_kernel<<<1, 256, 0, st>>>(s, params, sigma, data_var, chan_dev, (long long)N, jitter_rel, comps, chanbuf);
+                        cudaStream_t st, const double* x, double* winsum) {
+    if (s.window && (!x || !winsum)) return cudaErrorInvalidValue;
+    prep_kernel<<<1, 256, 0, st>>>(s, params, sigma, data_var, chan_dev, (long long)N, jitter_rel, comps, chanbuf, x, winsum);
     MOGP_COUNT(1);
     return cudaGetLastError();
 }
@@ -170,7 +206,8 @@ struct TileSmem {
     double xb[MOGP_TILE * MOGP_MAX_D];
     double rc[RC][MOGP_TILE], rs[RC][MOGP_TILE];     // cos/sin of the row angles
     double cc[RC][MOGP_TILE], cs[RC][MOGP_TILE];     // cos/sin of the column angles
-    double comp[RC][2 + 3 * MOGP_MAX_D];
+    double comp[RC][MOGP_MAX_STRIDE];
+    double x0[MOGP_MAX_D];                           // the shift applied to xa / xb (window kinds shift their centre by it)
     double expt[64];                                 // 2^(j/64), see exp_nonpos
     uint64_t bar;
 };
@@ -191,6 +228,7 @@ __device__ __forceinline__ void load_tile_x(TileSmem& sm, const CovTile& t, cons
     for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
         if (d < D) x0[d] = sm.xb[d];
     __syncthreads();
+    if (tid < D) sm.x0[tid] = x0[tid];
     for (int e = tid; e < MOGP_TILE * D; e += 256) {
         const int d = e % D, r = e / D;
         sm.xa[e] = (r < t.nr) ? sm.xa[e] - x0[d] : 0.0;
@@ -201,9 +239,8 @@ __device__ __forceinline__ void load_tile_x(TileSmem& sm, const CovTile& t, cons
 // Fills the comp records and trig tables for components [rbase, rbase+nr) of `pair`.
 template <int DT, bool COS>
 __device__ __forceinline__ void fill_tables(TileSmem& sm, const double* __restrict__ comps, int pair, int R, int rbase,
-                                            int nrc, int Drt, int tid) {
+                                            int nrc, int Drt, int st, int tid) {
     const int D = dims<DT>(Drt);
-    const int st = comp_stride(D);
     for (int e = tid; e < nrc * st; e += 256) sm.comp[e / st][e % st] = comps[(size_t)(pair * R + rbase) * st + e];
     __syncthreads();
     if (COS) {
@@ -230,10 +267,24 @@ __device__ __forceinline__ void fill_tables(TileSmem& sm, const double* __restri
     __syncthreads();
 }
 
+// Prior variance of a window kind at one input: sum_q alpha_q exp(-1/2 l_q sum_d (x_d - c_qd)^2) over the records of the
+// diagonal pair (c, c).  Shared by the Gram diagonal of kbuild and by kdiag_x so that K_diag == diag(K) bit for bit.
+__device__ __forceinline__ double win_diag_value(const double* __restrict__ cpair, int R, int D, int st,
+                                                 const double* __restrict__ xrow, const double* __restrict__ tab) {
+    double acc = 0.0;
+    for (int r = 0; r < R; ++r) {
+        const double* cp = cpair + (size_t)r * st;
+        double ss = 0.0;
+        for (int d = 0; d < D; ++d) { const double sd = xrow[d] - cp[3 + 3 * D + d]; ss = fma(sd, sd, ss); }
+        acc = fma(cp[0], exp_nonpos(-0.5 * (cp[2 + 3 * D] * ss), tab), acc);
+    }
+    return acc;
+}
+
 // ------------------------------------------------------------------ kbuild
 // mode 0: Gram lower tiles into the padded factor buffer (+ padding rows);  mode 1: Gram, every
 // lower tile is also written transposed (full symmetric output);  mode 2: cross-covariance.
-template <int DT, bool COS, int MINB>
+template <int DT, bool COS, int MINB, bool WIN>
 __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const CovTile* __restrict__ tiles, int ntiles, int mode,
                                                      const double* __restrict__ comps, const double* __restrict__ chanbuf,
                                                      const double* __restrict__ x1, const double* __restrict__ x2,
@@ -271,7 +322,7 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
         for (int rbase = 0; rbase < s.R; rbase += RC) {
             const int nrc = min(RC, s.R - rbase);
             __syncthreads();
-            fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, tid);
+            fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, s.st, tid);
             double xb[4][DT > 0 ? DT : MOGP_MAX_D];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -281,6 +332,7 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
             for (int r = 0; r < nrc; ++r) {
                 const double* cp = sm.comp[r];
                 const double alpha = cp[0];
+                const double ell = WIN ? cp[2 + 3 * D] : 0.0;
                 double cB[4], sB[4];
                 if (COS) {
 #pragma unroll
@@ -289,10 +341,15 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = ty + 16 * i;
-                    double ua[DT > 0 ? DT : MOGP_MAX_D];
+                    double ua[DT > 0 ? DT : MOGP_MAX_D], ha[DT > 0 ? DT : MOGP_MAX_D];
 #pragma unroll
                     for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                        if (d < D) ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                        if (d < D) {
+                            ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                            // mid-point minus centre in the tile's shifted coordinates, (xa + xb)/2 - (c - x0); the sum first, so
+                            // that the value is bit-for-bit symmetric in (a, b) (the diagonal tiles compute both halves)
+                            if (WIN) ha[d] = sm.xa[row * D + d];
+                        }
                     double cA = 1.0, sA = 0.0;
                     if (COS) { cA = sm.rc[r][row]; sA = sm.rs[r][row]; }
 #pragma unroll
@@ -300,7 +357,10 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
                         double e = 0.0;
 #pragma unroll
                         for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                            if (d < D) { const double u = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u, u, e); }
+                            if (d < D) {
+                                const double u = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u, u, e);
+                                if (WIN) { const double sd = fma(0.5, ha[d] + xb[j][d], sm.x0[d] - cp[3 + 3 * D + d]); e = fma(ell * sd, sd, e); }
+                            }
                         double val = alpha * exp_nonpos(-0.5 * e, sm.expt);
                         if (COS) val *= fma(cA, cB[j], sA * sB[j]);
                         acc[i][j] += val;
@@ -318,7 +378,9 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
             for (int j = 0; j < 4; ++j) {
                 const int row = ty + 16 * i, col = tx + 16 * j;
                 if (row == col && row < t.nr) {
-                    double v = chanbuf[pi];
+                    double v = WIN ? win_diag_value(comps + (size_t)(pi * s.C + pi) * s.R * s.st, s.R, D, s.st,
+                                                    x1 + (size_t)(t.r0 + row) * D, sm.expt)
+                                   : chanbuf[pi];
                     if (add_diag) {
                         v += chanbuf[2 * s.C + pi];
                         if (data_var) v += data_var[t.r0 + row];
@@ -362,12 +424,12 @@ __global__ void __launch_bounds__(256, MINB) kbuild_kernel(KernSpec s, const Cov
 static int g_cov_minb = std::getenv("MOGP_COV_MINB") ? std::atoi(std::getenv("MOGP_COV_MINB")) : 2;
 extern "C" int mogp_set_cov_minb(int v) { g_cov_minb = v == 3 ? 3 : 2; ++g_mogp_cfg_epoch; return 0; }
 
-template <int DT, bool COS, int MINB>
+template <int DT, bool COS, int MINB, bool WIN = false>
 static cudaError_t launch_kbuild_t(const KernSpec& s, const TileList& tl, int nblocks, const double* comps,
                                    const double* chanbuf, const double* x1, const double* x2, const double* data_var,
                                    int add_diag, double* K, long long ldk, int64_t N, int64_t Np, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem) + 64 * 65 * sizeof(double);
-    auto kern = kbuild_kernel<DT, COS, MINB>;
+    auto kern = kbuild_kernel<DT, COS, MINB, WIN>;
     static PerDeviceOnce once;
     if (OnceGuard og{once}; og.needed()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -386,6 +448,7 @@ cudaError_t launch_kbuild(const KernSpec& s, const TileList& tl, const double* c
     (void)chan1_dev;
     const int nblocks = tl.n + (tl.mode == 0 ? (int)(Np - N) : 0);
 #define KB_ARGS s, tl, nblocks, comps, chanbuf, x1, x2, data_var, add_diag, K, ldk, N, Np, st
+    if (s.window) return s.D == 1 ? launch_kbuild_t<1, true, 2, true>(KB_ARGS) : launch_kbuild_t<0, true, 2, true>(KB_ARGS);
     if (g_cov_minb == 3) {
         if (s.D == 1) return s.has_cos ? launch_kbuild_t<1, true, 3>(KB_ARGS) : launch_kbuild_t<1, false, 3>(KB_ARGS);
         return s.has_cos ? launch_kbuild_t<0, true, 3>(KB_ARGS) : launch_kbuild_t<0, false, 3>(KB_ARGS);
@@ -403,16 +466,35 @@ __global__ void kdiag_kernel(int C, const double* __restrict__ chanbuf, const in
     while (c + 1 < C && r >= chan[c + 1]) ++c;
     out[r] = chanbuf[C + c];
 }
+// window kinds: the prior variance depends on the input (gpr/multioutput.py:389-395)
+__global__ void __launch_bounds__(256) kdiag_win_kernel(KernSpec s, const double* __restrict__ comps,
+                                                        const int32_t* __restrict__ chan, const double* __restrict__ x,
+                                                        long long N, double* __restrict__ out) {
+    __shared__ double expt[64];
+    if (threadIdx.x < 64) expt[threadIdx.x] = EXP2_TABLE[threadIdx.x];
+    __syncthreads();
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int c = 0;
+    while (c + 1 < s.C && r >= chan[c + 1]) ++c;
+    out[r] = win_diag_value(comps + (size_t)(c * s.C + c) * s.R * s.st, s.R, s.D, s.st, x + (size_t)r * s.D, expt);
+}
 cudaError_t launch_kdiag(const KernSpec& s, const double* chanbuf, const int32_t* chan_dev, int64_t N, double* out,
-                         cudaStream_t st) {
-    kdiag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s.C, chanbuf, chan_dev, (long long)N, out);
+                         cudaStream_t st, const double* comps, const double* x) {
+    if (s.window) {
+        if (!comps || !x) return cudaErrorInvalidValue;
+        kdiag_win_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s, comps, chan_dev, x, (long long)N, out);
+    } else {
+        kdiag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(s.C, chanbuf, chan_dev, (long long)N, out);
+    }
     MOGP_COUNT(1);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ grad_reduce
-// Per tile and component: [S0, S4, S1[D], S2[D], S3[D]] with the symmetric weight folded into W.
-template <int DT, bool COS, int MINB>
+// Per tile and component: [S0, S4, S1[D], S2[D], S3[D]] (+ [S5, S6[D]] for the window kinds) with the symmetric weight folded
+// into W.
+template <int DT, bool COS, int MINB, bool WIN>
 __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, const CovTile* __restrict__ tiles,
                                                           const double* __restrict__ comps, const double* __restrict__ x,
                                                           const double* __restrict__ W, long long ldw,
@@ -424,7 +506,7 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const CovTile t = tiles[blockIdx.x];
     const int D = dims<DT>(s.D);
-    const int st = comp_stride(D);
+    const int st = s.st;
     const int ty = tid >> 4, tx = tid & 15;
     const int pi = t.pair / s.C, pj = t.pair % s.C;
     double* outp = tile_part + (size_t)blockIdx.x * s.R * st;
@@ -463,7 +545,7 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
     for (int rbase = 0; rbase < s.R; rbase += RC) {
         const int nrc = min(RC, s.R - rbase);
         __syncthreads();
-        fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, tid);
+        fill_tables<DT, COS>(sm, comps, t.pair, s.R, rbase, nrc, s.D, st, tid);
         double xb[4][DT > 0 ? DT : MOGP_MAX_D];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -472,10 +554,12 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
                 if (d < D) xb[j][d] = sm.xb[(tx + 16 * j) * D + d];
         for (int r = 0; r < nrc; ++r) {
             const double* cp = sm.comp[r];
-            double s0 = 0.0, s4 = 0.0;
+            const double ell = WIN ? cp[2 + 3 * D] : 0.0;
+            double s0 = 0.0, s4 = 0.0, s5 = 0.0;
             double s1[DT > 0 ? DT : MOGP_MAX_D], s2[DT > 0 ? DT : MOGP_MAX_D], s3[DT > 0 ? DT : MOGP_MAX_D];
+            double s6[DT > 0 ? DT : MOGP_MAX_D];
 #pragma unroll
-            for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d) s1[d] = s2[d] = s3[d] = 0.0;
+            for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d) s1[d] = s2[d] = s3[d] = s6[d] = 0.0;
             double cB[4], sB[4];
             if (COS) {
 #pragma unroll
@@ -484,19 +568,26 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = ty + 16 * i;
-                double ua[DT > 0 ? DT : MOGP_MAX_D];
+                double ua[DT > 0 ? DT : MOGP_MAX_D], ha[DT > 0 ? DT : MOGP_MAX_D];
 #pragma unroll
                 for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                    if (d < D) ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                    if (d < D) {
+                        ua[d] = sm.xa[row * D + d] + cp[2 + 2 * D + d];
+                        if (WIN) ha[d] = sm.xa[row * D + d];
+                    }
                 double cA = 1.0, sA = 0.0;
                 if (COS) { cA = sm.rc[r][row]; sA = sm.rs[r][row]; }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    double u[DT > 0 ? DT : MOGP_MAX_D];
-                    double e = 0.0;
+                    double u[DT > 0 ? DT : MOGP_MAX_D], sd[DT > 0 ? DT : MOGP_MAX_D];
+                    double e = 0.0, ss = 0.0;
 #pragma unroll
                     for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                        if (d < D) { u[d] = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u[d], u[d], e); }
+                        if (d < D) {
+                            u[d] = ua[d] - xb[j][d]; e = fma(cp[2 + d] * u[d], u[d], e);
+                            if (WIN) { sd[d] = fma(0.5, ha[d] + xb[j][d], sm.x0[d] - cp[3 + 3 * D + d]); ss = fma(sd[d], sd[d], ss); }
+                        }
+                    if (WIN) e = fma(ell, ss, e);
                     const double we = wv[i][j] * exp_nonpos(-0.5 * e, sm.expt);
                     double wec = we, wes = 0.0;
                     if (COS) {
@@ -512,7 +603,9 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
                             s3[d] += wu;
                             s1[d] = fma(wu, u[d], s1[d]);
                             s2[d] = fma(wes, u[d], s2[d]);
+                            if (WIN) s6[d] = fma(wec, sd[d], s6[d]);
                         }
+                    if (WIN) s5 = fma(wec, ss, s5);
                 }
             }
             // warp reduction, lane 0 parks the warp's partial in shared memory
@@ -526,14 +619,20 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
                         s1[d] += __shfl_xor_sync(0xffffffffu, s1[d], o);
                         s2[d] += __shfl_xor_sync(0xffffffffu, s2[d], o);
                         s3[d] += __shfl_xor_sync(0xffffffffu, s3[d], o);
+                        if (WIN) s6[d] += __shfl_xor_sync(0xffffffffu, s6[d], o);
                     }
+                if (WIN) s5 += __shfl_xor_sync(0xffffffffu, s5, o);
             }
             if (lane == 0) {
                 double* wp = wpart + (size_t)(warp * RC + r) * st;
                 wp[0] = s0; wp[1] = s4;
 #pragma unroll
                 for (int d = 0; d < (DT > 0 ? DT : MOGP_MAX_D); ++d)
-                    if (d < D) { wp[2 + d] = s1[d]; wp[2 + D + d] = s2[d]; wp[2 + 2 * D + d] = s3[d]; }
+                    if (d < D) {
+                        wp[2 + d] = s1[d]; wp[2 + D + d] = s2[d]; wp[2 + 2 * D + d] = s3[d];
+                        if (WIN) wp[3 + 3 * D + d] = s6[d];
+                    }
+                if (WIN) wp[2 + 3 * D] = s5;
             }
         }
         __syncthreads();
@@ -548,15 +647,16 @@ __global__ void __launch_bounds__(256, MINB) grad_reduce_kernel(KernSpec s, cons
 
 cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const double* comps, const double* x,
                                const double* W, long long ldw, const double* avec, double* tile_part, cudaStream_t st) {
-    const size_t smem = sizeof(TileSmem) + (size_t)8 * RC * (2 + 3 * MOGP_MAX_D) * sizeof(double);
+    const size_t smem = sizeof(TileSmem) + (size_t)8 * RC * MOGP_MAX_STRIDE * sizeof(double);
     if (tl.n <= 0) return cudaSuccess;
 #define LAUNCH_GR(DT, COS)                                                                                         \
     do {                                                                                                           \
         if (g_cov_minb == 3) { LAUNCH_GR_M(DT, COS, 3); } else { LAUNCH_GR_M(DT, COS, 2); }                       \
     } while (0)
-#define LAUNCH_GR_M(DT, COS, MB)                                                                                   \
+#define LAUNCH_GR_M(DT, COS, MB) LAUNCH_GR_W(DT, COS, MB, false)
+#define LAUNCH_GR_W(DT, COS, MB, WIN)                                                                              \
     do {                                                                                                           \
-        auto kern = grad_reduce_kernel<DT, COS, MB>;                                                               \
+        auto kern = grad_reduce_kernel<DT, COS, MB, WIN>;                                                            \
         static PerDeviceOnce once;                                                                                 \
         if (OnceGuard og{once}; og.needed()) {                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
@@ -565,10 +665,12 @@ cudaError_t launch_grad_reduce(const KernSpec& s, const TileList& tl, const doub
         kern<<<tl.n, 256, smem, st>>>(s, tl.dev, comps, x, W, ldw, avec, tile_part);                                     \
         MOGP_COUNT(1);                                                                                             \
     } while (0)
-    if (s.D == 1) { if (s.has_cos) LAUNCH_GR(1, true); else LAUNCH_GR(1, false); }
+    if (s.window) { if (s.D == 1) LAUNCH_GR_W(1, true, 2, true); else LAUNCH_GR_W(0, true, 2, true); }
+    else if (s.D == 1) { if (s.has_cos) LAUNCH_GR(1, true); else LAUNCH_GR(1, false); }
     else { if (s.has_cos) LAUNCH_GR(0, true); else LAUNCH_GR(0, false); }
 #undef LAUNCH_GR
 #undef LAUNCH_GR_M
+#undef LAUNCH_GR_W
     return cudaGetLastError();
 }
 
@@ -599,7 +701,8 @@ __device__ double block_sum_256(double v, double* red) {
 
 __global__ void __launch_bounds__(256) finalize_kernel(KernSpec s, int want_grad, const double* __restrict__ params,
                                                        const double* __restrict__ sigma, const double* __restrict__ comps,
-                                                       const double* __restrict__ gsum, const double* __restrict__ z,
+                                                       double* __restrict__ gsum, const double* __restrict__ winsum,
+                                                       const double* __restrict__ z,
                                                        const double* __restrict__ alpha, const double* __restrict__ kinv_diag,
                                                        const double* __restrict__ logdet_part, const int32_t* __restrict__ info,
                                                        const int32_t* __restrict__ chan, long long N, long long Np,
@@ -632,20 +735,36 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernSpec s, int want_grad
     const double trW = trW_s;
     if (tid < s.C) adj[tid] = jitter_rel / (double)N * trW * (double)(chan[tid + 1] - chan[tid]);
     __syncthreads();
+    if (tid < s.C) out[2 + s.P + tid] = 2.0 * sigma[tid] * (csum[tid] + adj[tid]);
+    if (s.window) {
+        // row-dependent Gram diagonal: d (jitter term) / d (alpha_q, l_q, c_q) of the diagonal pair (c, c) comes from the row sums
+        // of prep (winsum) instead of the row count; fold it into the pair's gradient sums [S0, S5, S6] and clear adj
+        const double f = jitter_rel / (double)N * trW;
+        const int wst = 2 + s.D;
+        for (int e = tid; e < s.C * s.R; e += 256) {
+            const int c = e / s.R, r = e % s.R;
+            double* S = gsum + (size_t)((c * (c + 1) / 2 + c) * s.R + r) * s.st;
+            S[0] += f * winsum[(size_t)e * wst];
+            S[2 + 3 * s.D] += f * winsum[(size_t)e * wst + 1];
+            for (int d = 0; d < s.D; ++d) S[3 + 3 * s.D + d] += f * winsum[(size_t)e * wst + 2 + d];
+        }
+        __syncthreads();
+        if (tid < s.C) adj[tid] = 0.0;
+        __syncthreads();
+    }
     const int owners = n_chain_owners(s.kind, s.C, s.Q);
     for (int o = tid; o < owners; o += 256) chain_owner(s.kind, s.C, s.Q, s.D, params, comps, gsum, adj, o, out + 2);
-    if (tid < s.C)
-        out[2 + s.P + tid] = 2.0 * sigma[tid] * (csum[tid] + adj[tid]);
 }
 
 cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad, const double* params,
                             const double* sigma, const double* comps, const double* chanbuf, const double* tile_part,
                             const double* z, const double* alpha, const double* kinv_diag, const double* logdet_part,
                             const int32_t* info, const int32_t* chan_dev, int64_t N, int64_t Np, double jitter_rel,
-                            double* out, cudaStream_t st) {
+                            double* out, cudaStream_t st, const double* winsum) {
     (void)chanbuf;
     if (s.C > 64) return cudaErrorInvalidValue;
-    const int stc = comp_stride(s.D);
+    if (s.window && want_grad && !winsum) return cudaErrorInvalidValue;
+    const int stc = s.st;
     double* gsum = nullptr;
     if (want_grad) {
         const int npl = s.C * (s.C + 1) / 2;
@@ -653,7 +772,7 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
         pairsum_kernel<<<npl, 128, 0, st>>>(s.R, stc, tl->pair_first_dev, tile_part, gsum);
         MOGP_COUNT(1);
     }
-    finalize_kernel<<<1, 256, 0, st>>>(s, want_grad, params, sigma, comps, gsum, z, alpha, kinv_diag, logdet_part, info,
+    finalize_kernel<<<1, 256, 0, st>>>(s, want_grad, params, sigma, comps, gsum, winsum, z, alpha, kinv_diag, logdet_part, info,
                                        chan_dev, (long long)N, (long long)Np, jitter_rel, out);
     MOGP_COUNT(1);
     return cudaGetLastError();
@@ -664,7 +783,7 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 extern "C" int mogp_host_pair_comps(int kind, int C, int Q, int D, const double* params, double* comps_out) {
     KernSpec s;
     if (spec_init(s, kind, C, Q, D)) return -1;
-    const int st = comp_stride(D);
+    const int st = comp_stride(kind, D);
     for (int i = 0; i < C; ++i)
         for (int j = 0; j < C; ++j)
             for (int r = 0; r < s.R; ++r) pair_comp(kind, C, Q, D, params, i, j, r, comps_out + (size_t)((i * C + j) * s.R + r) * st);
@@ -674,7 +793,7 @@ extern "C" int mogp_host_chain(int kind, int C, int Q, int D, const double* para
                                const double* adj, double* grad_out) {
     KernSpec s;
     if (spec_init(s, kind, C, Q, D)) return -1;
-    const int st = comp_stride(D);
+    const int st = comp_stride(kind, D);
     std::vector<double> comps((size_t)C * C * s.R * st);
     mogp_host_pair_comps(kind, C, Q, D, params, comps.data());
     const int owners = n_chain_owners(kind, C, Q);

@@ -29,9 +29,9 @@ __host__ __device__ inline const double* gs_rec(const double* gsum, int i, int j
     const int pl = i * (i + 1) / 2 + j;
     return gsum + (size_t)(pl * R + r) * st;
 }
-#include "covmath_next.cuh"     // CSM / SM-LMC / uMOSM tables (families >= MOGP_KIND_CSM)
+#include "covmath_next.cuh"     // CSM / SM-LMC / uMOSM / MOHSM tables (families >= MOGP_KIND_CSM)
 
-// comp record: [alpha, phi, v[D], m[D], theta[D]].  kind = family | Rq << 8.
+// comp record: [alpha, phi, v[D], m[D], theta[D]] (+ [l, c[D]] for MOHSM).  kind = family | Rq << 8.
 __host__ __device__ inline void pair_comp(int kind, int C, int Q, int D, const double* __restrict__ p, int i, int j,
                                           int r, double* __restrict__ out) {
     if (kind_family(kind) >= MOGP_KIND_CSM) {
@@ -97,7 +97,7 @@ __host__ __device__ inline void pair_comp(int kind, int C, int Q, int D, const d
 // multioutput.py:549-553): for SM this is sum_q magnitude_q whatever D is.
 __host__ __device__ inline double kdiag_api_value(int kind, int C, int Q, int D, const double* p,
                                                   const double* comps, int R, int c) {
-    const int st = comp_stride(D);
+    const int st = comp_stride(kind, D);
     double s = 0.0;
     if (kind == MOGP_KIND_SM) {
         const SmOff o = sm_off(C, Q, D);
@@ -119,7 +119,7 @@ __host__ __device__ inline double kdiag_api_value(int kind, int C, int Q, int D,
 }
 
 // ---- chain rule ----------------------------------------------------------------------
-// gsum: per lower pair pl = i(i+1)/2 + j, per component r, a record of comp_stride(D) sums
+// gsum: per lower pair pl = i(i+1)/2 + j, per component r, a record of comp_stride(kind, D) sums
 //   [S0 = sum W E C, S4 = sum W E Sn, S1[d] = sum W E C u_d^2, S2[d] = sum W E Sn u_d, S3[d] = sum W E C u_d]
 // (W already carries the symmetric weight).  adj[c] is added to S0 of the diagonal pair (c,c)
 // (relative-jitter term).  `owner` enumerates disjoint output slices, see n_chain_owners().
@@ -135,7 +135,7 @@ __host__ __device__ inline void chain_owner(int kind, int C, int Q, int D, const
         chain_owner_next(kind_family(kind), C, Q, kind_rq(kind), D, p, comps, gsum, adj, owner, g);
         return;
     }
-    const int st = comp_stride(D);
+    const int st = comp_stride(kind, D);
     const double PI2 = MOGP_PI * MOGP_PI;
     if (kind == MOGP_KIND_MOSM) {
         const MosmOff o = mosm_off(C, Q, D);

@@ -7,6 +7,10 @@
 //          packed  weight (C,Q,Rq) | magnitude (Q) | mean (Q,D) | variance (Q,D);       R = Q*D  components r = q*D + d
 //   UMOSM  MixtureKernel of Q UncoupledMultiOutputSpectralKernel (gpr/multioutput.py:261-293):
 //          packed  weight (Q,C,C; lower triangle used) | mean (Q,C,D) | variance (Q,C,D) | delay (Q,C,D) | phase (Q,C)
+//   MOHSM  MixtureKernel of Q MultiOutputHarmonizableSpectralKernel (gpr/multioutput.py:353-395): the MOSM-like stationary
+//          factor times a Gaussian window exp(-1/2 l_ij sum_d ((x_d + x'_d)/2 - c_d)^2) in the mid-point; the comp record
+//          carries [l_ij, c[D]] after theta, the gradient-sum record [S5 = sum W E C sum_d s_d^2, S6[d] = sum W E C s_d]
+//          packed  weight (Q,C) | mean (Q,C,D) | variance (Q,C,D) | lengthscale (Q,C) | center (Q,D) | delay (Q,C,D) | phase (Q,C)
 #pragma once
 
 struct CsmOff { int amp, mu, var, sh; };
@@ -21,12 +25,18 @@ struct UmosmOff { int w, mu, var, th, ph; };
 __host__ __device__ inline UmosmOff umosm_off(int C, int Q, int D) {
     UmosmOff o; o.w = 0; o.mu = Q * C * C; o.var = o.mu + Q * C * D; o.th = o.var + Q * C * D; o.ph = o.th + Q * C * D; return o;
 }
+struct MohsmOff { int w, mu, var, ls, ctr, th, ph; };
+__host__ __device__ inline MohsmOff mohsm_off(int C, int Q, int D) {
+    MohsmOff o; o.w = 0; o.mu = Q * C; o.var = o.mu + Q * C * D; o.ls = o.var + Q * C * D; o.ctr = o.ls + Q * C;
+    o.th = o.ctr + Q * D; o.ph = o.th + Q * C * D; return o;
+}
 __host__ __device__ inline int next_num_params(int kind, int C, int Q, int Rq, int D) {
+    if (kind == MOGP_KIND_MOHSM) return Q * (3 * C + 3 * C * D + D);
     if (kind == MOGP_KIND_UMOSM) return Q * C * C + 3 * Q * C * D + Q * C;
     return kind == MOGP_KIND_CSM ? 2 * Q * C * Rq + 2 * Q * D : C * Q * Rq + Q + 2 * Q * D;
 }
 __host__ __device__ inline int next_num_comps(int kind, int Q, int Rq, int D) {
-    return kind == MOGP_KIND_UMOSM ? Q : (kind == MOGP_KIND_CSM ? Q * Rq : Q * D);
+    return (kind == MOGP_KIND_UMOSM || kind == MOGP_KIND_MOHSM) ? Q : (kind == MOGP_KIND_CSM ? Q * Rq : Q * D);
 }
 // (L L^T)_ij of the lower triangle L of the q-th C x C weight matrix
 __host__ __device__ inline double umosm_mag(const double* w, int C, int i, int j) {
@@ -43,7 +53,29 @@ __host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, i
     double* m = out + 2 + D;
     double* th = out + 2 + 2 * D;
     for (int d = 0; d < D; ++d) v[d] = m[d] = th[d] = 0.0;
-    if (kind == MOGP_KIND_UMOSM) {                       // multioutput.py:266-286; the i == j branch is the same formula
+    if (kind == MOGP_KIND_MOHSM) {                       // multioutput.py:358-387; the i == j branch (:359-367) is the same formula
+        const MohsmOff o = mohsm_off(C, Q, D);
+        const int q = r;
+        const double* mui = p + o.mu + (q * C + i) * D; const double* muj = p + o.mu + (q * C + j) * D;
+        const double* si = p + o.var + (q * C + i) * D; const double* sj = p + o.var + (q * C + j) * D;
+        double esum = 0.0, prod = 1.0;
+        for (int d = 0; d < D; ++d) {
+            const double iv = 1.0 / (si[d] + sj[d]);
+            const double dm = mui[d] - muj[d];
+            esum += dm * iv * dm;
+            m[d] = iv * (si[d] * muj[d] + sj[d] * mui[d]);
+            v[d] = 2.0 * si[d] * iv * sj[d];
+            th[d] = p[o.th + (q * C + i) * D + d] - p[o.th + (q * C + j) * D + d];
+            prod *= v[d];
+            out[3 + 3 * D + d] = p[o.ctr + q * D + d];
+        }
+        const double li = p[o.ls + q * C + i] * p[o.ls + q * C + i], lj = p[o.ls + q * C + j] * p[o.ls + q * C + j];
+        const double ell = 2.0 * li * (1.0 / (li + lj)) * lj;                                           // :379
+        out[0] = p[o.w + q * C + i] * p[o.w + q * C + j] * exp(-MOGP_PI * MOGP_PI * esum) * pow(2.0 * MOGP_PI, (double)D) *
+                 sqrt(prod) * pow(sqrt(ell), (double)D);                                                // :375,382 (twopi = (2 pi)^D, :350)
+        out[1] = (p[o.ph + q * C + i] - p[o.ph + q * C + j]) / (2.0 * MOGP_PI);                         // phase outside the 2 pi factor (:385)
+        out[2 + 3 * D] = ell;
+    } else if (kind == MOGP_KIND_UMOSM) {                // multioutput.py:266-286; the i == j branch is the same formula
         const UmosmOff o = umosm_off(C, Q, D);
         const int q = r;
         const double* mui = p + o.mu + (q * C + i) * D; const double* muj = p + o.mu + (q * C + j) * D;
@@ -81,7 +113,9 @@ __host__ __device__ inline void pair_comp_next(int kind, int C, int Q, int Rq, i
 // owners: CSM: [0, Q*C*Rq) one (q, c, s) each (amplitude, shift), then Q owners (mean, variance of q);
 //         SMLMC: [0, C*Q*Rq) one (c, q, s) each (weight), then Q owners (magnitude, mean, variance of q)
 //         UMOSM: Q*C owners (q, c): row c of the weight matrix, mean, variance, delay, phase of channel c
+//         MOHSM: Q*C owners (q, c): weight, mean, variance, lengthscale, delay, phase of channel c, then Q owners (center of q)
 __host__ __device__ inline int n_chain_owners_next(int kind, int C, int Q, int Rq) {
+    if (kind == MOGP_KIND_MOHSM) return Q * C + Q;
     if (kind == MOGP_KIND_UMOSM) return Q * C;
     return (kind == MOGP_KIND_CSM ? Q * C * Rq : C * Q * Rq) + Q;
 }
@@ -89,9 +123,78 @@ __host__ __device__ inline int n_chain_owners_next(int kind, int C, int Q, int R
 __host__ __device__ inline void chain_owner_next(int kind, int C, int Q, int Rq, int D, const double* __restrict__ p,
                                                  const double* __restrict__ comps, const double* __restrict__ gsum,
                                                  const double* __restrict__ adj, int owner, double* __restrict__ g) {
-    const int st = comp_stride(D);
+    const int st = comp_stride(kind, D);
     const int R = next_num_comps(kind, Q, Rq, D);
-    if (kind == MOGP_KIND_UMOSM) {
+    if (kind == MOGP_KIND_MOHSM) {
+        // (the relative-jitter term of the row-dependent Gram diagonal is folded into gsum by the caller: adj is not used)
+        const MohsmOff o = mohsm_off(C, Q, D);
+        const double PI2 = MOGP_PI * MOGP_PI;
+        if (owner >= Q * C) {                            // center of component q: d K / d c_d = K l s_d
+            const int q = owner - Q * C;
+            double gc[MOGP_MAX_D];
+            for (int d = 0; d < D; ++d) gc[d] = 0.0;
+            for (int i = 0; i < C; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    const double* S = gs_rec(gsum, i, j, R, st, q);
+                    const double* cp = comps + (size_t)((i * C + j) * R + q) * st;
+                    for (int d = 0; d < D; ++d) gc[d] += cp[0] * cp[2 + 3 * D] * S[3 + 3 * D + d];
+                }
+            for (int d = 0; d < D; ++d) g[o.ctr + q * D + d] = gc[d];
+            return;
+        }
+        const int q = owner / C, c = owner % C;
+        double gw = 0.0, gph = 0.0, gls = 0.0, gmu[MOGP_MAX_D], gs[MOGP_MAX_D], gth[MOGP_MAX_D];
+        for (int d = 0; d < D; ++d) gmu[d] = gs[d] = gth[d] = 0.0;
+        for (int other = 0; other < C; ++other) {
+            const int i = c > other ? c : other, j = c > other ? other : c;
+            const double* S = gs_rec(gsum, i, j, R, st, q);
+            const double* cp = comps + (size_t)((i * C + j) * R + q) * st;
+            const double alpha = cp[0];
+            const double* v = cp + 2; const double* m = cp + 2 + D;
+            const double ell = cp[2 + 3 * D];
+            const double S0 = S[0], S4 = S[1], S5 = S[2 + 3 * D];
+            const double aGa = alpha * S0;
+            const double Gph = -alpha * S4;                  // d loss / d (phase_i - phase_j)
+            const double Gell = aGa * 0.5 * (double)D / ell - 0.5 * alpha * S5;      // alpha ~ l^(D/2); window exp(-1/2 l sum s^2)
+            const double wi = p[o.w + q * C + i], wj = p[o.w + q * C + j];
+            const double lsi = p[o.ls + q * C + i], lsj = p[o.ls + q * C + j];
+            const double li = lsi * lsi, lj = lsj * lsj, il = 1.0 / (li + lj);
+            for (int side = 0; side < 2; ++side) {
+                if (i != j && ((side == 0) != (c == i))) continue;
+                gw += aGa / (side == 0 ? wi : wj);
+                gph += side == 0 ? Gph : -Gph;
+                // l_ij = 2 li lj / (li + lj), li = ls_i^2: d l_ij / d ls_i = 2 lj^2 / (li + lj)^2 * 2 ls_i
+                gls += Gell * (side == 0 ? 2.0 * lj * lj * il * il * 2.0 * lsi : 2.0 * li * li * il * il * 2.0 * lsj);
+                for (int d = 0; d < D; ++d) {
+                    const double si = p[o.var + (q * C + i) * D + d], sj = p[o.var + (q * C + j) * D + d];
+                    const double mui = p[o.mu + (q * C + i) * D + d], muj = p[o.mu + (q * C + j) * D + d];
+                    const double iv = 1.0 / (si + sj), dm = mui - muj;
+                    const double Gv = -0.5 * alpha * S[2 + d];
+                    const double Gm = -2.0 * MOGP_PI * alpha * S[2 + D + d];
+                    const double Gth = alpha * (-v[d] * S[2 + 2 * D + d] - 2.0 * MOGP_PI * m[d] * S4);
+                    if (side == 0) {
+                        gmu[d] += aGa * (-2.0 * PI2 * dm * iv) + Gm * sj * iv;
+                        gs[d] += aGa * (PI2 * dm * dm * iv * iv + 0.5 * sj * iv / si) + Gv * (2.0 * sj * sj * iv * iv)
+                                 + Gm * (-sj * dm * iv * iv);
+                        gth[d] += Gth;
+                    } else {
+                        gmu[d] += aGa * (2.0 * PI2 * dm * iv) + Gm * si * iv;
+                        gs[d] += aGa * (PI2 * dm * dm * iv * iv + 0.5 * si * iv / sj) + Gv * (2.0 * si * si * iv * iv)
+                                 + Gm * (si * dm * iv * iv);
+                        gth[d] -= Gth;
+                    }
+                }
+            }
+        }
+        g[o.w + q * C + c] = gw;
+        g[o.ph + q * C + c] = gph;
+        g[o.ls + q * C + c] = gls;
+        for (int d = 0; d < D; ++d) {
+            g[o.mu + (q * C + c) * D + d] = gmu[d];
+            g[o.var + (q * C + c) * D + d] = gs[d];
+            g[o.th + (q * C + c) * D + d] = gth[d];
+        }
+    } else if (kind == MOGP_KIND_UMOSM) {
         const UmosmOff o = umosm_off(C, Q, D);
         const double PI2 = MOGP_PI * MOGP_PI;
         const int q = owner / C, c = owner % C;

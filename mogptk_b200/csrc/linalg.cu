@@ -1645,16 +1645,18 @@ cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, 
 }
 
 __global__ void pred_var_kernel(const double* __restrict__ chanbuf, int C, const int32_t* __restrict__ chan_s,
-                                const double* __restrict__ colsq, int64_t M, double* __restrict__ var) {
+                                const double* __restrict__ colsq, int64_t M, double* __restrict__ var,
+                                const double* __restrict__ kss) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= M) return;
+    if (kss) { var[s] = kss[s] - colsq[s]; return; }
     int c = 0;
     while (c + 1 < C && s >= chan_s[c + 1]) ++c;
     var[s] = chanbuf[C + c] - colsq[s];
 }
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
-                            double* var, cudaStream_t st) {
-    pred_var_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(chanbuf, C, chan_s_dev, colsq, M, var);
+                            double* var, cudaStream_t st, const double* kss) {
+    pred_var_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(chanbuf, C, chan_s_dev, colsq, M, var, kss);
     MOGP_COUNT(1);
     return cudaGetLastError();
 }

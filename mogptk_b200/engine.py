@@ -21,6 +21,7 @@ PARAM_ORDER = _ParamOrder({
     "CSM": ("amplitude", "mean", "variance", "shift"),
     "SMLMC": ("weight", "magnitude", "mean", "variance"),
     "UMOSM": ("weight", "mean", "variance", "delay", "phase"),
+    "MOHSM": ("weight", "mean", "variance", "lengthscale", "center", "delay", "phase"),
 })
 
 
@@ -57,7 +58,7 @@ def kernel_dims(kind, params):
     elif family(kind) == "SMLMC":
         C_, Q, _ = params["weight"].shape
         D = params["mean"].shape[1]
-    elif kind == "UMOSM":
+    elif kind in ("UMOSM", "MOHSM"):
         Q, C_, D = params["mean"].shape
     else:
         raise ValueError("unknown kernel kind %r" % (kind,))
@@ -78,6 +79,9 @@ def param_shapes(kind, C_, Q, D):
         return {"weight": (C_, Q, Rq), "magnitude": (Q,), "mean": (Q, D), "variance": (Q, D)}
     if kind == "UMOSM":
         return {"weight": (Q, C_, C_), "mean": (Q, C_, D), "variance": (Q, C_, D), "delay": (Q, C_, D), "phase": (Q, C_)}
+    if kind == "MOHSM":
+        return {"weight": (Q, C_), "mean": (Q, C_, D), "variance": (Q, C_, D), "lengthscale": (Q, C_), "center": (Q, D),
+                "delay": (Q, C_, D), "phase": (Q, C_)}
     raise ValueError("unknown kernel kind %r" % (kind,))
 
 
@@ -214,8 +218,8 @@ class Engine:
         r = Rows(X, C_, self.device)
         p = pack_params(kind, params, self.device)
         out = torch.empty(r.N, dtype=torch.float64, device=self.device)
-        self._check(self.lib.mogp_kdiag(self.h, _cabi.KIND[kind], C_, Q, D, self._p(p), r.off_p, self._p(out),
-                                        self._stream()))
+        self._check(self.lib.mogp_kdiag_x(self.h, _cabi.KIND[kind], C_, Q, D, self._p(p), self._p(r.x), r.off_p, self._p(out),
+                                          self._stream()))
         return out if r.sorted else out[r.inv_t]
 
     # ---------------------------------------------------------------- dense building blocks

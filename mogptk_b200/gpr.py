@@ -343,6 +343,13 @@ def kernel_spec(kernel):
             for k in [kernel] + subs:
                 _require_all_dims(k, int(D))
             return "UMOSM", p, (int(C_), int(Q), int(D))
+        if all(k.__class__.__name__ == "MultiOutputHarmonizableSpectralKernel" for k in subs):    # what mogptk.MOHSM builds
+            names = ("weight", "mean", "variance", "lengthscale", "center", "delay", "phase")
+            p = {n: torch.stack([getattr(k, n)() for k in subs]) for n in names}
+            Q, C_, D = p["mean"].shape
+            for k in [kernel] + subs:
+                _require_all_dims(k, int(D))
+            return "MOHSM", p, (int(C_), int(Q), int(D))
         if all(k.__class__.__name__ == "GaussianConvolutionProcessKernel" for k in subs):
             p = {"weight": torch.stack([k.weight() for k in subs]),
                  "variance": torch.stack([k.variance() for k in subs]),
@@ -374,8 +381,9 @@ def kernel_spec(kernel):
     raise NotImplementedError(
         "mogptk_b200 implements the exact-GP path for MOSM, SM (IndependentMultiOutputKernel of SpectralMixtureKernel), "
         "CONV (MixtureKernel of GaussianConvolutionProcessKernel), CSM (MixtureKernel of CrossSpectralKernel), SM-LMC "
-        "(LinearModelOfCoregionalizationKernel of SpectralKernel) and uMOSM (MixtureKernel of "
-        "UncoupledMultiOutputSpectralKernel) only; got %s" % cname)
+        "(LinearModelOfCoregionalizationKernel of SpectralKernel), uMOSM (MixtureKernel of "
+        "UncoupledMultiOutputSpectralKernel) and MOHSM (MixtureKernel of MultiOutputHarmonizableSpectralKernel) only; got %s"
+        % cname)
 
 
 def _param_tensors(kind, kernel):
@@ -394,6 +402,8 @@ def _param_tensors(kind, kernel):
         return [[k.amplitude for k in subs], [k.mean for k in subs], [k.variance for k in subs], [k.shift for k in subs]]
     if fam == "UMOSM":
         return [[getattr(k, n) for k in subs] for n in ("weight", "mean", "variance", "delay", "phase")]
+    if fam == "MOHSM":
+        return [[getattr(k, n) for k in subs] for n in ("weight", "mean", "variance", "lengthscale", "center", "delay", "phase")]
     return [[k.weight for k in subs], [k.variance for k in subs], [k.base_variance for k in subs]]
 
 
@@ -565,6 +575,24 @@ class UncoupledMultiOutputSpectralKernel(MultiOutputKernel):
         self.weight.num_parameters = (output_dims * output_dims + output_dims) // 2
         self.mean = Parameter(torch.zeros(output_dims, input_dims), lower=config.positive_minimum)
         self.variance = Parameter(torch.ones(output_dims, input_dims), lower=config.positive_minimum)
+        self.delay = Parameter(torch.zeros(output_dims, input_dims))
+        self.phase = Parameter(torch.zeros(output_dims))
+        if output_dims == 1:
+            self.delay.train = False
+            self.phase.train = False
+
+
+class MultiOutputHarmonizableSpectralKernel(MultiOutputKernel):
+    """MOHSM term (gpr/multioutput.py:295-351): weight / lengthscale / phase (C,), mean / variance / delay (C,D), center (D,).
+    Non-stationary: a Gaussian window in the mid-point of the two inputs multiplies the MOSM-like stationary factor."""
+
+    def __init__(self, output_dims, input_dims=1, active_dims=None):
+        super().__init__(output_dims, input_dims, active_dims)
+        self.weight = Parameter(torch.ones(output_dims), lower=config.positive_minimum)
+        self.mean = Parameter(torch.zeros(output_dims, input_dims), lower=config.positive_minimum)
+        self.variance = Parameter(torch.ones(output_dims, input_dims), lower=config.positive_minimum)
+        self.lengthscale = Parameter(torch.ones(output_dims), lower=config.positive_minimum)
+        self.center = Parameter(torch.zeros(input_dims))
         self.delay = Parameter(torch.zeros(output_dims, input_dims))
         self.phase = Parameter(torch.zeros(output_dims))
         if output_dims == 1:

@@ -156,6 +156,7 @@ _KSUB_DIAG = {"MOSM": mosm_ksub_diag, "SM": sm_ksub_diag, "CONV": conv_ksub_diag
 
 
 _N_CHANNELS = {"CONV": lambda p: p["weight"].shape[1]}
+_DIAG_NEEDS_X = set()      # kinds whose Ksub_diag depends on the inputs (non-stationary: MOHSM): ksub_diag(i, x, p)
 
 
 def n_channels(kind, p):
@@ -164,12 +165,14 @@ def n_channels(kind, p):
     return p[PARAM_NAMES[kind][0]].shape[0]
 
 
-def register_kind(kind, param_names, ksub, ksub_diag, n_channels_fn=None):
+def register_kind(kind, param_names, ksub, ksub_diag, n_channels_fn=None, diag_needs_x=False):
     """Let another test-infrastructure module (oracle/next_kernels.py) reuse the block assembly / LML / prediction
     restatements above for a further kernel family."""
     PARAM_NAMES[kind] = tuple(param_names)
     _KSUB[kind] = ksub
     _KSUB_DIAG[kind] = ksub_diag
+    if diag_needs_x:
+        _DIAG_NEEDS_X.add(kind)
     if n_channels_fn is not None:
         _N_CHANNELS[kind] = n_channels_fn
 
@@ -221,10 +224,10 @@ def K_diag(kind, p, X1):
     """kernel.py:483-495."""
     X1 = t64(X1)
     C = n_channels(kind, p)
-    rows, _ = _split(X1, C)
+    rows, xs = _split(X1, C)
     out = torch.empty(X1.shape[0], dtype=DT)
     for i in range(C):
-        out[rows[i]] = _KSUB_DIAG[kind](i, rows[i].shape[0], p).detach()
+        out[rows[i]] = _KSUB_DIAG[kind](i, xs[i] if kind in _DIAG_NEEDS_X else rows[i].shape[0], p).detach()
     return out
 
 

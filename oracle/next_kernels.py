@@ -13,7 +13,8 @@ Parameter layouts (constrained values, fp64):
   CSM    amplitude (Q,C,Rq)  mean (Q,D)  variance (Q,D)  shift (Q,C,Rq)      MixtureKernel of Q CrossSpectralKernel
   SMLMC  weight (C,Q,Rq)  magnitude (Q,)  mean (Q,D)  variance (Q,D)          LMC of Q SpectralKernel
   UMOSM  weight (Q,C,C) (lower triangle used)  mean/variance/delay (Q,C,D)  phase (Q,C)     mixture of Q uMOSM kernels
-  MOHSM  weight (Q,C)  mean/variance/delay (Q,C,D)  lengthscale (Q,C)  center (Q,D)  phase (Q,C)   (K only: non-stationary)
+  MOHSM  weight (Q,C)  mean/variance/delay (Q,C,D)  lengthscale (Q,C)  center (Q,D)  phase (Q,C)   (non-stationary: one more factor,
+         a Gaussian window in the mid-point, and a row-dependent Gram diagonal)
 """
 import math
 
@@ -137,6 +138,17 @@ def mohsm_ksub(i, j, x1, x2, p):
     return out
 
 
+def mohsm_ksub_diag(i, x, p):
+    """gpr/multioutput.py:389-395 summed over the mixture: the prior variance depends on the input."""
+    D = x.shape[1]
+    out = 0.0
+    for q in range(p["weight"].shape[0]):
+        ls = p["lengthscale"][q, i] ** 2
+        alpha = p["weight"][q, i] ** 2 * (2.0 * PI) ** float(D) * p["variance"][q, i].prod().sqrt() * torch.pow(ls.sqrt(), float(D))
+        out = out + alpha * torch.exp(-0.5 * torch.tensordot((x - p["center"][q]) ** 2, ls * torch.ones(D, dtype=torch.float64), dims=1))
+    return out
+
+
 def derived_components(kind, p, i, j):
     """Per channel-pair component records (alpha, phi, v[D], m[D], theta[D]) of the derived form."""
     comps = []
@@ -195,7 +207,7 @@ def smlmc_ksub_diag(i, n, p):
 
 
 KSUB = {"CSM": csm_ksub, "SMLMC": smlmc_ksub, "UMOSM": umosm_ksub, "MOHSM": mohsm_ksub}
-KSUB_DIAG = {"CSM": csm_ksub_diag, "SMLMC": smlmc_ksub_diag, "UMOSM": umosm_ksub_diag}
+KSUB_DIAG = {"CSM": csm_ksub_diag, "SMLMC": smlmc_ksub_diag, "UMOSM": umosm_ksub_diag, "MOHSM": mohsm_ksub_diag}
 PARAM_NAMES = {"CSM": ("amplitude", "mean", "variance", "shift"), "SMLMC": ("weight", "magnitude", "mean", "variance"),
                "UMOSM": ("weight", "mean", "variance", "delay", "phase"),
                "MOHSM": ("weight", "mean", "variance", "lengthscale", "center", "delay", "phase")}
@@ -210,4 +222,5 @@ def register():
     orc.register_kind("CSM", PARAM_NAMES["CSM"], csm_ksub, csm_ksub_diag, lambda p: p["amplitude"].shape[1])
     orc.register_kind("SMLMC", PARAM_NAMES["SMLMC"], smlmc_ksub, smlmc_ksub_diag)
     orc.register_kind("UMOSM", PARAM_NAMES["UMOSM"], umosm_ksub, umosm_ksub_diag, lambda p: p["weight"].shape[1])
+    orc.register_kind("MOHSM", PARAM_NAMES["MOHSM"], mohsm_ksub, mohsm_ksub_diag, lambda p: p["weight"].shape[1], diag_needs_x=True)
     return orc

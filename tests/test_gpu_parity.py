@@ -327,15 +327,16 @@ def _next_case(name):
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"), allow_pickle=False)
     g = {k: z[k] for k in z.files}
     fam = str(g["kind"])
-    kind = fam if fam == "UMOSM" else "%s:%d" % (fam, int(g["Rq"]))
+    kind = fam if fam in ("UMOSM", "MOHSM") else "%s:%d" % (fam, int(g["Rq"]))
     p = {k[2:]: torch.tensor(v, dtype=torch.float64) for k, v in g.items() if k.startswith("p_")}
     return g, kind, p
 
 
-@pytest.mark.parametrize("name", [n for n in next_golden_names() if "mohsm" not in n])
+@pytest.mark.parametrize("name", next_golden_names())
 def test_further_kernel_families_match_the_reference(engine, name):
-    """CSM (gpr/multioutput.py:397-454), SM-LMC (:456-502) and uMOSM (:212-293) on the same tile kernels: K, K_diag,
-    LML (rtol 1e-8), constrained-space gradients (1e-6) and predictions (1e-6) against the live-reference fixtures."""
+    """CSM (gpr/multioutput.py:397-454), SM-LMC (:456-502), uMOSM (:212-293) and MOHSM (:295-395, non-stationary: mid-point
+    window, row-dependent Gram diagonal) on the same tile kernels: K, K_diag, LML (rtol 1e-8), constrained-space gradients
+    (1e-6) and predictions (1e-6) against the live-reference fixtures."""
     g, kind, p = _next_case(name)
     X, y, sigma, jitter = g["X"], g["y"], torch.tensor(g["sigma"]), float(g["jitter"])
     K = engine.K(kind, p, X)
@@ -358,3 +359,48 @@ def test_further_kernel_families_match_the_reference(engine, name):
     mu, var = engine.predict(g["Xs"])
     assert rel(mu, g["pred_mu"]) < 1e-6
     assert np.abs(var.cpu().numpy() - g["pred_var"]).max() <= 1e-6 * np.abs(g["pred_var"]).max()
+
+
+@pytest.mark.parametrize("C_,Q,D,ns,seed", [(3, 2, 1, [150, 97, 131], 0), (2, 3, 2, [90, 140], 1), (1, 2, 1, [200], 2)])
+def test_mohsm_multi_tile_case_against_the_oracle(engine, C_, Q, D, ns, seed):
+    """MOHSM beyond one tile per channel pair (ragged tiles, several components, D = 2, a single channel): K, K_diag (bit-equal
+    to diag K), cross-covariance, LML, every gradient (incl. lengthscale and center, and the relative-jitter term of the
+    row-dependent diagonal: jitter 1e-3 makes it visible) and predictions against the oracle restatement."""
+    from oracle import next_kernels as nk
+    orc = nk.register()
+    rng = np.random.default_rng(100 + seed)
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=gen, dtype=torch.float64)
+    p = {"weight": r(Q, C_) + 0.3, "mean": r(Q, C_, D) * 0.8 + 0.05, "variance": r(Q, C_, D) * 0.5 + 0.1,
+         "lengthscale": r(Q, C_) * 0.3 + 0.15, "center": r(Q, D) * 3.0 + 1.0,
+         "delay": 0.2 * (r(Q, C_, D) - 0.5), "phase": 0.6 * (r(Q, C_) - 0.5)}
+    X = np.concatenate([np.concatenate([np.full((n, 1), float(c)), np.sort(rng.uniform(0, 5, (n, D)), axis=0)], axis=1)
+                        for c, n in enumerate(ns)])
+    y = rng.standard_normal(X.shape[0])
+    # (the reference's cross-channel MOHSM formula is not positive semi-definite for arbitrary parameters -- smallest eigenvalue
+    #  -0.54 for the first case -- so the noise is chosen large enough for the Gram matrix to be factorisable)
+    sigma = torch.tensor(0.9 + 0.4 * rng.uniform(size=C_))
+    jitter = 1e-3
+    K = engine.K("MOHSM", p, X)
+    Kref = orc.K("MOHSM", p, torch.tensor(X))
+    assert rel(K, Kref) < 1e-12
+    assert torch.equal(K, K.T)
+    assert torch.equal(engine.K_diag("MOHSM", p, X), K.diagonal())
+    assert rel(engine.K_diag("MOHSM", p, X), orc.K_diag("MOHSM", p, torch.tensor(X))) < 1e-12
+    Xs = np.concatenate([np.concatenate([np.full((7, 1), float(c)), rng.uniform(0, 5, (7, D))], axis=1) for c in range(C_)])
+    assert rel(engine.K("MOHSM", p, X, Xs), orc.K("MOHSM", p, torch.tensor(X), torch.tensor(Xs))) < 1e-12
+    for _ in range(3):                    # plain run, graph capture, replay
+        res = engine.lml_grad("MOHSM", p, sigma, X, y, jitter, True)
+    lml_ref = float(orc.lml("MOHSM", p, sigma, torch.tensor(X), torch.tensor(y), jitter))
+    assert abs(res["lml"] - lml_ref) <= 1e-8 * abs(lml_ref)
+    _, g_ref = orc.loss_and_grad("MOHSM", p, sigma, torch.tensor(X), torch.tensor(y), jitter)
+    for k, got in res["grad"].items():
+        ref = g_ref[k].numpy()
+        assert np.abs(got.cpu().numpy().reshape(ref.shape) - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-12), k
+    mu, var = engine.predict(Xs)
+    mu_ref, var_ref = orc.predict_f("MOHSM", p, sigma, torch.tensor(X), torch.tensor(y), torch.tensor(Xs), jitter)
+    assert rel(mu, mu_ref.reshape(-1)) < 1e-6
+    assert np.abs(var.cpu().numpy() - var_ref.numpy().reshape(-1)).max() <= 1e-6 * float(var_ref.abs().max())
+    _, cov = engine.predict(Xs, full=True)
+    _, cov_ref = orc.predict_f("MOHSM", p, sigma, torch.tensor(X), torch.tensor(y), torch.tensor(Xs), jitter, full=True)
+    assert rel(cov, cov_ref) < 1e-6

@@ -282,10 +282,10 @@ def test_device_resident_adam_stops_at_a_cholesky_failure(mogptk):
     assert torch.equal(k.variance.data, raw_before)          # frozen at the failing iteration
 
 
-@pytest.mark.parametrize("family,kw", [("CSM", dict(Q=2, Rq=2)), ("SM_LMC", dict(Q=3, Rq=2))])
+@pytest.mark.parametrize("family,kw", [("CSM", dict(Q=2, Rq=2)), ("SM_LMC", dict(Q=3, Rq=2)), ("MOHSM", dict(P=2, Q=2))])
 def test_csm_and_sm_lmc_models_through_the_reference(mogptk, family, kw):
-    """mogptk.CSM / mogptk.SM_LMC (mogptk/models/csm.py, sm_lmc.py) with inference=B200Exact() against the stock
-    reference on the CPU: Adam training, predictions, and the device-resident loop after install()."""
+    """mogptk.CSM / mogptk.SM_LMC / mogptk.MOHSM (mogptk/models/csm.py, sm_lmc.py, mohsm.py) with inference=B200Exact() against
+    the stock reference on the CPU: Adam training, predictions, and the device-resident loop after install()."""
     import mogptk_b200 as mb
     from mogptk_b200 import synth
     X, y = synth.make_data(3, [60, 44, 72], seed=13)
@@ -299,6 +299,8 @@ def test_csm_and_sm_lmc_models_through_the_reference(mogptk, family, kw):
                 p.assign(0.2 + torch.rand(p.shape, generator=g, dtype=torch.float64))
             elif n.endswith(".shift"):
                 p.assign(0.3 * torch.randn(p.shape, generator=g, dtype=torch.float64))
+            elif n.endswith(".center"):
+                p.assign(2.0 + 6.0 * torch.rand(p.shape, generator=g, dtype=torch.float64))
     b = cls(dataset(mogptk, X, y, 3), inference=mb.B200Exact(), **kw)
     c = cls(dataset(mogptk, X, y, 3), inference=mb.B200Exact(), **kw)
     for (na, u), (nb, v), (nc, w) in zip(a.gpr.named_parameters(), b.gpr.named_parameters(), c.gpr.named_parameters()):
