@@ -360,13 +360,22 @@ extern "C" int mogp_potrf(mogp_handle_t h, double* A_dev, int64_t n, int64_t lda
     // int8 trailing updates (large n) only for the handle's standard leading dimension: one set of tile lists per handle
     const bool i8 = use_i8(Np) && (!direct || lda == Np);
     if (i8 && i8_ready(h, Np, Np, st)) return -2;
+    // (large sizes: the recursive scheme, which needs the inverses of its leading blocks: Linv and W are its scratch)
+    auto factor = [&](double* Af, long long ldf) -> cudaError_t {
+        // (measured, profiles/r02_recursive_cholesky.txt: factor alone 6.74 -> 6.21 ms at N = 8192, but 1.63 -> 1.77 ms at 4096, where
+        //  the inverses of the leading blocks are pure overhead for a caller that only wants L)
+        cudaError_t er = (i8 && ldf == Np && Np >= 8192) ? rchol_padded(Af, ldf, h->Linv, h->W, Np, h->logdet_part, h->info, st, &h->ps, h->i8,
+                                                          g_i8_slices, 0)
+                                           : cudaErrorNotSupported;
+        if (er != cudaErrorNotSupported) return er;
+        return potrf_padded(Af, ldf, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps, nullptr, i8 ? h->i8 : nullptr,
+                            g_i8_slices);
+    };
     if (direct) {
-        MOGP_CHECK(h, potrf_padded(A_dev, lda, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps, nullptr,
-                                   i8 ? h->i8 : nullptr, g_i8_slices));
+        MOGP_CHECK(h, factor(A_dev, lda));
     } else {
         MOGP_CHECK(h, launch_copy_tri(0, A_dev, lda, h->A, Np, n, Np, st));
-        MOGP_CHECK(h, potrf_padded(h->A, Np, h->Linv, Np, h->W, Np, Np, h->logdet_part, h->info, st, &h->ps, nullptr,
-                                   i8 ? h->i8 : nullptr, g_i8_slices));
+        MOGP_CHECK(h, factor(h->A, Np));
         MOGP_CHECK(h, launch_copy_tri(1, A_dev, lda, h->A, Np, n, Np, st));
     }
     if (info_dev) MOGP_CHECK(h, cudaMemcpyAsync(info_dev, h->info, 4, cudaMemcpyDeviceToDevice, st));
@@ -446,6 +455,12 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     // Small sizes (row-wise pipeline, linalg.cu): Linv AND K^-1 (into W) are built behind the panel chain; the scratch is T then.
     bool fused_inverse = false, fused_kinv = false;
     const bool rowp = want_grad && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
+    // Large sizes: recursive factor + inverse, everything above the 2048-row leaves on the int8 tensor pipe
+    cudaError_t er = use_i8(Np) ? rchol_padded(h->A, ld, h->Linv, h->W, Np, h->logdet_part, h->info, st, &h->ps, h->i8, g_i8_slices, 1)
+                                : cudaErrorNotSupported;
+    if (er == cudaSuccess) fused_inverse = true;
+    else if (er != cudaErrorNotSupported) MOGP_CHECK(h, er);
+    else
     MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, rowp ? h->T : h->W, ld, Np, h->logdet_part, h->info, st, &h->ps,
                                &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp && g_rowpipe_kinv ? h->W : nullptr,
                                &fused_kinv));

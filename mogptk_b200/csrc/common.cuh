@@ -271,6 +271,18 @@ extern long long g_i8_trtri_min;
 cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64_t k0, int64_t Np, int part, int S,
                            cudaStream_t st);
 extern long long g_i8_potrf_min;
+// recursive Cholesky + inverse (linalg.cu: rchol_padded): the four int8-pipe products of one 2h x 2h diagonal block (i8mm.cu)
+bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h);
+cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scratch, long long ld, int64_t o, int64_t h,
+                         int want_inv, int S, cudaStream_t st);
+cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long long ld, int64_t o, int64_t h, int S,
+                          cudaStream_t st);
+// Recursive factor (+ inverse) for padded sizes leaf * 2^k: leaves by the blocked sweep with its pipelined inverse, everything above
+// them by the products above.  want_inverse = 0: only what the factor itself needs (Linv is partially filled).  Returns
+// cudaErrorNotSupported when the size / plan does not qualify (the caller runs the blocked sweep).
+cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, int64_t Np, double* logdet_part, int32_t* info,
+                         cudaStream_t st, const PotrfStreams* ps, I8Plan* i8, int i8_slices, int want_inverse);
+bool rchol_applies(int64_t Np);
 // W(lower tiles) = Linv^T Linv via tcgen05.mma kind::i8 (S digit planes of 7 bits); pure enqueue
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st);
 // Smallest padded size that takes the int8 path (0 = never) and the number of digit planes (7 or 8)

@@ -467,6 +467,9 @@ struct I8Lists {                                 // the tile lists of one tile w
     // ordered by row tile, so that the list for a smaller trailing matrix is a prefix (prefix counts per row-tile count)
     I8List syrk_a, syrk_b;
     std::vector<size_t> syrk_a_count, syrk_b_count;
+    // recursive Cholesky + inverse (i8_blk_*): the four products of one 2h x 2h diagonal block, coordinates relative to the
+    // block (index = log2 of h in 64-blocks): A21 X11^T, A22 -= L21 L21^T, T = L21 X11, X21 = -X22 T
+    std::vector<I8List> blk_trsm, blk_syrk, blk_pa, blk_pb;
 };
 struct I8Plan {
     I8Operand opA, opB, opP;                 // opP: the 1024-column super-panel of the blocked Cholesky
@@ -644,6 +647,38 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
                     }
             L.lvl_b[lev].count = T.size() - L.lvl_b[lev].first;
         }
+        // recursive Cholesky + inverse: one 2h x 2h diagonal block [[L11, .], [A21, A22]] with X11 = L11^-1, X22 = L22^-1 (all h x h);
+        // output coordinates relative to the h x h block each product writes
+        L.blk_trsm.assign(32, I8List()); L.blk_syrk.assign(32, I8List());
+        L.blk_pa.assign(32, I8List()); L.blk_pb.assign(32, I8List());
+        lev = 4;
+        for (int64_t h = 1024; 2 * h <= Np; h *= 2, ++lev) {
+            const int hn = (int)h, ntm = hn / I8_TM, ntn = hn / TN, hk = hn / I8_KC;
+            // L21 = A21 X11^T: operand A rows = rows of A21, operand B rows = rows of X11 (nonzero k <= n); longest K (large n) first
+            L.blk_trsm[lev].first = T.size();
+            for (int tn = ntn - 1; tn >= 0; --tn)
+                for (int tm = 0; tm < ntm; ++tm)
+                    T.push_back({tm * I8_TM, tn * TN, 0, (tn + 1) * TN / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.blk_trsm[lev].count = T.size() - L.blk_trsm[lev].first;
+            // A22 -= L21 L21^T (lower tiles)
+            L.blk_syrk[lev].first = T.size();
+            for (int tm = 0; tm < ntm; ++tm)
+                for (int tn = 0; tn * TN < (tm + 1) * I8_TM; ++tn)
+                    T.push_back({tm * I8_TM, tn * TN, 0, hk, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.blk_syrk[lev].count = T.size() - L.blk_syrk[lev].first;
+            // T = L21 X11: operand B rows = columns of X11 (nonzero k >= n); longest K (small n) first
+            L.blk_pa[lev].first = T.size();
+            for (int tn = 0; tn < ntn; ++tn)
+                for (int tm = 0; tm < ntm; ++tm)
+                    T.push_back({tm * I8_TM, tn * TN, tn * TN / I8_KC, hk, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.blk_pa[lev].count = T.size() - L.blk_pa[lev].first;
+            // X21 = -X22 T: operand A rows = rows of X22 (nonzero k <= m), operand B rows = columns of T; longest K (large m) first
+            L.blk_pb[lev].first = T.size();
+            for (int tm = ntm - 1; tm >= 0; --tm)
+                for (int tn = 0; tn < ntn; ++tn)
+                    T.push_back({tm * I8_TM, tn * TN, 0, (tm + 1) * I8_TM / I8_KC, (long long)tm * I8_TM * ld + (long long)tn * TN});
+            L.blk_pb[lev].count = T.size() - L.blk_pb[lev].first;
+        }
         // trailing updates C -= P P^T (K = I8_PANEL): (a) the I8_PANEL columns of the next super-panel, (b) the rest (lower tiles)
         const int ntm = (int)(Np / I8_TM);
         L.syrk_a.first = T.size();
@@ -724,6 +759,44 @@ cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scr
     if ((e = i8_slice(p->opA, Linv + S_ * ld + S_, ld, 1, bs, npair, R, K, S, 2, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, scratch + S_ * ld, 1, ld, bs, npair, R, K, S, 0, st)) != cudaSuccess) return e;
     return i8_launch(p->opA, p->opB, p->tiles + TL.lvl_b[lev].first, (int)TL.lvl_b[lev].count, S, -1.0, 0.0, Linv, ld, st, width);
+}
+
+// ------------------------------------------------------------------ recursive Cholesky + inverse: the products of one block
+// The 2h x 2h diagonal block at origin o of A (factor, in place) and Linv: A = [[L11, .], [A21, A22]], X11 = L11^-1 is complete.
+//   i8_blk_first : A21 <- L21 = A21 X11^T;  A22 -= L21 L21^T (lower);  if want_inv: scratch21 <- T = L21 X11
+//   i8_blk_second: (X22 = L22^-1 complete)  Linv21 <- X21 = -X22 T
+// Replaces the panel-by-panel trailing updates of the blocked sweep above a leaf size by products whose K is the block size,
+// i.e. almost all of the N^3/3 + N^3/3 flops of factor + inverse run as large int8-pipe GEMMs.  Pure enqueue after i8_prepare.
+static int i8_blk_level(int64_t h) { int lev = 0; for (int64_t x = 64; x < h; x *= 2) ++lev; return lev; }
+bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h) {
+    if (!p || !p->ready(Np, ld, S) || h < 1024 || (h & (h - 1)) != 0 || 2 * h > Np) return false;
+    return p->L[0].blk_trsm[i8_blk_level(h)].count > 0;
+}
+cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scratch, long long ld, int64_t o, int64_t h, int want_inv,
+                         int S, cudaStream_t st) {
+    const int lev = i8_blk_level(h), hn = (int)h;
+    const int width = i8_width(S, h >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
+    const I8Lists& TL = p->L[width];
+    double* A21 = A + (o + h) * ld + o;
+    cudaError_t e;
+    if ((e = i8_slice(p->opA, A21, ld, 1, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
+    if ((e = i8_slice(p->opB, Linv + o * (ld + 1), ld, 1, 0, 1, hn, hn, S, 2, st)) != cudaSuccess) return e;
+    if ((e = i8_launch(p->opA, p->opB, p->tiles + TL.blk_trsm[lev].first, (int)TL.blk_trsm[lev].count, S, 1.0, 0.0, A21, ld, st, width)) != cudaSuccess) return e;
+    if ((e = i8_slice(p->opA, A21, ld, 1, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
+    if ((e = i8_launch(p->opA, p->opA, p->tiles + TL.blk_syrk[lev].first, (int)TL.blk_syrk[lev].count, S, -1.0, 1.0,
+                       A + (o + h) * (ld + 1), ld, st, width)) != cudaSuccess) return e;
+    if (!want_inv) return cudaSuccess;
+    if ((e = i8_slice(p->opB, Linv + o * (ld + 1), 1, ld, 0, 1, hn, hn, S, 1, st)) != cudaSuccess) return e;
+    return i8_launch(p->opA, p->opB, p->tiles + TL.blk_pa[lev].first, (int)TL.blk_pa[lev].count, S, 1.0, 0.0, scratch + (o + h) * ld + o, ld, st, width);
+}
+cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long long ld, int64_t o, int64_t h, int S, cudaStream_t st) {
+    const int lev = i8_blk_level(h), hn = (int)h;
+    const int width = i8_width(S, h >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
+    const I8Lists& TL = p->L[width];
+    cudaError_t e;
+    if ((e = i8_slice(p->opA, Linv + (o + h) * (ld + 1), ld, 1, 0, 1, hn, hn, S, 2, st)) != cudaSuccess) return e;
+    if ((e = i8_slice(p->opB, scratch + (o + h) * ld + o, 1, ld, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
+    return i8_launch(p->opA, p->opB, p->tiles + TL.blk_pb[lev].first, (int)TL.blk_pb[lev].count, S, -1.0, 0.0, Linv + (o + h) * ld + o, ld, st, width);
 }
 
 // ------------------------------------------------------------------ self-test hooks (tests, tools/gpu_diag.py)

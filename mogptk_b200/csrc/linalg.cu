@@ -1474,6 +1474,68 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     return finish(two && last_bulk >= 0 ? ps->ev2[last_bulk] : nullptr);
 }
 
+// ============================================================================ recursive factor + inverse (large sizes)
+// chol(A) for A = [[A11, .], [A21, A22]] (halves h):  L11 = chol(A11), X11 = L11^-1;  L21 = A21 X11^T;  A22 -= L21 L21^T;
+// L22 = chol(A22), X22 = L22^-1;  X21 = -X22 (L21 X11).  The recursion stops at `leaf` rows, which the blocked sweep above
+// factors and inverts (row-wise pipeline); every product above the leaves has K = its block size and runs on the int8 tensor
+// pipe (i8_blk_first / i8_blk_second) -- at N = 8192 that is 94 % of the 2 N^3 / 3 flops of factor + inverse, against the
+// rank-64 / 256 / 1024 updates of the blocked sweep.  The multiplication by the explicit inverse X11 in place of a triangular
+// solve costs the same flops; its error is bounded by cond(L11) eps like that of the solve.
+static int g_rchol = std::getenv("MOGP_RCHOL") ? std::atoi(std::getenv("MOGP_RCHOL")) : 1;
+static long long g_rchol_min_np = std::getenv("MOGP_RCHOL_MIN_NP") ? std::atoll(std::getenv("MOGP_RCHOL_MIN_NP")) : 4096;
+static long long g_rchol_leaf = std::getenv("MOGP_RCHOL_LEAF") ? std::atoll(std::getenv("MOGP_RCHOL_LEAF")) : 2048;
+extern "C" int mogp_set_rchol(int on, long long min_np, long long leaf) {
+    if (leaf < 1024 || (leaf & (leaf - 1)) != 0) return -1;
+    g_rchol = on; g_rchol_min_np = min_np; g_rchol_leaf = leaf; ++g_mogp_cfg_epoch;
+    return 0;
+}
+bool rchol_applies(int64_t Np) {
+    if (!g_rchol || Np < g_rchol_min_np || Np < 2 * g_rchol_leaf) return false;
+    int64_t n = Np;
+    while (n > g_rchol_leaf && n % 2 == 0) n /= 2;
+    return n == g_rchol_leaf && Np / g_rchol_leaf <= 8;
+}
+// info[0] = first failing leaf's pivot index (1-based, global); leaf_info[i] are relative to leaf i
+__global__ void rchol_info_kernel(int32_t* info, int nleaf, int leaf_rows) {
+    int32_t v = 0;
+    for (int i = 0; i < nleaf && v == 0; ++i)
+        if (info[1 + i] != 0) v = info[1 + i] + i * leaf_rows;
+    info[0] = v;
+}
+cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, int64_t Np, double* logdet_part, int32_t* info,
+                         cudaStream_t st, const PotrfStreams* ps, I8Plan* i8, int i8_slices, int want_inverse) {
+    if (!rchol_applies(Np) || !i8 || !i8_blk_ok(i8, Np, ld, i8_slices, g_rchol_leaf)) return cudaErrorNotSupported;
+    const int64_t leaf = g_rchol_leaf;
+    int leaf_idx = 0;
+    cudaError_t err = cudaSuccess;
+    auto rec = [&](auto&& self, int64_t o, int64_t n, int need_inv) -> void {
+        if (err != cudaSuccess) return;
+        if (n <= leaf) {
+            bool fused = false;
+            double* As = A + o * (ld + 1);
+            double* Xs = Linv + o * (ld + 1);
+            double* Ts = Ltmp + o * (ld + 1);
+            err = potrf_padded(As, ld, Xs, ld, Ts, ld, n, logdet_part + o / 64, info + 1 + leaf_idx, st, ps, &fused, nullptr, i8_slices,
+                               nullptr, nullptr);
+            if (err == cudaSuccess && !fused) err = trtri_padded(As, Xs, Ts, n, ld, st, nullptr, i8_slices);
+            ++leaf_idx;
+            return;
+        }
+        const int64_t h = n / 2;
+        self(self, o, h, 1);
+        if (err != cudaSuccess) return;
+        if ((err = i8_blk_first(i8, A, Linv, Ltmp, ld, o, h, need_inv, i8_slices, st)) != cudaSuccess) return;
+        self(self, o + h, h, need_inv);
+        if (err != cudaSuccess || !need_inv) return;
+        err = i8_blk_second(i8, Linv, Ltmp, ld, o, h, i8_slices, st);
+    };
+    rec(rec, 0, Np, want_inverse);
+    if (err != cudaSuccess) return err;
+    rchol_info_kernel<<<1, 1, 0, st>>>(info, leaf_idx, (int)leaf);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
 // ============================================================================ triangular inverse
 // Linv = L^-1 by level-batched block doubling: at level s (in 64-blocks) every pair of
 // adjacent diagonal super-blocks (A, B) gets Linv_BA = -Linv_BB * (L_BA * Linv_AA).

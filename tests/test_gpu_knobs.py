@@ -233,3 +233,39 @@ def test_int8_path_survives_alternating_problem_sizes(engine):
         for _ in range(3):                               # plain run, capture, replay
             res = engine.lml_grad(g["kind"], g["params"], g["sigma"], g["X"], g["y"], g["jitter"], True)
             assert abs(res["lml"] - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+
+
+@pytest.mark.parametrize("leaf", [1024, 2048])
+@pytest.mark.parametrize("n", [8192])
+def test_recursive_cholesky_against_lapack(engine, n, leaf):
+    """mogp_potrf through the recursive scheme (leaves by the blocked sweep, everything above on the int8 tensor pipe): factor
+    against LAPACK, and the first bad pivot is reported with its global index whichever leaf it falls into."""
+    lib = engine.lib
+    assert lib.mogp_set_rchol(1, 4096, leaf) == 0
+    try:
+        gen = torch.Generator().manual_seed(n + leaf)
+        B = torch.randn((n, n + 8), generator=gen, dtype=torch.float64)
+        A = B @ B.T / n + 0.5 * torch.eye(n, dtype=torch.float64)
+        Ad = A.cuda().clone()
+        assert engine.potrf_(Ad) == 0
+        L = torch.tril(Ad).cpu()
+        Lref = torch.linalg.cholesky(A)
+        assert float((L - Lref).abs().max() / Lref.abs().max()) < 1e-11
+        for bad in (100, leaf + 77, n - 5):
+            Ab = A.clone()
+            Ab[bad, bad] = -1.0
+            assert engine.potrf_(Ab.cuda()) == bad + 1
+    finally:
+        lib.mogp_set_rchol(1, 4096, 2048)
+
+
+@pytest.mark.parametrize("rchol", [(0, 4096, 2048), (1, 4096, 2048), (1, 4096, 1024)])
+@pytest.mark.parametrize("name", ["cfg4", "cfg3"])
+def test_recursive_factor_and_inverse_in_the_step(engine, knobs, name, rchol):
+    """The whole step at N = 4096 / 8192 with the recursive factor + inverse (on / off, leaf sizes): LML 1e-8, gradients 1e-6."""
+    knobs()
+    assert engine.lib.mogp_set_rchol(*rchol) == 0
+    try:
+        _check(engine, load_golden(name))
+    finally:
+        engine.lib.mogp_set_rchol(1, 4096, 2048)
