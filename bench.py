@@ -22,6 +22,7 @@ Arms
                   PyTorch-CUDA path (ATen elementwise + cuSOLVER potrf) on the same B200.  Extra, clearly labelled.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -281,7 +282,7 @@ def int8_peak():
         return 4500.0, "nominal dense int8"
 
 
-def stage_rooflines(N, stages, dmma, hbm_gbs, traffic, i8=None):
+def stage_rooflines(N, stages, dmma, hbm_gbs, traffic, i8=None, rchol_share=0.0):
     """Achieved rates of the stages against their rooflines (algorithmic work per SURVEY 8d).  i8 = (slices S, fraction of
     the triangular inverse's flops that runs on the int8 pipe) when the large GEMMs of this size take the tcgen05 path."""
     n3 = float(N) ** 3 / 3.0
@@ -304,8 +305,15 @@ def stage_rooflines(N, stages, dmma, hbm_gbs, traffic, i8=None):
                                              "planes); achieved = those int8 operations / the whole stage time (operand slicing and "
                                              "the DMMA levels included); peak = %s.  `frac` above is the fp64-equivalent rate over "
                                              "the DMMA peak and may exceed 1." % (100 * i8_frac, S * (S + 1) // 2, S, i8_src)}
-    tensor("potrf_inverse" if fused else "potrf", (2.0 if fused else 1.0) * n3, stages.get("potrf"),
-           "Cholesky N^3/3" + (" + L^-1 N^3/3 issued behind the panel chain" if fused else "") + " (fp64 DMMA)", "potrf_inverse")
+    if fused and rchol_share > 0.0:
+        tensor("potrf_inverse", 2.0 * n3, stages.get("potrf"),
+               "recursive Cholesky N^3/3 + L^-1 N^3/3: leaves by the blocked fp64-DMMA sweep with its row-wise pipelined inverse, every "
+               "product above the leaves (%.0f%% of the flops) on the int8 tensor pipe" % (100 * rchol_share), "potrf_inverse",
+               rchol_share)
+    else:
+        tensor("potrf_inverse" if fused else "potrf", (2.0 if fused else 1.0) * n3, stages.get("potrf"),
+               "Cholesky N^3/3" + (" + L^-1 N^3/3 issued behind the panel chain (row-wise pipeline)" if fused else "") + " (fp64 DMMA)",
+               "potrf_inverse")
     if not fused:
         tensor("trtri", n3, stages.get("trtri"), "L^-1 by level-batched block doubling, N^3/3", "trtri", i8[1] if i8 else 0.0)
     tensor("kinv", n3, stages.get("kinv"), "K^-1 = L^-T L^-1 (lower tiles), N^3/3, one launch", "kinv", 1.0 if i8 else 0.0)
@@ -332,6 +340,17 @@ def i8_config(eng, N):
             share += float(Np) * S_ * S_
         S_ *= 2
     return int(eng.lib.mogp_get_i8_slices()), min(1.0, share / (float(Np) ** 3 / 3.0))
+
+
+def rchol_share(eng, N):
+    """Share of the factor + inverse flops above the leaves of the recursive scheme (0 when it does not apply)."""
+    Np = (N + 127) // 128 * 128
+    mn = int(eng.lib.mogp_get_i8_min_np())
+    if mn <= 0 or Np < mn or not eng.lib.mogp_rchol_applies(Np):
+        return 0.0
+    leaf = C.c_longlong()
+    eng.lib.mogp_get_rchol(None, C.byref(leaf))
+    return 1.0 - (float(leaf.value) / Np) ** 2
 
 
 def load_traffic(cfg):
@@ -400,7 +419,7 @@ def sub_record(cfg, device_index, dmma, hbm_gbs, steps=6):
                          "unit": "TFLOP/s", "what": "N^3 algorithmic flop / median CUDA-event step time"},
                 "cholesky": {"ms": potrf_ms, "achieved": chol, "peak": dmma, "frac": chol / dmma, "unit": "TFLOP/s", "info": info,
                              "what": "mogp_potrf alone on the same K~ (N^3/3 flop, best of 3, CUDA events)"},
-                "stages": stage_rooflines(N, stages, dmma, hbm_gbs, load_traffic(cfg), i8_config(eng, N))}
+                "stages": stage_rooflines(N, stages, dmma, hbm_gbs, load_traffic(cfg), i8_config(eng, N), rchol_share(eng, N))}
     finally:
         eng.close()
 
@@ -569,7 +588,7 @@ def run_b200(args):
         except Exception:
             dmma, dfma = DMMA_PEAK_FALLBACK_TFLOPS, None
         hbm, hbm_src = hbm_peak()
-        roofs = stage_rooflines(N, stages, dmma, hbm, load_traffic(args.config), i8_config(eng, N))
+        roofs = stage_rooflines(N, stages, dmma, hbm, load_traffic(args.config), i8_config(eng, N), rchol_share(eng, N))
         dom_name = max((k for k in roofs), key=lambda k: roofs[k]["ms"])
         dom = roofs[dom_name]
         ach = synth.flops_per_iteration(N) / (ms_per_step * 1e-3) / 1e12

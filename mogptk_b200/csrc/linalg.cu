@@ -1489,6 +1489,12 @@ extern "C" int mogp_set_rchol(int on, long long min_np, long long leaf) {
     g_rchol = on; g_rchol_min_np = min_np; g_rchol_leaf = leaf; ++g_mogp_cfg_epoch;
     return 0;
 }
+extern "C" int mogp_get_rchol(long long* min_np, long long* leaf) {
+    if (min_np) *min_np = g_rchol_min_np;
+    if (leaf) *leaf = g_rchol_leaf;
+    return g_rchol;
+}
+extern "C" int mogp_rchol_applies(long long Np) { return rchol_applies(Np) ? 1 : 0; }
 bool rchol_applies(int64_t Np) {
     if (!g_rchol || Np < g_rchol_min_np || Np < 2 * g_rchol_leaf) return false;
     int64_t n = Np;
