@@ -578,7 +578,7 @@ def run_b200(args):
     conc = None
     if not args.no_extras and world == 1:
         try:
-            conc = concurrent_replicas(args.config, local, 3, min(args.steps, 128))
+            conc = concurrent_replicas(args.config, local, 4, min(args.steps, 128))
         except Exception as e:
             conc = {"error": repr(e)}
 

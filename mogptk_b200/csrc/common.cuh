@@ -273,8 +273,13 @@ cudaError_t i8_syrk_update(I8Plan* p, double* A, long long ld, int64_t r0, int64
 extern long long g_i8_potrf_min;
 // recursive Cholesky + inverse (linalg.cu: rchol_padded): the four int8-pipe products of one 2h x 2h diagonal block (i8mm.cu)
 bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h);
+struct I8BlkAsync {                // overlap of a block's trailing products with the recursion into its second half
+    cudaStream_t side; cudaEvent_t ev_fork, ev_rest, ev_T;
+    int64_t split_rows;            // > 0: the second half needs only these rows of A22 at once (its first leaf)
+    int own_ops;                   // 1: operands in buffers of their own (the second half uses the shared ones)
+};
 cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scratch, long long ld, int64_t o, int64_t h,
-                         int want_inv, int S, cudaStream_t st);
+                         int want_inv, int S, cudaStream_t st, const I8BlkAsync* as = nullptr);
 cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long long ld, int64_t o, int64_t h, int S,
                           cudaStream_t st);
 // Recursive factor (+ inverse) for padded sizes leaf * 2^k: leaves by the blocked sweep with its pipelined inverse, everything above

@@ -473,6 +473,7 @@ struct I8Lists {                                 // the tile lists of one tile w
 };
 struct I8Plan {
     I8Operand opA, opB, opP;                 // opP: the 1024-column super-panel of the blocked Cholesky
+    I8Operand opC, opD;                      // recursive scheme: operands of products that overlap the second half's recursion
     I8Tile* tiles = nullptr; size_t tiles_cap = 0;
     std::vector<I8Tile> host_tiles;          // all tile lists back to back
     I8Lists L[2];                            // [0]: 128 x 64 tiles (one-pass kernel), [1]: 128 x 128 tiles (two-pass kernel)
@@ -580,7 +581,7 @@ static cudaError_t i8_upload_tiles(I8Plan& p, cudaStream_t st) {
 I8Plan* i8_plan_create() { return new I8Plan(); }
 void i8_plan_destroy(I8Plan* p) {
     if (!p) return;
-    for (I8Operand* op : {&p->opA, &p->opB, &p->opP}) {
+    for (I8Operand* op : {&p->opA, &p->opB, &p->opP, &p->opC, &p->opD}) {
         if (op->digits) cudaFree(op->digits);
         if (op->ex_bits) cudaFree(op->ex_bits);
         if (op->ex) cudaFree(op->ex);
@@ -607,6 +608,10 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
     if (changed) *changed = true;            // captured graphs that replay the old lists must be re-captured
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;      // nothing may still read the lists being replaced
     if ((e = i8_reserve(p->opP, (int)Np, I8_PANEL, S)) != cudaSuccess) return e;
+    if (Np >= 8192) {                        // (blocks above the lowest recursion level exist from 4 leaves on)
+        if ((e = i8_reserve(p->opC, (int)(Np / 2), (int)(Np / 2), S)) != cudaSuccess) return e;
+        if ((e = i8_reserve(p->opD, (int)(Np / 2), (int)(Np / 2), S)) != cudaSuccess) return e;
+    }
     p->host_tiles.clear();
     const int nkc = (int)(Np / I8_KC);
     for (int w = 0; w < 2; ++w) {
@@ -772,22 +777,49 @@ bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h) {
     if (!p || !p->ready(Np, ld, S) || h < 1024 || (h & (h - 1)) != 0 || 2 * h > Np) return false;
     return p->L[0].blk_trsm[i8_blk_level(h)].count > 0;
 }
+// as != NULL: the products the second half's recursion does not wait for run on as->side concurrently with it -- T = L21 X11
+// always, and, when the second half is itself a recursion (as->split_rows = rows of its first leaf), the part of the A22 update
+// below those rows; their operands then live in opC / opD (as->own_ops), which nothing else touches until i8_blk_second.
+// The caller waits for as->ev_rest before the second half reads A22 below split_rows and for as->ev_T before i8_blk_second.
 cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scratch, long long ld, int64_t o, int64_t h, int want_inv,
-                         int S, cudaStream_t st) {
+                         int S, cudaStream_t st, const I8BlkAsync* as) {
     const int lev = i8_blk_level(h), hn = (int)h;
     const int width = i8_width(S, h >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
     const I8Lists& TL = p->L[width];
+    const int TN = width == 0 ? I8_TN : 128;
     double* A21 = A + (o + h) * ld + o;
+    double* A22 = A + (o + h) * (ld + 1);
+    const bool own = as && as->own_ops && p->opC.digits_cap > 0 && p->opD.digits_cap > 0;
+    I8Operand& opL = own ? p->opC : p->opA;          // L21
+    I8Operand& opX = own ? p->opD : p->opB;          // columns of X11
     cudaError_t e;
     if ((e = i8_slice(p->opA, A21, ld, 1, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
     if ((e = i8_slice(p->opB, Linv + o * (ld + 1), ld, 1, 0, 1, hn, hn, S, 2, st)) != cudaSuccess) return e;
     if ((e = i8_launch(p->opA, p->opB, p->tiles + TL.blk_trsm[lev].first, (int)TL.blk_trsm[lev].count, S, 1.0, 0.0, A21, ld, st, width)) != cudaSuccess) return e;
-    if ((e = i8_slice(p->opA, A21, ld, 1, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
-    if ((e = i8_launch(p->opA, p->opA, p->tiles + TL.blk_syrk[lev].first, (int)TL.blk_syrk[lev].count, S, -1.0, 1.0,
-                       A + (o + h) * (ld + 1), ld, st, width)) != cudaSuccess) return e;
-    if (!want_inv) return cudaSuccess;
-    if ((e = i8_slice(p->opB, Linv + o * (ld + 1), 1, ld, 0, 1, hn, hn, S, 1, st)) != cudaSuccess) return e;
-    return i8_launch(p->opA, p->opB, p->tiles + TL.blk_pa[lev].first, (int)TL.blk_pa[lev].count, S, 1.0, 0.0, scratch + (o + h) * ld + o, ld, st, width);
+    if ((e = i8_slice(opL, A21, ld, 1, 0, 1, hn, hn, S, 0, st)) != cudaSuccess) return e;
+    // A22 -= L21 L21^T: the list is ordered by row tile, so the rows the second half needs first are a prefix
+    int n_all = (int)TL.blk_syrk[lev].count, n_first = n_all;
+    if (as && as->split_rows > 0 && as->split_rows < h) {
+        n_first = 0;
+        for (int tm = 0; tm < (int)(as->split_rows / I8_TM); ++tm) n_first += ((tm + 1) * I8_TM + TN - 1) / TN;
+    }
+    if ((e = i8_launch(opL, opL, p->tiles + TL.blk_syrk[lev].first, n_first, S, -1.0, 1.0, A22, ld, st, width)) != cudaSuccess) return e;
+    const bool fork = as && (n_first < n_all || want_inv);
+    cudaStream_t s2 = fork ? as->side : st;
+    if (fork) {
+        if ((e = cudaEventRecord(as->ev_fork, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s2, as->ev_fork, 0)) != cudaSuccess) return e;
+    }
+    if (n_first < n_all) {
+        if ((e = i8_launch(opL, opL, p->tiles + TL.blk_syrk[lev].first + n_first, n_all - n_first, S, -1.0, 1.0, A22, ld, s2, width)) != cudaSuccess) return e;
+        if (fork && (e = cudaEventRecord(as->ev_rest, s2)) != cudaSuccess) return e;
+    }
+    if (want_inv) {
+        if ((e = i8_slice(opX, Linv + o * (ld + 1), 1, ld, 0, 1, hn, hn, S, 1, s2)) != cudaSuccess) return e;
+        if ((e = i8_launch(opL, opX, p->tiles + TL.blk_pa[lev].first, (int)TL.blk_pa[lev].count, S, 1.0, 0.0, scratch + (o + h) * ld + o, ld, s2, width)) != cudaSuccess) return e;
+    }
+    if (fork && (e = cudaEventRecord(as->ev_T, s2)) != cudaSuccess) return e;      // everything on the side stream is done
+    return cudaSuccess;
 }
 cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long long ld, int64_t o, int64_t h, int S, cudaStream_t st) {
     const int lev = i8_blk_level(h), hn = (int)h;

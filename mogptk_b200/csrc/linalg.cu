@@ -1484,6 +1484,8 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
 static int g_rchol = std::getenv("MOGP_RCHOL") ? std::atoi(std::getenv("MOGP_RCHOL")) : 1;
 static long long g_rchol_min_np = std::getenv("MOGP_RCHOL_MIN_NP") ? std::atoll(std::getenv("MOGP_RCHOL_MIN_NP")) : 4096;
 static long long g_rchol_leaf = std::getenv("MOGP_RCHOL_LEAF") ? std::atoll(std::getenv("MOGP_RCHOL_LEAF")) : 2048;
+static int g_rchol_overlap = std::getenv("MOGP_RCHOL_OVERLAP") ? std::atoi(std::getenv("MOGP_RCHOL_OVERLAP")) : 1;
+extern "C" int mogp_set_rchol_overlap(int on) { g_rchol_overlap = on; ++g_mogp_cfg_epoch; return 0; }
 extern "C" int mogp_set_rchol(int on, long long min_np, long long leaf) {
     if (leaf < 1024 || (leaf & (leaf - 1)) != 0) return -1;
     g_rchol = on; g_rchol_min_np = min_np; g_rchol_leaf = leaf; ++g_mogp_cfg_epoch;
@@ -1514,7 +1516,11 @@ cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, in
     const int64_t leaf = g_rchol_leaf;
     int leaf_idx = 0;
     cudaError_t err = cudaSuccess;
-    auto rec = [&](auto&& self, int64_t o, int64_t n, int need_inv) -> void {
+    // overlap (g_rchol_overlap): the products of a block that its second half does not need at once (T = L21 X11, the A22 update
+    // below the second half's first leaf) run on a side stream while the second half's leaf chains -- which leave most of the
+    // machine idle -- proceed; one side stream / event triple per recursion depth (0: blocks whose halves are leaves)
+    const bool ovl = g_rchol_overlap != 0 && ps && ps->sl[4] && ps->sl[5] && ps->evq && ps->nevq >= 4 * 34 + 48;
+    auto rec = [&](auto&& self, int64_t o, int64_t n, int need_inv, cudaEvent_t pending) -> void {
         if (err != cudaSuccess) return;
         if (n <= leaf) {
             bool fused = false;
@@ -1528,14 +1534,32 @@ cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, in
             return;
         }
         const int64_t h = n / 2;
-        self(self, o, h, 1);
+        self(self, o, h, 1, pending);
         if (err != cudaSuccess) return;
-        if ((err = i8_blk_first(i8, A, Linv, Ltmp, ld, o, h, need_inv, i8_slices, st)) != cudaSuccess) return;
-        self(self, o + h, h, need_inv);
-        if (err != cudaSuccess || !need_inv) return;
+        // (`pending`: the parent's A22 update below this block's first leaf runs on the parent's side stream; it must be done
+        //  before this block's products read those rows)
+        if (pending && (err = cudaStreamWaitEvent(st, pending, 0)) != cudaSuccess) return;
+        const int depth = h > leaf ? 1 : 0;
+        const bool deep = h > 2 * leaf;                      // a third level would share the side resources of depth 1: sequential
+        I8BlkAsync as{};
+        const bool use_as = ovl && !deep;
+        if (use_as) {
+            as.side = ps->sl[4 + depth];
+            as.ev_fork = ps->evq[ps->nevq - 40 + 3 * depth];
+            as.ev_rest = ps->evq[ps->nevq - 40 + 3 * depth + 1];
+            as.ev_T = ps->evq[ps->nevq - 40 + 3 * depth + 2];
+            as.split_rows = depth ? leaf : 0;
+            as.own_ops = depth;
+        }
+        if ((err = i8_blk_first(i8, A, Linv, Ltmp, ld, o, h, need_inv, i8_slices, st, use_as ? &as : nullptr)) != cudaSuccess) return;
+        const bool forked = use_as && (need_inv || as.split_rows > 0);
+        self(self, o + h, h, need_inv, (forked && as.split_rows > 0) ? as.ev_rest : nullptr);
+        if (err != cudaSuccess) return;
+        if (forked && (err = cudaStreamWaitEvent(st, as.ev_T, 0)) != cudaSuccess) return;       // joins the side stream
+        if (!need_inv) return;
         err = i8_blk_second(i8, Linv, Ltmp, ld, o, h, i8_slices, st);
     };
-    rec(rec, 0, Np, want_inverse);
+    rec(rec, 0, Np, want_inverse, nullptr);
     if (err != cudaSuccess) return err;
     rchol_info_kernel<<<1, 1, 0, st>>>(info, leaf_idx, (int)leaf);
     MOGP_COUNT(1);
