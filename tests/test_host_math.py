@@ -166,3 +166,57 @@ def test_inverse_plan_computes_the_inverse(lib, nb):
         else:
             Linv[m:h, a:m] = -Linv[m:h, m:h] @ T[m:h, a:m]
     assert np.allclose(Linv, np.linalg.inv(L), rtol=1e-10, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-side schedules of the pipelined / recursive factorisation (pure index arithmetic, checked without a GPU)
+def _partition(lib, nb, G, S, taper):
+    out = (C.c_int32 * (4 * 256))()
+    n = lib.mogp_host_rowpipe_partition(nb, G, S, taper, out, 256)
+    assert n > 0
+    return np.array(out[:4 * n]).reshape(n, 4)
+
+
+@pytest.mark.parametrize("nb", [2, 5, 6, 7, 16, 32, 33, 64])
+@pytest.mark.parametrize("G,S,taper", [(1, 1, 0), (1, 4, 1), (2, 4, 0), (2, 8, 1), (4, 8, 1), (8, 8, 0), (1, 32, 1)])
+def test_rowwise_pipeline_partition(lib, nb, G, S, taper):
+    """Groups tile [0, nb) in order, every group lies inside its super-group, super-groups are whole groups, only the last
+    group of a super-group may be ragged, and with taper the last super-groups do not grow."""
+    a = _partition(lib, nb, G, S, taper)
+    assert a[0, 0] == 0 and a[-1, 1] == nb
+    assert all(a[i, 1] == a[i + 1, 0] for i in range(len(a) - 1))
+    for lo, hi, slo, shi in a:
+        assert slo <= lo < hi <= shi and hi - lo <= G
+        assert (lo - slo) % G == 0
+    sup = sorted(set((int(r[2]), int(r[3])) for r in a))
+    assert sup[0][0] == 0 and sup[-1][1] == nb and all(sup[i][1] == sup[i + 1][0] for i in range(len(sup) - 1))
+    if taper and len(sup) > 2:
+        sizes = [b - a_ for a_, b in sup]
+        assert sizes[-1] <= sizes[-2] <= max(sizes)
+
+
+@pytest.mark.parametrize("nb,G,wmin", [(32, 1, 4), (32, 2, 4), (6, 1, 4), (5, 1, 2), (64, 1, 8), (32, 1, 1), (7, 2, 4), (2, 1, 4)])
+def test_kinv_accumulation_chunks(lib, nb, G, wmin):
+    """The halving chunks of the progressive K^-1 accumulation tile [0, nb), end at group boundaries and shrink towards the end."""
+    ch = [(lib.mogp_host_kinv_chunk_start(nb, G, wmin, hi), hi) for hi in range(1, nb + 1)]
+    ch = [(lo, hi) for lo, hi in ch if lo >= 0]
+    assert ch[0][0] == 0 and ch[-1][1] == nb
+    assert all(ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
+    assert all(hi % G == 0 or hi == nb for _, hi in ch)
+    sizes = [hi - lo for lo, hi in ch]
+    assert all(sizes[i] >= sizes[i + 1] or sizes[i + 1] <= max(wmin, G) for i in range(len(sizes) - 1))
+
+
+def test_recursive_scheme_applies_to_leaf_times_power_of_two(lib):
+    assert lib.mogp_set_rchol(1, 4096, 2048) == 0
+    assert [int(lib.mogp_rchol_applies(n)) for n in (2048, 4096, 4224, 6144, 8192, 16384, 32768)] == [0, 1, 0, 0, 1, 1, 0]
+    assert lib.mogp_set_rchol(1, 4096, 1024) == 0
+    assert [int(lib.mogp_rchol_applies(n)) for n in (2048, 4096, 8192, 16384)] == [0, 1, 1, 0]      # at most 8 leaves
+    assert lib.mogp_set_rchol(0, 4096, 2048) == 0 and lib.mogp_rchol_applies(8192) == 0
+    assert lib.mogp_set_rchol(1, 4096, 1000) == -1
+    assert lib.mogp_set_rchol(1, 4096, 2048) == 0
+
+
+def test_mohsm_parameter_count_and_kdiag_needs_inputs(lib):
+    Cn, Q, D = 3, 2, 2
+    assert lib.mogp_num_params(_cabi.KIND["MOHSM"], Cn, Q, D) == Q * (3 * Cn + 3 * Cn * D + D)
