@@ -392,11 +392,12 @@ extern "C" int mogp_trtri_kinv(mogp_handle_t h, double* A_dev, double* Linv_dev,
     const bool i8 = use_i8(n);           // same dispatch as the fused step (int8 tensor pipe for large n)
     if (i8 && i8_ready(h, n, n, st)) return -2;
     bool fused_inverse = false, fused_kinv = false;
-    const bool rowp = rowpipe_applies(n);          // same dispatch as the fused step (row-wise pipeline for small n)
+    // same dispatch as the fused step: row-wise pipeline for small n; a scratch of its own only when K^-1 is accumulated behind
+    // the chain as well (then Kinv_dev cannot double as the scratch)
+    const bool rowp = rowpipe_applies(n) && g_rowpipe_kinv != 0;
     if (rowp && ensure(h, h->T, h->T_cap, (size_t)n * n)) return -2;
     MOGP_CHECK(h, potrf_padded(A_dev, n, Linv_dev, n, rowp ? h->T : Kinv_dev, n, n, h->logdet_part, h->info, st, &h->ps,
-                               &fused_inverse, i8 ? h->i8 : nullptr, g_i8_slices, rowp && g_rowpipe_kinv ? Kinv_dev : nullptr,
-                               &fused_kinv));
+                               &fused_inverse, i8 ? h->i8 : nullptr, g_i8_slices, rowp ? Kinv_dev : nullptr, &fused_kinv));
     if (!fused_inverse) MOGP_CHECK(h, trtri_padded(A_dev, Linv_dev, Kinv_dev, n, n, st, i8 ? h->i8 : nullptr, g_i8_slices));
     if (fused_kinv) MOGP_CHECK(h, cudaStreamWaitEvent(st, h->ps.ev_kinv, 0));
     else if (i8) MOGP_CHECK(h, i8_kinv(h->i8, Linv_dev, Kinv_dev, n, n, g_i8_slices, st));
@@ -454,7 +455,9 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     // (with the pipelined inverse the GEMMs of Linv = L^-1 are issued behind the panel chain, inside potrf_padded)
     // Small sizes (row-wise pipeline, linalg.cu): Linv AND K^-1 (into W) are built behind the panel chain; the scratch is T then.
     bool fused_inverse = false, fused_kinv = false;
-    const bool rowp = want_grad && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
+    // (`rowp`: K^-1 accumulated behind the chain as well, which needs the scratch T beside W; off by default -- the row-wise
+    //  pipeline of Linv alone runs with W as its scratch)
+    const bool rowp = want_grad && g_rowpipe_kinv != 0 && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
     // Large sizes: recursive factor + inverse, everything above the 2048-row leaves on the int8 tensor pipe
     cudaError_t er = use_i8(Np) ? rchol_padded(h->A, ld, h->Linv, h->W, Np, h->logdet_part, h->info, st, &h->ps, h->i8, g_i8_slices, 1)
                                 : cudaErrorNotSupported;
@@ -462,8 +465,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     else if (er != cudaErrorNotSupported) MOGP_CHECK(h, er);
     else
     MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, rowp ? h->T : h->W, ld, Np, h->logdet_part, h->info, st, &h->ps,
-                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp && g_rowpipe_kinv ? h->W : nullptr,
-                               &fused_kinv));
+                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp ? h->W : nullptr, &fused_kinv));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(2, st));
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
@@ -546,7 +548,8 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
         if (ensure(h, h->tile_part, h->tile_part_cap, need)) return -2;
     }
     if (use_i8(Np) && i8_ready(h, Np, Np, st)) return -2;
-    if (want_grad && rowpipe_applies(Np) && ensure(h, h->T, h->T_cap, (size_t)Np * Np)) return -2;
+    if (want_grad && g_rowpipe_kinv != 0 && rowpipe_applies(Np) && !(use_i8(Np) && rchol_applies(Np)) &&
+        ensure(h, h->T, h->T_cap, (size_t)Np * Np)) return -2;
     const size_t nout = 2 + (size_t)s.P + C;
     const size_t stage_need = (size_t)s.P + C + 2 * (size_t)N + nout + 16;
     if (ensure(h, h->gbuf, h->gbuf_cap, stage_need)) return -2;
