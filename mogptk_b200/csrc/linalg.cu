@@ -172,11 +172,20 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     const long long ldc = g.ldc;
     const double beta = ((g.first_touch_row1 > 0 && m0 >= g.first_touch_row1 - 1) ||
                          (g.first_touch_col1 > 0 && n0 >= g.first_touch_col1 - 1)) ? 0.0 : g.beta;   // first touch of this tile
+    // The old C values of a fragment row are loaded together BEFORE any of them is overwritten: C is not known to be free of
+    // aliases, so a load placed after a store waits for its own round trip -- 16 dependent L2 round trips per thread with the
+    // element-by-element form, which is what bounded the rank-64 updates (4 k-iterations of math per tile).
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int row = am0 + i * 8 + gq;
         if (row >= mvalid) continue;
         const long long r = m0 + row;
+        double2 old[NT];
+        if (beta != 0.0) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                old[j] = *reinterpret_cast<const double2*>(C + r * ldc + n0 + bn0 + j * 8 + 2 * tq);
+        }
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int col = n0 + bn0 + j * 8 + 2 * tq;
@@ -185,9 +194,8 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
             v.x = g.alpha * acc[i][j][0];
             v.y = g.alpha * acc[i][j][1];
             if (beta != 0.0) {
-                double2 o = *p;
-                v.x += beta * o.x;
-                v.y += beta * o.y;
+                v.x += beta * old[j].x;
+                v.y += beta * old[j].y;
             }
             if (g.epi == 1) {
                 const double ai = g.avec[r];
@@ -200,9 +208,122 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_f64_kernel(GemmArgs g)
     }   // pair loop
 }
 
+extern long long g_mogp_cfg_epoch;
 // explicit per-launch priorities (GemmArgs::prio, panel steps): 1 = on
 static int g_launch_prio = std::getenv("MOGP_LAUNCH_PRIO") ? std::atoi(std::getenv("MOGP_LAUNCH_PRIO")) : 1;
 extern "C" int mogp_set_launch_prio(int on) { g_launch_prio = on; ++g_mogp_cfg_epoch; return 0; }
+// Rank-64 updates (K = 64: the trailing updates of the single-level Cholesky sweep and the right-looking updates of the row-wise
+// inverse).  With four k-iterations the pipelined kernel above is a chain of four or five dependent memory round trips per
+// tile -- load, wait, load, wait, ..., then read C, then write -- and little math in between: 2048^2 x 64 runs at 13 TFLOP/s
+// (cuBLAS: 12).  Here a tile issues EVERYTHING it will read at once -- the whole 64-deep A and B panels by cp.async and its
+// old C values into registers -- waits once, multiplies, writes: one round trip per tile, four tiles per SM in flight.
+template <int BM, int BN, bool TB>
+__global__ void __launch_bounds__(128, 4) gemm_f64_k64_kernel(GemmArgs g) {
+    constexpr int KD = 64, PA = KD + 4, PB = TB ? KD + 4 : BN + 4;
+    constexpr int WTM = BM / 2, WTN = BN / 2, MT = WTM / 8, NT = WTN / 8;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                         // [BM][PA]
+    double* Bs = smem + BM * PA;               // TB: [BN][PB] (n, k)   else [KD][PB] (k, n)
+    const int tn = blockIdx.x, tm = blockIdx.y;
+    if (g.lower && (tm + 1) * BM <= tn * BN) return;
+    const long long bz = blockIdx.z;
+    const double* __restrict__ A = g.A + bz * g.strideA;
+    const double* __restrict__ B = g.B + bz * g.strideB;
+    double* C = g.C + bz * g.strideC;
+    const int m0 = tm * BM, n0 = tn * BN, tid = threadIdx.x;
+#pragma unroll
+    for (int c = tid; c < BM * (KD / 2); c += 128) {
+        const int row = c / (KD / 2), cc = c % (KD / 2);
+        cp_async16(As + row * PA + cc * 2, A + (long long)(m0 + row) * g.lda + cc * 2, true);
+    }
+    if (TB) {
+#pragma unroll
+        for (int c = tid; c < BN * (KD / 2); c += 128) {
+            const int row = c / (KD / 2), cc = c % (KD / 2);
+            cp_async16(Bs + row * PB + cc * 2, B + (long long)(n0 + row) * g.ldb + cc * 2, true);
+        }
+    } else {
+#pragma unroll
+        for (int c = tid; c < KD * (BN / 2); c += 128) {
+            const int kr = c / (BN / 2), cc = c % (BN / 2);
+            cp_async16(Bs + kr * PB + cc * 2, B + (long long)kr * g.ldb + n0 + cc * 2, true);
+        }
+    }
+    cp_async_commit();
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int am0 = (warp >> 1) * WTM, bn0 = (warp & 1) * WTN;
+    const double beta = ((g.first_touch_row1 > 0 && m0 >= g.first_touch_row1 - 1) ||
+                         (g.first_touch_col1 > 0 && n0 >= g.first_touch_col1 - 1)) ? 0.0 : g.beta;
+    const long long ldc = g.ldc;
+    double2 old[MT][NT];
+    if (beta != 0.0) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                old[i][j] = *reinterpret_cast<const double2*>(C + (long long)(m0 + am0 + i * 8 + gq) * ldc + n0 + bn0 + j * 8 + 2 * tq);
+    }
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < KD; kk += 4) {
+        double a[MT], b[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) a[i] = As[(am0 + i * 8 + gq) * PA + kk + tq];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = TB ? Bs[(bn0 + j * 8 + gq) * PB + kk + tq] : Bs[(kk + tq) * PB + bn0 + j * 8 + gq];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+            if (beta != 0.0) { v.x += beta * old[i][j].x; v.y += beta * old[i][j].y; }
+            *reinterpret_cast<double2*>(C + (long long)(m0 + am0 + i * 8 + gq) * ldc + n0 + bn0 + j * 8 + 2 * tq) = v;
+        }
+}
+// Measured (profiles/r02_gemm_k64.txt): stand-alone 4096^2 x 64 21.1 vs 19.8 TFLOP/s, 8192^2 x 64 25.0 vs 23.2 (cuBLAS 18.0 / 19.9), but
+// inside the step the four 52 KB tiles per SM crowd out the panel CTAs: cfg2 0.737 -> 0.768 ms, cfg4 2.58 -> 2.68 ms.  Off by default.
+static int g_gemm_k64 = std::getenv("MOGP_GEMM_K64") ? std::atoi(std::getenv("MOGP_GEMM_K64")) : 0;
+extern "C" int mogp_set_gemm_k64(int on) { g_gemm_k64 = on; ++g_mogp_cfg_epoch; return 0; }
+template <int BM, int BN, bool TB>
+static cudaError_t launch_gemm_k64(const GemmArgs& g, int batch, cudaStream_t s) {
+    constexpr size_t SMEM = (size_t)(BM * 68 + (TB ? BN * 68 : 64 * (BN + 4))) * sizeof(double);
+    auto kern = gemm_f64_k64_kernel<BM, BN, TB>;
+    static PerDeviceOnce once;
+    if (OnceGuard og{once}; og.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
+    dim3 grid(g.N / BN, g.M / BM, batch);
+    if (g.prio > 0 && g_launch_prio) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = -(g.prio - 1);
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MOGP_COUNT(1);
+        return cudaLaunchKernelEx(&cfg, kern, g);
+    }
+    kern<<<grid, 128, SMEM, s>>>(g);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
 std::atomic<long long> g_mogp_launches{0};
 long long g_mogp_cfg_epoch = 0;      // bumped by the tuning setters: captured step graphs are re-captured
 // 0 (default): 64x64 tiles   1: force 128x128 tiles (256 threads)   3: force 128x64 tiles
@@ -275,6 +396,8 @@ static cudaError_t launch_gemm_t(const GemmArgs& g, int batch, cudaStream_t s) {
 
 cudaError_t launch_gemm(int transa, int transb, const GemmArgs& g, int batch, cudaStream_t s) {
     if ((g.N % 64) || (g.K % 16) || (g.M % 64)) return cudaErrorInvalidValue;
+    if (g_gemm_k64 && g.K == 64 && transa == 0 && !g.klo_mode && !g.khi_mode && !g.pair && !g.epi)
+        return transb ? launch_gemm_k64<32, 64, true>(g, batch, s) : launch_gemm_k64<32, 64, false>(g, batch, s);
     if (transa == 0 && transb == 0) return launch_gemm_t<false, false>(g, batch, s);
     if (transa == 0 && transb == 1) return launch_gemm_t<false, true>(g, batch, s);
     if (transa == 1 && transb == 0) return launch_gemm_t<true, false>(g, batch, s);
@@ -652,6 +775,97 @@ __device__ __forceinline__ void ws_tensor_dispatch(int mask, const double* ZZ, c
     }
 }
 
+// Split hand-over (panel variant 3).  The only thing the next 8x8 pivot block waits for is the final rank-8 update of ITS OWN
+// row tile; everything else a sub-panel produces is needed one step later.  So the chain warp publishes the finished columns
+// in two parts -- first the 32-row group that holds the next pivot tile (barrier 3), then the rest (barrier 2) -- and the
+// tensor warp that owns the next pivot tile finishes that tile alone and hands it over (barrier 4) before it waits for the
+// rest, while the chain warp is still substituting the other row groups.  Barrier 1 ("Xr full") keeps its meaning.
+// `prio` = this warp's slot that holds the next pivot tile (-1: none).  The finishing DMMAs run under run-time predicates
+// (two k-steps per tile: the serialisation in front of predicated DMMAs does not matter here).
+template <int NS, int MASK, int PLW>
+__device__ __forceinline__ void ws_tensor_subpanel_split(const double* ZZ, const double* Lc, double* Xp, const int (&mt)[NS],
+                                                         const double* const (&rowp)[NS], int c0, int has_prev, int k_pre,
+                                                         int k_all, bool wait, int prio, int gq, int tq) {
+    double cf[NS][2];
+    double2 a0[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        cf[i][0] = 0.0; cf[i][1] = 0.0;
+        a0[i] = make_double2(0.0, 0.0);
+        if ((MASK >> i) & 1) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
+    }
+    if (has_prev) {
+#pragma unroll 4
+        for (int kk = 0; kk < 64; kk += 4) {
+            const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
+        }
+    }
+#pragma unroll 2
+    for (int k = 0; k < k_pre; k += 4) {
+        const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+            if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+    }
+    if (wait) {
+        if (prio >= 0) {
+            named_bar_sync(3, 64);                       // the group of the pivot tile is published
+            for (int k = k_pre; k < k_all; k += 4) {
+                const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+                    if (((MASK >> i) & 1) && i == prio) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+            }
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if (((MASK >> i) & 1) && i == prio)
+                    *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
+                        make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+            __threadfence_block();
+            named_bar_arrive(4, 64);                     // the next pivot block is ready
+        }
+        named_bar_sync(2, WS_BAR_THREADS);               // all finished columns are published
+        for (int k = k_pre; k < k_all; k += 4) {
+            const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+                if (((MASK >> i) & 1) && i != prio) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+        if (((MASK >> i) & 1) && !(wait && i == prio))
+            *reinterpret_cast<double2*>(Xp + (mt[i] * 8 + gq) * XP + 2 * tq) =
+                make_double2(cf[i][0] + a0[i].x, cf[i][1] + a0[i].y);
+    __threadfence_block();
+    named_bar_arrive(1, WS_BAR_THREADS);
+}
+#define WS_TENSOR_SPLIT_CASE(M)                                                                                      \
+    case M:                                                                                                          \
+        ws_tensor_subpanel_split<NS, (M) & ((1 << NS) - 1), PLW>(ZZ, Lc, Xp, mt, rowp, c0, has_prev, k_pre, k_all, wait, \
+                                                                 prio, gq, tq);                                       \
+        break;
+template <int NS, int PLW>
+__device__ __forceinline__ void ws_tensor_dispatch_split(int mask, const double* ZZ, const double* Lc, double* Xp,
+                                                         const int (&mt)[NS], const double* const (&rowp)[NS], int c0,
+                                                         int has_prev, int k_pre, int k_all, bool wait, int prio, int gq,
+                                                         int tq) {
+    switch (mask) {
+        WS_TENSOR_SPLIT_CASE(0) WS_TENSOR_SPLIT_CASE(1) WS_TENSOR_SPLIT_CASE(2) WS_TENSOR_SPLIT_CASE(3)
+        default:
+            if (NS == 3) {
+                switch (mask) {
+                    WS_TENSOR_SPLIT_CASE(4) WS_TENSOR_SPLIT_CASE(5) WS_TENSOR_SPLIT_CASE(6) WS_TENSOR_SPLIT_CASE(7)
+                    default: break;
+                }
+            }
+            break;
+    }
+}
+
 template <int OT>
 struct WsCfg {
     static constexpr int ROWS = 64 + 8 * OT;        // diagonal block + own rows
@@ -685,7 +899,7 @@ __device__ __forceinline__ int ws_tile(int warp, int slot) {
     }
 }
 
-template <int OT>
+template <int OT, bool SPLIT>
 __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restrict__ A, long long lda,
                                                                 double* __restrict__ Ltmp, long long ldt, int k0, int nrb,
                                                                 int has_prev, int32_t* info, long long* dbg) {
@@ -738,6 +952,14 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
             for (int i = 0; i < NS; ++i)
                 if (mt[i] >= 0 && (mt[i] >= 8 ? has_rows : mt[i] >= p)) mask |= 1 << i;
             double* Xp = Xr;
+            if (SPLIT) {
+                int prio = -1;                           // this warp's slot holding the pivot tile of this sub-panel
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+                    if (mt[i] == p) prio = i;
+                ws_tensor_dispatch_split<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 8, c0, p >= 1, prio, gq, tq);
+                continue;
+            }
             // columns [0, c0-8) were published before this warp's previous barrier wait; [c0-8, c0) follow barrier 2
             long long* ts = (dbg && warp == 1 && lane == 0 && b == 0 && (p == 0 || p == 3)) ? dbg + (p == 0 ? 40 : 48) : nullptr;
             ws_tensor_dispatch<NS, PLW>(mask, ZZ, Lc, Xp, mt, rowp, c0, has_prev, c0 - 8, c0, p >= 1 ? 2 : -1, 1,
@@ -753,12 +975,18 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
 #pragma unroll 1
     for (int p = 0; p < 8; ++p) {
         const int c0 = p * 8;
-        named_bar_sync(1, WS_BAR_THREADS);
+        if (SPLIT && p >= 1) named_bar_sync(4, 64);      // the pivot tile alone (handed over early by its owner warp)
+        else named_bar_sync(1, WS_BAR_THREADS);
         double D[8][8], rinv[8], acc[NG][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) D[i][j] = Xr[(c0 + i) * XP + j];
+        int badcol = 8;                       // first non-positive pivot of this block (8 = none)
+        if (SPLIT) {
+            factor_pivot8_pairs(D, rinv, badcol);        // needs the pivot block only: the other rows arrive meanwhile
+            if (p >= 1) named_bar_sync(1, WS_BAR_THREADS);
+        }
         bool gon[NG];
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -773,24 +1001,32 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_ws_kernel(double* __restri
                 for (int c = 0; c < 8; ++c) acc[g][c] = 0.0;
             }
         }
-        int badcol = 8;                       // first non-positive pivot of this block (8 = none)
-        factor_pivot8_pairs(D, rinv, badcol);
+        if (!SPLIT) factor_pivot8_pairs(D, rinv, badcol);
         if (badcol < 8 && lane == 0 && b == 0) atomicCAS(info, 0, k0 + c0 + badcol + 1);
+        // SPLIT: the 32-row group that holds the NEXT pivot tile first (published on its own: barrier 3), then the others
+        const int gfirst = (SPLIT && p < 7) ? (c0 + 8) >> 5 : -1;
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            if (!gon[g]) continue;
-            const int row = lane + 32 * g;
-            const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
+        for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double xc = acc[g][c] * rinv[c];
-                acc[g][c] = (c <= jrow) ? xc : 0.0;
+            for (int g = 0; g < NG; ++g) {
+                if (!gon[g] || (pass == 0) != (g == gfirst)) continue;
+                const int row = lane + 32 * g;
+                const int jrow = row - c0;            // 0..7: a row of the pivot block (entries right of the diagonal are masked)
 #pragma unroll
-                for (int cc = c + 1; cc < 8; ++cc) acc[g][cc] = fma(-xc, D[cc][c], acc[g][cc]);
+                for (int c = 0; c < 8; ++c) {
+                    const double xc = acc[g][c] * rinv[c];
+                    acc[g][c] = (c <= jrow) ? xc : 0.0;
+#pragma unroll
+                    for (int cc = c + 1; cc < 8; ++cc) acc[g][cc] = fma(-xc, D[cc][c], acc[g][cc]);
+                }
+                if (jrow >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[g][c];
+                }
             }
-            if (jrow >= 0) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) Lc[(c0 + c) * PLW + row] = acc[g][c];
+            if (pass == 0 && gfirst >= 0) {
+                __threadfence_block();
+                named_bar_arrive(3, 64);
             }
         }
         if (dbg && lane == 0 && b == 0) dbg[2 + p] = clock64();
@@ -982,7 +1218,7 @@ extern "C" int mogp_panel_debug(long long* out_host /*19*/) {
 // Ltmp is an Np x Np scratch whose diagonal blocks are used; diagonal blocks of Linv get inv(L_kk).
 // One warp-specialised panel step; n_cta_rows = number of 8*OT-row blocks below the diagonal block.  Steps that consume a
 // previous panel are launched with the programmatic-serialization attribute when g_panel_pdl asks for it (see above).
-template <int OT>
+template <int OT, bool SPLIT>
 static void launch_panel_ws(double* A, long long ld, double* Ltmp, long long ldt, int k, int n_cta_rows, int has_prev,
                             int32_t* info, long long* dbgp, cudaStream_t s_) {
     const unsigned grid = (unsigned)std::max(1, n_cta_rows);
@@ -998,7 +1234,7 @@ static void launch_panel_ws(double* A, long long ld, double* Ltmp, long long ldt
         at[1].id = cudaLaunchAttributePriority;
         at[1].val.priority = -5;
         cfg.attrs = at; cfg.numAttrs = g_launch_prio ? 2 : 1;
-        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
+        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT, SPLIT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
             return;
         cudaGetLastError();               // not supported in this context: plain launches from now on
         g_panel_pdl = 0;
@@ -1011,11 +1247,11 @@ static void launch_panel_ws(double* A, long long ld, double* Ltmp, long long ldt
         at[0].id = cudaLaunchAttributePriority;
         at[0].val.priority = -5;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
+        if (cudaLaunchKernelEx(&cfg, potrf_panel_ws_kernel<OT, SPLIT>, A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp) == cudaSuccess)
             return;
         cudaGetLastError();
     }
-    potrf_panel_ws_kernel<OT><<<grid, 256, WsCfg<OT>::SMEM, s_>>>(A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp);
+    potrf_panel_ws_kernel<OT, SPLIT><<<grid, 256, WsCfg<OT>::SMEM, s_>>>(A, ld, Ltmp, ldt, k, n_cta_rows, has_prev, info, dbgp);
 }
 
 // Operations of the pipelined triangular inverse, in issue order (see build_inverse_plan).
@@ -1152,24 +1388,31 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     // variant 0: phase-alternating kernel; 1: warp-specialised, 64 own rows per CTA; 2: warp-specialised, 32 own
     // rows per CTA while twice the CTAs still fit one wave (one CTA per SM), 64 otherwise
     auto launch_panel = [&](int64_t k, int nrb, int has_prev, long long* dbgp, cudaStream_t s_) {
-        if (g_panel_variant >= 2 && 2 * nrb <= n_sm)
-            launch_panel_ws<4>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp, s_);
+        if (g_panel_variant >= 3 && 2 * nrb <= n_sm)
+            launch_panel_ws<4, true>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp, s_);
+        else if (g_panel_variant >= 3)
+            launch_panel_ws<8, true>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp, s_);
+        else if (g_panel_variant >= 2 && 2 * nrb <= n_sm)
+            launch_panel_ws<4, false>(A, ld, Ltmp, ldt, (int)k, 2 * nrb, has_prev, info, dbgp, s_);
         else if (g_panel_variant >= 1)
-            launch_panel_ws<8>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp, s_);
+            launch_panel_ws<8, false>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp, s_);
         else
             potrf_panel_kernel<<<std::max(1, nrb), 256, smem_p, s_>>>(A, ld, Ltmp, ldt, (int)k, nrb, has_prev, info, dbgp);
     };
     if (OnceGuard og{once}; og.needed()) {
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<8>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<4>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(potrf_panel_ws_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
+        {
+            struct KA { const void* f; int smem; };
+            const KA ks[4] = {{(const void*)potrf_panel_ws_kernel<8, false>, (int)WsCfg<8>::SMEM},
+                              {(const void*)potrf_panel_ws_kernel<4, false>, (int)WsCfg<4>::SMEM},
+                              {(const void*)potrf_panel_ws_kernel<8, true>, (int)WsCfg<8>::SMEM},
+                              {(const void*)potrf_panel_ws_kernel<4, true>, (int)WsCfg<4>::SMEM}};
+            for (const KA& ka : ks) {
+                e = cudaFuncSetAttribute(ka.f, cudaFuncAttributeMaxDynamicSharedMemorySize, ka.smem);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(ka.f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                if (e != cudaSuccess) return e;
+            }
+        }
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,

@@ -40,7 +40,7 @@ def _check(engine, g, reps=3):
         assert float(np.abs(got.numpy().reshape(ref.shape) - ref).max()) <= 1e-6 * scale, k
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("name", ["mosm_mid", "cfg2"])
 def test_panel_variants_and_inverse_schedules(engine, knobs, name, variant, pipe):
@@ -85,7 +85,7 @@ def test_dependent_launch_and_graph_modes(engine, knobs, name, pdl, graphs):
     _check(engine, load_golden(name))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n", [64, 200, 1024, 4224, 4736])
 def test_potrf_variants_against_lapack(engine, knobs, variant, n):
     """4224 / 4736 rows take the two-level sweep; at 4736 the early panel steps use 64 own rows per CTA and the late ones 32."""

@@ -552,12 +552,24 @@ def sec_gemm3(eng):
 
 def sec_gemmk(eng):
     """GEMM efficiency versus K and tile configuration (NT form, as in the Cholesky updates)."""
-    for (M, N, K) in [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
-                      (2048, 2048, 64), (2048, 2048, 2048), (1024, 1024, 1024)]:
+    shapes = [(8192, 8192, 64), (8192, 8192, 256), (8192, 8192, 1024), (4096, 4096, 256), (2048, 2048, 256),
+              (2048, 2048, 64), (2048, 2048, 2048), (1024, 1024, 1024)]
+    if os.environ.get("GEMMK_SHAPES"):
+        shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["GEMMK_SHAPES"].split(",")]
+    for (M, N, K) in shapes:
         A = torch.randn((M, K), dtype=torch.float64, device="cuda")
         B = torch.randn((N, K), dtype=torch.float64, device="cuda")
         Cm = torch.zeros((M, N), dtype=torch.float64, device="cuda")
         line = "gemm NT %5dx%5dx%5d beta=1:" % (M, N, K)
+        if K == 64:                                   # the single-shot rank-64 kernel against the pipelined one (cfg columns)
+            Cr = Cm.clone()
+            eng.lib.mogp_set_gemm_k64(1)
+            med, mn = ev_time(lambda: eng.dgemm(0, 1, -1.0, A, B, 1.0, Cm), reps=7, warm=3)
+            eng.dgemm(0, 1, -1.0, A, B, 0.0, Cm)
+            eng.lib.mogp_set_gemm_k64(0)
+            eng.dgemm(0, 1, -1.0, A, B, 0.0, Cr)
+            line += "  k64 %.3f ms %.1f TF (diff %.1e)" % (mn, 2.0 * M * N * K / mn / 1e9, float((Cm - Cr).abs().max()))
+            Cm.zero_()
         for cfg in (3, 2, 4):
             eng.lib.mogp_set_gemm_config(cfg)
             med, mn = ev_time(lambda: eng.dgemm(0, 1, -1.0, A, B, 1.0, Cm), reps=5, warm=2)
@@ -566,6 +578,7 @@ def sec_gemmk(eng):
         line += "  | cuBLAS %.3f ms %.1f TF" % (mn, 2.0 * M * N * K / mn / 1e9)
         print(line)
     eng.lib.mogp_set_gemm_config(0)
+    eng.lib.mogp_set_gemm_k64(0)
 
 
 def sec_thresh(eng):
