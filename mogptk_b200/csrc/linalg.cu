@@ -786,30 +786,41 @@ template <int NS, int MASK, int PLW>
 __device__ __forceinline__ void ws_tensor_subpanel_split(const double* ZZ, const double* Lc, double* Xp, const int (&mt)[NS],
                                                          const double* const (&rowp)[NS], int c0, int has_prev, int k_pre,
                                                          int k_all, bool wait, int prio, int gq, int tq) {
-    double cf[NS][2];
+    // two accumulator pairs per tile (even / odd k-steps): the pre-accumulation is a chain of up to 30 dependent DMMAs per tile
+    // (26 cycles each) on a tensor pipe that is 20 % busy; two interleaved chains halve its length
+    double cf[NS][2], cg[NS][2];
     double2 a0[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        cf[i][0] = 0.0; cf[i][1] = 0.0;
+        cf[i][0] = 0.0; cf[i][1] = 0.0; cg[i][0] = 0.0; cg[i][1] = 0.0;
         a0[i] = make_double2(0.0, 0.0);
         if ((MASK >> i) & 1) a0[i] = *reinterpret_cast<const double2*>(rowp[i] + c0 + 2 * tq);
     }
     if (has_prev) {
-#pragma unroll 4
-        for (int kk = 0; kk < 64; kk += 4) {
-            const double nb = -ZZ[(c0 + gq) * PZ + kk + tq];
+#pragma unroll 2
+        for (int kk = 0; kk < 64; kk += 8) {
+            const double nb0 = -ZZ[(c0 + gq) * PZ + kk + tq], nb1 = -ZZ[(c0 + gq) * PZ + kk + 4 + tq];
 #pragma unroll
             for (int i = 0; i < NS; ++i)
-                if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb);
+                if ((MASK >> i) & 1) {
+                    dmma884(cf[i][0], cf[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + tq], nb0);
+                    dmma884(cg[i][0], cg[i][1], ZZ[(mt[i] * 8 + gq) * PZ + kk + 4 + tq], nb1);
+                }
         }
     }
+    // (k_pre is a multiple of 8: whole finished sub-panels)
 #pragma unroll 2
-    for (int k = 0; k < k_pre; k += 4) {
-        const double nb = -Lc[(k + tq) * PLW + c0 + gq];
+    for (int k = 0; k < k_pre; k += 8) {
+        const double nb0 = -Lc[(k + tq) * PLW + c0 + gq], nb1 = -Lc[(k + 4 + tq) * PLW + c0 + gq];
 #pragma unroll
         for (int i = 0; i < NS; ++i)
-            if ((MASK >> i) & 1) dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb);
+            if ((MASK >> i) & 1) {
+                dmma884(cf[i][0], cf[i][1], Lc[(k + tq) * PLW + mt[i] * 8 + gq], nb0);
+                dmma884(cg[i][0], cg[i][1], Lc[(k + 4 + tq) * PLW + mt[i] * 8 + gq], nb1);
+            }
     }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { cf[i][0] += cg[i][0]; cf[i][1] += cg[i][1]; }
     if (wait) {
         if (prio >= 0) {
             named_bar_sync(3, 64);                       // the group of the pivot tile is published
