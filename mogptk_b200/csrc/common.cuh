@@ -288,6 +288,7 @@ cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long l
 cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, int64_t Np, double* logdet_part, int32_t* info,
                          cudaStream_t st, const PotrfStreams* ps, I8Plan* i8, int i8_slices, int want_inverse);
 bool rchol_applies(int64_t Np);
+int64_t rchol_leaf_for(int64_t Np);      // leaf rows of the recursive scheme for a padded size (0: does not apply)
 // W(lower tiles) = Linv^T Linv via tcgen05.mma kind::i8 (S digit planes of 7 bits); pure enqueue
 cudaError_t i8_kinv(I8Plan* p, const double* Linv, double* W, int64_t Np, long long ld, int S, cudaStream_t st);
 // Smallest padded size that takes the int8 path (0 = never) and the number of digit planes (7 or 8)

@@ -468,7 +468,7 @@ struct I8Lists {                                 // the tile lists of one tile w
     I8List syrk_a, syrk_b;
     std::vector<size_t> syrk_a_count, syrk_b_count;
     // recursive Cholesky + inverse (i8_blk_*): the four products of one 2h x 2h diagonal block, coordinates relative to the
-    // block (index = log2 of h in 64-blocks): A21 X11^T, A22 -= L21 L21^T, T = L21 X11, X21 = -X22 T
+    // block (index j: h = leaf * 2^j): A21 X11^T, A22 -= L21 L21^T, T = L21 X11, X21 = -X22 T
     std::vector<I8List> blk_trsm, blk_syrk, blk_pa, blk_pb;
 };
 struct I8Plan {
@@ -479,6 +479,7 @@ struct I8Plan {
     I8Lists L[2];                            // [0]: 128 x 64 tiles (one-pass kernel), [1]: 128 x 128 tiles (two-pass kernel)
     long long tiles_key = -1;
     int64_t Np = 0; long long ld = 0; int S = 0;     // what the lists were built for
+    int64_t leaf = 0;                                // leaf of the recursive scheme the blk_* lists were built for (0: none)
     bool ready(int64_t Np_, long long ld_, int S_) const { return tiles_key >= 0 && Np == Np_ && ld == ld_ && S == S_; }
 };
 
@@ -603,12 +604,13 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
     cudaError_t e = i8_reserve(p->opA, (int)Np, (int)Np, S);
     if (e != cudaSuccess) return e;
     if ((e = i8_reserve(p->opB, (int)Np, (int)(Np / 2), S)) != cudaSuccess) return e;
-    const long long key = (Np * 16 + S) * 65536 + g_i8_trtri_min % 65536 + ld * 1000003ll;
+    const int64_t leaf = rchol_leaf_for(Np);
+    const long long key = (Np * 16 + S) * 65536 + g_i8_trtri_min % 65536 + ld * 1000003ll + leaf * 7919ll;
     if (p->tiles_key == key) return cudaSuccess;
     if (changed) *changed = true;            // captured graphs that replay the old lists must be re-captured
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;      // nothing may still read the lists being replaced
     if ((e = i8_reserve(p->opP, (int)Np, I8_PANEL, S)) != cudaSuccess) return e;
-    if (Np >= 8192) {                        // (blocks above the lowest recursion level exist from 4 leaves on)
+    if (leaf > 0 && Np >= 4 * leaf) {        // (blocks above the lowest recursion level exist from 4 leaves on)
         if ((e = i8_reserve(p->opC, (int)(Np / 2), (int)(Np / 2), S)) != cudaSuccess) return e;
         if ((e = i8_reserve(p->opD, (int)(Np / 2), (int)(Np / 2), S)) != cudaSuccess) return e;
     }
@@ -656,8 +658,8 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
         // output coordinates relative to the h x h block each product writes
         L.blk_trsm.assign(32, I8List()); L.blk_syrk.assign(32, I8List());
         L.blk_pa.assign(32, I8List()); L.blk_pb.assign(32, I8List());
-        lev = 4;
-        for (int64_t h = 1024; 2 * h <= Np; h *= 2, ++lev) {
+        lev = 0;
+        for (int64_t h = leaf; leaf > 0 && 2 * h <= Np; h *= 2, ++lev) {
             const int hn = (int)h, ntm = hn / I8_TM, ntn = hn / TN, hk = hn / I8_KC;
             // L21 = A21 X11^T: operand A rows = rows of A21, operand B rows = rows of X11 (nonzero k <= n); longest K (large n) first
             L.blk_trsm[lev].first = T.size();
@@ -706,7 +708,7 @@ cudaError_t i8_prepare(I8Plan* p, int64_t Np, long long ld, int S, cudaStream_t 
     e = i8_upload_tiles(*p, st);
     if (e != cudaSuccess) return e;
     p->tiles_key = key;
-    p->Np = Np; p->ld = ld; p->S = S;
+    p->Np = Np; p->ld = ld; p->S = S; p->leaf = leaf;
     return cudaStreamSynchronize(st);
 }
 
@@ -772,10 +774,10 @@ cudaError_t i8_trtri_level(I8Plan* p, const double* L, double* Linv, double* scr
 //   i8_blk_second: (X22 = L22^-1 complete)  Linv21 <- X21 = -X22 T
 // Replaces the panel-by-panel trailing updates of the blocked sweep above a leaf size by products whose K is the block size,
 // i.e. almost all of the N^3/3 + N^3/3 flops of factor + inverse run as large int8-pipe GEMMs.  Pure enqueue after i8_prepare.
-static int i8_blk_level(int64_t h) { int lev = 0; for (int64_t x = 64; x < h; x *= 2) ++lev; return lev; }
-bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h) {
-    if (!p || !p->ready(Np, ld, S) || h < 1024 || (h & (h - 1)) != 0 || 2 * h > Np) return false;
-    return p->L[0].blk_trsm[i8_blk_level(h)].count > 0;
+static int i8_blk_level(const I8Plan* p, int64_t h) { int lev = 0; for (int64_t x = p->leaf; x < h; x *= 2) ++lev; return lev; }
+bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t leaf) {
+    if (!p || !p->ready(Np, ld, S) || leaf <= 0 || p->leaf != leaf || leaf % I8_TM != 0 || 2 * leaf > Np) return false;
+    return p->L[0].blk_trsm[0].count > 0;
 }
 // as != NULL: the products the second half's recursion does not wait for run on as->side concurrently with it -- T = L21 X11
 // always, and, when the second half is itself a recursion (as->split_rows = rows of its first leaf), the part of the A22 update
@@ -783,7 +785,7 @@ bool i8_blk_ok(const I8Plan* p, int64_t Np, long long ld, int S, int64_t h) {
 // The caller waits for as->ev_rest before the second half reads A22 below split_rows and for as->ev_T before i8_blk_second.
 cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scratch, long long ld, int64_t o, int64_t h, int want_inv,
                          int S, cudaStream_t st, const I8BlkAsync* as) {
-    const int lev = i8_blk_level(h), hn = (int)h;
+    const int lev = i8_blk_level(p, h), hn = (int)h;
     const int width = i8_width(S, h >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
     const I8Lists& TL = p->L[width];
     const int TN = width == 0 ? I8_TN : 128;
@@ -822,7 +824,7 @@ cudaError_t i8_blk_first(I8Plan* p, double* A, const double* Linv, double* scrat
     return cudaSuccess;
 }
 cudaError_t i8_blk_second(I8Plan* p, double* Linv, const double* scratch, long long ld, int64_t o, int64_t h, int S, cudaStream_t st) {
-    const int lev = i8_blk_level(h), hn = (int)h;
+    const int lev = i8_blk_level(p, h), hn = (int)h;
     const int width = i8_width(S, h >= 4096 ? I8_USE_TRTRI_TOP : I8_USE_OTHER);
     const I8Lists& TL = p->L[width];
     cudaError_t e;

@@ -1751,12 +1751,21 @@ extern "C" int mogp_get_rchol(long long* min_np, long long* leaf) {
     return g_rchol;
 }
 extern "C" int mogp_rchol_applies(long long Np) { return rchol_applies(Np) ? 1 : 0; }
-bool rchol_applies(int64_t Np) {
-    if (!g_rchol || Np < g_rchol_min_np || Np < 2 * g_rchol_leaf) return false;
-    int64_t n = Np;
-    while (n > g_rchol_leaf && n % 2 == 0) n /= 2;
-    return n == g_rchol_leaf && Np / g_rchol_leaf <= 8;
+// Leaf size for a padded size: Np / 2^k (k = 1..3) with the leaf a multiple of 128 rows between half and 5/4 of the nominal
+// leaf (1024 .. 2560 for 2048); the largest such leaf is taken.  0: the recursive scheme does not apply (odd multiples of 128, ...).
+int64_t rchol_leaf_for(int64_t Np) {
+    if (!g_rchol || Np < g_rchol_min_np) return 0;
+    const int64_t lo = g_rchol_leaf / 2, hi = g_rchol_leaf + g_rchol_leaf / 4;
+    for (int k = 1; k <= 3; ++k) {
+        if (Np % ((int64_t)128 << k) != 0) break;
+        const int64_t leaf = Np >> k;
+        if (leaf >= lo && leaf <= hi) return leaf;
+        if (leaf < lo) break;
+    }
+    return 0;
 }
+extern "C" long long mogp_rchol_leaf_for(long long Np) { return rchol_leaf_for(Np); }
+bool rchol_applies(int64_t Np) { return rchol_leaf_for(Np) > 0; }
 // info[0] = first failing leaf's pivot index (1-based, global); leaf_info[i] are relative to leaf i
 __global__ void rchol_info_kernel(int32_t* info, int nleaf, int leaf_rows) {
     int32_t v = 0;
@@ -1766,8 +1775,8 @@ __global__ void rchol_info_kernel(int32_t* info, int nleaf, int leaf_rows) {
 }
 cudaError_t rchol_padded(double* A, long long ld, double* Linv, double* Ltmp, int64_t Np, double* logdet_part, int32_t* info,
                          cudaStream_t st, const PotrfStreams* ps, I8Plan* i8, int i8_slices, int want_inverse) {
-    if (!rchol_applies(Np) || !i8 || !i8_blk_ok(i8, Np, ld, i8_slices, g_rchol_leaf)) return cudaErrorNotSupported;
-    const int64_t leaf = g_rchol_leaf;
+    const int64_t leaf = rchol_leaf_for(Np);
+    if (leaf <= 0 || !i8 || !i8_blk_ok(i8, Np, ld, i8_slices, leaf)) return cudaErrorNotSupported;
     int leaf_idx = 0;
     cudaError_t err = cudaSuccess;
     // overlap (g_rchol_overlap): the products of a block that its second half does not need at once (T = L21 X11, the A22 update

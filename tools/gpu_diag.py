@@ -444,6 +444,35 @@ def sec_timeline(eng):
     eng.lib.mogp_set_rowpipe_super(1, 0)
 
 
+def sec_rsizes(eng):
+    """Recursive factor + inverse against the blocked sweep at sizes whose leaf is not 2048 (RS_SIZES = total rows): step time
+    and the difference of LML / gradient between the two schedules."""
+    from mogptk_b200 import synth
+    from mogptk_b200.engine import pack_params
+    sizes = [int(v) for v in os.environ.get("RS_SIZES", "4352,4608,5120,6144,7168").split(",")]
+    for N in sizes:
+        C_ = 4
+        kind = "MOSM"
+        X, y = synth.make_data(C_, [N // C_] * C_, seed=5)
+        p, sigma = synth.make_params(kind, C_, 3, 1, seed=5)
+        rows = eng.prepare(kind, p, X, y)
+        pk = pack_params(kind, p, eng.device)
+        sig = sigma.to(eng.device)
+        res = {}
+        for on in (1, 0):
+            eng.lib.mogp_set_rchol(on, 4096, 2048)
+            t, mn = ev_time(lambda: eng.lml_grad_prepared(rows, pk, sig, 1e-8, True, check=False), reps=7, warm=3)
+            out = eng.lml_grad_prepared(rows, pk, sig, 1e-8, True, check=False).cpu()
+            res[on] = (t, mn, out)
+        a, b = res[1][2], res[0][2]
+        gscale = float(b[2:].abs().max())
+        print("rsizes N=%d leaf %d: recursive %.3f ms (min %.3f) | blocked %.3f ms (min %.3f) | info %d/%d lml rel diff %.1e grad diff %.1e" % (
+            N, eng.lib.mogp_rchol_leaf_for((N + 127) // 128 * 128), res[1][0], res[1][1], res[0][0], res[0][1], int(a[1]), int(b[1]),
+            abs(float(a[0] - b[0])) / abs(float(b[0])), float((a[2:] - b[2:]).abs().max()) / gscale))
+        sys.stdout.flush()
+    eng.lib.mogp_set_rchol(1, 4096, 2048)
+
+
 def sec_gaps(eng):
     """Panel chain versus interference from the concurrent trailing updates (timing only: skip_bulk gives a wrong factor)."""
     for n in (2048, 4096):
@@ -633,7 +662,7 @@ def sec_train(eng):
             name, dt * 1e3, 1 / dt, dt2 * 1e3, float(l)))
 
 
-SECTIONS = {"timeline": sec_timeline, "rowp": sec_rowp, "i8p": sec_i8p, "gemm3": sec_gemm3, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
+SECTIONS = {"rsizes": sec_rsizes, "timeline": sec_timeline, "rowp": sec_rowp, "i8p": sec_i8p, "gemm3": sec_gemm3, "spans": sec_spans, "gaps": sec_gaps, "exp": sec_exp, "train": sec_train, "thresh": sec_thresh, "gemmk": sec_gemmk, "panel": sec_panel, "peak": sec_peak, "gemm": sec_gemm, "potrf": sec_potrf, "trtri": sec_trtri, "cov": sec_cov,
             "lml": sec_lml, "time": sec_time}
 
 if __name__ == "__main__":
