@@ -269,3 +269,30 @@ def test_recursive_factor_and_inverse_in_the_step(engine, knobs, name, rchol):
         _check(engine, load_golden(name))
     finally:
         engine.lib.mogp_set_rchol(1, 4096, 2048)
+
+
+@pytest.mark.parametrize("N,leaf", [(4352, 2176), (5120, 2560), (6144, 1536)])
+def test_recursive_scheme_at_other_leaf_sizes(engine, knobs, N, leaf):
+    """Padded sizes Np = leaf * 2^k with a leaf other than 2048 rows (any multiple of 128 in [1024, 2560]): the recursive factor +
+    inverse against the blocked sweep on the same problem (two different schedules of the same mathematics)."""
+    from mogptk_b200 import synth
+    knobs()
+    lib = engine.lib
+    assert lib.mogp_set_rchol(1, 4096, 2048) == 0
+    assert lib.mogp_rchol_leaf_for(N) == leaf
+    X, y = synth.make_data(4, [N // 4] * 4, seed=5)
+    p, sigma = synth.make_params("MOSM", 4, 3, 1, seed=5, random_delay_phase=True)
+    res = {}
+    try:
+        for on in (1, 0):
+            assert lib.mogp_set_rchol(on, 4096, 2048) == 0
+            for _ in range(3):                       # plain run, capture, replay
+                r = engine.lml_grad("MOSM", p, sigma, X, y, 1e-8, True)
+            assert r["info"] == 0
+            res[on] = r
+    finally:
+        lib.mogp_set_rchol(1, 4096, 2048)
+    assert abs(res[1]["lml"] - res[0]["lml"]) <= 1e-10 * abs(res[0]["lml"])
+    for k, g0 in res[0]["grad"].items():
+        scale = max(float(g0.abs().max()), 1e-12)
+        assert float((res[1]["grad"][k] - g0).abs().max()) <= 1e-8 * scale, k

@@ -466,6 +466,7 @@ def sec_rsizes(eng):
             res[on] = (t, mn, out)
         a, b = res[1][2], res[0][2]
         gscale = float(b[2:].abs().max())
+        eng.lib.mogp_set_rchol(1, 4096, 2048)
         print("rsizes N=%d leaf %d: recursive %.3f ms (min %.3f) | blocked %.3f ms (min %.3f) | info %d/%d lml rel diff %.1e grad diff %.1e" % (
             N, eng.lib.mogp_rchol_leaf_for((N + 127) // 128 * 128), res[1][0], res[1][1], res[0][0], res[0][1], int(a[1]), int(b[1]),
             abs(float(a[0] - b[0])) / abs(float(b[0])), float((a[2:] - b[2:]).abs().max()) / gscale))
