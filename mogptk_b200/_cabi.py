@@ -104,6 +104,8 @@ _EXTRA = {
     "mogp_get_rchol": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "mogp_rchol_applies": (C.c_int, [C.c_longlong]),
     "mogp_rchol_leaf_for": (C.c_longlong, [C.c_longlong]),
+    "mogp_padded_size": (C.c_longlong, [C.c_longlong]),
+    "mogp_set_pad_for_rchol": (C.c_int, [C.c_int]),
     "mogp_set_rchol_overlap": (C.c_int, [C.c_int]),
     "mogp_set_rowpipe_kinv": (C.c_int, [C.c_int]),
     "mogp_set_rowpipe_wmin": (C.c_int, [C.c_int]),

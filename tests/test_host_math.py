@@ -220,3 +220,23 @@ def test_recursive_scheme_applies_to_leaf_times_power_of_two(lib):
 def test_mohsm_parameter_count_and_kdiag_needs_inputs(lib):
     Cn, Q, D = 3, 2, 2
     assert lib.mogp_num_params(_cabi.KIND["MOHSM"], Cn, Q, D) == Q * (3 * Cn + 3 * Cn * D + D)
+
+
+def test_padding_policy_for_the_recursive_scheme(lib):
+    """A few more padding rows (<= ~3 %) when that makes the padded size leaf * 2^k; never for small problems, never when the
+    128-row padding already qualifies, and the result is always a multiple of 128 that is >= N."""
+    assert lib.mogp_set_rchol(1, 4096, 2048) == 0
+    want = {2048: 2048, 3000: 3072, 4096: 4096, 4224: 4352, 5000: 5120, 5130: 5248, 6000: 6144, 7500: 7680, 8000: 8192, 8192: 8192}
+    for n, np_ in want.items():
+        got = lib.mogp_padded_size(n)
+        assert got == np_, (n, got, np_)
+        assert got % 128 == 0 and got >= n
+    for n in range(4097, 9000, 37):
+        got = lib.mogp_padded_size(n)
+        base = (n + 127) // 128 * 128
+        assert got % 128 == 0 and base <= got and (got - n) * 33 <= n or got == base
+        if got != base:
+            assert lib.mogp_rchol_leaf_for(got) > 0 and lib.mogp_rchol_leaf_for(base) == 0
+    assert lib.mogp_set_pad_for_rchol(0) == 0
+    assert lib.mogp_padded_size(6000) == 6016
+    assert lib.mogp_set_pad_for_rchol(1) == 0
