@@ -208,10 +208,18 @@ def test_kinv_accumulation_chunks(lib, nb, G, wmin):
 
 
 def test_recursive_scheme_applies_to_leaf_times_power_of_two(lib):
+    """Padded sizes leaf * 2^k (k = 1..3) with the leaf a multiple of 128 rows between half and 5/4 of the nominal leaf."""
     assert lib.mogp_set_rchol(1, 4096, 2048) == 0
-    assert [int(lib.mogp_rchol_applies(n)) for n in (2048, 4096, 4224, 6144, 8192, 16384, 32768)] == [0, 1, 0, 0, 1, 1, 0]
+    want = {2048: 0, 4096: 2048, 4224: 0, 4352: 2176, 5120: 2560, 5248: 0, 6144: 1536, 7168: 1792, 8192: 2048, 10240: 2560,
+            16384: 2048, 20480: 2560, 32768: 0}
+    for n, leaf in want.items():
+        assert lib.mogp_rchol_leaf_for(n) == leaf, (n, lib.mogp_rchol_leaf_for(n), leaf)
+        assert int(lib.mogp_rchol_applies(n)) == int(leaf > 0)
+        if leaf:
+            k = (n // leaf).bit_length() - 1
+            assert leaf << k == n and 1 <= k <= 3 and leaf % 128 == 0
     assert lib.mogp_set_rchol(1, 4096, 1024) == 0
-    assert [int(lib.mogp_rchol_applies(n)) for n in (2048, 4096, 8192, 16384)] == [0, 1, 1, 0]      # at most 8 leaves
+    assert [int(lib.mogp_rchol_leaf_for(n)) for n in (2048, 4096, 8192, 16384)] == [0, 1024, 1024, 0]      # at most 8 leaves
     assert lib.mogp_set_rchol(0, 4096, 2048) == 0 and lib.mogp_rchol_applies(8192) == 0
     assert lib.mogp_set_rchol(1, 4096, 1000) == -1
     assert lib.mogp_set_rchol(1, 4096, 2048) == 0
