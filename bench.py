@@ -603,7 +603,10 @@ def run_b200(args):
                         "wall_s_incl_flush": round(t_wall, 4)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "plug-in Python API per step: x, y host->device from pinned memory, gpr.Exact.loss() (raw-space "
-                            "p.grad filled), torch.optim.Adam.step(), float(loss); wall clock, max over ranks",
+                            "p.grad filled), torch.optim.Adam.step(), float(loss); wall clock, max over ranks.  loss() returns "
+                            "when the step has published [lml, info] (mapped pinned memory, right after the solves; a Cholesky "
+                            "failure still raises there); K^-1, the gradient reduction and the chain rule finish in stream "
+                            "order under the optimiser's host-side work (MOGP_EARLY_LOSS=0: synchronise instead)",
                     "last_loss": api_loss,
                     "fused_optimizer": {"value": e2e_fused_val, "unit": UNIT,
                                         "what": "the same per-step loop with torch.optim.Adam(fused=True) (one optimiser kernel "

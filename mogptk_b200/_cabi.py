@@ -113,6 +113,8 @@ _EXTRA = {
     "mogp_set_rowpipe_super": (C.c_int, [C.c_int, C.c_int]),
     "mogp_host_rowpipe_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]),
     "mogp_set_stamps": (C.c_int, [C.c_int]),
+    "mogp_early_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_double))]),
+    "mogp_early_expected": (C.c_ulonglong, [C.c_void_p]),
     "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
     "mogp_set_two_level_above": (C.c_int, [C.c_longlong]),
     "mogp_set_panel_pdl": (C.c_int, [C.c_int]),

@@ -127,6 +127,8 @@ extern "C" int mogp_destroy(mogp_handle_t h) {
     if (h->i8) i8_plan_destroy(h->i8);
     if (h->pent_dev) cudaFree(h->pent_dev);
     if (h->pent_host) cudaFreeHost(h->pent_host);
+    if (h->early_host) cudaFreeHost(h->early_host);
+    if (h->early_ctr) cudaFree(h->early_ctr);
     for (StepGraph* g : h->graphs) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
         delete g;
@@ -500,6 +502,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     }
     MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
     MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
+    if (h->early_on) MOGP_CHECK(h, launch_lml_early(z, h->logdet_part, h->info, N, Np, h->early_host, h->early_ctr, st));
     MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(3, st));
@@ -660,6 +663,7 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
         MOGP_CHECK(h, cudaEventRecord(h->ev_out, st));
         MOGP_CHECK(h, cudaStreamWaitEvent(user, h->ev_out, 0));
     }
+    if (h->early_on) ++h->early_expected;      // exactly one lml_early_kernel was enqueued above (eager run or graph launch)
     h->have_factor = true;
     h->spec = s;
     h->chan_off.assign(chan_off_host, chan_off_host + C + 1);
@@ -667,6 +671,31 @@ extern "C" int mogp_lml_grad(mogp_handle_t h, int kind, int C, int Q, int D, con
     h->Np = Np;
     return 0;
 }
+
+// Early loss: the step writes [lml, info, seq] into mapped pinned host memory as soon as the solves are done (long before the
+// gradient is), seq counting the evaluations of this handle since the feature was switched on.  A caller that only needs the
+// loss value to return (gpr.Model.loss: the value and a possible CholeskyException, mogptk/gpr/model.py:279-292) polls
+// host_buf[2] for the value of mogp_early_expected() instead of synchronising the stream; the gradient buffers are then
+// complete in stream order, like the result of any asynchronous CUDA call.
+extern "C" int mogp_early_loss(mogp_handle_t h, int on, double** host_buf) {
+    if (!h) return -1;
+    MOGP_CHECK(h, cudaSetDevice(h->device));
+    if (on && !h->early_host) {
+        MOGP_CHECK(h, cudaHostAlloc(&h->early_host, 8 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+        MOGP_CHECK(h, cudaMalloc(&h->early_ctr, sizeof(unsigned long long)));
+        for (int i = 0; i < 8; ++i) h->early_host[i] = 0.0;
+    }
+    if (on) {
+        MOGP_CHECK(h, cudaDeviceSynchronize());
+        MOGP_CHECK(h, cudaMemset(h->early_ctr, 0, sizeof(unsigned long long)));
+        h->early_expected = 0;
+        h->early_host[2] = 0.0;
+    }
+    if ((on != 0) != h->early_on) { h->early_on = on != 0; h->realloc_epoch++; }      // captured steps change: re-capture
+    if (host_buf) *host_buf = h->early_host;
+    return 0;
+}
+extern "C" unsigned long long mogp_early_expected(mogp_handle_t h) { return h ? h->early_expected : 0; }
 
 extern "C" int mogp_lml_grad_host(mogp_handle_t h, int kind, int C, int Q, int D, const double* params_host,
                                   const double* x_host, const int32_t* chan_off_host, const double* y_host,

@@ -159,6 +159,9 @@ struct mogp_handle_s {
     std::vector<int32_t> chan_uploaded;                       // content of chan_dev slot 0
     double *gbuf = nullptr; size_t gbuf_cap = 0;              // graph staging: params | sigma | y | data_var | out
     I8Plan* i8 = nullptr;                                     // int8 tensor-pipe GEMM state (large problems)
+    // early loss: [lml, info, seq] in mapped pinned host memory, written by the step right after the solves (mogp_early_loss)
+    double* early_host = nullptr; unsigned long long* early_ctr = nullptr; bool early_on = false;
+    unsigned long long early_expected = 0;
     // optional stage timing (mogp_set_profile): events at the stage boundaries of mogp_lml_grad
     bool profile = false;
     cudaEvent_t ev[8] = {};
@@ -254,6 +257,9 @@ cudaError_t launch_copy_tri(int dir, double* user, long long ldu, double* work, 
 cudaError_t launch_pred_var(const double* chanbuf, int C, const int32_t* chan_s_dev, const double* colsq, int64_t M,
                             double* var, cudaStream_t st, const double* kss = nullptr);
 cudaError_t run_peak_fp64(double* dmma_tflops, double* dfma_tflops);
+// [lml, info, sequence number] into mapped pinned host memory right after the solves (see cov.cu)
+cudaError_t launch_lml_early(const double* z, const double* logdet_part, const int32_t* info, int64_t N, int64_t Np,
+                             double* host_out_dev, unsigned long long* counter, cudaStream_t st);
 cudaError_t launch_stamp(int slot, cudaStream_t st);      // diagnostics: global-timer stamp of a point of the step (mogp_set_stamps)
 
 // ------------------------------------------------------------------ fp64 GEMM on the int8 tensor pipe (i8mm.cu)

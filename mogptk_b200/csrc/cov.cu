@@ -699,6 +699,38 @@ __device__ double block_sum_256(double v, double* red) {
     return red[0];
 }
 
+// The log marginal likelihood as soon as the solves are done (same arithmetic as finalize_kernel below), written straight into
+// mapped pinned host memory with a sequence number behind it: the host can return from loss() while K^-1, the gradient
+// reduction and the chain rule are still running -- whatever the caller enqueues next (the optimiser's kernels) is ordered
+// behind them by the stream, as for any asynchronous CUDA work.
+__global__ void __launch_bounds__(256) lml_early_kernel(const double* __restrict__ z, const double* __restrict__ logdet_part,
+                                                        const int32_t* __restrict__ info, long long N, long long Np,
+                                                        volatile double* __restrict__ host_out,
+                                                        unsigned long long* __restrict__ counter) {
+    __shared__ double red[256];
+    const int tid = threadIdx.x;
+    double zz = 0.0;
+    for (long long r = tid; r < Np; r += 256) zz += z[r] * z[r];
+    zz = block_sum_256(zz, red);
+    double ld = 0.0;
+    for (long long b = tid; b < Np / 64; b += 256) ld += logdet_part[b];
+    ld = block_sum_256(ld, red);
+    if (tid == 0) {
+        const unsigned long long seq = ++(*counter);
+        host_out[0] = -0.5 * (double)N * log(2.0 * MOGP_PI) - ld - 0.5 * zz;
+        host_out[1] = (double)info[0];
+        __threadfence_system();
+        host_out[2] = (double)seq;
+        __threadfence_system();
+    }
+}
+cudaError_t launch_lml_early(const double* z, const double* logdet_part, const int32_t* info, int64_t N, int64_t Np,
+                             double* host_out_dev, unsigned long long* counter, cudaStream_t st) {
+    lml_early_kernel<<<1, 256, 0, st>>>(z, logdet_part, info, (long long)N, (long long)Np, host_out_dev, counter);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) finalize_kernel(KernSpec s, int want_grad, const double* __restrict__ params,
                                                        const double* __restrict__ sigma, const double* __restrict__ comps,
                                                        double* __restrict__ gsum, const double* __restrict__ winsum,

@@ -155,10 +155,12 @@ class Engine:
         self.h = h
         self._train = None        # Rows of the last lml_grad (for predict)
         self._kind = None
+        self._early = None        # numpy view of the handle's early-loss window (False: switched off)
 
     # ---------------------------------------------------------------- plumbing
     def close(self):
         if getattr(self, "h", None):
+            self._early = False                 # (the window lives in memory the handle owns)
             self.lib.mogp_destroy(self.h)
             self.h = None
 
@@ -167,6 +169,34 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ---------------------------------------------------------------- early loss (see mogp_early_loss in capi.cu)
+    def early_loss_buffer(self):
+        """The handle's [lml, info, seq] window in mapped pinned host memory (numpy view), or None when switched off
+        (MOGP_EARLY_LOSS=0).  Switched on at first use; must be requested BEFORE the evaluation it is to report."""
+        if getattr(self, "_early", None) is None:
+            import os
+            if os.environ.get("MOGP_EARLY_LOSS", "1") == "0":
+                self._early = False
+            else:
+                ptr = C.POINTER(C.c_double)()
+                self._check(self.lib.mogp_early_loss(self.h, 1, C.byref(ptr)))
+                self._early = np.ctypeslib.as_array(ptr, shape=(3,))
+        return self._early if self._early is not False else None
+
+    def wait_early_loss(self, buf, timeout_s=30.0):
+        """Spin until the step enqueued last has published its loss; returns (lml, info)."""
+        import time
+        want = float(self.lib.mogp_early_expected(self.h))
+        t0 = None
+        while buf[2] != want:
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout_s:
+                torch.cuda.synchronize(self.device)
+                if buf[2] != want:
+                    raise RuntimeError("early loss: the step did not report (sequence %r, expected %r)" % (float(buf[2]), want))
+        return float(buf[0]), float(buf[1])
 
     def _check(self, rc):
         if rc != 0:

@@ -961,16 +961,23 @@ class Exact(_Named):
         rows = self._rows
         st = eng._stream()
         base = bufs.data_ptr()
+        early = eng.early_loss_buffer()          # (before the call: the step must know that it has to report early)
         eng._check(lib.mogp_loss_grad(eng.h, _cabi.KIND[self._kind], C_, Q, D, C.addressof(entries), n_entries, eng._p(rows.x),
                                       rows.off_p, eng._p(rows.y), eng._p(rows.dv), float(self.jitter), C.c_void_p(base),
                                       C.c_void_p(base + 24 * n), st))
         eng._train, eng._kind = rows, self._kind
-        host = cache.get("host")
-        if host is None:
-            host = cache["host"] = torch.zeros(2, dtype=torch.float64).pin_memory()
-        host.copy_(out[:2], non_blocking=True)                 # [lml, info] into pinned memory:
-        torch.cuda.current_stream(eng.device).synchronize()    # the iteration's one synchronisation
-        lml, info = float(host[0]), float(host[1])
+        if early is not None:
+            # the step writes [lml, info, sequence number] into mapped pinned memory right after the solves: return as soon as the
+            # loss is known.  K^-1, the gradient reduction and the chain rule into p.grad are still running then; whatever
+            # comes next on this stream (the optimiser's kernels) is ordered behind them, as for any asynchronous CUDA op.
+            lml, info = eng.wait_early_loss(early)
+        else:
+            host = cache.get("host")
+            if host is None:
+                host = cache["host"] = torch.zeros(2, dtype=torch.float64).pin_memory()
+            host.copy_(out[:2], non_blocking=True)                 # [lml, info] into pinned memory:
+            torch.cuda.current_stream(eng.device).synchronize()    # the iteration's one synchronisation
+            lml, info = float(host[0]), float(host[1])
         if info != 0:
             # the reference raises in forward(), before backward() has produced anything (gpr/model.py:246-255,291):
             # do not leave the non-finite chain-rule output in p.grad for callers that catch and continue

@@ -190,3 +190,45 @@ def test_concurrent_restarts_on_one_gpu_equal_sequential_training(gpr):
 def build_with_engine(gpr, g, engine):
     from test_host_layer import build_mirror
     return build_mirror(g, engine)
+
+
+@pytest.mark.parametrize("name", ["mosm_mid", "cfg2_rdp"])
+def test_early_loss_equals_the_synchronous_path(gpr, name, monkeypatch):
+    """loss() returns as soon as the step has published [lml, info] (mapped pinned memory, right after the solves), while K^-1,
+    the gradient reduction and the chain rule are still running: the value is bit-identical to the synchronous path's, p.grad
+    read afterwards (stream order) is complete, an optimiser step enqueued right behind it sees the whole gradient, and a
+    Cholesky failure still raises inside loss()."""
+    g = load_golden(name)
+    m, plist = build(gpr, g)
+    eng = m._eng()
+    assert eng.early_loss_buffer() is not None
+    losses, grads = [], []
+    for _ in range(4):                                   # plain run, capture, replays
+        l = m.loss()
+        losses.append(float(l))
+        grads.append([p.grad.clone() for p in m.parameters()])
+    assert all(v == losses[0] for v in losses)
+    for gl in grads[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(gl, grads[0]))
+    # the synchronous path on a fresh model / engine state
+    monkeypatch.setenv("MOGP_EARLY_LOSS", "0")
+    from mogptk_b200.engine import Engine
+    eng2 = Engine(device=0, max_n=g["X"].shape[0])
+    try:
+        m2, _ = build(gpr, g)
+        m2._engine = eng2
+        l2 = m2.loss()
+        assert eng2.early_loss_buffer() is None
+        assert float(l2) == losses[0]
+        for a, b in zip(m2.parameters(), grads[0]):
+            assert torch.equal(a.grad, b)
+    finally:
+        eng2.close()
+    monkeypatch.delenv("MOGP_EARLY_LOSS")
+    # an optimiser step enqueued right behind the early return uses the complete gradient
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+    before = [p.detach().clone() for p in m.parameters()]
+    m.loss()
+    opt.step()
+    for p, b0, g0 in zip(m.parameters(), before, grads[0]):
+        assert torch.allclose(p.detach(), b0 - 1e-3 * g0, rtol=0, atol=1e-12 * max(1.0, float(b0.abs().max())))
