@@ -136,6 +136,14 @@ int mogp_predict(mogp_handle_t h, const double* xs_dev, const int32_t* chan_off_
  * from autograd through y - mean(X) (gpr/model.py:445-452). */
 int mogp_alpha(mogp_handle_t h, double* alpha_dev, void* stream);
 
+/* Early loss.  gpr.Model.loss() (gpr/model.py:279-292) returns the loss VALUE (and raises CholeskyException); its gradients are
+ * consumed by the optimiser afterwards.  With on = 1 every following mogp_lml_grad / mogp_loss_grad on this handle writes
+ * host_buf[0..2] = {lml, info, seq} into mapped pinned host memory as soon as the solves are done -- before K^-1, the gradient
+ * reduction and the chain rule -- where seq counts the evaluations since the switch.  The caller polls host_buf[2] for
+ * mogp_early_expected(h) instead of synchronising the stream; the gradient outputs are complete in stream order. */
+int mogp_early_loss(mogp_handle_t h, int on, double** host_buf);
+unsigned long long mogp_early_expected(mogp_handle_t h);
+
 /* ---- constrained parameters on the device ------------------------------------------------
  * Replaces Parameter.constrained / Softplus.forward / Sigmoid.forward (gpr/parameter.py:30-96,186-201) and
  * their autograd backward for the training loop (mogptk/model.py:563-565): forward maps the raw leaves to the

@@ -68,6 +68,8 @@ _SIGNATURES = {
                              c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.c_void_p]),
     "mogp_trtri_kinv": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, C.c_int64, C.c_void_p, C.c_void_p]),
     "mogp_peak_fp64": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mogp_early_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_double))]),
+    "mogp_early_expected": (C.c_ulonglong, [C.c_void_p]),
 }
 
 # not part of the public header: tuning / host self-check hooks
@@ -113,8 +115,6 @@ _EXTRA = {
     "mogp_set_rowpipe_super": (C.c_int, [C.c_int, C.c_int]),
     "mogp_host_rowpipe_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]),
     "mogp_set_stamps": (C.c_int, [C.c_int]),
-    "mogp_early_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_double))]),
-    "mogp_early_expected": (C.c_ulonglong, [C.c_void_p]),
     "mogp_set_skip_bulk": (C.c_int, [C.c_int]),
     "mogp_set_two_level_above": (C.c_int, [C.c_longlong]),
     "mogp_set_panel_pdl": (C.c_int, [C.c_int]),

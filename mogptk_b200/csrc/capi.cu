@@ -477,6 +477,8 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     // (`rowp`: K^-1 accumulated behind the chain as well, which needs the scratch T beside W; off by default -- the row-wise
     //  pipeline of Linv alone runs with W as its scratch)
     const bool rowp = want_grad && g_rowpipe_kinv != 0 && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
+    MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
+    ZChain zc{ypad, z, N, h->early_on ? h->early_host : nullptr, h->early_on ? h->early_ctr : nullptr, false};
     // Large sizes: recursive factor + inverse, everything above the 2048-row leaves on the int8 tensor pipe
     cudaError_t er = use_i8(Np) ? rchol_padded(h->A, ld, h->Linv, h->W, Np, h->logdet_part, h->info, st, &h->ps, h->i8, g_i8_slices, 1)
                                 : cudaErrorNotSupported;
@@ -484,7 +486,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     else if (er != cudaErrorNotSupported) MOGP_CHECK(h, er);
     else
     MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, rowp ? h->T : h->W, ld, Np, h->logdet_part, h->info, st, &h->ps,
-                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp ? h->W : nullptr, &fused_kinv));
+                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp ? h->W : nullptr, &fused_kinv, &zc));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(2, st));
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
@@ -500,9 +502,10 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
         MOGP_CHECK(h, kinv_dispatch(h, Np, ld, h->ps.s3));
         MOGP_CHECK(h, cudaEventRecord(h->ev_f2, h->ps.s3));
     }
-    MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
-    MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
-    if (h->early_on) MOGP_CHECK(h, launch_lml_early(z, h->logdet_part, h->info, N, Np, h->early_host, h->early_ctr, st));
+    if (!zc.done) {      // (with the row-wise pipeline z and the early loss came out of potrf_padded)
+        MOGP_CHECK(h, launch_trmv_lower(h->Linv, ld, ypad, z, Np, st));
+        if (h->early_on) MOGP_CHECK(h, launch_lml_early(z, h->logdet_part, h->info, N, Np, h->early_host, h->early_ctr, st));
+    }
     MOGP_CHECK(h, launch_colpass(h->Linv, ld, z, Np, Np, h->colpart, h->colpart_cap, alpha, kdiag, st));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(3, st));

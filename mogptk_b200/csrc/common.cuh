@@ -233,6 +233,14 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 // fused_inverse: NULL -> factor only (diagonal blocks of Linv get inv(L_kk)); else the triangular inverse may be
 // pipelined behind the panel chain (needs Ltmp == the scratch trtri_padded would use, ldt == ldi == lda); on return
 // *fused_inverse tells whether Linv is complete (true) or trtri_padded still has to run (false).
+// z = L^-1 y carried along the row-wise pipeline: as soon as a row block of Linv is complete its entries of z follow, and behind
+// the last block the early loss [lml, info, seq] (see launch_lml_early) -- instead of one triangular mat-vec after the join.
+struct ZChain {
+    const double* ypad; double* z;       // Np each (padding rows of y zero)
+    int64_t N;                           // true row count (constant of the log marginal likelihood)
+    double* early_host; unsigned long long* early_ctr;   // NULL: no early loss
+    bool done;                           // out: z (and the early loss) were produced inside potrf_padded
+};
 // Kacc != NULL (a further Np x Np buffer, ld = lda, distinct from Ltmp) allows the row-wise pipeline (small sizes): Linv
 // is built row group by row group behind the panel chain and K^-1 = Linv^T Linv (lower) is accumulated into Kacc by
 // rank updates as the rows complete; *fused_kinv then says that Kacc is (will be) complete once ps->ev_kinv -- recorded
@@ -240,7 +248,9 @@ cudaError_t launch_finalize(const KernSpec& s, const TileList* tl, int want_grad
 cudaError_t potrf_padded(double* A, long long lda, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
                          bool* fused_inverse = nullptr, I8Plan* i8 = nullptr, int i8_slices = 7, double* Kacc = nullptr,
-                         bool* fused_kinv = nullptr);
+                         bool* fused_kinv = nullptr, ZChain* zc = nullptr);
+cudaError_t launch_trmv_rows(const double* Linv, long long ld, const double* y, double* z, int64_t row0, int64_t row1,
+                             cudaStream_t st);
 bool rowpipe_applies(int64_t Np);
 cudaError_t trtri_padded(double* A /*L*/, double* Linv, double* scratch, int64_t Np, long long ld, cudaStream_t st,
                          I8Plan* i8 = nullptr, int i8_slices = 7);

@@ -1386,9 +1386,10 @@ extern "C" int mogp_host_rowpipe_partition(int nb, int G, int S, int taper, int3
 
 cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, double* Ltmp, long long ldt,
                          int64_t Np, double* logdet_part, int32_t* info, cudaStream_t st, const PotrfStreams* ps,
-                         bool* fused_inverse, I8Plan* i8, int i8_slices, double* Kacc, bool* fused_kinv) {
+                         bool* fused_inverse, I8Plan* i8, int i8_slices, double* Kacc, bool* fused_kinv, ZChain* zc) {
     if (fused_inverse) *fused_inverse = false;
     if (fused_kinv) *fused_kinv = false;
+    if (zc) zc->done = false;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     const size_t smem_p = (size_t)(128 * PS + 128 * PZ + 64 + 128 * 8) * sizeof(double);
@@ -1496,6 +1497,18 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
             if ((ee = launch_gemm(0, 0, g, 1, sX)) != cudaSuccess) return ee;
         }
         if ((ee = cudaEventRecord(ex, sX)) != cudaSuccess) return ee;
+        if (zc) {                    // z = Linv y for the rows that are complete now; behind the last ones, the early loss
+            cudaStream_t sZ = ps->sl[3];
+            level_used[3] = true;
+            if ((ee = cudaStreamWaitEvent(sZ, ex, 0)) != cudaSuccess) return ee;
+            if ((ee = launch_trmv_rows(Linv, ld, zc->ypad, zc->z, r0, c1, sZ)) != cudaSuccess) return ee;
+            if (c1 == Np) {
+                if (zc->early_host &&
+                    (ee = launch_lml_early(zc->z, logdet_part, info, zc->N, Np, zc->early_host, zc->early_ctr, sZ)) != cudaSuccess)
+                    return ee;
+                zc->done = true;
+            }
+        }
         const long long s0 = (long long)gr.slo * 64, s1 = (long long)gr.shi * 64;       // the super-group's rows / columns
         if (c1 < s1) {               // fine: T[rest of the super-group, 0:c1) += L[those rows, group columns] X[I, 0:c1)
             GemmArgs g{};            // (first touch of the group's own columns)
@@ -1899,9 +1912,9 @@ cudaError_t kinv_padded(const double* Linv, double* W, int64_t Np, long long ld,
 // z[r] = sum_{c<=r} Linv[r][c] * y[c]; one warp per row.
 __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ Linv, long long ld,
                                                          const double* __restrict__ y, double* __restrict__ z,
-                                                         int64_t Np) {
+                                                         int64_t row0, int64_t Np) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t r = row0 + blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= Np) return;
     const double* row = Linv + r * ld;
     double acc = 0.0;
@@ -1912,7 +1925,15 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
 }
 
 cudaError_t launch_trmv_lower(const double* Linv, long long ld, const double* y, double* z, int64_t Np, cudaStream_t st) {
-    trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Linv, ld, y, z, Np);
+    trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Linv, ld, y, z, 0, Np);
+    MOGP_COUNT(1);
+    return cudaGetLastError();
+}
+// rows [row0, row1) only (each row is summed exactly as in the full launch)
+cudaError_t launch_trmv_rows(const double* Linv, long long ld, const double* y, double* z, int64_t row0, int64_t row1,
+                             cudaStream_t st) {
+    if (row1 <= row0) return cudaSuccess;
+    trmv_lower_kernel<<<(unsigned)((row1 - row0 + 7) / 8), 256, 0, st>>>(Linv, ld, y, z, row0, row1);
     MOGP_COUNT(1);
     return cudaGetLastError();
 }
