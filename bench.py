@@ -220,11 +220,11 @@ def run_reference(args, device):
     if rank != 0:
         return
     if device != "cpu" and not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference-cuda", "unavailable": "no CUDA device"}))
+        emit({"impl": "reference-cuda", "unavailable": "no CUDA device"})
         return
     cb, n = time_reference(args.config, 0, args.steps, args.warmup, budget_s=150.0, device=device)
     if cb is None:
-        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref is missing"}))
+        emit({"impl": "reference-cuda", "unavailable": "oracle/_ref is missing"})
         return
     line = {"impl": "reference" if device == "cpu" else "reference-cuda", "metric": METRIC, "value": cb["value"],
             "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
@@ -233,7 +233,7 @@ def run_reference(args, device):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "loss": cb["loss"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- B200 arm helpers
@@ -664,7 +664,7 @@ def run_b200(args):
         if not args.no_cpu_baseline and world == 1:
             cb, _ = time_reference(args.config, 0, 20, 2, budget_s=25.0, device="cpu")
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     replicas.finish()
 
 
@@ -750,11 +750,44 @@ def reference_seam(cfg, iters):
             "final_loss": float(m.losses[-1]), "final_loss_installed": float(m2.losses[-1])}
 
 
+class _StdoutToStderr:
+    """Everything the libraries print while the bench runs (e.g. the NCCL version banner at N > 1, which goes to file
+    descriptor 1) is sent to stderr: stdout carries the ONE JSON line, printed after the descriptor is restored."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+
+
+_REDIRECT = None
+
+
+def emit(line):
+    """The single JSON line on the real stdout."""
+    if _REDIRECT is not None:
+        _REDIRECT.restore()
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a, "cpu")
-    elif a.impl == "reference-cuda":
-        run_reference(a, "cuda")
-    else:
-        run_b200(a)
+    with _StdoutToStderr() as _REDIRECT:
+        if a.impl == "reference":
+            run_reference(a, "cpu")
+        elif a.impl == "reference-cuda":
+            run_reference(a, "cuda")
+        else:
+            run_b200(a)
