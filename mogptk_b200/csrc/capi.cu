@@ -479,6 +479,9 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     const bool rowp = want_grad && g_rowpipe_kinv != 0 && rowpipe_applies(Np) && h->T != nullptr && h->T_cap >= (size_t)Np * Np;
     MOGP_CHECK(h, launch_pad_copy(y, N, ypad, Np, st));
     ZChain zc{ypad, z, N, h->early_on ? h->early_host : nullptr, h->early_on ? h->early_ctr : nullptr, false};
+    // (z along the pipeline: measured -1.3 % on the device-timed step for no visible end-to-end gain -- 32 more launches beside
+    //  the chain; off by default, MOGP_ZCHAIN=1)
+    static const int zchain_on = std::getenv("MOGP_ZCHAIN") ? std::atoi(std::getenv("MOGP_ZCHAIN")) : 0;
     // Large sizes: recursive factor + inverse, everything above the 2048-row leaves on the int8 tensor pipe
     cudaError_t er = use_i8(Np) ? rchol_padded(h->A, ld, h->Linv, h->W, Np, h->logdet_part, h->info, st, &h->ps, h->i8, g_i8_slices, 1)
                                 : cudaErrorNotSupported;
@@ -486,7 +489,7 @@ static int enqueue_step(mogp_handle_s* h, const KernSpec& s, TileList* tl, int64
     else if (er != cudaErrorNotSupported) MOGP_CHECK(h, er);
     else
     MOGP_CHECK(h, potrf_padded(h->A, ld, h->Linv, ld, rowp ? h->T : h->W, ld, Np, h->logdet_part, h->info, st, &h->ps,
-                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp ? h->W : nullptr, &fused_kinv, &zc));
+                               &fused_inverse, use_i8(Np) ? h->i8 : nullptr, g_i8_slices, rowp ? h->W : nullptr, &fused_kinv, zchain_on ? &zc : nullptr));
     STAGE_MARK();
     MOGP_CHECK(h, launch_stamp(2, st));
     // Linv, z = Linv y, alpha = Linv^T z, diag(K^-1)
