@@ -102,6 +102,7 @@ _EXTRA = {
     "mogp_get_rowpipe": (C.c_int, []),
     "mogp_set_launch_prio": (C.c_int, [C.c_int]),
     "mogp_set_gemm_k64": (C.c_int, [C.c_int]),
+    "mogp_set_xfuse": (C.c_int, [C.c_int]),
     "mogp_set_rchol": (C.c_int, [C.c_int, C.c_longlong, C.c_longlong]),
     "mogp_get_rchol": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "mogp_rchol_applies": (C.c_int, [C.c_longlong]),

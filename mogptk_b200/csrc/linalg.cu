@@ -1168,6 +1168,122 @@ __global__ void __launch_bounds__(64) diag_inv_kernel(double* __restrict__ A, lo
     }
 }
 
+// Row-wise pipeline with 64-row groups: the inverse of the diagonal block and the product X[I, 0:r0) = -X_II T[I, 0:r0) in ONE
+// launch (one kernel, one dependency and one launch latency less per panel step beside the chain -- every extra launch there
+// costs the chain about a microsecond, profiles/r02_early_loss_ab.txt).  CTA c takes columns [64 c, 64 c + 64); every CTA
+// inverts L_kk itself (the forward substitution of diag_inv_kernel, ~2 us, while its T tile is on its way by cp.async);
+// CTA 0 also moves L_kk into A, writes X_II into Linv and the block's log-determinant.  blk = 0: no columns, one CTA.
+#define XP2 68   // pitch of the X_II / T tiles in shared memory (== 4 mod 16: conflict-free DMMA fragment loads)
+__global__ void __launch_bounds__(128) xrow_fused_kernel(double* __restrict__ A, long long lda, const double* __restrict__ Ltmp,
+                                                         long long ldt, double* __restrict__ Linv, long long ldi,
+                                                         double* __restrict__ logdet_part, int blk) {
+    extern __shared__ __align__(16) double sm[];
+    double* Lt = sm;                    // [64][DP]   Lt[k][i] = L[i][k]
+    double* Xs = Lt + 64 * DP;          // [64][XP2]  X_II[m][k]
+    double* Ts = Xs + 64 * XP2;         // [64][XP2]  T tile [k][n]
+    double* dinv = Ts + 64 * XP2;       // [64] (+ 2 log partials)
+    const int tid = threadIdx.x, c = blockIdx.x;
+    const long long r0 = (long long)blk * 64;
+    const double* Ls = Ltmp + r0 * ldt + r0;
+    if (blk > 0) {                      // T[I rows, 64 c ..) on its way (Ltmp holds T below the block diagonal)
+        const double* Tg = Ltmp + r0 * ldt + (long long)c * 64;
+#pragma unroll
+        for (int q = tid; q < 64 * 32; q += 128) {
+            const int row = q >> 5, cc = q & 31;
+            cp_async16(Ts + row * XP2 + cc * 2, Tg + (long long)row * ldt + cc * 2, true);
+        }
+        cp_async_commit();
+    }
+    for (int q = tid; q < 64 * 64; q += 128) {
+        const int r = q >> 6, j = q & 63;
+        const double v = (j <= r) ? Ls[(long long)r * ldt + j] : 0.0;
+        Lt[j * DP + r] = v;
+        if (c == 0 && j <= r) A[(r0 + r) * lda + r0 + j] = v;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const int j = tid;
+        const double d = Lt[j * DP + j];
+        dinv[j] = 1.0 / d;
+        double lg = log(d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+        if ((j & 31) == 0) dinv[64 + (j >> 5)] = lg;
+    }
+    __syncthreads();
+    if (c == 0 && tid == 0) logdet_part[blk] = dinv[64] + dinv[65];
+    if (tid < 64) {
+        const int j = tid;
+        double* Lb = Linv + r0 * ldi + r0;
+        double r[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const double dk = dinv[k];
+            double x = -r[k] * dk;
+            x = (k == j) ? dk : ((k < j) ? 0.0 : x);
+            Xs[k * XP2 + j] = x;
+            if (c == 0) Lb[(long long)k * ldi + j] = x;
+#pragma unroll
+            for (int i = k + 1; i < 64; ++i) r[i] = fma(Lt[k * DP + i], x, r[i]);
+        }
+    }
+    if (blk == 0) return;
+    cp_async_wait<0>();
+    __syncthreads();
+    // C[64 x 64] = -X_II T: 4 warps as 2 x 2, warp tile 32 x 32
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int am0 = (warp >> 1) * 32, bn0 = (warp & 1) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < 64; kk += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Xs[(am0 + i * 8 + gq) * XP2 + kk + tq];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Ts[(kk + tq) * XP2 + bn0 + j * 8 + gq];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    double* Cg = Linv + r0 * ldi + (long long)c * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(Cg + (long long)(am0 + i * 8 + gq) * ldi + bn0 + j * 8 + 2 * tq) =
+                make_double2(-acc[i][j][0], -acc[i][j][1]);
+}
+// Measured (profiles/r02_xrow_fused.txt): correct, and much SLOWER -- the forward substitution repeated by every CTA of the row
+// product makes this launch longer than diag_inv_kernel + the GEMM, and the row pipeline falls behind the chain (cfg2 0.754 -> 1.229 ms).
+// Off; kept only as the record of the experiment.
+static int g_xfuse = std::getenv("MOGP_XFUSE") ? std::atoi(std::getenv("MOGP_XFUSE")) : 0;
+extern "C" int mogp_set_xfuse(int on) { g_xfuse = on; ++g_mogp_cfg_epoch; return 0; }
+static cudaError_t launch_xrow_fused(double* A, long long lda, const double* Ltmp, long long ldt, double* Linv, long long ldi,
+                                     double* logdet_part, int blk, cudaStream_t st) {
+    constexpr size_t SMEM = (size_t)(64 * DP + 2 * 64 * XP2 + 72) * sizeof(double);
+    static PerDeviceOnce once;
+    if (OnceGuard og{once}; og.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(xrow_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max(1, blk)); cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = -4;
+    cfg.attrs = at; cfg.numAttrs = g_launch_prio ? 1 : 0;
+    MOGP_COUNT(1);
+    return cudaLaunchKernelEx(&cfg, xrow_fused_kernel, A, lda, Ltmp, ldt, Linv, ldi, logdet_part, blk);
+}
+
 // on = 1: arm (resets the slots); on = 0: disarm and copy 2 * n values out (ns)
 extern "C" int mogp_panel_spans(int on, unsigned long long* out_host, int n) {
     if (on) {
@@ -1466,10 +1582,12 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
     std::vector<InvOp> plan;
     size_t next_op = 0, next_group = 0;
     bool level_used[8] = {};
+    bool s4_used = false;
     // (Kacc == NULL: Linv row-wise only, K^-1 is left to the caller)
     const bool rowp = pipe && (Kacc == nullptr || (fused_kinv != nullptr && Kacc != Ltmp && ps->ev_kinv != nullptr)) &&
                       rowpipe_applies(Np) && 4 * nb + 16 <= ps->nevq;
     std::vector<RowGroup> groups;
+    const bool xfuse = rowp && g_xfuse != 0 && g_rowpipe_group == 1;
     if (rowp) {
         int ne = 0;
         rowpipe_partition(nb, g_rowpipe_group, g_rowpipe_super, g_rowpipe_taper, groups);
@@ -1486,8 +1604,11 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         level_used[7] = Kacc != nullptr;
         const long long r0 = (long long)gr.lo * 64, R = (long long)(gr.hi - gr.lo) * 64, c1 = (long long)gr.hi * 64;
         cudaEvent_t ex = ps->evq[3 * nb + gi];
-        if ((ee = cudaStreamWaitEvent(sX, ps->evq[gr.ev_inv], 0)) != cudaSuccess) return ee;
-        if (r0 > 0) {                // X[I, 0:r0) = -X_II T[I, 0:r0)   (X_II lower triangular: k ends at the row tile)
+        if (xfuse) {                 // diagonal inverse + X[I, 0:r0) in one launch, right behind the group's (one) panel step
+            if ((ee = cudaStreamWaitEvent(sX, ps->evp[gr.hi - 1], 0)) != cudaSuccess) return ee;
+            if ((ee = launch_xrow_fused(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, gr.lo, sX)) != cudaSuccess) return ee;
+        } else if ((ee = cudaStreamWaitEvent(sX, ps->evq[gr.ev_inv], 0)) != cudaSuccess) return ee;
+        if (r0 > 0 && !xfuse) {      // X[I, 0:r0) = -X_II T[I, 0:r0)   (X_II lower triangular: k ends at the row tile)
             GemmArgs g{};
             g.A = Linv + r0 * ld + r0; g.lda = ld;
             g.B = Ltmp + r0 * ld; g.ldb = ld;
@@ -1560,7 +1681,9 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         for (; next_op < plan.size() && plan[next_op].ready <= s; ++next_op) {
             const InvOp& op = plan[next_op];
             if (op.kind == 0) {
+                if (xfuse) continue;          // the diagonal inverse is part of the group's fused launch (issue_group_ops)
                 if ((ee = cudaStreamWaitEvent(ps->s4, ps->evp[s], 0)) != cudaSuccess) return ee;
+                s4_used = true;
                 diag_inv_kernel<<<1, 64, 0, ps->s4>>>(A, ld, Ltmp, ldt, Linv, ldi, logdet_part, op.lo);
                 MOGP_COUNT(1);
                 if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
@@ -1600,8 +1723,10 @@ cudaError_t potrf_padded(double* A, long long ld, double* Linv, long long ldi, d
         if (last_bulk_ev && (ee = cudaStreamWaitEvent(user, last_bulk_ev, 0)) != cudaSuccess) return ee;
         if ((ee = cudaEventRecord(ps->ev1[ps->nev + 1], st)) != cudaSuccess) return ee;
         if ((ee = cudaStreamWaitEvent(user, ps->ev1[ps->nev + 1], 0)) != cudaSuccess) return ee;
-        if ((ee = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return ee;
-        if ((ee = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return ee;
+        if (s4_used) {               // (not forked at all when the diagonal inverses are part of the fused row launches)
+            if ((ee = cudaEventRecord(ps->evp[ps->nev + 1], ps->s4)) != cudaSuccess) return ee;
+            if ((ee = cudaStreamWaitEvent(user, ps->evp[ps->nev + 1], 0)) != cudaSuccess) return ee;
+        }
         for (int l = 0; l < 8; ++l) {
             if (!level_used[l]) continue;
             if (rowp && Kacc && l == 7) {        // the K^-1 accumulation is joined by the caller (the solves do not need it)
