@@ -48,7 +48,9 @@ def stage_of(name, state):
     if "kbuild_kernel" in n:
         state["seen_kbuild"] = True
         return "kbuild"
-    if "pad_copy" in n or "trmv_lower" in n or "colpass" in n:
+    if "pad_copy" in n:                      # (staged before the factorisation since the early-loss change: no state change)
+        return "solves"
+    if "trmv_lower" in n or "colpass" in n or "lml_early" in n:
         state["solves"] = True
         return "solves"
     if "grad_reduce" in n or "pairsum" in n or "finalize" in n or "copy_out" in n or "params_" in n:
@@ -70,9 +72,9 @@ def main():
     start = max(i for i, l in enumerate(launches[:last_fin]) if "prep_kernel" in l["name"])
     step = launches[start:last_fin + 1]
     state, stages = {}, {}
-    # the K^-1 product is launched (on a side stream) before the solves: it is the last GEMM before pad_copy -- together
+    # the K^-1 product is launched (on a side stream) before the solves: it is the last GEMM before trmv_lower -- together
     # with the three slicing kernels in front of it when it runs on the int8 pipe (i8_rowmax, i8_exponent, i8_slice_tiled)
-    idx_pad = next((i for i, l in enumerate(step) if "pad_copy" in l["name"]), None)
+    idx_pad = next((i for i, l in enumerate(step) if "trmv_lower" in l["name"]), None)
     kinv_set = set()
     if idx_pad is not None:
         i = idx_pad - 1
